@@ -1,0 +1,932 @@
+// dmv_api.cu -- the C ABI of libdmv_b200.so (see include/dmv_b200.h) and the per-GPU context.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only; the library itself is resolved with dlopen at dmv_comm_init
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/dmv_b200.h"
+#include "dmv_host.h"
+
+using namespace dmv;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define CUDA_CHECK(expr)                                                                        \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+  } while (0)
+
+#define API_BEGIN try {
+#define API_END                                         \
+  return 0;                                             \
+  }                                                     \
+  catch (const std::exception &e) {                     \
+    g_last_error = e.what();                            \
+    return 1;                                           \
+  }                                                     \
+  catch (...) {                                         \
+    g_last_error = "unknown error";                     \
+    return 1;                                           \
+  }
+
+template <typename T>
+struct DevBuf {
+  T *ptr = nullptr;
+  size_t count = 0;
+  void alloc(size_t n) {
+    if (n <= count && ptr) return;
+    release();
+    if (n == 0) n = 1;
+    CUDA_CHECK(cudaMalloc(&ptr, n * sizeof(T)));
+    count = n;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+  void upload(const std::vector<T> &h, cudaStream_t s) {
+    alloc(h.size());
+    if (!h.empty()) CUDA_CHECK(cudaMemcpyAsync(ptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  ~DevBuf() { release(); }
+};
+
+bool is_device_pointer(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+// ---- NCCL through dlopen ------------------------------------------------------------------------
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi &nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) return;
+#define LOAD(sym) api.sym = reinterpret_cast<decltype(api.sym)>(dlsym(api.handle, "nccl" #sym))
+    LOAD(GetUniqueId); LOAD(CommInitRank); LOAD(CommDestroy); LOAD(GroupStart); LOAD(GroupEnd);
+    LOAD(Send); LOAD(Recv); LOAD(AllGather); LOAD(GetErrorString);
+#undef LOAD
+  });
+  if (!api.handle || !api.Send) throw std::runtime_error("NCCL (libnccl.so.2) is not available");
+  return api;
+}
+#define NCCL_CHECK(expr)                                                                       \
+  do {                                                                                         \
+    ncclResult_t _r = (expr);                                                                  \
+    if (_r != ncclSuccess)                                                                     \
+      throw std::runtime_error(std::string(#expr) + ": " + nccl().GetErrorString(_r));        \
+  } while (0)
+
+enum Timing { T_H2D = 0, T_GENERATE, T_EXCHANGE, T_ACCUMULATE, T_D2H, T_TOTAL, T_COUNT };
+const char *kTimingNames[T_COUNT] = {"h2d", "generate(diag+offdiag+local accumulate)", "exchange(all-to-all)",
+                                     "accumulate(remote records)", "d2h", "total"};
+
+}  // namespace
+
+struct dmv_context {
+  int device = 0, rank = 0, num_ranks = 1;
+  // basis
+  int n_sites = 0, hamming_weight = -1, spin_inversion = 0;
+  bool has_permutations = false;
+  Projection proj = PROJ_NONE;
+  bool identity_index = false;
+  uint64_t site_mask = 0;
+  bool complex_coefficients = false;  // operator or characters are complex
+  HostOrbitProgram host_orbit;
+  DevBuf<uint64_t> d_orbit64;
+  DevBuf<int32_t> d_orbit32;
+  DevBuf<double> d_chars;
+  OrbitProgram orbit{};  // device view
+  // operator
+  std::vector<TermGroup> h_groups;
+  std::vector<OffTerm> h_terms;
+  std::vector<DiagTerm> h_diag;
+  DevBuf<TermGroup> d_groups;
+  DevBuf<OffTerm> d_terms;
+  DevBuf<DiagTerm> d_diag;
+  // representatives of this rank
+  int64_t n_states = -1;
+  DevBuf<uint64_t> d_reps;
+  DevBuf<double> d_norms;
+  DevBuf<uint32_t> d_dir;
+  uint64_t n_buckets = 0;
+  int dir_shift = 0;
+  // vectors staged for host callers
+  DevBuf<double> d_x, d_y;
+  // outgoing / incoming records
+  bool planned = false;
+  std::vector<int64_t> send_counts;        // [num_ranks]
+  std::vector<int64_t> recv_counts;        // [num_ranks] (filled by dmv_comm plan exchange)
+  std::vector<int64_t> h_out_offset;       // [num_ranks + 1]
+  DevBuf<int64_t> d_out_offset;
+  DevBuf<unsigned long long> d_out_count;
+  DevBuf<uint64_t> d_out_betas, d_in_betas;
+  DevBuf<double> d_out_coeffs, d_in_coeffs;
+  int record_width = 2;                    // doubles per coefficient of the current buckets
+  int64_t number_terms = 0;
+  DevBuf<unsigned long long> d_status;
+  // streams
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev[T_COUNT + 2] = {};
+  double timings[T_COUNT] = {};
+  // communicator
+  ncclComm_t comm = nullptr;
+
+  ~dmv_context() {
+    if (comm) nccl().CommDestroy(comm);
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
+    if (own_stream) cudaStreamDestroy(own_stream);
+  }
+};
+
+namespace {
+
+void use_device(const dmv_context *ctx) { CUDA_CHECK(cudaSetDevice(ctx->device)); }
+
+bool complex_values(const dmv_context *ctx, int elt) { return elt == DMV_C128 || ctx->complex_coefficients; }
+
+KernelParams base_params(dmv_context *ctx) {
+  KernelParams p{};
+  p.index.reps = ctx->d_reps.ptr;
+  p.index.n = ctx->n_states;
+  p.index.dir = ctx->d_dir.ptr;
+  p.index.n_buckets = ctx->n_buckets;
+  p.index.shift = ctx->dir_shift;
+  p.index.identity = (ctx->identity_index && ctx->num_ranks == 1) ? 1 : 0;
+  p.norms = ctx->d_norms.ptr;
+  p.groups = ctx->d_groups.ptr; p.n_groups = (int)ctx->h_groups.size();
+  p.terms = ctx->d_terms.ptr;   p.n_terms = (int)ctx->h_terms.size();
+  p.diag = ctx->d_diag.ptr;     p.n_diag = (int)ctx->h_diag.size();
+  p.orbit = ctx->orbit;
+  p.site_mask = ctx->site_mask;
+  p.inversion_character = (double)ctx->spin_inversion;
+  p.rank = ctx->rank;
+  p.num_ranks = ctx->num_ranks;
+  p.out_betas = ctx->d_out_betas.ptr;
+  p.out_coeffs = ctx->d_out_coeffs.ptr;
+  p.out_offset = ctx->d_out_offset.ptr;
+  p.out_count = ctx->d_out_count.ptr;
+  p.status = ctx->d_status.ptr;
+  p.row_begin = 0;
+  p.row_end = ctx->n_states;
+  return p;
+}
+
+void require_states(const dmv_context *ctx) {
+  if (ctx->n_states < 0) throw std::runtime_error("basis is not built");  // src/ForeignTypes.chpl:113-114
+}
+
+void check_status(dmv_context *ctx) {
+  unsigned long long st[3];
+  CUDA_CHECK(cudaMemcpyAsync(st, ctx->d_status.ptr, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (st[0] != 0 || st[2] != 0) {
+    CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    char buf[256];
+    if (st[2] != 0)
+      snprintf(buf, sizeof(buf), "outgoing bucket overflow (%llu records): plan is stale", st[2]);
+    else  // message of the reference: DMV:116-118
+      snprintf(buf, sizeof(buf), "invalid index: -1 for state %llu (%llu such records): the operator does "
+               "not respect the basis symmetries or the representatives are incomplete", st[1], st[0]);
+    throw std::runtime_error(buf);
+  }
+}
+
+void install_directory(dmv_context *ctx) {
+  const int64_t n = ctx->n_states;
+  uint64_t max_rep = 0;
+  if (n > 0) CUDA_CHECK(cudaMemcpyAsync(&max_rep, ctx->d_reps.ptr + (n - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  int bits = 0;
+  while (bits < 64 && (max_rep >> bits) != 0) ++bits;
+  // about 4 states per bucket on average, at least 2^10 and at most 2^26 buckets
+  int want = 10;
+  while (want < 26 && (1ll << (want + 2)) < n) ++want;
+  int shift = bits > want ? bits - want : 0;
+  ctx->dir_shift = shift;
+  ctx->n_buckets = (max_rep >> shift) + 1;
+  ctx->d_dir.alloc(ctx->n_buckets + 2);
+  launch_build_directory(ctx->d_reps.ptr, n, ctx->d_dir.ptr, ctx->n_buckets, shift, ctx->stream);
+  ctx->planned = false;
+}
+
+void upload_orbit(dmv_context *ctx) {
+  const HostOrbitProgram &H = ctx->host_orbit;
+  std::vector<uint64_t> h64 = H.benes_mask;
+  h64.insert(h64.end(), H.step_mask.begin(), H.step_mask.end());
+  std::vector<int32_t> h32 = H.benes_delta;
+  h32.insert(h32.end(), H.step_shift.begin(), H.step_shift.end());
+  ctx->d_orbit64.upload(h64, ctx->stream);
+  ctx->d_orbit32.upload(h32, ctx->stream);
+  ctx->d_chars.upload(H.characters, ctx->stream);
+  OrbitProgram P = H.view();
+  P.benes_mask = ctx->d_orbit64.ptr;
+  P.step_mask = ctx->d_orbit64.ptr + H.benes_mask.size();
+  P.benes_delta = ctx->d_orbit32.ptr;
+  P.step_shift = ctx->d_orbit32.ptr + H.benes_delta.size();
+  P.characters = reinterpret_cast<const double2 *>(ctx->d_chars.ptr);
+  ctx->orbit = P;
+}
+
+// binomial table for the combinadic ranking of fixed-Hamming-weight states
+struct Binomials {
+  uint64_t c[65][65];
+  Binomials() {
+    for (int n = 0; n <= 64; ++n)
+      for (int k = 0; k <= 64; ++k) {
+        if (k == 0 || k == n) c[n][k] = (k <= n) ? 1 : 0;
+        else if (k > n) c[n][k] = 0;
+        else {
+          const unsigned __int128 v = (unsigned __int128)c[n - 1][k - 1] + c[n - 1][k];
+          c[n][k] = v > (unsigned __int128)~0ull ? ~0ull : (uint64_t)v;
+        }
+      }
+  }
+};
+const Binomials &binom() { static Binomials b; return b; }
+
+// rank of a fixed-weight state among states of the same weight in ascending order
+// (what ls_hs_fixed_hamming_state_to_index computes, reference src/FFI.chpl:165)
+uint64_t fixed_hamming_rank(uint64_t s) {
+  uint64_t r = 0;
+  int k = 0;
+  while (s) {
+    const int pos = __builtin_ctzll(s);
+    ++k;
+    r += binom().c[pos][k];
+    s &= s - 1;
+  }
+  return r;
+}
+uint64_t fixed_hamming_unrank(uint64_t r, int weight) {  // ls_hs_fixed_hamming_index_to_state
+  uint64_t s = 0;
+  for (int k = weight; k >= 1; --k) {
+    int pos = k - 1;
+    while (pos + 1 <= 63 && binom().c[pos + 1][k] <= r) ++pos;
+    r -= binom().c[pos][k];
+    s |= 1ull << pos;
+  }
+  return s;
+}
+
+void zero_y_if_diag(dmv_context *ctx, int elt, void *y) {
+  // DMV:1062-1063: with diagonal terms y is overwritten by D x, otherwise it is accumulated into
+  if (!ctx->h_diag.empty())
+    CUDA_CHECK(cudaMemsetAsync(y, 0, (size_t)ctx->n_states * 8 * elt, ctx->stream));
+}
+
+struct VecStage {  // x / y either used in place (device pointers) or staged through context buffers
+  const void *x_dev; void *y_dev; bool y_host; void *y_user; size_t bytes;
+};
+VecStage stage_vectors(dmv_context *ctx, int elt, const void *x, void *y) {
+  VecStage v{};
+  v.bytes = (size_t)ctx->n_states * 8 * elt;
+  CUDA_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (is_device_pointer(x)) v.x_dev = x;
+  else {
+    ctx->d_x.alloc((size_t)ctx->n_states * elt);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->d_x.ptr, x, v.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    v.x_dev = ctx->d_x.ptr;
+  }
+  if (is_device_pointer(y)) { v.y_dev = y; v.y_host = false; }
+  else {
+    ctx->d_y.alloc((size_t)ctx->n_states * elt);
+    v.y_dev = ctx->d_y.ptr; v.y_host = true; v.y_user = y;
+    if (ctx->h_diag.empty())  // y is accumulated into: bring the caller's y over
+      CUDA_CHECK(cudaMemcpyAsync(ctx->d_y.ptr, y, v.bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CUDA_CHECK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  return v;
+}
+void finish_vectors(dmv_context *ctx, const VecStage &v) {
+  CUDA_CHECK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  if (v.y_host) CUDA_CHECK(cudaMemcpyAsync(v.y_user, v.y_dev, v.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaEventRecord(ctx->ev[5], ctx->stream));
+}
+
+void do_plan(dmv_context *ctx) {
+  require_states(ctx);
+  const int P = ctx->num_ranks;
+  ctx->d_out_count.alloc(P);
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_out_count.ptr, 0, sizeof(unsigned long long) * P, ctx->stream));
+  KernelParams p = base_params(ctx);
+  // counting pass: element type does not matter
+  launch_generate(p, ctx->proj, ctx->complex_coefficients, false, /*count_only=*/true, ctx->stream);
+  std::vector<unsigned long long> counts(P);
+  CUDA_CHECK(cudaMemcpyAsync(counts.data(), ctx->d_out_count.ptr, sizeof(unsigned long long) * P,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->send_counts.assign(P, 0);
+  ctx->number_terms = 0;
+  for (int d = 0; d < P; ++d) { ctx->send_counts[d] = (int64_t)counts[d]; ctx->number_terms += (int64_t)counts[d]; }
+  ctx->h_out_offset.assign(P + 1, 0);
+  for (int d = 0; d < P; ++d)
+    ctx->h_out_offset[d + 1] = ctx->h_out_offset[d] + (d == ctx->rank ? 0 : ctx->send_counts[d]);
+  ctx->d_out_offset.upload(ctx->h_out_offset, ctx->stream);
+  const int64_t total_out = ctx->h_out_offset[P];
+  ctx->d_out_betas.alloc((size_t)total_out);
+  ctx->d_out_coeffs.alloc((size_t)total_out * 2);
+  ctx->recv_counts.assign(P, -1);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->planned = true;
+}
+
+void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev) {
+  if (!ctx->planned) do_plan(ctx);
+  zero_y_if_diag(ctx, elt, y_dev);
+  if (ctx->num_ranks > 1)
+    CUDA_CHECK(cudaMemsetAsync(ctx->d_out_count.ptr, 0, sizeof(unsigned long long) * ctx->num_ranks, ctx->stream));
+  KernelParams p = base_params(ctx);
+  p.x = x_dev;
+  p.y = y_dev;
+  const bool cv = complex_values(ctx, elt);
+  ctx->record_width = cv ? 2 : 1;
+  launch_generate(p, ctx->proj, cv, elt == DMV_C128, false, ctx->stream);
+}
+
+void do_accumulate(dmv_context *ctx, int elt, int64_t count, const uint64_t *betas, const double *coeffs,
+                   void *y_dev) {
+  KernelParams p = base_params(ctx);
+  p.y = y_dev;
+  launch_accumulate(p, ctx->proj, complex_values(ctx, elt), elt == DMV_C128, count, betas, coeffs, ctx->stream);
+}
+
+void collect_timings(dmv_context *ctx) {
+  auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]); return (double)t; };
+  ctx->timings[T_H2D] = ms(0, 1);
+  ctx->timings[T_GENERATE] = ms(1, 2);
+  ctx->timings[T_EXCHANGE] = ms(2, 3);
+  ctx->timings[T_ACCUMULATE] = ms(3, 4);
+  ctx->timings[T_D2H] = ms(4, 5);
+  ctx->timings[T_TOTAL] = ms(0, 5);
+}
+
+std::mutex g_bind_mutex;
+std::map<const void *, dmv_context *> g_bindings;
+
+}  // namespace
+
+// ---- small kernels exposed with host-or-device pointers ----------------------------------------
+namespace {
+template <typename T>
+struct InArg {  // device view of an input array
+  DevBuf<T> buf; const T *ptr;
+  InArg(const T *p, size_t n, cudaStream_t s) {
+    if (is_device_pointer(p)) ptr = p;
+    else { buf.alloc(n); if (n) CUDA_CHECK(cudaMemcpyAsync(buf.ptr, p, n * sizeof(T), cudaMemcpyHostToDevice, s)); ptr = buf.ptr; }
+  }
+};
+template <typename T>
+struct OutArg {  // device view of an output array, copied back by finish()
+  DevBuf<T> buf; T *ptr; T *user; size_t n; bool host;
+  OutArg(T *p, size_t n_) : user(p), n(n_) {
+    host = !is_device_pointer(p);
+    if (host) { buf.alloc(n); ptr = buf.ptr; } else ptr = p;
+  }
+  void finish(cudaStream_t s, size_t used = (size_t)-1) {
+    if (host && user) { const size_t m = used == (size_t)-1 ? n : used; if (m) CUDA_CHECK(cudaMemcpyAsync(user, ptr, m * sizeof(T), cudaMemcpyDeviceToHost, s)); }
+  }
+};
+}  // namespace
+
+
+// =================================================================================================
+extern "C" {
+
+void ls_chpl_init(void) {}      // no runtime to start (reference src/library.c:19-32 boots the Chapel runtime)
+void ls_chpl_finalize(void) {}  // reference src/library.c:34
+const char *dmv_last_error(void) { return g_last_error.c_str(); }
+int dmv_version(void) { return 100; }
+int64_t dmv_launch_count(void) { return launch_counter(); }
+
+int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op, int device, int rank,
+                       int num_ranks, dmv_context **out) {
+  API_BEGIN
+  if (!basis || !op || !out) throw std::runtime_error("null argument");
+  if (basis->number_sites <= 0 || basis->number_sites > 64)
+    throw std::runtime_error("bases with more than 64 bits are not yet implemented");  // DMV:1099-1100
+  if (num_ranks < 1 || num_ranks > 256 || rank < 0 || rank >= num_ranks)
+    throw std::runtime_error("need 0 <= rank < num_ranks <= 256");                     // DMV:664: uint8 keys
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) {
+    cudaGetLastError();
+    throw std::runtime_error("no CUDA device: libdmv_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= n_dev) throw std::runtime_error("bad device ordinal");
+  std::unique_ptr<dmv_context> ctx(new dmv_context());
+  ctx->device = device; ctx->rank = rank; ctx->num_ranks = num_ranks;
+  use_device(ctx.get());
+  CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  for (auto &e : ctx->ev) CUDA_CHECK(cudaEventCreate(&e));
+  ctx->n_sites = basis->number_sites;
+  ctx->hamming_weight = basis->hamming_weight;
+  ctx->spin_inversion = basis->spin_inversion;
+  ctx->has_permutations = basis->has_permutations != 0;
+  ctx->site_mask = basis->number_sites == 64 ? ~0ull : ((1ull << basis->number_sites) - 1);
+  if (ctx->has_permutations) ctx->proj = PROJ_GROUP;                   // BO:163
+  else if (ctx->spin_inversion != 0) ctx->proj = PROJ_INVERSION;       // BO:119
+  else ctx->proj = PROJ_NONE;                                          // BO:89
+  ctx->identity_index = (ctx->proj == PROJ_NONE && ctx->hamming_weight < 0);
+
+  bool cplx = false;
+  // ---- operator: group off-diagonal terms by flip mask
+  std::map<uint64_t, std::vector<OffTerm>> by_x;
+  for (int64_t t = 0; t < op->n_off; ++t) {
+    OffTerm o{op->off_m[t], op->off_r[t], op->off_s[t], op->off_v[2 * t], op->off_v[2 * t + 1]};
+    if (op->off_x[t] == 0) throw std::runtime_error("off-diagonal term with zero flip mask");
+    if (o.v_im != 0.0) cplx = true;
+    by_x[op->off_x[t]].push_back(o);
+  }
+  for (auto &kv : by_x) {
+    TermGroup g{kv.first, (int32_t)ctx->h_terms.size(), (int32_t)kv.second.size()};
+    ctx->h_groups.push_back(g);
+    for (auto &o : kv.second) ctx->h_terms.push_back(o);
+  }
+  for (int64_t t = 0; t < op->n_diag; ++t) {
+    DiagTerm d{op->diag_m[t], op->diag_r[t], op->diag_s[t], op->diag_v[2 * t], op->diag_v[2 * t + 1]};
+    if (d.v_im != 0.0) cplx = true;
+    ctx->h_diag.push_back(d);
+  }
+  ctx->d_groups.upload(ctx->h_groups, ctx->stream);
+  ctx->d_terms.upload(ctx->h_terms, ctx->stream);
+  ctx->d_diag.upload(ctx->h_diag, ctx->stream);
+
+  // ---- symmetry group
+  if (ctx->proj == PROJ_GROUP) {
+    if (basis->group_order <= 0 || !basis->perms || !basis->flips || !basis->characters)
+      throw std::runtime_error("basis with permutation symmetries needs the group tables");
+    ctx->host_orbit = compile_orbit_program(basis->number_sites, basis->group_order, basis->perms,
+                                            basis->flips, basis->characters);
+    for (double v : ctx->host_orbit.characters) (void)v;
+    for (size_t e = 0; e < ctx->host_orbit.characters.size(); e += 2)
+      if (ctx->host_orbit.characters[e + 1] != 0.0) cplx = true;
+    upload_orbit(ctx.get());
+  }
+  ctx->complex_coefficients = cplx;
+  ctx->d_status.alloc(3);
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  ctx->d_out_count.alloc(num_ranks);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  *out = ctx.release();
+  API_END
+}
+
+int dmv_context_destroy(dmv_context *ctx) {
+  API_BEGIN
+  if (ctx) {
+    {
+      std::lock_guard<std::mutex> lock(g_bind_mutex);
+      for (auto it = g_bindings.begin(); it != g_bindings.end();)
+        it = (it->second == ctx) ? g_bindings.erase(it) : std::next(it);
+    }
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    delete ctx;
+  }
+  API_END
+}
+
+int dmv_set_stream(dmv_context *ctx, void *cuda_stream) {
+  API_BEGIN
+  use_device(ctx);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  API_END
+}
+
+int dmv_synchronize(dmv_context *ctx) {
+  API_BEGIN
+  use_device(ctx);
+  check_status(ctx);   // synchronises the stream and surfaces device-side errors (DMV:115-118)
+  API_END
+}
+
+int dmv_set_representatives(dmv_context *ctx, const uint64_t *representatives, int64_t count,
+                            const double *norms) {
+  API_BEGIN
+  use_device(ctx);
+  if (count < 0 || (count > 0 && !representatives)) throw std::runtime_error("bad representatives");
+  if (count >= (1ll << 32)) throw std::runtime_error("more than 2^32 states per rank are not supported");
+  ctx->d_reps.alloc((size_t)count);
+  if (count > 0)
+    CUDA_CHECK(cudaMemcpyAsync(ctx->d_reps.ptr, representatives, (size_t)count * 8, cudaMemcpyDefault, ctx->stream));
+  ctx->n_states = count;
+  if (ctx->proj == PROJ_GROUP) {
+    ctx->d_norms.alloc((size_t)count);
+    if (norms) {
+      if (count > 0)
+        CUDA_CHECK(cudaMemcpyAsync(ctx->d_norms.ptr, norms, (size_t)count * 8, cudaMemcpyDefault, ctx->stream));
+    } else {
+      launch_compute_norms(ctx->orbit, count, ctx->d_reps.ptr, ctx->d_norms.ptr, ctx->stream);
+    }
+  }
+  install_directory(ctx);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+int dmv_basis_build(dmv_context *ctx) {
+  API_BEGIN
+  use_device(ctx);
+  const int n = ctx->n_sites, w = ctx->hamming_weight;
+  const bool fixed = w >= 0;
+  // candidate range (mirror of ls_hs_min/max_state_estimate, reference src/ForeignTypes.chpl:102-109);
+  // with spin inversion the top site is never set in a representative
+  uint64_t lo, hi;
+  const bool inv = ctx->spin_inversion != 0;
+  if (fixed) {
+    if (w > n) throw std::runtime_error("hamming weight exceeds the number of sites");
+    lo = w == 0 ? 0 : ((w == 64) ? ~0ull : ((1ull << w) - 1));
+    const int top = (inv && n - 1 >= w) ? n - 1 : n;
+    hi = w == 0 ? 0 : (((w == 64) ? ~0ull : ((1ull << w) - 1)) << (top - w));
+  } else {
+    lo = 0;
+    hi = inv ? (ctx->site_mask >> 1) : ctx->site_mask;
+  }
+  const uint64_t first_rank = fixed ? fixed_hamming_rank(lo) : lo;
+  const uint64_t last_rank = fixed ? fixed_hamming_rank(hi) : hi;
+  const uint64_t total = last_rank - first_rank + 1;
+  uint64_t chunk_len = total / (148ull * 128 * 16);
+  chunk_len = std::min<uint64_t>(std::max<uint64_t>(chunk_len, 64), 4096);
+  const int64_t n_chunks = (int64_t)((total + chunk_len - 1) / chunk_len);
+  std::vector<uint64_t> h_first((size_t)n_chunks), h_last((size_t)n_chunks);
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const uint64_t r0 = first_rank + (uint64_t)c * chunk_len;
+    const uint64_t r1 = std::min(r0 + chunk_len - 1, last_rank);
+    h_first[c] = fixed ? fixed_hamming_unrank(r0, w) : r0;
+    h_last[c] = fixed ? fixed_hamming_unrank(r1, w) : r1;
+  }
+  DevBuf<uint64_t> d_first, d_last;
+  DevBuf<unsigned long long> d_count, d_offset;
+  d_first.upload(h_first, ctx->stream);
+  d_last.upload(h_last, ctx->stream);
+  d_count.alloc((size_t)n_chunks);
+  d_offset.alloc((size_t)n_chunks);
+  launch_enumerate(ctx->orbit, ctx->proj, ctx->site_mask, fixed, ctx->rank, ctx->num_ranks, n_chunks,
+                   d_first.ptr, d_last.ptr, d_count.ptr, d_offset.ptr, nullptr, nullptr, false, ctx->stream);
+  std::vector<unsigned long long> h_count((size_t)n_chunks), h_offset((size_t)n_chunks);
+  CUDA_CHECK(cudaMemcpyAsync(h_count.data(), d_count.ptr, sizeof(unsigned long long) * n_chunks,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  unsigned long long acc = 0;
+  for (int64_t c = 0; c < n_chunks; ++c) { h_offset[c] = acc; acc += h_count[c]; }
+  if (acc >= (1ull << 32)) throw std::runtime_error("more than 2^32 states per rank are not supported");
+  d_offset.upload(h_offset, ctx->stream);
+  ctx->d_reps.alloc((size_t)acc);
+  if (ctx->proj == PROJ_GROUP) ctx->d_norms.alloc((size_t)acc);
+  launch_enumerate(ctx->orbit, ctx->proj, ctx->site_mask, fixed, ctx->rank, ctx->num_ranks, n_chunks,
+                   d_first.ptr, d_last.ptr, d_count.ptr, d_offset.ptr, ctx->d_reps.ptr,
+                   ctx->proj == PROJ_GROUP ? ctx->d_norms.ptr : nullptr, true, ctx->stream);
+  ctx->n_states = (int64_t)acc;
+  install_directory(ctx);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+int64_t dmv_number_states(const dmv_context *ctx) { return ctx ? ctx->n_states : -1; }
+
+int dmv_get_representatives(dmv_context *ctx, uint64_t *representatives, double *norms) {
+  API_BEGIN
+  use_device(ctx);
+  require_states(ctx);
+  if (representatives && ctx->n_states > 0)
+    CUDA_CHECK(cudaMemcpyAsync(representatives, ctx->d_reps.ptr, (size_t)ctx->n_states * 8, cudaMemcpyDefault, ctx->stream));
+  if (norms && ctx->n_states > 0) {
+    if (ctx->proj == PROJ_GROUP)
+      CUDA_CHECK(cudaMemcpyAsync(norms, ctx->d_norms.ptr, (size_t)ctx->n_states * 8, cudaMemcpyDefault, ctx->stream));
+    else {
+      std::vector<double> ones((size_t)ctx->n_states, ctx->proj == PROJ_INVERSION ? std::sqrt(0.5) : 1.0);
+      CUDA_CHECK(cudaMemcpyAsync(norms, ones.data(), ones.size() * 8, cudaMemcpyDefault, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+int dmv_state_index(dmv_context *ctx, int64_t count, const uint64_t *spins, int64_t *indices) {
+  API_BEGIN
+  use_device(ctx);
+  require_states(ctx);
+  InArg<uint64_t> in(spins, (size_t)count, ctx->stream);
+  OutArg<int64_t> out(indices, (size_t)count);
+  KernelParams p = base_params(ctx);
+  launch_state_index(p.index, count, in.ptr, out.ptr, ctx->stream);
+  out.finish(ctx->stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+int dmv_state_info(dmv_context *ctx, int64_t count, const uint64_t *alphas, uint64_t *betas,
+                   double *characters, double *norms) {
+  API_BEGIN
+  use_device(ctx);
+  InArg<uint64_t> in(alphas, (size_t)count, ctx->stream);
+  OutArg<uint64_t> ob(betas, (size_t)count);
+  OutArg<double> oc(characters, (size_t)count * 2);
+  OutArg<double> on(norms, (size_t)count);
+  launch_state_info(ctx->orbit, ctx->proj, ctx->site_mask, (double)ctx->spin_inversion, count, in.ptr,
+                    ob.ptr, oc.ptr, on.ptr, ctx->stream);
+  ob.finish(ctx->stream); oc.finish(ctx->stream); on.finish(ctx->stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+int dmv_locale_idx_of(dmv_context *ctx, int64_t count, const uint64_t *states, int num_locales, uint8_t *keys) {
+  API_BEGIN
+  use_device(ctx);
+  InArg<uint64_t> in(states, (size_t)count, ctx->stream);
+  OutArg<uint8_t> out(keys, (size_t)count);
+  launch_locale_idx(count, in.ptr, num_locales, out.ptr, ctx->stream);
+  out.finish(ctx->stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+int64_t dmv_max_number_off_diag(const dmv_context *ctx) { return ctx ? (int64_t)ctx->h_groups.size() : -1; }
+
+int dmv_plan(dmv_context *ctx, int64_t *send_counts) {
+  API_BEGIN
+  use_device(ctx);
+  do_plan(ctx);
+  if (send_counts) std::copy(ctx->send_counts.begin(), ctx->send_counts.end(), send_counts);
+  API_END
+}
+
+int64_t dmv_number_terms(const dmv_context *ctx) { return ctx ? ctx->number_terms : -1; }
+
+int dmv_generate(dmv_context *ctx, int elt, const void *x, void *y) {
+  API_BEGIN
+  use_device(ctx);
+  require_states(ctx);
+  if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
+  if (!is_device_pointer(x) || !is_device_pointer(y))
+    throw std::runtime_error("dmv_generate needs device pointers (y is accumulated into by later steps)");
+  do_generate(ctx, elt, x, y);
+  check_status(ctx);
+  API_END
+}
+
+int dmv_outgoing(dmv_context *ctx, int dest, const uint64_t **betas, const double **coeffs, int64_t *count) {
+  API_BEGIN
+  if (!ctx->planned) throw std::runtime_error("no plan");
+  if (dest < 0 || dest >= ctx->num_ranks) throw std::runtime_error("bad destination");
+  const int64_t off = ctx->h_out_offset[dest];
+  if (betas) *betas = ctx->d_out_betas.ptr + off;
+  if (coeffs) *coeffs = ctx->d_out_coeffs.ptr + off * ctx->record_width;
+  if (count) *count = ctx->h_out_offset[dest + 1] - off;
+  API_END
+}
+
+int dmv_accumulate(dmv_context *ctx, int elt, int64_t count, const uint64_t *betas, const double *coeffs, void *y) {
+  API_BEGIN
+  use_device(ctx);
+  require_states(ctx);
+  if (!is_device_pointer(y)) throw std::runtime_error("dmv_accumulate needs a device y");
+  const int width = complex_values(ctx, elt) ? 2 : 1;
+  InArg<uint64_t> b(betas, (size_t)count, ctx->stream);
+  InArg<double> c(coeffs, (size_t)count * width, ctx->stream);
+  do_accumulate(ctx, elt, count, b.ptr, c.ptr, y);
+  check_status(ctx);
+  API_END
+}
+
+int dmv_local_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
+  API_BEGIN
+  use_device(ctx);
+  require_states(ctx);
+  if (ctx->num_ranks != 1) throw std::runtime_error("dmv_local_matvec needs num_ranks == 1; use dmv_matvec");
+  if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
+  if (!ctx->planned) do_plan(ctx);
+  VecStage v = stage_vectors(ctx, elt, x, y);
+  do_generate(ctx, elt, v.x_dev, v.y_dev);
+  CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  finish_vectors(ctx, v);
+  if (v.y_host || !is_device_pointer(x)) {
+    // host callers get a finished result (and the error check) on return
+    check_status(ctx);
+    collect_timings(ctx);
+  }
+  API_END
+}
+
+int dmv_comm_unique_id(void *id128) {
+  API_BEGIN
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  NCCL_CHECK(nccl().GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  API_END
+}
+
+int dmv_comm_init(dmv_context *ctx, const void *id128) {
+  API_BEGIN
+  use_device(ctx);
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NCCL_CHECK(nccl().CommInitRank(&ctx->comm, ctx->num_ranks, id, ctx->rank));
+  API_END
+}
+
+int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
+  API_BEGIN
+  use_device(ctx);
+  require_states(ctx);
+  if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
+  const int P = ctx->num_ranks;
+  if (P == 1) {
+    const int rc = dmv_local_matvec(ctx, elt, x, y);
+    if (rc) throw std::runtime_error(g_last_error);
+    return 0;
+  }
+  if (!ctx->comm) throw std::runtime_error("dmv_matvec on several ranks needs dmv_comm_init");
+  NcclApi &N = nccl();
+  if (!ctx->planned) do_plan(ctx);
+  if (ctx->recv_counts[0] < 0) {
+    // one-time exchange of the plan: every rank learns how many records each peer will send it
+    DevBuf<int64_t> d_send, d_all;
+    d_send.upload(ctx->send_counts, ctx->stream);
+    d_all.alloc((size_t)P * P);
+    NCCL_CHECK(N.AllGather(d_send.ptr, d_all.ptr, (size_t)P, ncclInt64, ctx->comm, ctx->stream));
+    std::vector<int64_t> all((size_t)P * P);
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.ptr, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    int64_t total_in = 0;
+    for (int q = 0; q < P; ++q) {
+      ctx->recv_counts[q] = (q == ctx->rank) ? 0 : all[(size_t)q * P + ctx->rank];
+      total_in += ctx->recv_counts[q];
+    }
+    ctx->d_in_betas.alloc((size_t)total_in);
+    ctx->d_in_coeffs.alloc((size_t)total_in * 2);
+  }
+  VecStage v = stage_vectors(ctx, elt, x, y);
+  do_generate(ctx, elt, v.x_dev, v.y_dev);
+  CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  const int width = ctx->record_width;
+  int64_t total_in = 0;
+  NCCL_CHECK(N.GroupStart());
+  {
+    int64_t in_off = 0;
+    for (int q = 0; q < P; ++q) {
+      if (q == ctx->rank) continue;
+      const int64_t off = ctx->h_out_offset[q], cnt = ctx->h_out_offset[q + 1] - off;
+      if (cnt > 0) {
+        NCCL_CHECK(N.Send(ctx->d_out_betas.ptr + off, (size_t)cnt, ncclUint64, q, ctx->comm, ctx->stream));
+        NCCL_CHECK(N.Send(ctx->d_out_coeffs.ptr + off * width, (size_t)cnt * width, ncclDouble, q, ctx->comm, ctx->stream));
+      }
+      const int64_t rc = ctx->recv_counts[q];
+      if (rc > 0) {
+        NCCL_CHECK(N.Recv(ctx->d_in_betas.ptr + in_off, (size_t)rc, ncclUint64, q, ctx->comm, ctx->stream));
+        NCCL_CHECK(N.Recv(ctx->d_in_coeffs.ptr + in_off * width, (size_t)rc * width, ncclDouble, q, ctx->comm, ctx->stream));
+      }
+      in_off += rc;
+    }
+    total_in = in_off;
+  }
+  NCCL_CHECK(N.GroupEnd());
+  CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  do_accumulate(ctx, elt, total_in, ctx->d_in_betas.ptr, ctx->d_in_coeffs.ptr, v.y_dev);
+  finish_vectors(ctx, v);
+  if (v.y_host || !is_device_pointer(x)) {
+    check_status(ctx);
+    collect_timings(ctx);
+  }
+  API_END
+}
+
+int dmv_last_timings(dmv_context *ctx, double *ms, int capacity) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  if (cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
+    try { collect_timings(ctx); } catch (...) {}
+  }
+  for (int i = 0; i < T_COUNT && i < capacity; ++i) ms[i] = ctx->timings[i];
+  return T_COUNT;
+}
+const char *dmv_timing_name(int i) { return (i >= 0 && i < T_COUNT) ? kTimingNames[i] : ""; }
+
+int dmv_compute_off_diag(dmv_context *ctx, int64_t count, const uint64_t *alphas, const void *xs, int elt,
+                         int64_t *n, uint64_t *betas, double *coeffs, uint8_t *keys) {
+  API_BEGIN
+  // BatchedOperator.computeOffDiag (reference src/BatchedOperator.chpl:82-213) through the same kernel
+  // as the product: the given alphas play the role of the source block and every record is written to
+  // one flat output (emit_all) together with its locale key.
+  use_device(ctx);
+  if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
+  const size_t cap = (size_t)count * std::max<size_t>(1, ctx->h_groups.size());
+  InArg<uint64_t> a(alphas, (size_t)count, ctx->stream);
+  InArg<double> x(reinterpret_cast<const double *>(xs), (size_t)count * elt, ctx->stream);
+  OutArg<uint64_t> ob(betas, cap);
+  OutArg<double> oc(coeffs, cap * 2);
+  OutArg<uint8_t> ok(keys, cap);
+  DevBuf<double> d_src_norms;
+  DevBuf<int64_t> d_off;
+  DevBuf<unsigned long long> d_cnt;
+  std::vector<int64_t> off = {0, (int64_t)cap};
+  d_off.upload(off, ctx->stream);
+  d_cnt.alloc(1);
+  CUDA_CHECK(cudaMemsetAsync(d_cnt.ptr, 0, sizeof(unsigned long long), ctx->stream));
+  KernelParams p = base_params(ctx);
+  p.index.reps = a.ptr; p.index.n = count; p.index.identity = 0;
+  if (ctx->proj == PROJ_GROUP) {  // norms of the sources: BO:178-194 appends the alphas to state_info
+    d_src_norms.alloc((size_t)count);
+    launch_compute_norms(ctx->orbit, count, a.ptr, d_src_norms.ptr, ctx->stream);
+    p.norms = d_src_norms.ptr;
+  }
+  p.x = x.ptr; p.y = nullptr;
+  p.emit_all = 1;
+  p.out_betas = ob.ptr; p.out_coeffs = oc.ptr; p.out_keys = ok.ptr;
+  p.out_offset = d_off.ptr; p.out_count = d_cnt.ptr;
+  p.row_begin = 0; p.row_end = count;
+  launch_generate(p, ctx->proj, /*complex values*/ true, elt == DMV_C128, false, ctx->stream);
+  unsigned long long total = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&total, d_cnt.ptr, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (total > cap) throw std::runtime_error("dmv_compute_off_diag: output overflow");
+  ob.finish(ctx->stream, (size_t)total); oc.finish(ctx->stream, (size_t)total * 2); ok.finish(ctx->stream, (size_t)total);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (n) *n = (int64_t)total;
+  API_END
+}
+
+int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t count,
+                            const uint64_t *states, uint64_t *reps, int32_t *stab) {
+  API_BEGIN
+  HostOrbitProgram H = compile_orbit_program(basis->number_sites, basis->group_order, basis->perms,
+                                             basis->flips, basis->characters);
+  if (info) {
+    info[0] = H.n_q; info[1] = H.n_stages; info[2] = H.n_t; info[3] = H.n_left; info[4] = H.n_right;
+    info[5] = H.has_flip;
+  }
+  OrbitProgram P = H.view();
+  for (int64_t k = 0; k < count; ++k) {
+    const OrbitResult r = orbit_scan<true, false>(P, states[k]);
+    if (reps) reps[k] = r.rep;
+    if (stab) stab[k] = r.stab;
+  }
+  API_END
+}
+
+int dmv_bind_operator(const void *ls_hs_operator_ptr, dmv_context *ctx) {
+  API_BEGIN
+  std::lock_guard<std::mutex> lock(g_bind_mutex);
+  if (ctx) g_bindings[ls_hs_operator_ptr] = ctx;
+  else g_bindings.erase(ls_hs_operator_ptr);
+  API_END
+}
+
+// reference: src/DistributedMatrixVector.chpl:1095-1110.  Halts (abort) on error like the reference.
+void ls_chpl_matrix_vector_product(const void *ls_hs_operator_ptr, int num_vectors, double *x, double *y) {
+  dmv_context *ctx = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_bind_mutex);
+    auto it = g_bindings.find(ls_hs_operator_ptr);
+    if (it != g_bindings.end()) ctx = it->second;
+  }
+  if (!ctx) { fprintf(stderr, "ls_chpl_matrix_vector_product: operator is not bound to a dmv context\n"); abort(); }
+  if (num_vectors != 1) {  // DMV:1101-1102
+    fprintf(stderr, "applying the Operator to more than 1 vector is not yet implemented\n");
+    abort();
+  }
+  if (dmv_local_matvec(ctx, DMV_F64, x, y) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+// dmv_device.cuh -- device-side data structures and helpers of the H.x hot path (sm_100a).
+//
+// Everything here is integer / bit-twiddling + sparse FP64 FMA: no tensor cores (north_star).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dmv {
+
+// ---------------------------------------------------------------------------------------------
+// Operator tables (device copies of dmv_operator_desc, regrouped by flip mask)
+// ---------------------------------------------------------------------------------------------
+struct OffTerm {      // one non-branching term of a group: c += v [alpha & m == r] (-1)^popc(alpha & s)
+  uint64_t m, r, s;
+  double v_re, v_im;
+};
+struct TermGroup {    // all terms with the same flip mask x: beta = alpha ^ x
+  uint64_t x;
+  int32_t first, count;
+};
+struct DiagTerm {
+  uint64_t m, r, s;
+  double v_re, v_im;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Orbit program: the symmetry group enumerated as  g = t_j . q_i  (+ optional spin flip)
+//   q_i : coset representatives, applied as Benes butterfly networks (padded to n_stages)
+//   t_j : a chain through a subgroup of "cheap" elements, t_j = c_j . t_{j-1}; every step c_j is a
+//         short list of masked shifts (n_left left shifts + n_right right shifts, zero padded)
+// Built on the host by compile_orbit_program() (dmv_group.cpp).
+// ---------------------------------------------------------------------------------------------
+struct OrbitProgram {
+  int32_t n_sites;
+  int32_t n_q, n_stages, n_t, n_left, n_right;
+  int32_t has_flip;            // group doubled by global spin inversion
+  int32_t trivial_characters;  // every character == 1
+  uint64_t site_mask;
+  const uint64_t *benes_mask;  // [n_q][n_stages]
+  const int32_t *benes_delta;  // [n_stages]
+  const uint64_t *step_mask;   // [n_t-1][n_left + n_right]  (mask in OUTPUT positions)
+  const int32_t *step_shift;   // [n_t-1][n_left + n_right]
+  const double2 *characters;   // [n_q][n_t][2]  character of (t_j . q_i, flip); conj NOT applied
+  int64_t group_order;         // n_q * n_t * (has_flip ? 2 : 1)
+};
+
+// ---------------------------------------------------------------------------------------------
+// hash64_01 / localeIdxOf            reference: src/StatesEnumeration.chpl:122-136
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t hash64_01(uint64_t x) {
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  x = x ^ (x >> 31);
+  return x;
+}
+
+// owner = hash % P.  P is tiny (<= 256): use a 32-bit friendly path for powers of two.
+__host__ __device__ __forceinline__ int locale_idx_of(uint64_t state, int num_ranks) {
+  if (num_ranks <= 1) return 0;
+  const uint64_t h = hash64_01(state);
+  if ((num_ranks & (num_ranks - 1)) == 0) return (int)(h & (uint64_t)(num_ranks - 1));
+  return (int)(h % (uint64_t)num_ranks);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sorted-representatives index:  directory over the top bits + bounded binary search.
+// Replaces ls_hs_state_index (reference src/FFI.chpl:173-175, call DMV:102).
+// ---------------------------------------------------------------------------------------------
+struct StateIndex {
+  const uint64_t *reps;   // ascending, this rank's block
+  int64_t n;
+  const uint32_t *dir;    // dir[b] = lower_bound(reps, b << shift), n_buckets + 1 entries
+  uint64_t n_buckets;
+  int32_t shift;
+  int32_t identity;       // state_index_is_identity (DMV:86): index == state
+};
+
+// dir entries are 4 bytes: dir[b] and dir[b+1] normally share one 32-byte sector.
+__device__ __forceinline__ int64_t locate(const StateIndex &ix, uint64_t key) {
+  if (ix.identity) return (key < (uint64_t)ix.n) ? (int64_t)key : -1;
+  const uint64_t b = key >> ix.shift;
+  if (b >= ix.n_buckets) return -1;
+  uint32_t lo = __ldg(ix.dir + b), hi = __ldg(ix.dir + b + 1);
+  const uint32_t end = hi;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    const uint64_t v = __ldg(ix.reps + mid);
+    if (v < key) lo = mid + 1; else hi = mid;
+  }
+  if (lo < end && __ldg(ix.reps + lo) == key) return (int64_t)lo;
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bit permutations
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t butterfly(uint64_t s, uint64_t mask, int delta) {
+  const uint64_t t = ((s >> delta) ^ s) & mask;
+  return s ^ t ^ (t << delta);
+}
+
+// Result of an orbit scan
+struct OrbitResult {
+  uint64_t rep;     // min_g g(s)
+  int32_t arg;      // ((q * n_t + j) << 1) | flipped   of a minimising element
+  int32_t stab;     // number of elements with g(s) == s   (only filled by orbit_scan<.., true>)
+};
+
+// Scan the whole group.  COUNT_STAB additionally counts stabiliser elements (needs the full scan).
+// EARLY_EXIT returns as soon as a candidate smaller than `s` is seen (is_representative test).
+template <bool COUNT_STAB, bool EARLY_EXIT>
+__host__ __device__ __forceinline__ OrbitResult orbit_scan(const OrbitProgram &P, uint64_t s) {
+  OrbitResult out;
+  out.rep = ~0ull;
+  out.arg = 0;
+  out.stab = 0;
+  const int n_pairs = P.n_left + P.n_right;
+  for (int q = 0; q < P.n_q; ++q) {
+    uint64_t cur = s;
+    const uint64_t *bm = P.benes_mask + (int64_t)q * P.n_stages;
+    for (int st = 0; st < P.n_stages; ++st) cur = butterfly(cur, bm[st], P.benes_delta[st]);
+    for (int j = 0; j < P.n_t; ++j) {
+      if (j > 0) {
+        const uint64_t *sm = P.step_mask + (int64_t)(j - 1) * n_pairs;
+        const int32_t *sh = P.step_shift + (int64_t)(j - 1) * n_pairs;
+        uint64_t nxt = 0;
+        for (int k = 0; k < P.n_left; ++k) nxt |= (cur << sh[k]) & sm[k];
+        for (int k = P.n_left; k < n_pairs; ++k) nxt |= (cur >> sh[k]) & sm[k];
+        cur = nxt;
+      }
+      uint64_t cand = cur;
+      int flipped = 0;
+      if (P.has_flip) {
+        const uint64_t inv = cur ^ P.site_mask;
+        if (COUNT_STAB) out.stab += (inv == s);
+        if (inv < cur) { cand = inv; flipped = 1; }
+      }
+      if (COUNT_STAB) out.stab += (cur == s);
+      if (cand < out.rep) {
+        out.rep = cand;
+        out.arg = (((q * P.n_t) + j) << 1) | flipped;
+        if (EARLY_EXIT && cand < s) return out;
+      }
+    }
+  }
+  return out;
+}
+
+// Full-precision stabiliser sum  sum_{g : g(s) = s} Re chi(g)  (only needed with non-trivial characters)
+__host__ __device__ inline double orbit_stabiliser_sum(const OrbitProgram &P, uint64_t s) {
+  double acc = 0.0;
+  const int n_pairs = P.n_left + P.n_right;
+  for (int q = 0; q < P.n_q; ++q) {
+    uint64_t cur = s;
+    const uint64_t *bm = P.benes_mask + (int64_t)q * P.n_stages;
+    for (int st = 0; st < P.n_stages; ++st) cur = butterfly(cur, bm[st], P.benes_delta[st]);
+    for (int j = 0; j < P.n_t; ++j) {
+      if (j > 0) {
+        const uint64_t *sm = P.step_mask + (int64_t)(j - 1) * n_pairs;
+        const int32_t *sh = P.step_shift + (int64_t)(j - 1) * n_pairs;
+        uint64_t nxt = 0;
+        for (int k = 0; k < P.n_left; ++k) nxt |= (cur << sh[k]) & sm[k];
+        for (int k = P.n_left; k < n_pairs; ++k) nxt |= (cur >> sh[k]) & sm[k];
+        cur = nxt;
+      }
+      const int64_t e = ((int64_t)q * P.n_t + j) * 2;
+      if (cur == s) acc += P.trivial_characters ? 1.0 : P.characters[e].x;
+      if (P.has_flip && (cur ^ P.site_mask) == s) acc += P.trivial_characters ? 1.0 : P.characters[e + 1].x;
+    }
+  }
+  return acc;
+}
+
+}  // namespace dmv

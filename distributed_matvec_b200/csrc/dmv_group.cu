@@ -1,0 +1,330 @@
+// dmv_group.cu -- host-side compilation of a symmetry group into an OrbitProgram.
+//
+// The reference delegates orbit scans to the third-party ls_hs_state_info / ls_hs_is_representative
+// (reference src/FFI.chpl:177-184).  Here the group  G = { t_j . q_i } x {1, flip}  is factored into a
+// chain through a subgroup of elements that are cheap as masked shifts (translations) and a right
+// transversal applied as Benes networks, so that one orbit scan costs
+//     n_q * n_stages butterflies + |G_perm| * (n_left + n_right) masked shifts
+// instead of |G_perm| full networks.
+#include "dmv_host.h"
+
+#include <algorithm>
+#include <map>
+#include <random>
+#include <set>
+#include <stdexcept>
+
+namespace dmv {
+
+namespace {
+
+using Perm = std::vector<int>;  // result bit i = input bit p[i]
+
+Perm compose(const Perm &p, const Perm &q) {  // apply q first, then p:  (p.(q.s))[i] = s[q[p[i]]]
+  Perm r(p.size());
+  for (size_t i = 0; i < p.size(); ++i) r[i] = q[p[i]];
+  return r;
+}
+Perm inverse(const Perm &p) {
+  Perm r(p.size());
+  for (size_t i = 0; i < p.size(); ++i) r[p[i]] = (int)i;
+  return r;
+}
+bool is_identity(const Perm &p) {
+  for (size_t i = 0; i < p.size(); ++i)
+    if (p[i] != (int)i) return false;
+  return true;
+}
+
+uint64_t apply_naive(const Perm &p, uint64_t s) {
+  uint64_t out = 0;
+  for (size_t i = 0; i < p.size(); ++i) out |= ((s >> p[i]) & 1ull) << i;
+  return out;
+}
+
+// masked-shift form: output bit i takes input bit p[i]; d = i - p[i] > 0 is a left shift.
+struct ShiftForm {
+  std::vector<std::pair<int, uint64_t>> left, right;  // (shift amount, mask over OUTPUT bits)
+  int cost() const { return (int)(left.size() + right.size()); }
+};
+ShiftForm shift_form(const Perm &p) {
+  std::map<int, uint64_t> groups;
+  for (size_t i = 0; i < p.size(); ++i) groups[(int)i - p[i]] |= 1ull << i;
+  ShiftForm f;
+  for (auto &kv : groups) {
+    if (kv.first >= 0) f.left.push_back({kv.first, kv.second});
+    else f.right.push_back({-kv.first, kv.second});
+  }
+  return f;
+}
+
+// Benes routing (looping algorithm).  src[i] = input position that must arrive at output i, width W
+// (power of two).  Emits (mask, delta) stages in application order.
+void benes_route(std::vector<int> src, int lo_delta_level, int W,
+                 std::vector<std::pair<uint64_t, int>> &front,
+                 std::vector<std::pair<uint64_t, int>> &back) {
+  const int d = W >> (lo_delta_level + 1);
+  if (d == 0) return;
+  if (d == 1) {
+    uint64_t mask = 0;
+    for (int p = 0; p < W; p += 2)
+      if (src[p] == p + 1) mask |= 1ull << p;
+    front.push_back({mask, 1});
+    return;
+  }
+  std::vector<int> dst(W);
+  for (int i = 0; i < W; ++i) dst[src[i]] = i;
+  std::vector<int> colour_in(W, -1);
+  for (int j0 = 0; j0 < W; ++j0) {
+    if (colour_in[j0] != -1) continue;
+    int j = j0;
+    for (;;) {
+      colour_in[j] = 0;
+      const int jp = j ^ d;          // partner input goes through the upper sub-network
+      colour_in[jp] = 1;
+      const int ip = dst[jp];        // the output it must reach ...
+      const int ipp = ip ^ d;        // ... whose partner output must be fed from the lower sub-network
+      const int jn = src[ipp];
+      if (colour_in[jn] != -1) break;
+      j = jn;
+    }
+  }
+  uint64_t mask_in = 0, mask_out = 0;
+  std::vector<int> pos1(W), pos2(W);
+  for (int j = 0; j < W; ++j) pos1[j] = colour_in[j] ? (j | d) : (j & ~d);
+  for (int i = 0; i < W; ++i) pos2[i] = colour_in[src[i]] ? (i | d) : (i & ~d);
+  for (int p = 0; p < W; ++p) {
+    if (p & d) continue;
+    if (colour_in[p] == 1) mask_in |= 1ull << p;
+    if (colour_in[src[p]] == 1) mask_out |= 1ull << p;
+  }
+  std::vector<int> inner(W);
+  for (int i = 0; i < W; ++i) inner[pos2[i]] = pos1[src[i]];
+  front.push_back({mask_in, d});
+  back.push_back({mask_out, d});
+  benes_route(inner, lo_delta_level + 1, W, front, back);
+}
+
+std::vector<std::pair<uint64_t, int>> benes_network(const Perm &p, int W) {
+  std::vector<int> src(W);
+  for (int i = 0; i < W; ++i) src[i] = i;
+  for (size_t i = 0; i < p.size(); ++i) src[i] = p[i];
+  std::vector<std::pair<uint64_t, int>> front, back;
+  benes_route(src, 0, W, front, back);
+  std::vector<std::pair<uint64_t, int>> stages = front;
+  for (auto it = back.rbegin(); it != back.rend(); ++it) stages.push_back(*it);
+  return stages;  // 2 log2(W) - 1 stages, zero masks included
+}
+
+struct Candidate {
+  std::vector<Perm> chain;      // t_0 = identity, t_1, ...
+  std::vector<Perm> steps;      // c_j with t_j = c_j . t_{j-1}
+  std::vector<Perm> transversal;
+  int n_left = 0, n_right = 0;
+  double cost = 0;
+};
+
+}  // namespace
+
+HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const int32_t *perms,
+                                       const uint8_t *flips, const double *characters) {
+  HostOrbitProgram H;
+  H.n_sites = n_sites;
+  H.site_mask = (n_sites == 64) ? ~0ull : ((1ull << n_sites) - 1);
+  if (group_order <= 0) throw std::runtime_error("empty symmetry group");
+
+  // split into permutation part and flip
+  std::map<Perm, int> perm_index;
+  std::vector<Perm> plist;
+  std::map<std::pair<int, int>, std::pair<double, double>> chi;  // (perm idx, flip) -> character
+  bool any_flip = false;
+  for (int64_t g = 0; g < group_order; ++g) {
+    Perm p(perms + g * n_sites, perms + (g + 1) * n_sites);
+    auto it = perm_index.find(p);
+    int idx;
+    if (it == perm_index.end()) {
+      idx = (int)plist.size();
+      perm_index[p] = idx;
+      plist.push_back(p);
+    } else idx = it->second;
+    const int f = flips[g] ? 1 : 0;
+    any_flip |= (f == 1);
+    if (chi.count({idx, f})) throw std::runtime_error("duplicate group element");
+    chi[{idx, f}] = {characters[2 * g], characters[2 * g + 1]};
+  }
+  const int Gp = (int)plist.size();
+  if ((int64_t)Gp * (any_flip ? 2 : 1) != group_order)
+    throw std::runtime_error("group is not a direct product of permutations and spin inversion");
+  H.has_flip = any_flip ? 1 : 0;
+  bool trivial = true;
+  for (auto &kv : chi) trivial &= (kv.second.first == 1.0 && kv.second.second == 0.0);
+  H.trivial_characters = trivial ? 1 : 0;
+
+  Perm ident(n_sites);
+  for (int i = 0; i < n_sites; ++i) ident[i] = i;
+  if (!perm_index.count(ident)) throw std::runtime_error("group lacks the identity");
+
+  const int W = (n_sites > 32) ? 64 : 32;
+  const int full_stages = (W == 64) ? 11 : 9;
+  std::vector<int> pair_cost(Gp);
+  for (int i = 0; i < Gp; ++i) pair_cost[i] = shift_form(plist[i]).cost();
+
+  // candidate factorisations for several "cheap generator" thresholds; kmax = 0: no chain at all
+  Candidate best;
+  bool have_best = false;
+  const double butterfly_cost = (W == 64) ? 8.0 : 4.0, pair_cost_instr = (W == 64) ? 4.0 : 2.0;
+  for (int kmax : {0, 2, 3, 4, 6, 8}) {
+    Candidate c;
+    std::vector<Perm> gens;
+    for (int i = 0; i < Gp; ++i)
+      if (!is_identity(plist[i]) && pair_cost[i] <= kmax) gens.push_back(plist[i]);
+    // subgroup generated by gens
+    std::set<Perm> T{ident};
+    std::vector<Perm> frontier{ident};
+    while (!frontier.empty()) {
+      std::vector<Perm> nxt;
+      for (auto &e : frontier)
+        for (auto &g : gens) {
+          Perm x = compose(g, e);
+          if (T.insert(x).second) nxt.push_back(x);
+        }
+      frontier.swap(nxt);
+    }
+    // greedy walk through T
+    std::set<Perm> visited{ident};
+    c.chain.push_back(ident);
+    Perm cur = ident;
+    while (visited.size() < T.size()) {
+      bool moved = false;
+      int best_cost = 1 << 30;
+      Perm best_next, best_step;
+      for (auto &g : gens) {
+        Perm x = compose(g, cur);
+        if (!visited.count(x)) {
+          const int k = shift_form(g).cost();
+          if (k < best_cost) { best_cost = k; best_next = x; best_step = g; moved = true; }
+        }
+      }
+      if (!moved) {  // jump: cheapest connecting element
+        const Perm cur_inv = inverse(cur);
+        for (auto &x : T) {
+          if (visited.count(x)) continue;
+          Perm step = compose(x, cur_inv);
+          const int k = shift_form(step).cost();
+          if (k < best_cost) { best_cost = k; best_next = x; best_step = step; }
+        }
+      }
+      c.chain.push_back(best_next);
+      c.steps.push_back(best_step);
+      visited.insert(best_next);
+      cur = best_next;
+    }
+    for (auto &s : c.steps) {
+      ShiftForm f = shift_form(s);
+      c.n_left = std::max(c.n_left, (int)f.left.size());
+      c.n_right = std::max(c.n_right, (int)f.right.size());
+    }
+    // right transversal:  G = union_i T q_i
+    std::set<Perm> covered;
+    for (auto &p : plist) {
+      if (covered.count(p)) continue;
+      c.transversal.push_back(p);
+      for (auto &t : c.chain) covered.insert(compose(t, p));
+    }
+    if ((int)covered.size() != Gp || (int)(c.transversal.size() * c.chain.size()) != Gp) continue;
+    c.cost = c.transversal.size() * full_stages * butterfly_cost +
+             (double)Gp * ((c.n_left + c.n_right) * pair_cost_instr + 8.0);
+    if (!have_best || c.cost < best.cost) { best = c; have_best = true; }
+  }
+  if (!have_best) throw std::runtime_error("could not factor the symmetry group");
+
+  // prefer the identity as the first coset representative (cheaper network: all-zero masks)
+  H.n_q = (int)best.transversal.size();
+  H.n_t = (int)best.chain.size();
+  H.n_left = best.n_left;
+  H.n_right = best.n_right;
+
+  // Benes networks of the transversal; keep only stages used by at least one q
+  std::vector<std::vector<std::pair<uint64_t, int>>> nets;
+  for (auto &q : best.transversal) nets.push_back(benes_network(q, W));
+  std::vector<int> keep;
+  for (int st = 0; st < full_stages; ++st) {
+    bool used = false;
+    for (auto &net : nets) used |= (net[st].first != 0);
+    if (used) keep.push_back(st);
+  }
+  H.n_stages = (int)keep.size();
+  for (int st : keep) H.benes_delta.push_back(nets[0][st].second);
+  for (auto &net : nets)
+    for (int st : keep) H.benes_mask.push_back(net[st].first);
+
+  const int n_pairs = H.n_left + H.n_right;
+  for (auto &s : best.steps) {
+    ShiftForm f = shift_form(s);
+    for (int k = 0; k < H.n_left; ++k) {
+      if (k < (int)f.left.size()) { H.step_shift.push_back(f.left[k].first); H.step_mask.push_back(f.left[k].second); }
+      else { H.step_shift.push_back(0); H.step_mask.push_back(0); }
+    }
+    for (int k = 0; k < H.n_right; ++k) {
+      if (k < (int)f.right.size()) { H.step_shift.push_back(f.right[k].first); H.step_mask.push_back(f.right[k].second); }
+      else { H.step_shift.push_back(0); H.step_mask.push_back(0); }
+    }
+  }
+  (void)n_pairs;
+
+  H.characters.resize((size_t)H.n_q * H.n_t * 2 * 2, 0.0);
+  for (int q = 0; q < H.n_q; ++q)
+    for (int j = 0; j < H.n_t; ++j) {
+      const Perm g = compose(best.chain[j], best.transversal[q]);
+      const int idx = perm_index.at(g);
+      for (int f = 0; f < 2; ++f) {
+        std::pair<double, double> c = {1.0, 0.0};
+        if (f == 0 || any_flip) c = chi.at({idx, f});
+        const size_t e = (((size_t)q * H.n_t + j) * 2 + f) * 2;
+        H.characters[e] = c.first;
+        H.characters[e + 1] = c.second;
+      }
+    }
+  H.group_order = group_order;
+
+  // self-check against bit-by-bit application on random states
+  OrbitProgram P = H.view();
+  std::mt19937_64 rng(12345);
+  for (int trial = 0; trial < 64; ++trial) {
+    const uint64_t s = rng() & H.site_mask;
+    uint64_t expect = ~0ull;
+    int stab = 0;
+    for (int i = 0; i < Gp; ++i) {
+      const uint64_t y = apply_naive(plist[i], s);
+      expect = std::min(expect, y);
+      stab += (y == s);
+      if (any_flip) { expect = std::min(expect, y ^ H.site_mask); stab += ((y ^ H.site_mask) == s); }
+    }
+    OrbitResult r = orbit_scan<true, false>(P, s);
+    if (r.rep != expect || r.stab != stab) throw std::runtime_error("orbit program self-check failed");
+    // the element reported as minimising must really map s to rep
+    const int e = r.arg >> 1;
+    const Perm g = compose(best.chain[e % H.n_t], best.transversal[e / H.n_t]);
+    uint64_t y = apply_naive(g, s);
+    if (r.arg & 1) y ^= H.site_mask;
+    if (y != r.rep) throw std::runtime_error("orbit program argmin self-check failed");
+  }
+  return H;
+}
+
+OrbitProgram HostOrbitProgram::view() const {
+  OrbitProgram P;
+  P.n_sites = n_sites;
+  P.n_q = n_q; P.n_stages = n_stages; P.n_t = n_t; P.n_left = n_left; P.n_right = n_right;
+  P.has_flip = has_flip; P.trivial_characters = trivial_characters;
+  P.site_mask = site_mask;
+  P.benes_mask = benes_mask.data();
+  P.benes_delta = benes_delta.data();
+  P.step_mask = step_mask.data();
+  P.step_shift = step_shift.data();
+  P.characters = reinterpret_cast<const double2 *>(characters.data());
+  P.group_order = group_order;
+  return P;
+}
+
+}  // namespace dmv

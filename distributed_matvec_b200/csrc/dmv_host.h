@@ -1,0 +1,87 @@
+// dmv_host.h -- host-side declarations shared by the translation units of libdmv_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "dmv_device.cuh"
+
+namespace dmv {
+
+struct HostOrbitProgram {
+  int32_t n_sites = 0, n_q = 0, n_stages = 0, n_t = 0, n_left = 0, n_right = 0;
+  int32_t has_flip = 0, trivial_characters = 1;
+  uint64_t site_mask = 0;
+  int64_t group_order = 0;
+  std::vector<uint64_t> benes_mask;
+  std::vector<int32_t> benes_delta;
+  std::vector<uint64_t> step_mask;
+  std::vector<int32_t> step_shift;
+  std::vector<double> characters;  // interleaved, [n_q][n_t][2][2]
+  OrbitProgram view() const;       // pointers into the host vectors
+};
+
+HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const int32_t *perms,
+                                       const uint8_t *flips, const double *characters);
+
+// projection mode of the basis: which branch of BatchedOperator.computeOffDiag applies
+// (reference src/BatchedOperator.chpl:89, 119, 163)
+enum Projection { PROJ_NONE = 0, PROJ_INVERSION = 1, PROJ_GROUP = 2 };
+
+// Everything a kernel needs, passed by value (fits the 4 KB kernel-parameter space).
+struct KernelParams {
+  // basis block of this rank
+  StateIndex index;
+  const double *norms;        // [n] (PROJ_GROUP only)
+  // operator
+  const TermGroup *groups; int32_t n_groups;
+  const OffTerm *terms;    int32_t n_terms;
+  const DiagTerm *diag;    int32_t n_diag;
+  // symmetry
+  OrbitProgram orbit;         // device pointers (PROJ_GROUP)
+  uint64_t site_mask;
+  double inversion_character; // PROJ_INVERSION: spin_inversion as a double
+  // partition
+  int32_t rank, num_ranks;
+  // vectors
+  const void *x; void *y;
+  // outgoing buckets (num_ranks > 1): records for destination d go to out_betas + out_offset[d]
+  uint64_t *out_betas; double *out_coeffs;
+  const int64_t *out_offset;      // [num_ranks + 1] device
+  unsigned long long *out_count;  // [num_ranks] device, reset before each generate
+  // emit_all: computeOffDiag mode -- every record goes to one flat output with its locale key
+  int32_t emit_all; uint8_t *out_keys;
+  // error reporting: status[0] = number of bad records, status[1] = first bad state, status[2] = overflow
+  unsigned long long *status;
+  // source range of this launch
+  int64_t row_begin, row_end;
+};
+
+// launchers (dmv_kernels.cu)
+struct LaunchConfig { int blocks; int threads; size_t smem; };
+void launch_generate(const KernelParams &p, Projection proj, bool complex_values, bool complex_elements,
+                     bool count_only, cudaStream_t stream);
+void launch_accumulate(const KernelParams &p, Projection proj, bool complex_values, bool complex_elements,
+                       int64_t count, const uint64_t *betas, const double *coeffs, cudaStream_t stream);
+void launch_build_directory(const uint64_t *reps, int64_t n, uint32_t *dir, uint64_t n_buckets, int shift,
+                            cudaStream_t stream);
+void launch_state_index(const StateIndex &ix, int64_t count, const uint64_t *spins, int64_t *indices,
+                        cudaStream_t stream);
+void launch_state_info(const OrbitProgram &P, Projection proj, uint64_t site_mask, double inv_char,
+                       int64_t count, const uint64_t *alphas, uint64_t *betas, double *characters,
+                       double *norms, cudaStream_t stream);
+void launch_locale_idx(int64_t count, const uint64_t *states, int num_ranks, uint8_t *keys, cudaStream_t stream);
+void launch_compute_norms(const OrbitProgram &P, int64_t count, const uint64_t *reps, double *norms,
+                          cudaStream_t stream);
+// enumeration: chunk c covers candidates [chunk_first[c], chunk_first[c] + chunk_len[c]) in the
+// combinadic (fixed Hamming weight) or plain integer order; pass 0 counts, pass 1 writes.
+void launch_enumerate(const OrbitProgram &P, Projection proj, uint64_t site_mask, bool fixed_hamming,
+                      int rank, int num_ranks, int64_t n_chunks, const uint64_t *chunk_first,
+                      const uint64_t *chunk_last, unsigned long long *chunk_count,
+                      const unsigned long long *chunk_offset, uint64_t *out, double *out_norms,
+                      bool write_pass, cudaStream_t stream);
+int64_t launch_counter();
+
+}  // namespace dmv

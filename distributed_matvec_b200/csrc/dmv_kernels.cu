@@ -1,0 +1,609 @@
+// dmv_kernels.cu -- hand-written sm_100a kernels of the distributed matrix-free H.x product.
+//
+//   k_generate   : diagonal + off-diagonal term generation (BatchedOperator.computeOffDiag, reference
+//                  src/BatchedOperator.chpl:82-213) fused with the destination hash (localeIdxOf,
+//                  src/StatesEnumeration.chpl:129-136), the per-destination bucketing (radixOneStep,
+//                  DMV:265-311) and -- for the records this rank owns -- the index search and atomic
+//                  accumulate (localProcess, DMV:73-127).
+//   k_accumulate : localProcess for records received from other ranks.
+//
+// Work decomposition of k_generate: a warp owns 32 consecutive source states (one per lane, coalesced
+// 8-byte loads of sigma_i and x_i), walks the flip-mask groups of the operator in lock step (tables in
+// shared memory, broadcast reads), and compacts the emitted (beta, c*x_i) pairs into a warp-private
+// ring buffer in shared memory.  Whenever 32 entries are queued the warp drains them with all lanes
+// busy: symmetry projection (orbit scan in registers), hash, directory + bounded binary search in the
+// sorted representatives, FP64 atomic add.  This keeps the expensive part (projection, search,
+// atomics) at full lane occupancy although only ~half of the (state, bond) pairs emit a term.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <stdexcept>
+#include <string>
+
+#include "dmv_host.h"
+
+namespace dmv {
+
+static std::atomic<int64_t> g_launches{0};
+int64_t launch_counter() { return g_launches.load(); }
+
+#define DMV_CUDA_CHECK(expr)                                                                    \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+  } while (0)
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kQueue = 64;  // ring capacity per warp (>= 31 pending + 32 appended)
+
+// ---- value helpers: V = double (real coefficients and real x) or double2 (complex) -------------
+template <bool CV> struct ValT { using type = double; };
+template <> struct ValT<true> { using type = double2; };
+
+__device__ __forceinline__ double v_make(double re, double, double *) { return re; }
+__device__ __forceinline__ double2 v_make(double re, double im, double2 *) { return make_double2(re, im); }
+__device__ __forceinline__ double v_mul(double a, double b) { return a * b; }
+__device__ __forceinline__ double2 v_mul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double v_scale(double a, double s) { return a * s; }
+__device__ __forceinline__ double2 v_scale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+__device__ __forceinline__ bool v_nonzero(double a) { return a != 0.0; }
+__device__ __forceinline__ bool v_nonzero(double2 a) { return a.x != 0.0 || a.y != 0.0; }
+__device__ __forceinline__ void v_acc(double &a, double re, double) { a += re; }
+__device__ __forceinline__ void v_acc(double2 &a, double re, double im) { a.x += re; a.y += im; }
+
+template <bool CE>
+__device__ __forceinline__ void atomic_accumulate(void *y, int64_t idx, double re, double im) {
+  if (CE) {
+    double *p = reinterpret_cast<double *>(y) + 2 * idx;
+    atomicAdd(p, re);
+    atomicAdd(p + 1, im);
+  } else {
+    atomicAdd(reinterpret_cast<double *>(y) + idx, re);
+  }
+}
+__device__ __forceinline__ double v_re(double a) { return a; }
+__device__ __forceinline__ double v_re(double2 a) { return a.x; }
+__device__ __forceinline__ double v_im(double) { return 0.0; }
+__device__ __forceinline__ double v_im(double2 a) { return a.y; }
+
+// ---- shared-memory staging of the operator / orbit tables ---------------------------------------
+struct SmemLayout {
+  size_t groups, terms, diag, orbit64, orbit32, queues, total;
+};
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+__host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int proj, size_t val_bytes) {
+  SmemLayout L;
+  size_t off = 0;
+  L.groups = off; off += sizeof(TermGroup) * p.n_groups;
+  off = align_up(off, 8);
+  L.terms = off; off += sizeof(OffTerm) * p.n_terms;
+  L.diag = off; off += sizeof(DiagTerm) * p.n_diag;
+  L.orbit64 = off;
+  size_t n64 = 0, n32 = 0;
+  if (proj == PROJ_GROUP) {
+    const int np = p.orbit.n_left + p.orbit.n_right;
+    n64 = (size_t)p.orbit.n_q * p.orbit.n_stages + (size_t)(p.orbit.n_t - 1) * np;
+    n32 = (size_t)p.orbit.n_stages + (size_t)(p.orbit.n_t - 1) * np;
+  }
+  off += 8 * n64;
+  L.orbit32 = off; off += 4 * n32;
+  off = align_up(off, 16);
+  L.queues = off; off += (size_t)kWarps * kQueue * (8 + val_bytes);
+  L.total = off;
+  return L;
+}
+
+template <typename T>
+__device__ __forceinline__ void stage(T *dst, const T *src, int count) {
+  for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+}
+
+// ---- the consumer side: one record per lane -----------------------------------------------------
+// Projects beta (inversion / full group), and either accumulates it locally or appends it to the
+// bucket of its owner.  `active` lanes carry a record; all 32 lanes must call this (warp collectives).
+template <int PROJ, bool CV, bool CE, bool COUNT_ONLY>
+__device__ __forceinline__ void consume(const KernelParams &p, const OrbitProgram &orbit, bool active,
+                                        uint64_t beta, typename ValT<CV>::type c) {
+  using V = typename ValT<CV>::type;
+  const unsigned lane = threadIdx.x & 31u;
+  if (PROJ == PROJ_INVERSION) {
+    // reference src/BatchedOperator.chpl:145-152
+    const uint64_t inv = beta ^ p.site_mask;
+    if (inv < beta) { beta = inv; c = v_scale(c, p.inversion_character); }
+  } else if (PROJ == PROJ_GROUP) {
+    if (active) {
+      const OrbitResult r = orbit_scan<false, false>(orbit, beta);
+      beta = r.rep;
+      if (!orbit.trivial_characters) {
+        const double2 chi = __ldg(orbit.characters + r.arg);   // state_info returns conj(chi)
+        c = v_mul(c, v_make(chi.x, -chi.y, (V *)nullptr));
+      }
+    }
+  }
+  int owner = p.rank;
+  if (p.num_ranks > 1) owner = locale_idx_of(beta, p.num_ranks);
+
+  if (p.emit_all) {   // BatchedOperator.computeOffDiag output: (beta, coeff, key) flat, unordered
+    if (active && !COUNT_ONLY) {
+      if (PROJ == PROJ_GROUP) {   // norm of the representative: BO:200 `norms[k]`
+        const double stab = orbit.trivial_characters ? (double)orbit_scan<true, false>(orbit, beta).stab
+                                                     : orbit_stabiliser_sum(orbit, beta);
+        const double nn = stab / (double)orbit.group_order;
+        c = v_scale(c, nn > 1e-12 ? sqrt(nn) : 0.0);
+      }
+      const unsigned long long pos = atomicAdd(p.out_count, 1ull);
+      if ((int64_t)pos < p.out_offset[1]) {
+        p.out_betas[pos] = beta;
+        reinterpret_cast<V *>(p.out_coeffs)[pos] = c;
+        p.out_keys[pos] = (uint8_t)owner;
+      }
+    }
+    return;
+  }
+
+  if (p.num_ranks > 1) {
+    // ---- remote records: warp-aggregated slot claim per destination, then scattered 8/16-byte stores
+    const bool remote = active && (COUNT_ONLY || owner != p.rank);
+    const unsigned remote_mask = __ballot_sync(0xffffffffu, remote);
+    if (remote) {
+      const unsigned peers = __match_any_sync(remote_mask, owner);
+      const int leader = __ffs(peers) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(p.out_count + owner, (unsigned long long)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      if (!COUNT_ONLY) {
+        const int64_t pos = (int64_t)base + __popc(peers & ((1u << lane) - 1u));
+        const int64_t cap = p.out_offset[owner + 1] - p.out_offset[owner];
+        if (pos < cap) {
+          const int64_t slot = p.out_offset[owner] + pos;
+          p.out_betas[slot] = beta;
+          reinterpret_cast<V *>(p.out_coeffs)[slot] = c;
+        } else {
+          atomicAdd(p.status + 2, 1ull);
+        }
+      }
+    }
+    if (COUNT_ONLY) return;
+    active = active && owner == p.rank;
+  } else if (COUNT_ONLY) {
+    const unsigned m = __ballot_sync(0xffffffffu, active);
+    if (lane == 0 && m) atomicAdd(p.out_count, (unsigned long long)__popc(m));
+    return;
+  }
+
+  // ---- local records: localProcess (reference DMV:73-127)
+  if (active) {
+    const int64_t idx = locate(p.index, beta);
+    if (idx >= 0) {
+      if (PROJ == PROJ_GROUP) c = v_scale(c, __ldg(p.norms + idx));
+      if (v_nonzero(c)) atomic_accumulate<CE>(p.y, idx, v_re(c), v_im(c));   // DMV:110: skip c == 0
+    } else if (v_nonzero(c)) {
+      bool fatal = true;
+      if (PROJ == PROJ_GROUP && !orbit.trivial_characters)
+        fatal = orbit_stabiliser_sum(orbit, beta) > 1e-12 * (double)orbit.group_order;  // zero-norm orbit
+      if (fatal) {                                                             // DMV:115-118
+        if (atomicAdd(p.status, 1ull) == 0) p.status[1] = beta;
+      }
+    }
+  }
+}
+
+template <int PROJ, bool CV, bool CE, bool COUNT_ONLY>
+__global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
+  using V = typename ValT<CV>::type;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(p, PROJ, sizeof(V));
+  TermGroup *s_groups = reinterpret_cast<TermGroup *>(smem + L.groups);
+  OffTerm *s_terms = reinterpret_cast<OffTerm *>(smem + L.terms);
+  DiagTerm *s_diag = reinterpret_cast<DiagTerm *>(smem + L.diag);
+  stage(s_groups, p.groups, p.n_groups);
+  stage(s_terms, p.terms, p.n_terms);
+  stage(s_diag, p.diag, p.n_diag);
+  OrbitProgram orbit = p.orbit;
+  if (PROJ == PROJ_GROUP) {
+    const int np = orbit.n_left + orbit.n_right;
+    uint64_t *s64 = reinterpret_cast<uint64_t *>(smem + L.orbit64);
+    int32_t *s32 = reinterpret_cast<int32_t *>(smem + L.orbit32);
+    const int nb = orbit.n_q * orbit.n_stages, ns = (orbit.n_t - 1) * np;
+    stage(s64, p.orbit.benes_mask, nb);
+    stage(s64 + nb, p.orbit.step_mask, ns);
+    stage(s32, p.orbit.benes_delta, orbit.n_stages);
+    stage(s32 + orbit.n_stages, p.orbit.step_shift, ns);
+    orbit.benes_mask = s64;
+    orbit.step_mask = s64 + nb;
+    orbit.benes_delta = s32;
+    orbit.step_shift = s32 + orbit.n_stages;
+  }
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  uint64_t *qb = reinterpret_cast<uint64_t *>(smem + L.queues) + warp * kQueue;
+  V *qc = reinterpret_cast<V *>(smem + L.queues + (size_t)kWarps * kQueue * 8) + warp * kQueue;
+  unsigned head = 0, count = 0;  // warp-uniform
+
+  const int64_t n_rows = p.row_end - p.row_begin;
+  const int64_t n_tiles = (n_rows + 31) / 32;
+  const int64_t warps_total = (int64_t)gridDim.x * kWarps;
+  for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += warps_total) {
+    const int64_t i = p.row_begin + tile * 32 + lane;
+    const bool valid = i < p.row_end;
+    uint64_t alpha = 0;
+    V xi = v_make(0.0, 0.0, (V *)nullptr);
+    if (valid) {
+      alpha = __ldg(p.index.reps + i);
+      if (!COUNT_ONLY) {
+        if (CE) {
+          const double2 t = __ldg(reinterpret_cast<const double2 *>(p.x) + i);
+          xi = v_make(t.x, t.y, (V *)nullptr);
+        } else {
+          xi = v_make(__ldg(reinterpret_cast<const double *>(p.x) + i), 0.0, (V *)nullptr);
+        }
+      }
+    }
+    // ---- diagonal: y[i] += x[i] * sum_t v_t [alpha & m == r] (-1)^popc(alpha & s)   (DMV:36-53)
+    if (!COUNT_ONLY && p.n_diag > 0 && valid) {
+      double dre = 0.0, dim = 0.0;
+      for (int t = 0; t < p.n_diag; ++t) {
+        const DiagTerm d = s_diag[t];
+        if ((alpha & d.m) == d.r) {
+          const double sg = (__popcll(alpha & d.s) & 1) ? -1.0 : 1.0;
+          dre += sg * d.v_re;
+          dim += sg * d.v_im;
+        }
+      }
+      if (CE) {
+        const double2 t = __ldg(reinterpret_cast<const double2 *>(p.x) + i);
+        atomic_accumulate<true>(p.y, i, dre * t.x - dim * t.y, dre * t.y + dim * t.x);
+      } else {
+        // real vectors take the real part of the diagonal (ls_internal_operator_apply_diag_x1 on real(64))
+        atomic_accumulate<false>(p.y, i, dre * __ldg(reinterpret_cast<const double *>(p.x) + i), 0.0);
+      }
+    }
+    if (PROJ == PROJ_GROUP && valid && !COUNT_ONLY)
+      xi = v_scale(xi, 1.0 / __ldg(p.norms + i));   // 1 / norm(alpha): BO:200
+
+    // ---- off-diagonal: walk the flip-mask groups in lock step
+    for (int g = 0; g < p.n_groups; ++g) {
+      const TermGroup grp = s_groups[g];
+      V c = v_make(0.0, 0.0, (V *)nullptr);
+      bool hit = false;
+      for (int t = grp.first; t < grp.first + grp.count; ++t) {
+        const OffTerm term = s_terms[t];
+        if ((alpha & term.m) == term.r) {
+          const double sg = (__popcll(alpha & term.s) & 1) ? -1.0 : 1.0;
+          v_acc(c, sg * term.v_re, sg * term.v_im);
+          hit = true;
+        }
+      }
+      const bool emit = valid && hit && (COUNT_ONLY || v_nonzero(c));
+      const unsigned m = __ballot_sync(0xffffffffu, emit);
+      if (m) {
+        if (emit) {
+          const unsigned pos = (head + count + __popc(m & ((1u << lane) - 1u))) & (kQueue - 1);
+          qb[pos] = alpha ^ grp.x;
+          qc[pos] = v_mul(c, xi);
+        }
+        count += __popc(m);
+        if (count >= 32) {
+          __syncwarp();
+          const unsigned pos = (head + lane) & (kQueue - 1);
+          consume<PROJ, CV, CE, COUNT_ONLY>(p, orbit, true, qb[pos], qc[pos]);
+          head = (head + 32) & (kQueue - 1);
+          count -= 32;
+          __syncwarp();
+        }
+      }
+    }
+  }
+  if (count > 0) {
+    __syncwarp();
+    const unsigned pos = (head + lane) & (kQueue - 1);
+    const bool active = lane < count;
+    consume<PROJ, CV, CE, COUNT_ONLY>(p, orbit, active, active ? qb[pos] : 0ull,
+                                      active ? qc[pos] : v_make(0.0, 0.0, (V *)nullptr));
+  }
+}
+
+// localProcess for records that arrived from other ranks: already projected and hashed by the sender.
+template <int PROJ, bool CV, bool CE>
+__global__ void __launch_bounds__(kThreads) k_accumulate(const KernelParams p, int64_t count,
+                                                         const uint64_t *__restrict__ betas,
+                                                         const double *__restrict__ coeffs) {
+  using V = typename ValT<CV>::type;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+    const uint64_t beta = __ldg(betas + k);
+    V c = __ldg(reinterpret_cast<const V *>(coeffs) + k);
+    const int64_t idx = locate(p.index, beta);
+    if (idx >= 0) {
+      if (PROJ == PROJ_GROUP) c = v_scale(c, __ldg(p.norms + idx));
+      if (v_nonzero(c)) atomic_accumulate<CE>(p.y, idx, v_re(c), v_im(c));
+    } else if (v_nonzero(c)) {
+      bool fatal = true;
+      if (PROJ == PROJ_GROUP && !p.orbit.trivial_characters)
+        fatal = orbit_stabiliser_sum(p.orbit, beta) > 1e-12 * (double)p.orbit.group_order;
+      if (fatal && atomicAdd(p.status, 1ull) == 0) p.status[1] = beta;
+    }
+  }
+}
+
+// dir[b] = lower_bound(reps, b << shift) for b in [0, n_buckets]
+__global__ void k_build_directory(const uint64_t *__restrict__ reps, int64_t n, uint32_t *dir,
+                                  uint64_t n_buckets, int shift) {
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_buckets) return;
+  const uint64_t key = (b == n_buckets) ? ~0ull : (b << shift);
+  int64_t lo = 0, hi = n;
+  if (b == n_buckets) lo = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (reps[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  dir[b] = (uint32_t)lo;
+}
+
+__global__ void k_state_index(const StateIndex ix, int64_t count, const uint64_t *__restrict__ spins,
+                              int64_t *indices) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) indices[k] = locate(ix, spins[k]);
+}
+
+__global__ void k_locale_idx(int64_t count, const uint64_t *__restrict__ states, int num_ranks, uint8_t *keys) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) keys[k] = (uint8_t)locale_idx_of(states[k], num_ranks);
+}
+
+// ls_hs_state_info (reference src/FFI.chpl:181-184): representative, conj(character), norm
+template <int PROJ>
+__global__ void k_state_info(const OrbitProgram P, uint64_t site_mask, double inv_char, int64_t count,
+                             const uint64_t *__restrict__ alphas, uint64_t *betas, double2 *characters,
+                             double *norms) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const uint64_t a = alphas[k];
+  if (PROJ == PROJ_NONE) {
+    betas[k] = a; characters[k] = make_double2(1.0, 0.0); norms[k] = 1.0;
+  } else if (PROJ == PROJ_INVERSION) {
+    const uint64_t inv = a ^ site_mask;
+    const bool flip = inv < a;
+    betas[k] = flip ? inv : a;
+    characters[k] = make_double2(flip ? inv_char : 1.0, 0.0);
+    norms[k] = sqrt(0.5);   // stabiliser = {identity}: |Stab| / |G| = 1/2
+    if (inv == a) norms[k] = (inv_char > 0) ? 1.0 : 0.0;
+  } else {
+    const OrbitResult r = orbit_scan<true, false>(P, a);
+    betas[k] = r.rep;
+    double2 chi = make_double2(1.0, 0.0);
+    double stab = (double)r.stab;
+    if (!P.trivial_characters) {
+      chi = P.characters[r.arg];
+      stab = orbit_stabiliser_sum(P, a);
+    }
+    characters[k] = make_double2(chi.x, -chi.y);
+    const double nn = stab / (double)P.group_order;
+    norms[k] = nn > 1e-12 ? sqrt(nn) : 0.0;
+  }
+}
+
+__global__ void k_compute_norms(const OrbitProgram P, int64_t count, const uint64_t *__restrict__ reps,
+                                double *norms) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  double stab;
+  if (P.trivial_characters) stab = (double)orbit_scan<true, false>(P, reps[k]).stab;
+  else stab = orbit_stabiliser_sum(P, reps[k]);
+  const double nn = stab / (double)P.group_order;
+  norms[k] = nn > 1e-12 ? sqrt(nn) : 0.0;
+}
+
+// nextStateFixedHamming (reference src/StatesEnumeration.chpl:31-34)
+__device__ __forceinline__ uint64_t next_state_fixed_hamming(uint64_t v) {
+  const uint64_t t = v | (v - 1);
+  return (t + 1) | (((~t & (t + 1)) - 1) >> (__ffsll((long long)v)));
+}
+
+// One thread per chunk of consecutive candidates [first, last]; keeps a candidate iff it is owned by
+// this rank, is the minimum of its orbit and has non-zero norm (reference
+// src/StatesEnumeration.chpl:158-224).  Pass 0 counts, pass 1 writes at chunk_offset[c].
+template <int PROJ, bool WRITE>
+__global__ void k_enumerate(const OrbitProgram P, uint64_t site_mask, bool fixed_hamming, int rank,
+                            int num_ranks, int64_t n_chunks, const uint64_t *__restrict__ chunk_first,
+                            const uint64_t *__restrict__ chunk_last, unsigned long long *chunk_count,
+                            const unsigned long long *__restrict__ chunk_offset, uint64_t *out,
+                            double *out_norms) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  uint64_t v = chunk_first[c];
+  const uint64_t last = chunk_last[c];
+  unsigned long long n = 0;
+  unsigned long long base = WRITE ? chunk_offset[c] : 0ull;
+  for (;;) {
+    bool keep = (num_ranks <= 1) || (locale_idx_of(v, num_ranks) == rank);
+    double norm = 1.0;
+    if (keep) {
+      if (PROJ == PROJ_INVERSION) {
+        keep = v < (v ^ site_mask);
+      } else if (PROJ == PROJ_GROUP) {
+        const OrbitResult r = orbit_scan<true, true>(P, v);
+        keep = (r.rep == v);
+        if (keep) {
+          const double stab = P.trivial_characters ? (double)r.stab : orbit_stabiliser_sum(P, v);
+          const double nn = stab / (double)P.group_order;
+          norm = nn > 1e-12 ? sqrt(nn) : 0.0;
+          keep = norm > 0.0;
+        }
+      }
+    }
+    if (keep) {
+      if (WRITE) { out[base + n] = v; if (out_norms) out_norms[base + n] = norm; }
+      ++n;
+    }
+    if (v == last) break;
+    v = fixed_hamming ? next_state_fixed_hamming(v) : v + 1;
+  }
+  if (!WRITE) chunk_count[c] = n;
+}
+
+int grid_for(int64_t work_items, int per_block, int max_blocks) {
+  int64_t b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int PROJ, bool CV, bool CE, bool COUNT_ONLY>
+void launch_generate_t(const KernelParams &p, cudaStream_t stream) {
+  using V = typename ValT<CV>::type;
+  const SmemLayout L = smem_layout(p, PROJ, sizeof(V));
+  auto kernel = k_generate<PROJ, CV, CE, COUNT_ONLY>;
+  if (L.total > 48 * 1024)
+    DMV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  int per_sm = 0;
+  DMV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, L.total));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t tiles = (p.row_end - p.row_begin + 31) / 32;
+  // grid = a whole number of waves of resident CTAs (148 SMs x per_sm), or fewer when the work is small
+  const int blocks = grid_for(tiles, kWarps, sm_count() * per_sm);
+  kernel<<<blocks, kThreads, L.total, stream>>>(p);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
+template <int PROJ, bool CV, bool CE>
+void launch_generate_c(const KernelParams &p, bool count_only, cudaStream_t s) {
+  if (count_only) launch_generate_t<PROJ, CV, CE, true>(p, s);
+  else launch_generate_t<PROJ, CV, CE, false>(p, s);
+}
+template <int PROJ>
+void launch_generate_p(const KernelParams &p, bool cv, bool ce, bool count_only, cudaStream_t s) {
+  if (!cv && !ce) launch_generate_c<PROJ, false, false>(p, count_only, s);
+  else if (cv && ce) launch_generate_c<PROJ, true, true>(p, count_only, s);
+  else if (cv && !ce) launch_generate_c<PROJ, true, false>(p, count_only, s);
+  else throw std::runtime_error("complex vectors need complex values");
+}
+
+template <int PROJ>
+void launch_accumulate_p(const KernelParams &p, bool cv, bool ce, int64_t count, const uint64_t *b,
+                         const double *c, cudaStream_t s) {
+  const int blocks = grid_for(count, kThreads, sm_count() * 8);
+  if (!cv && !ce) k_accumulate<PROJ, false, false><<<blocks, kThreads, 0, s>>>(p, count, b, c);
+  else if (cv && ce) k_accumulate<PROJ, true, true><<<blocks, kThreads, 0, s>>>(p, count, b, c);
+  else if (cv && !ce) k_accumulate<PROJ, true, false><<<blocks, kThreads, 0, s>>>(p, count, b, c);
+  else throw std::runtime_error("complex vectors need complex values");
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
+}  // namespace
+
+void launch_generate(const KernelParams &p, Projection proj, bool cv, bool ce, bool count_only,
+                     cudaStream_t stream) {
+  if (p.row_end <= p.row_begin) return;
+  switch (proj) {
+    case PROJ_NONE: launch_generate_p<PROJ_NONE>(p, cv, ce, count_only, stream); break;
+    case PROJ_INVERSION: launch_generate_p<PROJ_INVERSION>(p, cv, ce, count_only, stream); break;
+    case PROJ_GROUP: launch_generate_p<PROJ_GROUP>(p, cv, ce, count_only, stream); break;
+  }
+}
+
+void launch_accumulate(const KernelParams &p, Projection proj, bool cv, bool ce, int64_t count,
+                       const uint64_t *betas, const double *coeffs, cudaStream_t stream) {
+  if (count <= 0) return;
+  switch (proj) {
+    case PROJ_NONE: launch_accumulate_p<PROJ_NONE>(p, cv, ce, count, betas, coeffs, stream); break;
+    case PROJ_INVERSION: launch_accumulate_p<PROJ_INVERSION>(p, cv, ce, count, betas, coeffs, stream); break;
+    case PROJ_GROUP: launch_accumulate_p<PROJ_GROUP>(p, cv, ce, count, betas, coeffs, stream); break;
+  }
+}
+
+void launch_build_directory(const uint64_t *reps, int64_t n, uint32_t *dir, uint64_t n_buckets, int shift,
+                            cudaStream_t stream) {
+  const int64_t items = (int64_t)n_buckets + 1;
+  k_build_directory<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(reps, n, dir, n_buckets, shift);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
+void launch_state_index(const StateIndex &ix, int64_t count, const uint64_t *spins, int64_t *indices,
+                        cudaStream_t stream) {
+  if (count <= 0) return;
+  k_state_index<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(ix, count, spins, indices);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
+void launch_locale_idx(int64_t count, const uint64_t *states, int num_ranks, uint8_t *keys, cudaStream_t stream) {
+  if (count <= 0) return;
+  k_locale_idx<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(count, states, num_ranks, keys);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
+void launch_state_info(const OrbitProgram &P, Projection proj, uint64_t site_mask, double inv_char,
+                       int64_t count, const uint64_t *alphas, uint64_t *betas, double *characters,
+                       double *norms, cudaStream_t stream) {
+  if (count <= 0) return;
+  const unsigned blocks = (unsigned)((count + 127) / 128);
+  double2 *ch = reinterpret_cast<double2 *>(characters);
+  switch (proj) {
+    case PROJ_NONE: k_state_info<PROJ_NONE><<<blocks, 128, 0, stream>>>(P, site_mask, inv_char, count, alphas, betas, ch, norms); break;
+    case PROJ_INVERSION: k_state_info<PROJ_INVERSION><<<blocks, 128, 0, stream>>>(P, site_mask, inv_char, count, alphas, betas, ch, norms); break;
+    case PROJ_GROUP: k_state_info<PROJ_GROUP><<<blocks, 128, 0, stream>>>(P, site_mask, inv_char, count, alphas, betas, ch, norms); break;
+  }
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
+void launch_compute_norms(const OrbitProgram &P, int64_t count, const uint64_t *reps, double *norms,
+                          cudaStream_t stream) {
+  if (count <= 0) return;
+  k_compute_norms<<<(unsigned)((count + 127) / 128), 128, 0, stream>>>(P, count, reps, norms);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
+void launch_enumerate(const OrbitProgram &P, Projection proj, uint64_t site_mask, bool fixed_hamming,
+                      int rank, int num_ranks, int64_t n_chunks, const uint64_t *chunk_first,
+                      const uint64_t *chunk_last, unsigned long long *chunk_count,
+                      const unsigned long long *chunk_offset, uint64_t *out, double *out_norms,
+                      bool write_pass, cudaStream_t stream) {
+  if (n_chunks <= 0) return;
+  const unsigned blocks = (unsigned)((n_chunks + 127) / 128);
+#define DMV_ENUM(PR)                                                                                      \
+  if (write_pass)                                                                                         \
+    k_enumerate<PR, true><<<blocks, 128, 0, stream>>>(P, site_mask, fixed_hamming, rank, num_ranks,       \
+                                                      n_chunks, chunk_first, chunk_last, chunk_count,     \
+                                                      chunk_offset, out, out_norms);                      \
+  else                                                                                                    \
+    k_enumerate<PR, false><<<blocks, 128, 0, stream>>>(P, site_mask, fixed_hamming, rank, num_ranks,      \
+                                                       n_chunks, chunk_first, chunk_last, chunk_count,    \
+                                                       chunk_offset, out, out_norms)
+  switch (proj) {
+    case PROJ_NONE: DMV_ENUM(PROJ_NONE); break;
+    case PROJ_INVERSION: DMV_ENUM(PROJ_INVERSION); break;
+    case PROJ_GROUP: DMV_ENUM(PROJ_GROUP); break;
+  }
+#undef DMV_ENUM
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
+}  // namespace dmv

@@ -1,0 +1,122 @@
+"""Hash-partitioned (multi-GPU) form of the product: ``matrixVectorProduct`` (DMV:1072-1093).
+
+Two ways to run P ranks:
+
+* ``DistributedOperator``: one process per GPU under torch.distributed (the bench / production shape).
+  The all-to-all of (beta, coeff) records is done by NCCL inside libdmv_b200 (``dmv_matvec``); torch is
+  only used to share the NCCL unique id and for barriers.
+* ``EmulatedCluster``: P logical ranks (P contexts) on ONE GPU, the analogue of the reference's
+  GASNet-smp oversubscription (reference env/setup-env.sh:5,13).  The exchange is replaced by handing
+  each destination context the sender's outgoing bucket (same device, so the pointers are valid).
+  Used by the single-GPU tests to cover the bucketing / accumulate path for P in {2, 3, 4, ...}.
+
+The block <-> hashed conversions of vectors (arrFromBlockToHashed / arrFromHashedToBlock,
+src/BlockToHashed.chpl:87, src/HashedToBlock.chpl:67) are host-side numpy helpers here ("next" row f2).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+from .config import OperatorSpec
+from .operator import Operator, _elt_of, locale_idx_of
+
+
+def masks_of(op: Operator, states: np.ndarray, num_ranks: int) -> np.ndarray:
+    """masks[i] = owner of the i-th state in global sorted order (SE:138-156)."""
+    if num_ranks == 1:
+        return np.zeros(states.shape[0], dtype=np.uint8)
+    return locale_idx_of(op, states, num_ranks)
+
+
+def block_to_hashed(arr: np.ndarray, masks: np.ndarray, num_ranks: int) -> list[np.ndarray]:
+    return [np.ascontiguousarray(arr[masks == p]) for p in range(num_ranks)]
+
+
+def hashed_to_block(blocks: list[np.ndarray], masks: np.ndarray) -> np.ndarray:
+    out = np.zeros(masks.shape[0], dtype=blocks[0].dtype)
+    for p, blk in enumerate(blocks):
+        out[masks == p] = blk
+    return out
+
+
+class EmulatedCluster:
+    """P logical ranks on one GPU."""
+
+    def __init__(self, spec: OperatorSpec, num_ranks: int, device: int = 0):
+        self.num_ranks = num_ranks
+        self.ops = [Operator(spec, device=device, rank=r, num_ranks=num_ranks) for r in range(num_ranks)]
+
+    def build(self):
+        for op in self.ops:
+            op.basis.build()
+        return self
+
+    def set_representatives(self, blocks, norms=None):
+        for r, op in enumerate(self.ops):
+            op.basis.uncheckedSetRepresentatives(blocks[r], None if norms is None else norms[r])
+        return self
+
+    def representatives(self) -> list[np.ndarray]:
+        return [op.basis.representatives() for op in self.ops]
+
+    def matvec(self, x_blocks):
+        """x_blocks / result: list of torch CUDA tensors, one per logical rank."""
+        import torch
+        ys = [torch.zeros_like(x) for x in x_blocks]
+        elt = _elt_of(x_blocks[0])
+        for op in self.ops:
+            op.plan()
+        # generate everywhere (each rank also accumulates the records it owns itself) ...
+        for r, op in enumerate(self.ops):
+            op.generate(x_blocks[r], ys[r])
+        # ... then the "exchange": destination q consumes the bucket rank r made for it
+        for r, op in enumerate(self.ops):
+            op.synchronize()
+        for r, src in enumerate(self.ops):
+            for q, dst in enumerate(self.ops):
+                if q == r:
+                    continue
+                betas, coeffs, n = src.outgoing(q)
+                if n > 0:
+                    dst.accumulate(elt, n, betas, coeffs, ys[q])
+        for op in self.ops:
+            op.synchronize()
+        return ys
+
+    def close(self):
+        for op in self.ops:
+            op.close()
+
+
+class DistributedOperator:
+    """One rank of the real multi-GPU product.  Requires torch.distributed to be initialised."""
+
+    def __init__(self, spec: OperatorSpec, device: int | None = None):
+        import torch
+        import torch.distributed as dist
+        self.rank, self.num_ranks = dist.get_rank(), dist.get_world_size()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.op = Operator(spec, device=device, rank=self.rank, num_ranks=self.num_ranks)
+        if self.num_ranks > 1:
+            ident = [None]
+            if self.rank == 0:
+                buf = (C.c_ubyte * 128)()
+                nat.check(nat.lib().dmv_comm_unique_id(buf))
+                ident[0] = bytes(buf)
+            dist.broadcast_object_list(ident, src=0)
+            buf = (C.c_ubyte * 128).from_buffer_copy(ident[0])
+            nat.check(nat.lib().dmv_comm_init(self.op._ctx, buf))
+        self.basis = self.op.basis
+
+    def matvec(self, x, y=None):
+        return self.op.matvec(x, y)
+
+
+def matrix_vector_product(matrix, x, y=None):
+    """``matrixVectorProduct(matrix, x, y, representatives)`` (DMV:1072-1075) on this rank's blocks;
+    `matrix` is an Operator (one rank) or a DistributedOperator."""
+    return matrix.matvec(x, y)

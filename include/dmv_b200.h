@@ -1,0 +1,162 @@
+/*
+ * dmv_b200.h -- C ABI of libdmv_b200.so: the B200-native distributed matrix-free H.x hot path.
+ *
+ * This is the drop-in boundary for the reference's hot path.  Plain pointers
+ * and sizes only; no torch / C++ types.  Every entry point names the reference interface it replaces.
+ * All functions returning int return 0 on success and a non-zero code on failure, with a message
+ * available from dmv_last_error() (the reference halts instead: src/DistributedMatrixVector.chpl:116,
+ * 1099-1102; the ls_chpl_* wrappers below abort() on failure to stay drop-in).
+ *
+ * Threading: one context per GPU; a context is not thread-safe; dmv_matvec() is collective over the
+ * ranks of the communicator (like the reference's allLocalesBarrier use, DMV:895,954,1013).
+ */
+#ifndef DMV_B200_H
+#define DMV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dmv_context dmv_context;
+
+/* Element type of x / y.  The reference's vectors are real(64) (DMV:1095-1096); complex128 is the
+ * extension BASELINE.json asks for. */
+enum { DMV_F64 = 1, DMV_C128 = 2 };
+
+/* Flat description of a spin basis: the visible part of `ls_hs_basis` (reference src/FFI.chpl:94-105)
+ * plus the symmetry group the third-party library keeps opaque.  Group element g maps a state s to
+ * g.s with (g.s) bit i = s bit perms[g*number_sites + i], followed by a global spin flip when
+ * flips[g] != 0.  characters are interleaved (re, im).  group_order == 0: no projection. */
+typedef struct {
+  int32_t number_sites;      /* <= 64 (DMV:1099: numberWords == 1) */
+  int32_t hamming_weight;    /* -1: not fixed */
+  int32_t spin_inversion;    /* 0, +1, -1 */
+  int32_t has_permutations;  /* basis.hasPermutationSymmetries(), src/ForeignTypes.chpl:96-98 */
+  int64_t group_order;       /* all elements, including the inversion-doubled ones */
+  const int32_t *perms;
+  const uint8_t *flips;
+  const double *characters;
+} dmv_basis_desc;
+
+/* Flat non-branching term tables: <beta|t|alpha> = v [alpha & m == r] (-1)^popcount(alpha & s),
+ * beta = alpha ^ x (the content of `ls_hs_nonbranching_terms`, reference src/FFI.chpl:109-113, whose
+ * tail is opaque there).  v interleaved (re, im).  Diagonal terms have x == 0 and carry no x array. */
+typedef struct {
+  int64_t n_off;
+  const double *off_v;
+  const uint64_t *off_m, *off_r, *off_x, *off_s;
+  int64_t n_diag;
+  const double *diag_v;
+  const uint64_t *diag_m, *diag_r, *diag_s;
+} dmv_operator_desc;
+
+/* ---- library lifetime: replaces ls_chpl_init / ls_chpl_finalize (reference src/library.c:19-34) */
+void ls_chpl_init(void);
+void ls_chpl_finalize(void);
+const char *dmv_last_error(void);
+int dmv_version(void);
+/* number of kernel launches issued by this library since load (evidence for bench.py's gpu_launches) */
+int64_t dmv_launch_count(void);
+
+/* ---- context: replaces the per-call setup of matrixVectorProduct (DMV:1077-1084: operator clone,
+ * uncheckedSetRepresentatives) and of localOffDiagonalNoQueue (DMV:864-955: buffers, pointer wiring)
+ * with a persistent object.  `device` is the CUDA device ordinal; rank / num_ranks define the hash
+ * partition  owner(s) = hash64_01(s) % num_ranks  (reference src/StatesEnumeration.chpl:122-136). */
+int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op, int device, int rank,
+                       int num_ranks, dmv_context **out);
+int dmv_context_destroy(dmv_context *ctx);
+/* launch on this stream (a cudaStream_t); NULL selects the context's own stream */
+int dmv_set_stream(dmv_context *ctx, void *cuda_stream);
+int dmv_synchronize(dmv_context *ctx);
+
+/* ---- basis
+ * dmv_basis_build: replaces Basis.build() / enumerateStates for this rank (reference
+ *   src/ForeignTypes.chpl:72, src/StatesEnumeration.chpl:516-603): enumerates on the GPU the ascending
+ *   representatives owned by this rank and their norms, and installs them.
+ * dmv_set_representatives: replaces Basis.uncheckedSetRepresentatives (src/ForeignTypes.chpl:74-77,
+ *   DMV:1084).  `representatives` must be ascending and owned by this rank; `norms` may be NULL (they
+ *   are then computed on the GPU when the basis needs them).  Host or device pointers.
+ * dmv_get_representatives copies them out (host or device destination); pass NULL to query the count. */
+int dmv_basis_build(dmv_context *ctx);
+int dmv_set_representatives(dmv_context *ctx, const uint64_t *representatives, int64_t count,
+                            const double *norms);
+int64_t dmv_number_states(const dmv_context *ctx);
+int dmv_get_representatives(dmv_context *ctx, uint64_t *representatives, double *norms);
+
+/* ---- third-party kernels the path consumes, now on the GPU (host or device pointers)
+ * dmv_state_index: ls_hs_state_index (reference src/FFI.chpl:173-175; call DMV:102); -1 when absent.
+ * dmv_state_info:  ls_hs_state_info  (src/FFI.chpl:181-184; call src/BatchedOperator.chpl:188-194).
+ * dmv_locale_idx_of: localeIdxOf     (src/StatesEnumeration.chpl:129-136). */
+int dmv_state_index(dmv_context *ctx, int64_t count, const uint64_t *spins, int64_t *indices);
+int dmv_state_info(dmv_context *ctx, int64_t count, const uint64_t *alphas, uint64_t *betas,
+                   double *characters, double *norms);
+int dmv_locale_idx_of(dmv_context *ctx, int64_t count, const uint64_t *states, int num_locales,
+                      uint8_t *keys);
+
+/* ---- BatchedOperator.computeOffDiag (reference src/BatchedOperator.chpl:82-213)
+ * Generates, for alphas[0..count) with values xs, the flat list (betas, coeffs, keys) after
+ * projection; *n receives the number of entries.  Output arrays must hold count * max_off_diag
+ * entries (dmv_max_number_off_diag).  Entry ORDER is unspecified (the reference's is row-major;
+ * consumers only bucket and accumulate).  coeffs interleaved complex128.  Host or device pointers. */
+int64_t dmv_max_number_off_diag(const dmv_context *ctx);
+int dmv_compute_off_diag(dmv_context *ctx, int64_t count, const uint64_t *alphas, const void *xs,
+                         int elt, int64_t *n, uint64_t *betas, double *coeffs, uint8_t *keys);
+
+/* ---- the hot path
+ * dmv_local_matvec: localMatrixVector(matrix, x, y, representatives) (DMV:1055-1070) on this rank's
+ *   block when num_ranks == 1.  y = D x + O x if the operator has diagonal terms, else y += O x
+ *   (DMV:1062-1069: without diagonal terms y is not cleared).  x, y: host or device pointers of
+ *   dmv_number_states() elements of type `elt`.
+ * dmv_matvec: matrixVectorProduct (DMV:1072-1093), collective over the communicator: generation,
+ *   hash bucketing, all-to-all exchange (NCCL) and owner-side search + accumulate. */
+int dmv_local_matvec(dmv_context *ctx, int elt, const void *x, void *y);
+int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y);
+
+/* ---- stepwise form of the distributed product, for hosts that own the exchange themselves (a Chapel
+ * host with GASNet PUTs as in DMV:361-371, torch.distributed, or several logical ranks on one GPU):
+ *   dmv_plan:      one counting pass; fills send_counts[num_ranks] (records this rank emits for each
+ *                  destination in one product; the own entry is processed locally and reported too).
+ *   dmv_generate:  y (+)= D x; emits all records; own bucket is searched + accumulated into y at once,
+ *                  the others are left in the context's outgoing buckets.
+ *   dmv_outgoing:  device pointers + count of the bucket for `dest` (valid until the next generate).
+ *   dmv_accumulate: localProcess (DMV:73-127) on `count` received records (device or host pointers):
+ *                  y[index(beta)] += coeff (* norm).  A record that is non-zero and not in the basis
+ *                  is an error (DMV:115-118). */
+int dmv_plan(dmv_context *ctx, int64_t *send_counts);
+int dmv_generate(dmv_context *ctx, int elt, const void *x, void *y);
+int dmv_outgoing(dmv_context *ctx, int dest, const uint64_t **betas, const double **coeffs,
+                 int64_t *count);
+int dmv_accumulate(dmv_context *ctx, int elt, int64_t count, const uint64_t *betas,
+                   const double *coeffs, void *y);
+
+/* ---- communicator (NCCL over NVLink): 128-byte unique id made on rank 0, shared by the host */
+int dmv_comm_unique_id(void *id128);
+int dmv_comm_init(dmv_context *ctx, const void *id128);
+
+/* ---- per-stage timings of the last product, in milliseconds (the reference's timing tree,
+ * DMV:1028-1052).  names: see dmv_timing_name(i); returns the number of stages. */
+int dmv_last_timings(dmv_context *ctx, double *ms, int capacity);
+const char *dmv_timing_name(int i);
+/* algorithmic counters of the last plan: number of emitted off-diagonal terms of this rank */
+int64_t dmv_number_terms(const dmv_context *ctx);
+
+/* ---- the reference's plugin surface (src/FFI.chpl:233-239, DMV:1095-1110).  `op` is the
+ * ls_hs_operator* the Haskell library hands out; it must have been bound to a context with
+ * dmv_bind_operator (see INTEGRATION.md for the shim that extracts the flat tables). */
+int dmv_bind_operator(const void *ls_hs_operator_ptr, dmv_context *ctx);
+void ls_chpl_matrix_vector_product(const void *ls_hs_operator_ptr, int num_vectors, double *x, double *y);
+
+/* ---- self-check of the host-side group compiler (no device needed; NOT on the product path).
+ * Compiles the symmetry group of `basis` into the device orbit program, verifies it against bit-by-bit
+ * permutation and evaluates the compiled program on the host for `count` states: reps[k] = min_g g(s_k),
+ * stab[k] = |{g : g(s_k) = s_k}|.  info[0..5] = {n_q, n_stages, n_t, n_left, n_right, has_flip}. */
+int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t count,
+                            const uint64_t *states, uint64_t *reps, int32_t *stab);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMV_B200_H */

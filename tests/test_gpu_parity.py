@@ -1,0 +1,237 @@
+"""Parity of the CUDA hot path (through the C ABI) against the CPU oracle -- the parity tests proper.
+
+Tolerances: bit-exact for representatives, indices, hashes and orbit representatives; y within
+1e-10 relative (BASELINE.json north_star), checked with the reference's own criterion shape
+|a-b| <= max(atol, rtol*max(|a|,|b|)) (test/TestMatrixVectorProduct.chpl:15-20) at rtol = 1e-12 scaled
+by the vector norm to allow for the different summation order of atomics.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from distributed_matvec_b200 import (BatchedOperator, EmulatedCluster, Operator, block_to_hashed,  # noqa: E402
+                                     hashed_to_block, load_config_from_yaml, locale_idx_of)
+from oracle import pyoracle as po  # noqa: E402
+
+DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data")
+
+SMALL = ["heisenberg_chain_4", "heisenberg_chain_6", "heisenberg_chain_8", "heisenberg_chain_10",
+         "heisenberg_chain_12", "heisenberg_chain_16", "heisenberg_kagome_12", "heisenberg_kagome_12_symm",
+         "heisenberg_kagome_16", "heisenberg_square_4x4", "issue_01"]
+MEDIUM = ["heisenberg_chain_20", "heisenberg_chain_24_symm"]
+
+
+def _load(name):
+    return load_config_from_yaml(os.path.join(DATA, name + ".yaml"))
+
+
+def _x(n, cplx, seed=42):
+    rng = np.random.default_rng(seed)   # recipe of input_for_matvec.py:8,31: uniform(-0.5, 0.5)
+    x = rng.random(n) - 0.5
+    if cplx:
+        x = x + 1j * (rng.random(n) - 0.5)
+    return x
+
+
+def _close(a, b, rtol=1e-12):
+    scale = max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() <= 1e-14 + rtol * scale * 50
+
+
+@pytest.fixture(scope="module")
+def need_cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("these tests need a CUDA device (no CPU fallback exists)")
+
+
+@pytest.mark.parametrize("name", SMALL + MEDIUM)
+def test_enumeration_matches_oracle(need_cuda, name):
+    basis, matrix = _load(name)
+    op = Operator(matrix)
+    op.basis.build()
+    reps = op.basis.representatives()
+    o_reps, o_norms = po.enumerate_states(basis)
+    assert reps.dtype == np.uint64
+    assert np.array_equal(reps, o_reps)           # bit-exact, ascending
+    if basis.has_permutation_symmetries():
+        assert np.allclose(op.basis.norms(), o_norms, rtol=0, atol=1e-15)
+    op.close()
+
+
+@pytest.mark.parametrize("num_ranks", [2, 3, 4])
+@pytest.mark.parametrize("name", ["heisenberg_chain_10", "heisenberg_kagome_12_symm", "heisenberg_chain_16",
+                                  "heisenberg_square_4x4"])
+def test_enumeration_hash_partition(need_cuda, name, num_ranks):
+    basis, matrix = _load(name)
+    o_reps, _ = po.enumerate_states(basis)
+    masks, blocks = po.partition_by_hash(o_reps, num_ranks)
+    cl = EmulatedCluster(matrix, num_ranks).build()
+    for r, blk in enumerate(cl.representatives()):
+        assert np.array_equal(blk, blocks[r])
+    cl.close()
+
+
+def test_hash_and_locale_index_bit_exact(need_cuda):
+    basis, matrix = _load("heisenberg_chain_10")
+    op = Operator(matrix)
+    rng = np.random.default_rng(7)
+    states = rng.integers(0, 2**63, size=100000, dtype=np.uint64)
+    states[:4] = [0, 1, 2**64 - 1, 0x8000000000000000]
+    for P in (1, 2, 3, 4, 5, 7, 8, 16, 255, 256):
+        assert np.array_equal(locale_idx_of(op, states, P), po.locale_idx_of(states, P)), P
+    op.close()
+
+
+@pytest.mark.parametrize("name", ["heisenberg_chain_16", "heisenberg_kagome_16", "heisenberg_chain_24_symm",
+                                  "heisenberg_chain_12"])
+def test_state_index_bit_exact(need_cuda, name):
+    basis, matrix = _load(name)
+    op = Operator(matrix)
+    op.basis.build()
+    reps = op.basis.representatives()
+    rng = np.random.default_rng(3)
+    probe = np.concatenate([reps, reps ^ np.uint64(1), rng.integers(0, 2**basis.number_sites, 5000, dtype=np.uint64),
+                            np.array([0, 2**64 - 1], dtype=np.uint64)])
+    got = op.basis.stateIndex(probe)
+    want = po.state_index(reps, probe)
+    assert np.array_equal(got, want)
+    op.close()
+
+
+@pytest.mark.parametrize("name", ["heisenberg_chain_10", "heisenberg_kagome_12_symm", "issue_01",
+                                  "heisenberg_square_4x4", "heisenberg_chain_24_symm", "heisenberg_chain_32_symm",
+                                  "heisenberg_square_6x6"])
+def test_state_info_matches_oracle(need_cuda, name):
+    basis, matrix = _load(name)
+    op = Operator(matrix)
+    rng = np.random.default_rng(11)
+    alphas = rng.integers(0, 2**basis.number_sites, 3000, dtype=np.uint64)
+    b, c, n = op.basis.stateInfo(alphas)
+    ob, oc, on = po.state_info(basis, alphas)
+    assert np.array_equal(b, ob)
+    ok = on > 0        # characters are only meaningful for states with non-zero norm
+    assert np.allclose(c[ok], oc[ok], atol=1e-15)
+    assert np.allclose(n, on, atol=1e-15)
+    op.close()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("name", SMALL + MEDIUM)
+def test_local_matvec_matches_oracle(need_cuda, name, cplx):
+    """test/TestMatrixVectorProduct.chpl on one locale: host vectors through the C ABI."""
+    basis, matrix = _load(name)
+    op = Operator(matrix)
+    op.basis.build()
+    reps = op.basis.representatives()
+    x = _x(reps.shape[0], cplx)
+    y = op.matvec(x)
+    y_ref = po.matvec_global(matrix, reps, x, 1)
+    assert _close(y, y_ref), np.abs(y - y_ref).max()
+    # device-resident vectors give the same answer
+    xd = torch.from_numpy(x).cuda()
+    yd = op.matvec(xd)
+    torch.cuda.synchronize()
+    assert _close(yd.cpu().numpy(), y_ref)
+    op.close()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("num_ranks", [2, 3, 4, 8])
+@pytest.mark.parametrize("name", ["heisenberg_chain_10", "heisenberg_chain_12", "heisenberg_kagome_16",
+                                  "heisenberg_kagome_12_symm", "heisenberg_square_4x4", "issue_01",
+                                  "heisenberg_chain_24_symm"])
+def test_emulated_ranks_match_oracle(need_cuda, name, num_ranks, cplx):
+    """P logical ranks on one GPU (GASNet-smp analogue): bucketing + accumulate of remote records."""
+    basis, matrix = _load(name)
+    o_reps, _ = po.enumerate_states(basis)
+    masks, blocks = po.partition_by_hash(o_reps, num_ranks)
+    x = _x(o_reps.shape[0], cplx)
+    y_ref = po.matvec_global(matrix, o_reps, x, num_ranks)
+    y_one = po.matvec_global(matrix, o_reps, x, 1)
+    assert _close(y_ref, y_one)        # P-invariance of the oracle itself
+    cl = EmulatedCluster(matrix, num_ranks).build()
+    xb = [torch.from_numpy(b).cuda() for b in block_to_hashed(x, masks, num_ranks)]
+    yb = cl.matvec(xb)
+    torch.cuda.synchronize()
+    y = hashed_to_block([t.cpu().numpy() for t in yb], masks)
+    assert _close(y, y_ref), np.abs(y - y_ref).max()
+    # the plan is exact: what each rank sends is what the oracle's bucketing produces
+    counts = np.array([op.plan() for op in cl.ops])
+    for r in range(num_ranks):
+        xs = np.ones(blocks[r].shape[0])
+        _, _, keys, _ = po.compute_off_diag(matrix, num_ranks, blocks[r], xs)
+        assert np.array_equal(counts[r], np.bincount(keys, minlength=num_ranks)), r
+    cl.close()
+
+
+@pytest.mark.parametrize("name", ["heisenberg_chain_10", "heisenberg_kagome_16", "heisenberg_kagome_12_symm",
+                                  "heisenberg_square_4x4", "issue_01"])
+def test_compute_off_diag_matches_oracle(need_cuda, name):
+    """BatchedOperator.computeOffDiag, all three branches, as multisets of (beta, coeff, key)."""
+    basis, matrix = _load(name)
+    o_reps, _ = po.enumerate_states(basis)
+    op = Operator(matrix)
+    bo = BatchedOperator(op, o_reps.shape[0])
+    for cplx in (False, True):
+        xs = _x(o_reps.shape[0], cplx, seed=5)
+        n, betas, coeffs, keys = bo.computeOffDiag(o_reps.shape[0], o_reps, xs)
+        ob, oc, ok, _ = po.compute_off_diag(matrix, 3 if False else 1, o_reps, xs)
+        assert n == ob.shape[0]
+        order = np.lexsort((coeffs.imag, coeffs.real, betas))
+        oorder = np.lexsort((oc.imag, oc.real, ob))
+        assert np.array_equal(betas[order], ob[oorder])
+        assert np.allclose(coeffs[order], oc[oorder], rtol=1e-13, atol=1e-15)
+    op.close()
+
+
+def test_missing_state_is_an_error(need_cuda):
+    """DMV:115-118: a generated state that is not in the basis halts."""
+    basis, matrix = _load("heisenberg_chain_10")
+    op = Operator(matrix)
+    reps, _ = po.enumerate_states(basis)
+    op.basis.uncheckedSetRepresentatives(reps[:-7])     # drop a few states
+    x = np.ones(reps.shape[0] - 7)
+    with pytest.raises(Exception, match="invalid index"):
+        op.matvec(x)
+    op.close()
+
+
+def test_no_diagonal_accumulates_into_y(need_cuda):
+    """DMV:1062-1069: without diagonal terms y is not cleared."""
+    from distributed_matvec_b200.config import basis_from_dict, operator_from_dict
+    n = 8
+    bonds = [[i, (i + 1) % n] for i in range(n)]
+    basis = basis_from_dict({"number_spins": n, "hamming_weight": 4})
+    matrix = operator_from_dict({"terms": [{"expression": "σ⁺₀ σ⁻₁", "sites": bonds},
+                                           {"expression": "σ⁻₀ σ⁺₁", "sites": bonds}]}, basis)
+    op = Operator(matrix)
+    op.basis.build()
+    reps = op.basis.representatives()
+    x = _x(reps.shape[0], False)
+    y0 = _x(reps.shape[0], False, seed=9)
+    y = op.matvec(x, y0.copy())
+    y_ref = po.matvec_blocks(matrix, [reps], [x], y_blocks=[y0.copy()])[0]
+    assert _close(y, y_ref)
+    op.close()
+
+
+def test_hermiticity_and_linearity_at_size(need_cuda):
+    """Size-independent properties on a basis the oracle would be slow on: <u,Hv> = <Hu,v>, linearity."""
+    basis, matrix = _load("heisenberg_chain_24")
+    op = Operator(matrix)
+    op.basis.build()
+    n = op.basis.numberStates()
+    assert n == 2704156
+    u = torch.from_numpy(_x(n, True, 1)).cuda()
+    v = torch.from_numpy(_x(n, True, 2)).cuda()
+    Hu, Hv = op.matvec(u), op.matvec(v)
+    lhs, rhs = torch.vdot(u, Hv), torch.vdot(Hu, v)
+    assert abs(lhs - rhs) <= 1e-10 * abs(lhs)
+    w = op.matvec(2.0 * u - 0.5j * v)
+    assert torch.allclose(w, 2.0 * Hu - 0.5j * Hv, rtol=1e-11, atol=1e-11)
+    op.close()
