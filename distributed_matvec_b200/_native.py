@@ -43,8 +43,10 @@ _SIGNATURES = [
     ("dmv_context_create", C.c_int, [C.POINTER(BasisDesc), C.POINTER(OperatorDesc), C.c_int, C.c_int, C.c_int,
                                      C.POINTER(C.c_void_p)]),
     ("dmv_context_destroy", C.c_int, [C.c_void_p]),
-    ("dmv_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("dmv_set_stream", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("dmv_synchronize", C.c_int, [C.c_void_p]),
+    ("dmv_set_option", C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    ("dmv_get_info", C.c_int64, [C.c_void_p, C.c_char_p]),
     ("dmv_basis_build", C.c_int, [C.c_void_p]),
     ("dmv_set_representatives", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     ("dmv_number_states", C.c_int64, [C.c_void_p]),

@@ -137,9 +137,17 @@ struct dmv_context {
   std::vector<TermGroup> h_groups;
   std::vector<OffTerm> h_terms;
   std::vector<DiagTerm> h_diag;
+  std::vector<OffTerm> h_terms_adj;   // row-traversal form, see k_pull
   DevBuf<TermGroup> d_groups;
-  DevBuf<OffTerm> d_terms;
+  DevBuf<OffTerm> d_terms, d_terms_adj;
   DevBuf<DiagTerm> d_diag;
+  // options
+  int opt_mode = -1;    // -1 auto (pull when one rank owns the basis), 0 push (scatter), 1 pull (gather)
+  int opt_index = -1;   // -1 auto, 0 directory search, 2 combinadic rank
+  int index_mode = INDEX_DIRECTORY;
+  DevBuf<uint32_t> d_binom;
+  int binom_stride = 0;
+  uint64_t rank_total = 0;
   // representatives of this rank
   int64_t n_states = -1;
   DevBuf<uint64_t> d_reps;
@@ -188,7 +196,14 @@ KernelParams base_params(dmv_context *ctx) {
   p.index.dir = ctx->d_dir.ptr;
   p.index.n_buckets = ctx->n_buckets;
   p.index.shift = ctx->dir_shift;
-  p.index.identity = (ctx->identity_index && ctx->num_ranks == 1) ? 1 : 0;
+  p.index.mode = ctx->index_mode;
+  p.index.binom = ctx->d_binom.ptr;
+  p.index.stride = ctx->binom_stride;
+  p.index.n_sites = ctx->n_sites;
+  p.index.weight = ctx->hamming_weight;
+  p.index.site_mask = ctx->site_mask;
+  p.rank_total = ctx->rank_total;
+  p.terms_adj = ctx->d_terms_adj.ptr;
   p.norms = ctx->d_norms.ptr;
   p.groups = ctx->d_groups.ptr; p.n_groups = (int)ctx->h_groups.size();
   p.terms = ctx->d_terms.ptr;   p.n_terms = (int)ctx->h_terms.size();
@@ -228,6 +243,54 @@ void check_status(dmv_context *ctx) {
   }
 }
 
+// binomial table for the combinadic ranking of fixed-Hamming-weight states
+struct Binomials {
+  uint64_t c[65][65];
+  Binomials() {
+    for (int n = 0; n <= 64; ++n)
+      for (int k = 0; k <= 64; ++k) {
+        if (k == 0 || k == n) c[n][k] = (k <= n) ? 1 : 0;
+        else if (k > n) c[n][k] = 0;
+        else {
+          const unsigned __int128 v = (unsigned __int128)c[n - 1][k - 1] + c[n - 1][k];
+          c[n][k] = v > (unsigned __int128)~0ull ? ~0ull : (uint64_t)v;
+        }
+      }
+  }
+};
+const Binomials &binom() { static Binomials b; return b; }
+
+// Which state -> index kernel applies (the reference's per-basis `state_index_kernel`, FFI:90-93).
+void select_index_mode(dmv_context *ctx) {
+  ctx->index_mode = INDEX_DIRECTORY;
+  if (ctx->identity_index && ctx->num_ranks == 1) { ctx->index_mode = INDEX_IDENTITY; return; }
+  const int n = ctx->n_sites, w = ctx->hamming_weight;
+  const bool eligible = ctx->num_ranks == 1 && w >= 0 && ctx->proj != PROJ_GROUP && ctx->opt_index != 0;
+  if (!eligible) return;
+  const uint64_t total = binom().c[n][w];
+  const uint64_t expect = (ctx->proj == PROJ_INVERSION) ? total / 2 : total;
+  if ((uint64_t)ctx->n_states != expect || total >= (1ull << 32)) return;
+  const int stride = w + 2;
+  std::vector<uint32_t> table((size_t)n * stride);
+  for (int pos = 0; pos < n; ++pos)
+    for (int k = 0; k < stride; ++k)
+      table[(size_t)pos * stride + k] = (uint32_t)std::min<uint64_t>(binom().c[pos][k], 0xffffffffull);
+  ctx->d_binom.upload(table, ctx->stream);
+  ctx->binom_stride = stride;
+  ctx->rank_total = total;
+  // the block must be exactly the first `expect` fixed-weight states: rank(reps[i]) == i for all i
+  StateIndex ix{};
+  ix.reps = ctx->d_reps.ptr; ix.n = ctx->n_states; ix.mode = INDEX_RANK; ix.binom = ctx->d_binom.ptr;
+  ix.stride = stride; ix.n_sites = n; ix.weight = w; ix.site_mask = ctx->site_mask;
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  launch_verify_rank(ix, ctx->d_status.ptr, ctx->stream);
+  unsigned long long bad = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&bad, ctx->d_status.ptr, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  if (bad == 0) ctx->index_mode = INDEX_RANK;
+}
+
 void install_directory(dmv_context *ctx) {
   const int64_t n = ctx->n_states;
   uint64_t max_rep = 0;
@@ -244,6 +307,7 @@ void install_directory(dmv_context *ctx) {
   ctx->d_dir.alloc(ctx->n_buckets + 2);
   launch_build_directory(ctx->d_reps.ptr, n, ctx->d_dir.ptr, ctx->n_buckets, shift, ctx->stream);
   ctx->planned = false;
+  select_index_mode(ctx);
 }
 
 void upload_orbit(dmv_context *ctx) {
@@ -263,23 +327,6 @@ void upload_orbit(dmv_context *ctx) {
   P.characters = reinterpret_cast<const double2 *>(ctx->d_chars.ptr);
   ctx->orbit = P;
 }
-
-// binomial table for the combinadic ranking of fixed-Hamming-weight states
-struct Binomials {
-  uint64_t c[65][65];
-  Binomials() {
-    for (int n = 0; n <= 64; ++n)
-      for (int k = 0; k <= 64; ++k) {
-        if (k == 0 || k == n) c[n][k] = (k <= n) ? 1 : 0;
-        else if (k > n) c[n][k] = 0;
-        else {
-          const unsigned __int128 v = (unsigned __int128)c[n - 1][k - 1] + c[n - 1][k];
-          c[n][k] = v > (unsigned __int128)~0ull ? ~0ull : (uint64_t)v;
-        }
-      }
-  }
-};
-const Binomials &binom() { static Binomials b; return b; }
 
 // rank of a fixed-weight state among states of the same weight in ascending order
 // (what ls_hs_fixed_hamming_state_to_index computes, reference src/FFI.chpl:165)
@@ -367,7 +414,18 @@ void do_plan(dmv_context *ctx) {
   ctx->planned = true;
 }
 
+bool use_pull(const dmv_context *ctx) {
+  return ctx->num_ranks == 1 && ctx->opt_mode != 0;
+}
+
 void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev) {
+  if (use_pull(ctx)) {   // one rank owns the basis: traverse by rows (gather), see k_pull
+    KernelParams p = base_params(ctx);
+    p.x = x_dev;
+    p.y = y_dev;
+    launch_pull(p, ctx->proj, complex_values(ctx, elt), elt == DMV_C128, ctx->stream);
+    return;
+  }
   if (!ctx->planned) do_plan(ctx);
   zero_y_if_diag(ctx, elt, y_dev);
   if (ctx->num_ranks > 1)
@@ -477,7 +535,13 @@ int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op,
   for (auto &kv : by_x) {
     TermGroup g{kv.first, (int32_t)ctx->h_terms.size(), (int32_t)kv.second.size()};
     ctx->h_groups.push_back(g);
-    for (auto &o : kv.second) ctx->h_terms.push_back(o);
+    for (auto &o : kv.second) {
+      ctx->h_terms.push_back(o);
+      // <b|t|b^x> = v (-1)^popc(x&s) [b & m == r ^ (x & m)] (-1)^popc(b & s)
+      const uint64_t x = kv.first;
+      const double sg = (__builtin_popcountll(x & o.s) & 1) ? -1.0 : 1.0;
+      ctx->h_terms_adj.push_back(OffTerm{o.m, o.r ^ (x & o.m), o.s, sg * o.v_re, sg * o.v_im});
+    }
   }
   for (int64_t t = 0; t < op->n_diag; ++t) {
     DiagTerm d{op->diag_m[t], op->diag_r[t], op->diag_s[t], op->diag_v[2 * t], op->diag_v[2 * t + 1]};
@@ -486,6 +550,7 @@ int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op,
   }
   ctx->d_groups.upload(ctx->h_groups, ctx->stream);
   ctx->d_terms.upload(ctx->h_terms, ctx->stream);
+  ctx->d_terms_adj.upload(ctx->h_terms_adj, ctx->stream);
   ctx->d_diag.upload(ctx->h_diag, ctx->stream);
 
   // ---- symmetry group
@@ -523,12 +588,45 @@ int dmv_context_destroy(dmv_context *ctx) {
   API_END
 }
 
-int dmv_set_stream(dmv_context *ctx, void *cuda_stream) {
+int dmv_set_stream(dmv_context *ctx, void *cuda_stream, int use_own_stream) {
   API_BEGIN
   use_device(ctx);
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  // a NULL handle is the legacy default stream, which is what torch's default stream is
+  ctx->stream = use_own_stream ? ctx->own_stream : reinterpret_cast<cudaStream_t>(cuda_stream);
   API_END
+}
+
+int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
+  API_BEGIN
+  use_device(ctx);
+  const std::string key(name ? name : "");
+  if (key == "mode") {
+    if (value < -1 || value > 1) throw std::runtime_error("mode: -1 auto, 0 push, 1 pull");
+    ctx->opt_mode = (int)value;
+  } else if (key == "index") {
+    if (value != -1 && value != 0 && value != 2) throw std::runtime_error("index: -1 auto, 0 directory, 2 rank");
+    ctx->opt_index = (int)value;
+    if (ctx->n_states >= 0) { CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); select_index_mode(ctx); }
+  } else {
+    throw std::runtime_error("unknown option '" + key + "'");
+  }
+  API_END
+}
+
+int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
+  const std::string key(name ? name : "");
+  if (!ctx) return -1;
+  if (key == "index_mode") return ctx->index_mode;
+  if (key == "pull") return use_pull(ctx) ? 1 : 0;
+  if (key == "projection") return (int64_t)ctx->proj;
+  if (key == "n_groups") return (int64_t)ctx->h_groups.size();
+  if (key == "orbit_n_q") return ctx->host_orbit.n_q;
+  if (key == "orbit_n_t") return ctx->host_orbit.n_t;
+  if (key == "orbit_n_stages") return ctx->host_orbit.n_stages;
+  if (key == "group_order") return ctx->host_orbit.group_order;
+  if (key == "n_buckets") return (int64_t)ctx->n_buckets;
+  return -1;
 }
 
 int dmv_synchronize(dmv_context *ctx) {
@@ -734,7 +832,7 @@ int dmv_local_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
   require_states(ctx);
   if (ctx->num_ranks != 1) throw std::runtime_error("dmv_local_matvec needs num_ranks == 1; use dmv_matvec");
   if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
-  if (!ctx->planned) do_plan(ctx);
+  if (x == y) throw std::runtime_error("x and y must not alias");
   VecStage v = stage_vectors(ctx, elt, x, y);
   do_generate(ctx, elt, v.x_dev, v.y_dev);
   CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -865,7 +963,7 @@ int dmv_compute_off_diag(dmv_context *ctx, int64_t count, const uint64_t *alphas
   d_cnt.alloc(1);
   CUDA_CHECK(cudaMemsetAsync(d_cnt.ptr, 0, sizeof(unsigned long long), ctx->stream));
   KernelParams p = base_params(ctx);
-  p.index.reps = a.ptr; p.index.n = count; p.index.identity = 0;
+  p.index.reps = a.ptr; p.index.n = count; p.index.mode = INDEX_DIRECTORY;
   if (ctx->proj == PROJ_GROUP) {  // norms of the sources: BO:178-194 appends the alphas to state_info
     d_src_norms.alloc((size_t)count);
     launch_compute_norms(ctx->orbit, count, a.ptr, d_src_norms.ptr, ctx->stream);

@@ -63,23 +63,34 @@ __host__ __device__ __forceinline__ int locale_idx_of(uint64_t state, int num_ra
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sorted-representatives index:  directory over the top bits + bounded binary search.
-// Replaces ls_hs_state_index (reference src/FFI.chpl:173-175, call DMV:102).
+// State -> index.  Replaces ls_hs_state_index (reference src/FFI.chpl:173-175, call DMV:102) and the
+// per-basis `state_index_kernel` the third-party library installs (src/FFI.chpl:90-93):
+//   INDEX_DIRECTORY : sorted representatives; directory over the top bits + bounded binary search
+//   INDEX_IDENTITY  : state_index_is_identity (DMV:86): index == state
+//   INDEX_RANK      : full fixed-Hamming-weight basis (optionally halved by spin inversion) on one
+//                     rank: the index is the combinadic rank, computed from a binomial table with no
+//                     memory traffic to the representatives (ls_hs_fixed_hamming_state_to_index,
+//                     reference src/FFI.chpl:165).  Results are bit-identical to the search.
 // ---------------------------------------------------------------------------------------------
+enum IndexMode { INDEX_DIRECTORY = 0, INDEX_IDENTITY = 1, INDEX_RANK = 2 };
+
 struct StateIndex {
   const uint64_t *reps;   // ascending, this rank's block
   int64_t n;
   const uint32_t *dir;    // dir[b] = lower_bound(reps, b << shift), n_buckets + 1 entries
   uint64_t n_buckets;
   int32_t shift;
-  int32_t identity;       // state_index_is_identity (DMV:86): index == state
+  int32_t mode;           // IndexMode
+  // INDEX_RANK
+  const uint32_t *binom;  // [n_sites][weight + 2]: binom[pos * stride + k] = C(pos, k) (saturated)
+  int32_t stride, n_sites, weight;
+  uint64_t site_mask;
 };
 
-// dir entries are 4 bytes: dir[b] and dir[b+1] normally share one 32-byte sector.
-__device__ __forceinline__ int64_t locate(const StateIndex &ix, uint64_t key) {
-  if (ix.identity) return (key < (uint64_t)ix.n) ? (int64_t)key : -1;
+__device__ __forceinline__ int64_t locate_directory(const StateIndex &ix, uint64_t key) {
   const uint64_t b = key >> ix.shift;
   if (b >= ix.n_buckets) return -1;
+  // dir entries are 4 bytes: dir[b] and dir[b+1] normally share one 32-byte sector
   uint32_t lo = __ldg(ix.dir + b), hi = __ldg(ix.dir + b + 1);
   const uint32_t end = hi;
   while (lo < hi) {
@@ -89,6 +100,46 @@ __device__ __forceinline__ int64_t locate(const StateIndex &ix, uint64_t key) {
   }
   if (lo < end && __ldg(ix.reps + lo) == key) return (int64_t)lo;
   return -1;
+}
+
+// sum over the set bits of `bits` (ascending) of C(pos, k), k = k0 + 1, k0 + 2, ...
+__device__ __forceinline__ uint32_t combinadic_sum(const uint32_t *binom, int stride, uint64_t bits, int k0) {
+  uint32_t acc = 0;
+  int k = k0;
+  while (bits) {
+    const int pos = __ffsll((long long)bits) - 1;
+    ++k;
+    acc += binom[pos * stride + k];
+    bits &= bits - 1;
+  }
+  return acc;
+}
+
+__device__ __forceinline__ int64_t locate_rank(const StateIndex &ix, const uint32_t *binom, uint64_t key) {
+  if ((key & ~ix.site_mask) != 0 || __popcll(key) != ix.weight) return -1;
+  const int64_t r = (int64_t)combinadic_sum(binom, ix.stride, key, 0);
+  return r < ix.n ? r : -1;   // with spin inversion only the first half are representatives
+}
+
+// Rank of key = src ^ flip given rank(src) = src_index: only the bits inside the span of `flip` move.
+__device__ __forceinline__ int64_t locate_rank_incremental(const StateIndex &ix, const uint32_t *binom,
+                                                           uint64_t key, uint64_t src, int64_t src_index,
+                                                           uint64_t flip) {
+  const int lo = __ffsll((long long)flip) - 1;
+  const int hi = 63 - __clzll((long long)flip);
+  const uint64_t span = ((hi == 63) ? ~0ull : ((1ull << (hi + 1)) - 1)) & ~((1ull << lo) - 1);
+  const uint64_t ob = src & span, nb = key & span;
+  if ((key & ~ix.site_mask) != 0 || __popcll(ob) != __popcll(nb)) return -1;   // weight not preserved
+  const int k0 = __popcll(src & ((1ull << lo) - 1));
+  const int64_t r = src_index - (int64_t)combinadic_sum(binom, ix.stride, ob, k0) +
+                    (int64_t)combinadic_sum(binom, ix.stride, nb, k0);
+  return r < ix.n ? r : -1;
+}
+
+__device__ __forceinline__ int64_t locate(const StateIndex &ix, uint64_t key) {
+  if (ix.mode == INDEX_IDENTITY) return (key < (uint64_t)ix.n) ? (int64_t)key : -1;
+  if (ix.mode == INDEX_RANK) return locate_rank(ix, ix.binom, key);
+  return locate_directory(ix, key);
 }
 
 // ---------------------------------------------------------------------------------------------

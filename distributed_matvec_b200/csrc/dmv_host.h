@@ -38,6 +38,8 @@ struct KernelParams {
   // operator
   const TermGroup *groups; int32_t n_groups;
   const OffTerm *terms;    int32_t n_terms;
+  const OffTerm *terms_adj;   // row-traversal (pull) form of the same terms, see k_pull
+  uint64_t rank_total;        // INDEX_RANK: C(n_sites, weight)
   const DiagTerm *diag;    int32_t n_diag;
   // symmetry
   OrbitProgram orbit;         // device pointers (PROJ_GROUP)
@@ -63,6 +65,8 @@ struct KernelParams {
 struct LaunchConfig { int blocks; int threads; size_t smem; };
 void launch_generate(const KernelParams &p, Projection proj, bool complex_values, bool complex_elements,
                      bool count_only, cudaStream_t stream);
+void launch_pull(const KernelParams &p, Projection proj, bool complex_values, bool complex_elements,
+                 cudaStream_t stream);
 void launch_accumulate(const KernelParams &p, Projection proj, bool complex_values, bool complex_elements,
                        int64_t count, const uint64_t *betas, const double *coeffs, cudaStream_t stream);
 void launch_build_directory(const uint64_t *reps, int64_t n, uint32_t *dir, uint64_t n_buckets, int shift,
@@ -72,6 +76,7 @@ void launch_state_index(const StateIndex &ix, int64_t count, const uint64_t *spi
 void launch_state_info(const OrbitProgram &P, Projection proj, uint64_t site_mask, double inv_char,
                        int64_t count, const uint64_t *alphas, uint64_t *betas, double *characters,
                        double *norms, cudaStream_t stream);
+void launch_verify_rank(const StateIndex &ix, unsigned long long *status, cudaStream_t stream);
 void launch_locale_idx(int64_t count, const uint64_t *states, int num_ranks, uint8_t *keys, cudaStream_t stream);
 void launch_compute_norms(const OrbitProgram &P, int64_t count, const uint64_t *reps, double *norms,
                           cudaStream_t stream);

@@ -74,7 +74,7 @@ __device__ __forceinline__ double v_im(double2 a) { return a.y; }
 
 // ---- shared-memory staging of the operator / orbit tables ---------------------------------------
 struct SmemLayout {
-  size_t groups, terms, diag, orbit64, orbit32, queues, total;
+  size_t groups, terms, diag, orbit64, orbit32, binom, queues, total;
 };
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int proj, size_t val_bytes) {
@@ -93,8 +93,11 @@ __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int pro
   }
   off += 8 * n64;
   L.orbit32 = off; off += 4 * n32;
+  L.binom = off;
+  if (p.index.mode == INDEX_RANK) off += 4 * (size_t)p.index.n_sites * p.index.stride;
   off = align_up(off, 16);
-  L.queues = off; off += (size_t)kWarps * kQueue * (8 + val_bytes);
+  // per warp: ring of (beta, value) + (pull mode) source lane and a row accumulator
+  L.queues = off; off += (size_t)kWarps * (kQueue * (8 + val_bytes) + kQueue + 32 * val_bytes);
   L.total = off;
   return L;
 }
@@ -108,8 +111,9 @@ __device__ __forceinline__ void stage(T *dst, const T *src, int count) {
 // Projects beta (inversion / full group), and either accumulates it locally or appends it to the
 // bucket of its owner.  `active` lanes carry a record; all 32 lanes must call this (warp collectives).
 template <int PROJ, bool CV, bool CE, bool COUNT_ONLY>
-__device__ __forceinline__ void consume(const KernelParams &p, const OrbitProgram &orbit, bool active,
-                                        uint64_t beta, typename ValT<CV>::type c) {
+__device__ __forceinline__ void consume(const KernelParams &p, const OrbitProgram &orbit,
+                                        const StateIndex &index, bool active, uint64_t beta,
+                                        typename ValT<CV>::type c) {
   using V = typename ValT<CV>::type;
   const unsigned lane = threadIdx.x & 31u;
   if (PROJ == PROJ_INVERSION) {
@@ -179,7 +183,7 @@ __device__ __forceinline__ void consume(const KernelParams &p, const OrbitProgra
 
   // ---- local records: localProcess (reference DMV:73-127)
   if (active) {
-    const int64_t idx = locate(p.index, beta);
+    const int64_t idx = locate(index, beta);
     if (idx >= 0) {
       if (PROJ == PROJ_GROUP) c = v_scale(c, __ldg(p.norms + idx));
       if (v_nonzero(c)) atomic_accumulate<CE>(p.y, idx, v_re(c), v_im(c));   // DMV:110: skip c == 0
@@ -220,6 +224,12 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
     orbit.benes_delta = s32;
     orbit.step_shift = s32 + orbit.n_stages;
   }
+  StateIndex index = p.index;
+  if (index.mode == INDEX_RANK) {
+    uint32_t *sb = reinterpret_cast<uint32_t *>(smem + L.binom);
+    stage(sb, p.index.binom, index.n_sites * index.stride);
+    index.binom = sb;
+  }
   __syncthreads();
 
   const unsigned lane = threadIdx.x & 31u;
@@ -248,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
       }
     }
     // ---- diagonal: y[i] += x[i] * sum_t v_t [alpha & m == r] (-1)^popc(alpha & s)   (DMV:36-53)
-    if (!COUNT_ONLY && p.n_diag > 0 && valid) {
+    if (!COUNT_ONLY && !p.emit_all && p.n_diag > 0 && valid) {
       double dre = 0.0, dim = 0.0;
       for (int t = 0; t < p.n_diag; ++t) {
         const DiagTerm d = s_diag[t];
@@ -294,7 +304,7 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
         if (count >= 32) {
           __syncwarp();
           const unsigned pos = (head + lane) & (kQueue - 1);
-          consume<PROJ, CV, CE, COUNT_ONLY>(p, orbit, true, qb[pos], qc[pos]);
+          consume<PROJ, CV, CE, COUNT_ONLY>(p, orbit, index, true, qb[pos], qc[pos]);
           head = (head + 32) & (kQueue - 1);
           count -= 32;
           __syncwarp();
@@ -306,8 +316,218 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
     __syncwarp();
     const unsigned pos = (head + lane) & (kQueue - 1);
     const bool active = lane < count;
-    consume<PROJ, CV, CE, COUNT_ONLY>(p, orbit, active, active ? qb[pos] : 0ull,
+    consume<PROJ, CV, CE, COUNT_ONLY>(p, orbit, index, active, active ? qb[pos] : 0ull,
                                       active ? qc[pos] : v_make(0.0, 0.0, (V *)nullptr));
+  }
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// k_pull: the same product traversed by ROWS (gather) -- used when one rank owns the whole basis.
+//   y[b] = D(b) x[b] + sum_t <b|t|b^x_t> chi(g) n_a / n_b x[index(a)],   a = rep(b ^ x_t), g(b^x_t) = a
+// with <b|t|b^x> = v (-1)^popc(x&s) [b & m == r ^ (x & m)] (-1)^popc(b & s): the term table is
+// transformed once on the host (terms_adj).  Same generate -> project -> search pipeline as
+// k_generate, but the scattered FP64 atomics of localProcess (DMV:107-120) become scattered loads of x
+// and every y element is written exactly once (deterministic, no memset, half the L2 traffic).
+// -------------------------------------------------------------------------------------------------
+template <bool CE>
+__device__ __forceinline__ typename ValT<CE>::type load_x(const void *x, int64_t i) {
+  if (CE) {
+    const double2 t = __ldg(reinterpret_cast<const double2 *>(x) + i);
+    return v_make(t.x, t.y, (typename ValT<CE>::type *)nullptr);
+  }
+  return v_make(__ldg(reinterpret_cast<const double *>(x) + i), 0.0, (typename ValT<CE>::type *)nullptr);
+}
+__device__ __forceinline__ double to_v(double a, double *) { return a; }
+__device__ __forceinline__ double2 to_v(double a, double2 *) { return make_double2(a, 0.0); }
+__device__ __forceinline__ double2 to_v(double2 a, double2 *) { return a; }
+__device__ __forceinline__ void v_add(double &a, double b) { a += b; }
+__device__ __forceinline__ void v_add(double2 &a, double2 b) { a.x += b.x; a.y += b.y; }
+__device__ __forceinline__ void smem_add(double *p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void smem_add(double2 *p, double2 v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
+
+template <int PROJ, bool CV, bool CE>
+__global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
+  using V = typename ValT<CV>::type;
+  using E = typename ValT<CE>::type;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(p, PROJ, sizeof(V));
+  TermGroup *s_groups = reinterpret_cast<TermGroup *>(smem + L.groups);
+  OffTerm *s_terms = reinterpret_cast<OffTerm *>(smem + L.terms);
+  DiagTerm *s_diag = reinterpret_cast<DiagTerm *>(smem + L.diag);
+  stage(s_groups, p.groups, p.n_groups);
+  stage(s_terms, p.terms_adj, p.n_terms);
+  stage(s_diag, p.diag, p.n_diag);
+  OrbitProgram orbit = p.orbit;
+  if (PROJ == PROJ_GROUP) {
+    const int np = orbit.n_left + orbit.n_right;
+    uint64_t *s64 = reinterpret_cast<uint64_t *>(smem + L.orbit64);
+    int32_t *s32 = reinterpret_cast<int32_t *>(smem + L.orbit32);
+    const int nb = orbit.n_q * orbit.n_stages, ns = (orbit.n_t - 1) * np;
+    stage(s64, p.orbit.benes_mask, nb);
+    stage(s64 + nb, p.orbit.step_mask, ns);
+    stage(s32, p.orbit.benes_delta, orbit.n_stages);
+    stage(s32 + orbit.n_stages, p.orbit.step_shift, ns);
+    orbit.benes_mask = s64;
+    orbit.step_mask = s64 + nb;
+    orbit.benes_delta = s32;
+    orbit.step_shift = s32 + orbit.n_stages;
+  }
+  StateIndex index = p.index;
+  if (index.mode == INDEX_RANK) {
+    uint32_t *sb = reinterpret_cast<uint32_t *>(smem + L.binom);
+    stage(sb, p.index.binom, index.n_sites * index.stride);
+    index.binom = sb;
+  }
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  unsigned char *qbase = smem + L.queues;
+  uint64_t *qb = reinterpret_cast<uint64_t *>(qbase) + warp * kQueue;
+  V *qc = reinterpret_cast<V *>(qbase + (size_t)kWarps * kQueue * 8) + warp * kQueue;
+  V *acc_s = reinterpret_cast<V *>(qbase + (size_t)kWarps * kQueue * (8 + sizeof(V))) + warp * 32;
+  unsigned char *ql = qbase + (size_t)kWarps * (kQueue * (8 + sizeof(V)) + 32 * sizeof(V)) + warp * kQueue;
+  if (PROJ == PROJ_GROUP) acc_s[lane] = v_make(0.0, 0.0, (V *)nullptr);
+  __syncthreads();
+  unsigned head = 0, count = 0;
+
+  // drains `k` queued entries (PROJ_GROUP): orbit scan, search, gather, add into the owner row's slot
+  auto drain = [&](unsigned k) {
+    const bool active = lane < k;
+    if (active) {
+      const unsigned pos = (head + lane) & (kQueue - 1);
+      const uint64_t raw = qb[pos];
+      V h = qc[pos];
+      const unsigned src = ql[pos];
+      const OrbitResult r = orbit_scan<false, false>(orbit, raw);
+      if (!orbit.trivial_characters) {
+        const double2 chi = __ldg(orbit.characters + r.arg);   // chi(g), not conjugated (see header)
+        h = v_mul(h, v_make(chi.x, chi.y, (V *)nullptr));
+      }
+      const int64_t idx = locate(index, r.rep);
+      if (idx >= 0) {
+        h = v_scale(h, __ldg(p.norms + idx));
+        const V val = v_mul(h, to_v(load_x<CE>(p.x, idx), (V *)nullptr));
+        smem_add(acc_s + src, val);
+      } else if (v_nonzero(h)) {
+        bool fatal = true;
+        if (!orbit.trivial_characters)
+          fatal = orbit_stabiliser_sum(orbit, r.rep) > 1e-12 * (double)orbit.group_order;
+        if (fatal && atomicAdd(p.status, 1ull) == 0) p.status[1] = r.rep;
+      }
+    }
+  };
+
+  const int64_t n_rows = p.row_end - p.row_begin;
+  const int64_t n_tiles = (n_rows + 31) / 32;
+  const int64_t warps_total = (int64_t)gridDim.x * kWarps;
+  for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += warps_total) {
+    const int64_t i = p.row_begin + tile * 32 + lane;
+    const bool valid = i < p.row_end;
+    const uint64_t b = valid ? __ldg(p.index.reps + i) : 0ull;
+    V acc = v_make(0.0, 0.0, (V *)nullptr);
+    double inv_nb = 1.0;
+    if (PROJ == PROJ_GROUP && valid) inv_nb = 1.0 / __ldg(p.norms + i);
+
+    for (int g = 0; g < p.n_groups; ++g) {
+      const TermGroup grp = s_groups[g];
+      V h = v_make(0.0, 0.0, (V *)nullptr);
+      bool hit = false;
+      for (int t = grp.first; t < grp.first + grp.count; ++t) {
+        const OffTerm term = s_terms[t];
+        if ((b & term.m) == term.r) {
+          const double sg = (__popcll(b & term.s) & 1) ? -1.0 : 1.0;
+          v_acc(h, sg * term.v_re, sg * term.v_im);
+          hit = true;
+        }
+      }
+      const bool emit = valid && hit && v_nonzero(h);
+      if (PROJ != PROJ_GROUP) {
+        if (emit) {
+          uint64_t a = b ^ grp.x;
+          bool flipped = false;
+          if (PROJ == PROJ_INVERSION) {
+            const uint64_t inv = a ^ p.site_mask;
+            flipped = inv < a;
+            if (flipped) h = v_scale(h, p.inversion_character);
+          }
+          int64_t idx;
+          if (index.mode == INDEX_RANK) {
+            // rank over the full fixed-weight set, incrementally from rank(b) = i
+            const int lo = __ffsll((long long)grp.x) - 1;
+            const int hi = 63 - __clzll((long long)grp.x);
+            const uint64_t span = ((hi == 63) ? ~0ull : ((1ull << (hi + 1)) - 1)) & ~((1ull << lo) - 1);
+            const uint64_t ob = b & span, nb = a & span;
+            idx = -1;
+            if ((a & ~index.site_mask) == 0 && __popcll(ob) == __popcll(nb)) {
+              const int k0 = __popcll(b & ((1ull << lo) - 1));
+              int64_t r = i - (int64_t)combinadic_sum(index.binom, index.stride, ob, k0) +
+                          (int64_t)combinadic_sum(index.binom, index.stride, nb, k0);
+              if (flipped) r = (int64_t)p.rank_total - 1 - r;   // complement reverses the order
+              if (r >= 0 && r < index.n) idx = r;
+            }
+          } else {
+            idx = locate(index, flipped ? (a ^ p.site_mask) : a);
+          }
+          if (idx >= 0) {
+            v_add(acc, v_mul(h, to_v(load_x<CE>(p.x, idx), (V *)nullptr)));
+          } else if (atomicAdd(p.status, 1ull) == 0) {
+            p.status[1] = a;
+          }
+        }
+      } else {
+        const unsigned m = __ballot_sync(0xffffffffu, emit);
+        if (m) {
+          if (emit) {
+            const unsigned pos = (head + count + __popc(m & ((1u << lane) - 1u))) & (kQueue - 1);
+            qb[pos] = b ^ grp.x;
+            qc[pos] = v_scale(h, inv_nb);
+            ql[pos] = (unsigned char)lane;
+          }
+          count += __popc(m);
+          if (count >= 32) {
+            __syncwarp();
+            drain(32);
+            head = (head + 32) & (kQueue - 1);
+            count -= 32;
+            __syncwarp();
+          }
+        }
+      }
+    }
+    if (PROJ == PROJ_GROUP) {
+      if (count > 0) {
+        __syncwarp();
+        drain(count);
+        head = (head + count) & (kQueue - 1);
+        count = 0;
+      }
+      __syncwarp();
+      acc = acc_s[lane];
+      acc_s[lane] = v_make(0.0, 0.0, (V *)nullptr);
+      __syncwarp();
+    }
+    if (valid) {
+      // diagonal (DMV:36-53) and the single store of y[i]; without diagonal terms y is accumulated into
+      E out;
+      if (p.n_diag > 0) {
+        double dre = 0.0, dim = 0.0;
+        for (int t = 0; t < p.n_diag; ++t) {
+          const DiagTerm d = s_diag[t];
+          if ((b & d.m) == d.r) {
+            const double sg = (__popcll(b & d.s) & 1) ? -1.0 : 1.0;
+            dre += sg * d.v_re;
+            dim += sg * d.v_im;
+          }
+        }
+        const E xi = load_x<CE>(p.x, i);
+        if (CE) out = v_make(dre * v_re(xi) - dim * v_im(xi), dre * v_im(xi) + dim * v_re(xi), (E *)nullptr);
+        else out = v_make(dre * v_re(xi), 0.0, (E *)nullptr);
+      } else {
+        out = reinterpret_cast<const E *>(p.y)[i];
+      }
+      out = v_make(v_re(out) + v_re(acc), v_im(out) + v_im(acc), (E *)nullptr);
+      reinterpret_cast<E *>(p.y)[i] = out;
+    }
   }
 }
 
@@ -353,6 +573,11 @@ __global__ void k_state_index(const StateIndex ix, int64_t count, const uint64_t
                               int64_t *indices) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < count) indices[k] = locate(ix, spins[k]);
+}
+
+__global__ void k_verify_rank(const StateIndex ix, unsigned long long *status) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < ix.n && locate_rank(ix, ix.binom, ix.reps[k]) != k) atomicAdd(status, 1ull);
 }
 
 __global__ void k_locale_idx(int64_t count, const uint64_t *__restrict__ states, int num_ranks, uint8_t *keys) {
@@ -500,6 +725,31 @@ void launch_generate_p(const KernelParams &p, bool cv, bool ce, bool count_only,
   else throw std::runtime_error("complex vectors need complex values");
 }
 
+
+template <int PROJ, bool CV, bool CE>
+void launch_pull_t(const KernelParams &p, cudaStream_t stream) {
+  using V = typename ValT<CV>::type;
+  const SmemLayout L = smem_layout(p, PROJ, sizeof(V));
+  auto kernel = k_pull<PROJ, CV, CE>;
+  if (L.total > 48 * 1024)
+    DMV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  int per_sm = 0;
+  DMV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, L.total));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t tiles = (p.row_end - p.row_begin + 31) / 32;
+  const int blocks = grid_for(tiles, kWarps, sm_count() * per_sm);
+  kernel<<<blocks, kThreads, L.total, stream>>>(p);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+template <int PROJ>
+void launch_pull_p(const KernelParams &p, bool cv, bool ce, cudaStream_t s) {
+  if (!cv && !ce) launch_pull_t<PROJ, false, false>(p, s);
+  else if (cv && ce) launch_pull_t<PROJ, true, true>(p, s);
+  else if (cv && !ce) launch_pull_t<PROJ, true, false>(p, s);
+  else throw std::runtime_error("complex vectors need complex values");
+}
+
 template <int PROJ>
 void launch_accumulate_p(const KernelParams &p, bool cv, bool ce, int64_t count, const uint64_t *b,
                          const double *c, cudaStream_t s) {
@@ -521,6 +771,15 @@ void launch_generate(const KernelParams &p, Projection proj, bool cv, bool ce, b
     case PROJ_NONE: launch_generate_p<PROJ_NONE>(p, cv, ce, count_only, stream); break;
     case PROJ_INVERSION: launch_generate_p<PROJ_INVERSION>(p, cv, ce, count_only, stream); break;
     case PROJ_GROUP: launch_generate_p<PROJ_GROUP>(p, cv, ce, count_only, stream); break;
+  }
+}
+
+void launch_pull(const KernelParams &p, Projection proj, bool cv, bool ce, cudaStream_t stream) {
+  if (p.row_end <= p.row_begin) return;
+  switch (proj) {
+    case PROJ_NONE: launch_pull_p<PROJ_NONE>(p, cv, ce, stream); break;
+    case PROJ_INVERSION: launch_pull_p<PROJ_INVERSION>(p, cv, ce, stream); break;
+    case PROJ_GROUP: launch_pull_p<PROJ_GROUP>(p, cv, ce, stream); break;
   }
 }
 
@@ -546,6 +805,13 @@ void launch_state_index(const StateIndex &ix, int64_t count, const uint64_t *spi
                         cudaStream_t stream) {
   if (count <= 0) return;
   k_state_index<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(ix, count, spins, indices);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
+void launch_verify_rank(const StateIndex &ix, unsigned long long *status, cudaStream_t stream) {
+  if (ix.n <= 0) return;
+  k_verify_rank<<<(unsigned)((ix.n + 255) / 256), 256, 0, stream>>>(ix, status);
   DMV_CUDA_CHECK(cudaGetLastError());
   g_launches++;
 }

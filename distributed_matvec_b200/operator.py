@@ -180,13 +180,21 @@ class Operator:
         """emitted off-diagonal terms of this rank in one product (from the last plan)"""
         return int(nat.lib().dmv_number_terms(self._ctx))
 
+    def set_option(self, name: str, value: int):
+        """"mode": -1 auto / 0 push (scatter + atomics) / 1 pull (gather); "index": -1 auto / 0 directory / 2 rank"""
+        nat.check(nat.lib().dmv_set_option(self._ctx, name.encode(), int(value)))
+        return self
+
+    def info(self, name: str) -> int:
+        return int(nat.lib().dmv_get_info(self._ctx, name.encode()))
+
     # -- streams ---------------------------------------------------------------------------------
     def use_torch_stream(self):
         """Launch on torch's current stream (so torch tensors and CUDA events order correctly)."""
         import torch
         handle = torch.cuda.current_stream(self.device).cuda_stream
         if getattr(self, "_stream_handle", -1) != handle:
-            nat.check(nat.lib().dmv_set_stream(self._ctx, C.c_void_p(handle)))
+            nat.check(nat.lib().dmv_set_stream(self._ctx, C.c_void_p(handle), 0))
             self._stream_handle = handle
 
     def synchronize(self):

@@ -68,9 +68,16 @@ int64_t dmv_launch_count(void);
 int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op, int device, int rank,
                        int num_ranks, dmv_context **out);
 int dmv_context_destroy(dmv_context *ctx);
-/* launch on this stream (a cudaStream_t); NULL selects the context's own stream */
-int dmv_set_stream(dmv_context *ctx, void *cuda_stream);
+/* launch on `cuda_stream` (a cudaStream_t; NULL is the legacy default stream), or on the context's own
+ * non-blocking stream when use_own_stream != 0 (the initial state) */
+int dmv_set_stream(dmv_context *ctx, void *cuda_stream, int use_own_stream);
 int dmv_synchronize(dmv_context *ctx);
+/* options: "mode"  = -1 auto | 0 push: scatter with FP64 atomics, the reference's traversal (DMV:73-127)
+ *                  | 1 pull: the same product traversed by rows (gather), only when num_ranks == 1;
+ *          "index" = -1 auto | 0 directory + binary search | 2 combinadic rank (full fixed-Hamming bases).
+ * dmv_get_info: "index_mode", "pull", "projection", "n_groups", "orbit_n_q", "orbit_n_t", ... (-1: unknown) */
+int dmv_set_option(dmv_context *ctx, const char *name, int64_t value);
+int64_t dmv_get_info(const dmv_context *ctx, const char *name);
 
 /* ---- basis
  * dmv_basis_build: replaces Basis.build() / enumerateStates for this rank (reference

@@ -121,23 +121,46 @@ def test_state_info_matches_oracle(need_cuda, name):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("mode", ["push", "pull"])
 @pytest.mark.parametrize("name", SMALL + MEDIUM)
-def test_local_matvec_matches_oracle(need_cuda, name, cplx):
-    """test/TestMatrixVectorProduct.chpl on one locale: host vectors through the C ABI."""
+def test_local_matvec_matches_oracle(need_cuda, name, cplx, mode):
+    """test/TestMatrixVectorProduct.chpl on one locale: host vectors through the C ABI.
+    push = the reference's traversal (scatter with atomics), pull = by rows (gather); both index kernels."""
     basis, matrix = _load(name)
     op = Operator(matrix)
+    op.set_option("mode", 0 if mode == "push" else 1)
     op.basis.build()
     reps = op.basis.representatives()
     x = _x(reps.shape[0], cplx)
-    y = op.matvec(x)
     y_ref = po.matvec_global(matrix, reps, x, 1)
-    assert _close(y, y_ref), np.abs(y - y_ref).max()
-    # device-resident vectors give the same answer
-    xd = torch.from_numpy(x).cuda()
-    yd = op.matvec(xd)
-    torch.cuda.synchronize()
-    assert _close(yd.cpu().numpy(), y_ref)
+    for index in (-1, 0):          # auto (rank / identity where they apply) and forced directory search
+        op.set_option("index", index)
+        y = op.matvec(x)
+        assert _close(y, y_ref), (index, op.info("index_mode"), np.abs(y - y_ref).max())
+        # device-resident vectors give the same answer
+        xd = torch.from_numpy(x).cuda()
+        yd = op.matvec(xd)
+        torch.cuda.synchronize()
+        assert _close(yd.cpu().numpy(), y_ref)
+    assert op.info("pull") == (1 if mode == "pull" else 0)
     op.close()
+
+
+def test_rank_index_is_selected_and_bit_exact(need_cuda):
+    """The combinadic-rank index kernel must agree bit for bit with the sorted-array search."""
+    for name, expect in (("heisenberg_chain_16", 2), ("heisenberg_chain_10", 2), ("heisenberg_chain_12", 1),
+                         ("heisenberg_kagome_12_symm", 0)):
+        basis, matrix = _load(name)
+        op = Operator(matrix)
+        op.basis.build()
+        assert op.info("index_mode") == expect, name
+        reps = op.basis.representatives()
+        rng = np.random.default_rng(5)
+        probe = np.concatenate([reps, reps ^ np.uint64(3), rng.integers(0, 2**(basis.number_sites + 1), 4000,
+                                                                        dtype=np.uint64)])
+        got = op.basis.stateIndex(probe)
+        assert np.array_equal(got, po.state_index(reps, probe)), name
+        op.close()
 
 
 @pytest.mark.parametrize("cplx", [False, True])
@@ -192,13 +215,15 @@ def test_compute_off_diag_matches_oracle(need_cuda, name):
 def test_missing_state_is_an_error(need_cuda):
     """DMV:115-118: a generated state that is not in the basis halts."""
     basis, matrix = _load("heisenberg_chain_10")
-    op = Operator(matrix)
     reps, _ = po.enumerate_states(basis)
-    op.basis.uncheckedSetRepresentatives(reps[:-7])     # drop a few states
-    x = np.ones(reps.shape[0] - 7)
-    with pytest.raises(Exception, match="invalid index"):
-        op.matvec(x)
-    op.close()
+    for mode in (0, 1):
+        op = Operator(matrix)
+        op.set_option("mode", mode)
+        op.basis.uncheckedSetRepresentatives(reps[:-7])     # drop a few states
+        x = np.ones(reps.shape[0] - 7)
+        with pytest.raises(Exception, match="invalid index"):
+            op.matvec(x)
+        op.close()
 
 
 def test_no_diagonal_accumulates_into_y(need_cuda):
@@ -209,15 +234,17 @@ def test_no_diagonal_accumulates_into_y(need_cuda):
     basis = basis_from_dict({"number_spins": n, "hamming_weight": 4})
     matrix = operator_from_dict({"terms": [{"expression": "σ⁺₀ σ⁻₁", "sites": bonds},
                                            {"expression": "σ⁻₀ σ⁺₁", "sites": bonds}]}, basis)
-    op = Operator(matrix)
-    op.basis.build()
-    reps = op.basis.representatives()
-    x = _x(reps.shape[0], False)
-    y0 = _x(reps.shape[0], False, seed=9)
-    y = op.matvec(x, y0.copy())
-    y_ref = po.matvec_blocks(matrix, [reps], [x], y_blocks=[y0.copy()])[0]
-    assert _close(y, y_ref)
-    op.close()
+    for mode in (0, 1):
+        op = Operator(matrix)
+        op.set_option("mode", mode)
+        op.basis.build()
+        reps = op.basis.representatives()
+        x = _x(reps.shape[0], False)
+        y0 = _x(reps.shape[0], False, seed=9)
+        y = op.matvec(x, y0.copy())
+        y_ref = po.matvec_blocks(matrix, [reps], [x], y_blocks=[y0.copy()])[0]
+        assert _close(y, y_ref)
+        op.close()
 
 
 def test_hermiticity_and_linearity_at_size(need_cuda):
@@ -229,9 +256,14 @@ def test_hermiticity_and_linearity_at_size(need_cuda):
     assert n == 2704156
     u = torch.from_numpy(_x(n, True, 1)).cuda()
     v = torch.from_numpy(_x(n, True, 2)).cuda()
-    Hu, Hv = op.matvec(u), op.matvec(v)
-    lhs, rhs = torch.vdot(u, Hv), torch.vdot(Hu, v)
-    assert abs(lhs - rhs) <= 1e-10 * abs(lhs)
-    w = op.matvec(2.0 * u - 0.5j * v)
-    assert torch.allclose(w, 2.0 * Hu - 0.5j * Hv, rtol=1e-11, atol=1e-11)
+    results = []
+    for mode in (0, 1):
+        op.set_option("mode", mode)
+        Hu, Hv = op.matvec(u), op.matvec(v)
+        lhs, rhs = torch.vdot(u, Hv), torch.vdot(Hu, v)
+        assert abs(lhs - rhs) <= 1e-10 * abs(lhs)
+        w = op.matvec(2.0 * u - 0.5j * v)
+        assert torch.allclose(w, 2.0 * Hu - 0.5j * Hv, rtol=1e-11, atol=1e-11)
+        results.append(Hu)
+    assert torch.allclose(results[0], results[1], rtol=1e-12, atol=1e-12)   # push == pull
     op.close()

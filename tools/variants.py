@@ -1,0 +1,66 @@
+#!/usr/bin/env python3
+"""Time the product kernel for every (mode, index, dtype) variant of a workload (device-resident vectors,
+L2 flushed between iterations, CUDA events).  Usage: python tools/variants.py [workload ...]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from distributed_matvec_b200 import Operator, load_config_from_yaml  # noqa: E402
+
+
+def main():
+    workloads = sys.argv[1:] or ["heisenberg_chain_24"]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for name in workloads:
+        basis, matrix = load_config_from_yaml(os.path.join(ROOT, "data", name + ".yaml"))
+        op = Operator(matrix)
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(); op.basis.build(); t1.record(); torch.cuda.synchronize()
+        n = op.basis.numberStates()
+        op.use_torch_stream()
+        op.set_option("mode", 0)
+        nnz = int(op.plan().sum())
+        print(f"== {name}: N={n} nnz={nnz} build {t0.elapsed_time(t1):.1f} ms "
+              f"orbit(q,t,stages)=({op.info('orbit_n_q')},{op.info('orbit_n_t')},{op.info('orbit_n_stages')})", flush=True)
+        rng = np.random.default_rng(42)
+        for cplx in (True, False):
+            x = rng.random(n) - 0.5
+            if cplx:
+                x = x + 1j * (rng.random(n) - 0.5)
+            xd = torch.from_numpy(x).cuda()
+            yd = torch.zeros_like(xd)
+            ref = None
+            for mode in (0, 1):
+                for index in (0, -1):
+                    op.set_option("mode", mode)
+                    op.set_option("index", index)
+                    if index == -1 and op.info("index_mode") == 0:
+                        continue
+                    for _ in range(3):
+                        op.matvec(xd, yd)
+                    torch.cuda.synchronize()
+                    times = []
+                    for k in range(10):
+                        flush.fill_(k)
+                        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+                        s.record(); op.matvec(xd, yd); e.record(); torch.cuda.synchronize()
+                        times.append(s.elapsed_time(e))
+                    op.synchronize()
+                    if ref is None:
+                        ref = yd.clone()
+                    err = float((yd - ref).abs().max() / ref.abs().max())
+                    E = 16 if cplx else 8
+                    ms = float(np.median(times))
+                    gbs = (n * (8 + 2 * E) + nnz * (8 + 2 * E)) / (ms * 1e-3) / 1e9
+                    print(f"  {'c128' if cplx else 'f64 '} mode={'pull' if mode else 'push'} index_mode={op.info('index_mode')}"
+                          f"  median {ms:.4f} ms  min {min(times):.4f} ms  {n / ms / 1e6:.2f} Gstates/s "
+                          f"{nnz / ms / 1e6:.1f} Gterms/s  alg {gbs:.0f} GB/s  diff_vs_first {err:.1e}", flush=True)
+        op.close()
+
+
+if __name__ == "__main__":
+    main()
