@@ -119,6 +119,70 @@ const char *kTimingNames[T_COUNT] = {"h2d", "generate(diag+offdiag+local accumul
 
 }  // namespace
 
+namespace {
+
+// Flip-mask groups of an operator in look-up-table form (see LutGroup in dmv_device.cuh).
+struct HostTables {
+  std::vector<LutGroup> groups;
+  std::vector<double> lut_re, lut_c;   // real parts only / interleaved complex
+  std::vector<OffTerm> terms;
+  bool any_generic = false, any_s_out = false;
+};
+struct DevTables {
+  DevBuf<LutGroup> groups;
+  DevBuf<double> lut_re, lut_c;
+  DevBuf<OffTerm> terms;
+  void upload(const HostTables &h, cudaStream_t s) {
+    groups.upload(h.groups, s); lut_re.upload(h.lut_re, s); lut_c.upload(h.lut_c, s); terms.upload(h.terms, s);
+  }
+};
+
+HostTables build_tables(const std::map<uint64_t, std::vector<OffTerm>> &by_x) {
+  HostTables H;
+  for (const auto &kv : by_x) {
+    LutGroup g{};
+    g.x = kv.first;
+    g.first = (int32_t)H.terms.size();
+    g.count = (int32_t)kv.second.size();
+    uint64_t support = 0;
+    for (const auto &t : kv.second) { H.terms.push_back(t); support |= t.m; }
+    const int k = __builtin_popcountll(support);
+    bool lutable = k <= 6;
+    const uint64_t s_out = kv.second.front().s & ~support;
+    for (const auto &t : kv.second) lutable &= ((t.s & ~support) == s_out);
+    if (lutable) {
+      int pos[6] = {0, 0, 0, 0, 0, 0}, nb = 0;
+      for (int b = 0; b < 64; ++b) if ((support >> b) & 1) pos[nb++] = b;
+      g.posk = (uint64_t)k << 48;
+      for (int b = 0; b < k; ++b) g.posk |= (uint64_t)pos[b] << (8 * b);
+      g.s_out = s_out;
+      g.lut_offset = (uint32_t)H.lut_re.size();
+      for (int idx = 0; idx < (1 << k); ++idx) {
+        uint64_t a = 0;
+        for (int b = 0; b < k; ++b) if ((idx >> b) & 1) a |= 1ull << pos[b];
+        double re = 0.0, im = 0.0;
+        bool hit = false;
+        for (const auto &t : kv.second)
+          if ((a & t.m) == t.r) {
+            const double sg = (__builtin_popcountll(a & t.s & support) & 1) ? -1.0 : 1.0;
+            re += sg * t.v_re; im += sg * t.v_im; hit = true;
+          }
+        if (hit && (re != 0.0 || im != 0.0)) g.emit_bits |= 1ull << idx;
+        H.lut_re.push_back(re);
+        H.lut_c.push_back(re); H.lut_c.push_back(im);
+      }
+      if (s_out) H.any_s_out = true;
+    } else {
+      g.posk = 1ull << 56;
+      H.any_generic = true;
+    }
+    H.groups.push_back(g);
+  }
+  return H;
+}
+
+}  // namespace
+
 struct dmv_context {
   int device = 0, rank = 0, num_ranks = 1;
   // basis
@@ -134,12 +198,9 @@ struct dmv_context {
   DevBuf<double> d_chars;
   OrbitProgram orbit{};  // device view
   // operator
-  std::vector<TermGroup> h_groups;
-  std::vector<OffTerm> h_terms;
   std::vector<DiagTerm> h_diag;
-  std::vector<OffTerm> h_terms_adj;   // row-traversal form, see k_pull
-  DevBuf<TermGroup> d_groups;
-  DevBuf<OffTerm> d_terms, d_terms_adj;
+  HostTables h_push, h_pull;          // column-traversal (scatter) / row-traversal (gather) tables
+  DevTables d_push, d_pull;
   DevBuf<DiagTerm> d_diag;
   // options
   int opt_mode = -1;    // -1 auto (pull when one rank owns the basis), 0 push (scatter), 1 pull (gather)
@@ -203,10 +264,7 @@ KernelParams base_params(dmv_context *ctx) {
   p.index.weight = ctx->hamming_weight;
   p.index.site_mask = ctx->site_mask;
   p.rank_total = ctx->rank_total;
-  p.terms_adj = ctx->d_terms_adj.ptr;
   p.norms = ctx->d_norms.ptr;
-  p.groups = ctx->d_groups.ptr; p.n_groups = (int)ctx->h_groups.size();
-  p.terms = ctx->d_terms.ptr;   p.n_terms = (int)ctx->h_terms.size();
   p.diag = ctx->d_diag.ptr;     p.n_diag = (int)ctx->h_diag.size();
   p.orbit = ctx->orbit;
   p.site_mask = ctx->site_mask;
@@ -221,6 +279,17 @@ KernelParams base_params(dmv_context *ctx) {
   p.row_begin = 0;
   p.row_end = ctx->n_states;
   return p;
+}
+
+// point the kernel at the column-traversal (push) or row-traversal (pull) tables
+void select_tables(dmv_context *ctx, KernelParams &p, bool pull, bool complex_vals) {
+  const HostTables &h = pull ? ctx->h_pull : ctx->h_push;
+  DevTables &d = pull ? ctx->d_pull : ctx->d_push;
+  p.groups = d.groups.ptr; p.n_groups = (int)h.groups.size();
+  p.lut = complex_vals ? d.lut_c.ptr : d.lut_re.ptr; p.n_lut = (int)h.lut_re.size();
+  p.terms = d.terms.ptr; p.n_terms = (int)h.terms.size();
+  p.any_generic = h.any_generic ? 1 : 0;
+  p.any_s_out = h.any_s_out ? 1 : 0;
 }
 
 void require_states(const dmv_context *ctx) {
@@ -393,6 +462,7 @@ void do_plan(dmv_context *ctx) {
   ctx->d_out_count.alloc(P);
   CUDA_CHECK(cudaMemsetAsync(ctx->d_out_count.ptr, 0, sizeof(unsigned long long) * P, ctx->stream));
   KernelParams p = base_params(ctx);
+  select_tables(ctx, p, false, ctx->complex_coefficients);
   // counting pass: element type does not matter
   launch_generate(p, ctx->proj, ctx->complex_coefficients, false, /*count_only=*/true, ctx->stream);
   std::vector<unsigned long long> counts(P);
@@ -423,6 +493,7 @@ void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev) {
     KernelParams p = base_params(ctx);
     p.x = x_dev;
     p.y = y_dev;
+    select_tables(ctx, p, true, complex_values(ctx, elt));
     launch_pull(p, ctx->proj, complex_values(ctx, elt), elt == DMV_C128, ctx->stream);
     return;
   }
@@ -435,6 +506,7 @@ void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev) {
   p.y = y_dev;
   const bool cv = complex_values(ctx, elt);
   ctx->record_width = cv ? 2 : 1;
+  select_tables(ctx, p, false, cv);
   launch_generate(p, ctx->proj, cv, elt == DMV_C128, false, ctx->stream);
 }
 
@@ -532,25 +604,23 @@ int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op,
     if (o.v_im != 0.0) cplx = true;
     by_x[op->off_x[t]].push_back(o);
   }
-  for (auto &kv : by_x) {
-    TermGroup g{kv.first, (int32_t)ctx->h_terms.size(), (int32_t)kv.second.size()};
-    ctx->h_groups.push_back(g);
+  std::map<uint64_t, std::vector<OffTerm>> by_x_rows;
+  for (auto &kv : by_x)
     for (auto &o : kv.second) {
-      ctx->h_terms.push_back(o);
-      // <b|t|b^x> = v (-1)^popc(x&s) [b & m == r ^ (x & m)] (-1)^popc(b & s)
+      // row traversal: <b|t|b^x> = v (-1)^popc(x&s) [b & m == r ^ (x & m)] (-1)^popc(b & s)
       const uint64_t x = kv.first;
       const double sg = (__builtin_popcountll(x & o.s) & 1) ? -1.0 : 1.0;
-      ctx->h_terms_adj.push_back(OffTerm{o.m, o.r ^ (x & o.m), o.s, sg * o.v_re, sg * o.v_im});
+      by_x_rows[x].push_back(OffTerm{o.m, o.r ^ (x & o.m), o.s, sg * o.v_re, sg * o.v_im});
     }
-  }
+  ctx->h_push = build_tables(by_x);
+  ctx->h_pull = build_tables(by_x_rows);
   for (int64_t t = 0; t < op->n_diag; ++t) {
     DiagTerm d{op->diag_m[t], op->diag_r[t], op->diag_s[t], op->diag_v[2 * t], op->diag_v[2 * t + 1]};
     if (d.v_im != 0.0) cplx = true;
     ctx->h_diag.push_back(d);
   }
-  ctx->d_groups.upload(ctx->h_groups, ctx->stream);
-  ctx->d_terms.upload(ctx->h_terms, ctx->stream);
-  ctx->d_terms_adj.upload(ctx->h_terms_adj, ctx->stream);
+  ctx->d_push.upload(ctx->h_push, ctx->stream);
+  ctx->d_pull.upload(ctx->h_pull, ctx->stream);
   ctx->d_diag.upload(ctx->h_diag, ctx->stream);
 
   // ---- symmetry group
@@ -620,7 +690,7 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
   if (key == "index_mode") return ctx->index_mode;
   if (key == "pull") return use_pull(ctx) ? 1 : 0;
   if (key == "projection") return (int64_t)ctx->proj;
-  if (key == "n_groups") return (int64_t)ctx->h_groups.size();
+  if (key == "n_groups") return (int64_t)ctx->h_push.groups.size();
   if (key == "orbit_n_q") return ctx->host_orbit.n_q;
   if (key == "orbit_n_t") return ctx->host_orbit.n_t;
   if (key == "orbit_n_stages") return ctx->host_orbit.n_stages;
@@ -778,7 +848,7 @@ int dmv_locale_idx_of(dmv_context *ctx, int64_t count, const uint64_t *states, i
   API_END
 }
 
-int64_t dmv_max_number_off_diag(const dmv_context *ctx) { return ctx ? (int64_t)ctx->h_groups.size() : -1; }
+int64_t dmv_max_number_off_diag(const dmv_context *ctx) { return ctx ? (int64_t)ctx->h_push.groups.size() : -1; }
 
 int dmv_plan(dmv_context *ctx, int64_t *send_counts) {
   API_BEGIN
@@ -949,7 +1019,7 @@ int dmv_compute_off_diag(dmv_context *ctx, int64_t count, const uint64_t *alphas
   // one flat output (emit_all) together with its locale key.
   use_device(ctx);
   if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
-  const size_t cap = (size_t)count * std::max<size_t>(1, ctx->h_groups.size());
+  const size_t cap = (size_t)count * std::max<size_t>(1, ctx->h_push.groups.size());
   InArg<uint64_t> a(alphas, (size_t)count, ctx->stream);
   InArg<double> x(reinterpret_cast<const double *>(xs), (size_t)count * elt, ctx->stream);
   OutArg<uint64_t> ob(betas, cap);
@@ -974,6 +1044,7 @@ int dmv_compute_off_diag(dmv_context *ctx, int64_t count, const uint64_t *alphas
   p.out_betas = ob.ptr; p.out_coeffs = oc.ptr; p.out_keys = ok.ptr;
   p.out_offset = d_off.ptr; p.out_count = d_cnt.ptr;
   p.row_begin = 0; p.row_end = count;
+  select_tables(ctx, p, false, true);
   launch_generate(p, ctx->proj, /*complex values*/ true, elt == DMV_C128, false, ctx->stream);
   unsigned long long total = 0;
   CUDA_CHECK(cudaMemcpyAsync(&total, d_cnt.ptr, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));

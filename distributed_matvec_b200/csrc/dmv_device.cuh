@@ -23,6 +23,30 @@ struct DiagTerm {
   double v_re, v_im;
 };
 
+// Flip-mask group in look-up-table form.  All terms of the group act on the k <= 6 "support" bits
+// pos[0..k) (the union of their masks m); the coefficient is a function of those bits only,
+//     c(alpha) = lut[lut_offset + idx(alpha)] * (-1)^popc(alpha & s_out),   idx = sum_b bit(alpha, pos[b]) << b
+// and the group emits iff bit idx of emit_bits is set.  For a Heisenberg bond k = 2 and the whole
+// (state, bond) test is two bit extractions and one shift.  Groups that do not fit (k > 6, or terms with
+// different sign masks outside the support) keep generic = 1 and are evaluated term by term.
+struct LutGroup {
+  uint64_t x;          // flip mask: beta = alpha ^ x
+  uint64_t s_out;      // common sign mask outside the support
+  uint64_t emit_bits;
+  uint64_t posk;       // bytes 0..5: pos[b]; byte 6: k; byte 7: generic flag
+  uint32_t lut_offset;
+  int32_t first, count;  // term range for the generic evaluation
+  uint32_t pad;
+};
+static_assert(sizeof(LutGroup) == 48, "LutGroup layout");
+
+__host__ __device__ __forceinline__ unsigned lut_index(uint64_t posk, uint64_t a) {
+  const unsigned k = (unsigned)(posk >> 48) & 0xffu;
+  unsigned idx = 0;
+  for (unsigned b = 0; b < k; ++b) idx |= (unsigned)((a >> ((posk >> (8 * b)) & 0xffu)) & 1ull) << b;
+  return idx;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Orbit program: the symmetry group enumerated as  g = t_j . q_i  (+ optional spin flip)
 //   q_i : coset representatives, applied as Benes butterfly networks (padded to n_stages)

@@ -36,9 +36,11 @@ struct KernelParams {
   StateIndex index;
   const double *norms;        // [n] (PROJ_GROUP only)
   // operator
-  const TermGroup *groups; int32_t n_groups;
-  const OffTerm *terms;    int32_t n_terms;
-  const OffTerm *terms_adj;   // row-traversal (pull) form of the same terms, see k_pull
+  // (the host points these at the column-traversal (push) or row-traversal (pull) tables, see k_pull)
+  const LutGroup *groups;  int32_t n_groups;
+  const double *lut;       int32_t n_lut;     // real table (CV = false) or interleaved complex (CV = true)
+  const OffTerm *terms;    int32_t n_terms;   // only read by groups with the generic flag
+  int32_t any_generic, any_s_out;
   uint64_t rank_total;        // INDEX_RANK: C(n_sites, weight)
   const DiagTerm *diag;    int32_t n_diag;
   // symmetry

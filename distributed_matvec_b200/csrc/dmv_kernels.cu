@@ -74,15 +74,17 @@ __device__ __forceinline__ double v_im(double2 a) { return a.y; }
 
 // ---- shared-memory staging of the operator / orbit tables ---------------------------------------
 struct SmemLayout {
-  size_t groups, terms, diag, orbit64, orbit32, binom, queues, total;
+  size_t groups, lut, terms, diag, orbit64, orbit32, binom, queues, total;
 };
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int proj, size_t val_bytes) {
   SmemLayout L;
   size_t off = 0;
-  L.groups = off; off += sizeof(TermGroup) * p.n_groups;
+  L.groups = off; off += sizeof(LutGroup) * p.n_groups;
+  off = align_up(off, 16);
+  L.lut = off; off += val_bytes * p.n_lut;
   off = align_up(off, 8);
-  L.terms = off; off += sizeof(OffTerm) * p.n_terms;
+  L.terms = off; off += p.any_generic ? sizeof(OffTerm) * p.n_terms : 0;
   L.diag = off; off += sizeof(DiagTerm) * p.n_diag;
   L.orbit64 = off;
   size_t n64 = 0, n32 = 0;
@@ -105,6 +107,122 @@ __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int pro
 template <typename T>
 __device__ __forceinline__ void stage(T *dst, const T *src, int count) {
   for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+}
+
+// Everything a CTA keeps in shared memory, set up once per CTA.
+template <bool CV>
+struct Tables {
+  using V = typename ValT<CV>::type;
+  const LutGroup *groups;
+  const V *lut;
+  const OffTerm *terms;
+  const DiagTerm *diag;
+  OrbitProgram orbit;
+  StateIndex index;
+};
+
+template <int PROJ, bool CV>
+__device__ __forceinline__ Tables<CV> stage_tables(const KernelParams &p, unsigned char *smem, const SmemLayout &L) {
+  using V = typename ValT<CV>::type;
+  Tables<CV> T;
+  LutGroup *s_groups = reinterpret_cast<LutGroup *>(smem + L.groups);
+  V *s_lut = reinterpret_cast<V *>(smem + L.lut);
+  OffTerm *s_terms = reinterpret_cast<OffTerm *>(smem + L.terms);
+  DiagTerm *s_diag = reinterpret_cast<DiagTerm *>(smem + L.diag);
+  stage(s_groups, p.groups, p.n_groups);
+  stage(s_lut, reinterpret_cast<const V *>(p.lut), p.n_lut);
+  if (p.any_generic) stage(s_terms, p.terms, p.n_terms);
+  stage(s_diag, p.diag, p.n_diag);
+  T.groups = s_groups; T.lut = s_lut; T.terms = s_terms; T.diag = s_diag;
+  T.orbit = p.orbit;
+  if (PROJ == PROJ_GROUP) {
+    const int np = T.orbit.n_left + T.orbit.n_right;
+    uint64_t *s64 = reinterpret_cast<uint64_t *>(smem + L.orbit64);
+    int32_t *s32 = reinterpret_cast<int32_t *>(smem + L.orbit32);
+    const int nb = T.orbit.n_q * T.orbit.n_stages, ns = (T.orbit.n_t - 1) * np;
+    stage(s64, p.orbit.benes_mask, nb);
+    stage(s64 + nb, p.orbit.step_mask, ns);
+    stage(s32, p.orbit.benes_delta, T.orbit.n_stages);
+    stage(s32 + T.orbit.n_stages, p.orbit.step_shift, ns);
+    T.orbit.benes_mask = s64;
+    T.orbit.step_mask = s64 + nb;
+    T.orbit.benes_delta = s32;
+    T.orbit.step_shift = s32 + T.orbit.n_stages;
+  }
+  T.index = p.index;
+  if (T.index.mode == INDEX_RANK) {
+    uint32_t *sb = reinterpret_cast<uint32_t *>(smem + L.binom);
+    stage(sb, p.index.binom, T.index.n_sites * T.index.stride);
+    T.index.binom = sb;
+  }
+  return T;
+}
+
+// ---- term generation ----------------------------------------------------------------------------
+// generic (term by term) evaluation of one group: c = sum_t v_t [a & m == r] (-1)^popc(a & s)
+template <bool CV>
+__device__ __noinline__ typename ValT<CV>::type generic_coefficient(const OffTerm *terms, int first, int count,
+                                                                     uint64_t a, bool *hit) {
+  using V = typename ValT<CV>::type;
+  V c = v_make(0.0, 0.0, (V *)nullptr);
+  bool any = false;
+  for (int t = first; t < first + count; ++t) {
+    const OffTerm term = terms[t];
+    if ((a & term.m) == term.r) {
+      const double sg = (__popcll(a & term.s) & 1) ? -1.0 : 1.0;
+      v_acc(c, sg * term.v_re, sg * term.v_im);
+      any = true;
+    }
+  }
+  *hit = any;
+  return c;
+}
+
+// Bit g - g0 of the result is set iff group g emits a term for state a (g0 <= g < g1 <= g0 + 64).
+// All lanes walk the groups in lock step: the group header reads are shared-memory broadcasts.
+template <bool CV>
+__device__ __forceinline__ uint64_t emit_mask(const Tables<CV> &T, int g0, int g1, uint64_t a, bool count_only) {
+  uint64_t mask = 0;
+  for (int g = g0; g < g1; ++g) {
+    const uint64_t posk = T.groups[g].posk;
+    bool emit;
+    if (posk >> 56) {
+      bool hit;
+      const auto c = generic_coefficient<CV>(T.terms, T.groups[g].first, T.groups[g].count, a, &hit);
+      emit = hit && v_nonzero(c);   // same decision in the counting pass: the plan is exact
+    } else {
+      emit = (T.groups[g].emit_bits >> lut_index(posk, a)) & 1ull;
+    }
+    mask |= (uint64_t)emit << (g - g0);
+  }
+  return mask;
+}
+
+// coefficient of group g for state a (the caller knows it emits)
+template <bool CV>
+__device__ __forceinline__ typename ValT<CV>::type group_coefficient(const Tables<CV> &T, const LutGroup &grp,
+                                                                      uint64_t a, bool any_s_out) {
+  using V = typename ValT<CV>::type;
+  if (grp.posk >> 56) {
+    bool hit;
+    return generic_coefficient<CV>(T.terms, grp.first, grp.count, a, &hit);
+  }
+  V c = T.lut[grp.lut_offset + lut_index(grp.posk, a)];
+  if (any_s_out && (__popcll(a & grp.s_out) & 1)) c = v_scale(c, -1.0);
+  return c;
+}
+
+template <bool CV>
+__device__ __forceinline__ void diagonal(const Tables<CV> &T, int n_diag, uint64_t a, double &dre, double &dim) {
+  dre = 0.0; dim = 0.0;
+  for (int t = 0; t < n_diag; ++t) {
+    const DiagTerm d = T.diag[t];
+    if ((a & d.m) == d.r) {
+      const double sg = (__popcll(a & d.s) & 1) ? -1.0 : 1.0;
+      dre += sg * d.v_re;
+      dim += sg * d.v_im;
+    }
+  }
 }
 
 // ---- the consumer side: one record per lane -----------------------------------------------------
@@ -203,33 +321,7 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
   using V = typename ValT<CV>::type;
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(p, PROJ, sizeof(V));
-  TermGroup *s_groups = reinterpret_cast<TermGroup *>(smem + L.groups);
-  OffTerm *s_terms = reinterpret_cast<OffTerm *>(smem + L.terms);
-  DiagTerm *s_diag = reinterpret_cast<DiagTerm *>(smem + L.diag);
-  stage(s_groups, p.groups, p.n_groups);
-  stage(s_terms, p.terms, p.n_terms);
-  stage(s_diag, p.diag, p.n_diag);
-  OrbitProgram orbit = p.orbit;
-  if (PROJ == PROJ_GROUP) {
-    const int np = orbit.n_left + orbit.n_right;
-    uint64_t *s64 = reinterpret_cast<uint64_t *>(smem + L.orbit64);
-    int32_t *s32 = reinterpret_cast<int32_t *>(smem + L.orbit32);
-    const int nb = orbit.n_q * orbit.n_stages, ns = (orbit.n_t - 1) * np;
-    stage(s64, p.orbit.benes_mask, nb);
-    stage(s64 + nb, p.orbit.step_mask, ns);
-    stage(s32, p.orbit.benes_delta, orbit.n_stages);
-    stage(s32 + orbit.n_stages, p.orbit.step_shift, ns);
-    orbit.benes_mask = s64;
-    orbit.step_mask = s64 + nb;
-    orbit.benes_delta = s32;
-    orbit.step_shift = s32 + orbit.n_stages;
-  }
-  StateIndex index = p.index;
-  if (index.mode == INDEX_RANK) {
-    uint32_t *sb = reinterpret_cast<uint32_t *>(smem + L.binom);
-    stage(sb, p.index.binom, index.n_sites * index.stride);
-    index.binom = sb;
-  }
+  const Tables<CV> T = stage_tables<PROJ, CV>(p, smem, L);
   __syncthreads();
 
   const unsigned lane = threadIdx.x & 31u;
@@ -237,6 +329,7 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
   uint64_t *qb = reinterpret_cast<uint64_t *>(smem + L.queues) + warp * kQueue;
   V *qc = reinterpret_cast<V *>(smem + L.queues + (size_t)kWarps * kQueue * 8) + warp * kQueue;
   unsigned head = 0, count = 0;  // warp-uniform
+  const bool any_s_out = p.any_s_out != 0;
 
   const int64_t n_rows = p.row_end - p.row_begin;
   const int64_t n_tiles = (n_rows + 31) / 32;
@@ -259,15 +352,8 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
     }
     // ---- diagonal: y[i] += x[i] * sum_t v_t [alpha & m == r] (-1)^popc(alpha & s)   (DMV:36-53)
     if (!COUNT_ONLY && !p.emit_all && p.n_diag > 0 && valid) {
-      double dre = 0.0, dim = 0.0;
-      for (int t = 0; t < p.n_diag; ++t) {
-        const DiagTerm d = s_diag[t];
-        if ((alpha & d.m) == d.r) {
-          const double sg = (__popcll(alpha & d.s) & 1) ? -1.0 : 1.0;
-          dre += sg * d.v_re;
-          dim += sg * d.v_im;
-        }
-      }
+      double dre, dim;
+      diagonal<CV>(T, p.n_diag, alpha, dre, dim);
       if (CE) {
         const double2 t = __ldg(reinterpret_cast<const double2 *>(p.x) + i);
         atomic_accumulate<true>(p.y, i, dre * t.x - dim * t.y, dre * t.y + dim * t.x);
@@ -279,32 +365,27 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
     if (PROJ == PROJ_GROUP && valid && !COUNT_ONLY)
       xi = v_scale(xi, 1.0 / __ldg(p.norms + i));   // 1 / norm(alpha): BO:200
 
-    // ---- off-diagonal: walk the flip-mask groups in lock step
-    for (int g = 0; g < p.n_groups; ++g) {
-      const TermGroup grp = s_groups[g];
-      V c = v_make(0.0, 0.0, (V *)nullptr);
-      bool hit = false;
-      for (int t = grp.first; t < grp.first + grp.count; ++t) {
-        const OffTerm term = s_terms[t];
-        if ((alpha & term.m) == term.r) {
-          const double sg = (__popcll(alpha & term.s) & 1) ? -1.0 : 1.0;
-          v_acc(c, sg * term.v_re, sg * term.v_im);
-          hit = true;
-        }
-      }
-      const bool emit = valid && hit && (COUNT_ONLY || v_nonzero(c));
-      const unsigned m = __ballot_sync(0xffffffffu, emit);
-      if (m) {
-        if (emit) {
+    // ---- off-diagonal: which groups emit (bit mask), then compact the emitted terms into the ring
+    for (int g0 = 0; g0 < p.n_groups; g0 += 64) {
+      const int g1 = min(g0 + 64, p.n_groups);
+      uint64_t mask = valid ? emit_mask<CV>(T, g0, g1, alpha, COUNT_ONLY) : 0ull;
+      for (;;) {
+        const bool has = mask != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        if (m == 0) break;
+        if (has) {
+          const int g = g0 + __ffsll((long long)mask) - 1;
+          mask &= mask - 1;
+          const LutGroup grp = T.groups[g];
           const unsigned pos = (head + count + __popc(m & ((1u << lane) - 1u))) & (kQueue - 1);
           qb[pos] = alpha ^ grp.x;
-          qc[pos] = v_mul(c, xi);
+          if (!COUNT_ONLY) qc[pos] = v_mul(group_coefficient<CV>(T, grp, alpha, any_s_out), xi);
         }
         count += __popc(m);
         if (count >= 32) {
           __syncwarp();
           const unsigned pos = (head + lane) & (kQueue - 1);
-          consume<PROJ, CV, CE, COUNT_ONLY>(p, orbit, index, true, qb[pos], qc[pos]);
+          consume<PROJ, CV, CE, COUNT_ONLY>(p, T.orbit, T.index, true, qb[pos], qc[pos]);
           head = (head + 32) & (kQueue - 1);
           count -= 32;
           __syncwarp();
@@ -316,11 +397,10 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
     __syncwarp();
     const unsigned pos = (head + lane) & (kQueue - 1);
     const bool active = lane < count;
-    consume<PROJ, CV, CE, COUNT_ONLY>(p, orbit, index, active, active ? qb[pos] : 0ull,
+    consume<PROJ, CV, CE, COUNT_ONLY>(p, T.orbit, T.index, active, active ? qb[pos] : 0ull,
                                       active ? qc[pos] : v_make(0.0, 0.0, (V *)nullptr));
   }
 }
-
 
 // -------------------------------------------------------------------------------------------------
 // k_pull: the same product traversed by ROWS (gather) -- used when one rank owns the whole basis.
@@ -352,33 +432,9 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
   using E = typename ValT<CE>::type;
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(p, PROJ, sizeof(V));
-  TermGroup *s_groups = reinterpret_cast<TermGroup *>(smem + L.groups);
-  OffTerm *s_terms = reinterpret_cast<OffTerm *>(smem + L.terms);
-  DiagTerm *s_diag = reinterpret_cast<DiagTerm *>(smem + L.diag);
-  stage(s_groups, p.groups, p.n_groups);
-  stage(s_terms, p.terms_adj, p.n_terms);
-  stage(s_diag, p.diag, p.n_diag);
-  OrbitProgram orbit = p.orbit;
-  if (PROJ == PROJ_GROUP) {
-    const int np = orbit.n_left + orbit.n_right;
-    uint64_t *s64 = reinterpret_cast<uint64_t *>(smem + L.orbit64);
-    int32_t *s32 = reinterpret_cast<int32_t *>(smem + L.orbit32);
-    const int nb = orbit.n_q * orbit.n_stages, ns = (orbit.n_t - 1) * np;
-    stage(s64, p.orbit.benes_mask, nb);
-    stage(s64 + nb, p.orbit.step_mask, ns);
-    stage(s32, p.orbit.benes_delta, orbit.n_stages);
-    stage(s32 + orbit.n_stages, p.orbit.step_shift, ns);
-    orbit.benes_mask = s64;
-    orbit.step_mask = s64 + nb;
-    orbit.benes_delta = s32;
-    orbit.step_shift = s32 + orbit.n_stages;
-  }
-  StateIndex index = p.index;
-  if (index.mode == INDEX_RANK) {
-    uint32_t *sb = reinterpret_cast<uint32_t *>(smem + L.binom);
-    stage(sb, p.index.binom, index.n_sites * index.stride);
-    index.binom = sb;
-  }
+  const Tables<CV> T = stage_tables<PROJ, CV>(p, smem, L);   // p.groups / p.lut / p.terms: row-traversal tables
+  const OrbitProgram &orbit = T.orbit;
+  const StateIndex &index = T.index;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   unsigned char *qbase = smem + L.queues;
@@ -389,6 +445,7 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
   if (PROJ == PROJ_GROUP) acc_s[lane] = v_make(0.0, 0.0, (V *)nullptr);
   __syncthreads();
   unsigned head = 0, count = 0;
+  const bool any_s_out = p.any_s_out != 0;
 
   // drains `k` queued entries (PROJ_GROUP): orbit scan, search, gather, add into the owner row's slot
   auto drain = [&](unsigned k) {
@@ -428,21 +485,16 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
     double inv_nb = 1.0;
     if (PROJ == PROJ_GROUP && valid) inv_nb = 1.0 / __ldg(p.norms + i);
 
-    for (int g = 0; g < p.n_groups; ++g) {
-      const TermGroup grp = s_groups[g];
-      V h = v_make(0.0, 0.0, (V *)nullptr);
-      bool hit = false;
-      for (int t = grp.first; t < grp.first + grp.count; ++t) {
-        const OffTerm term = s_terms[t];
-        if ((b & term.m) == term.r) {
-          const double sg = (__popcll(b & term.s) & 1) ? -1.0 : 1.0;
-          v_acc(h, sg * term.v_re, sg * term.v_im);
-          hit = true;
-        }
-      }
-      const bool emit = valid && hit && v_nonzero(h);
+    for (int g0 = 0; g0 < p.n_groups; g0 += 64) {
+      const int g1 = min(g0 + 64, p.n_groups);
+      uint64_t mask = valid ? emit_mask<CV>(T, g0, g1, b, false) : 0ull;
       if (PROJ != PROJ_GROUP) {
-        if (emit) {
+        // every lane walks the set bits of ITS row: no lane idles on a bond that does not emit
+        while (mask) {
+          const int g = g0 + __ffsll((long long)mask) - 1;
+          mask &= mask - 1;
+          const LutGroup grp = T.groups[g];
+          V h = group_coefficient<CV>(T, grp, b, any_s_out);
           uint64_t a = b ^ grp.x;
           bool flipped = false;
           if (PROJ == PROJ_INVERSION) {
@@ -470,17 +522,22 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
           }
           if (idx >= 0) {
             v_add(acc, v_mul(h, to_v(load_x<CE>(p.x, idx), (V *)nullptr)));
-          } else if (atomicAdd(p.status, 1ull) == 0) {
+          } else if (v_nonzero(h) && atomicAdd(p.status, 1ull) == 0) {
             p.status[1] = a;
           }
         }
       } else {
-        const unsigned m = __ballot_sync(0xffffffffu, emit);
-        if (m) {
-          if (emit) {
+        for (;;) {
+          const bool has = mask != 0;
+          const unsigned m = __ballot_sync(0xffffffffu, has);
+          if (m == 0) break;
+          if (has) {
+            const int g = g0 + __ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            const LutGroup grp = T.groups[g];
             const unsigned pos = (head + count + __popc(m & ((1u << lane) - 1u))) & (kQueue - 1);
             qb[pos] = b ^ grp.x;
-            qc[pos] = v_scale(h, inv_nb);
+            qc[pos] = v_scale(group_coefficient<CV>(T, grp, b, any_s_out), inv_nb);
             ql[pos] = (unsigned char)lane;
           }
           count += __popc(m);
@@ -510,15 +567,8 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
       // diagonal (DMV:36-53) and the single store of y[i]; without diagonal terms y is accumulated into
       E out;
       if (p.n_diag > 0) {
-        double dre = 0.0, dim = 0.0;
-        for (int t = 0; t < p.n_diag; ++t) {
-          const DiagTerm d = s_diag[t];
-          if ((b & d.m) == d.r) {
-            const double sg = (__popcll(b & d.s) & 1) ? -1.0 : 1.0;
-            dre += sg * d.v_re;
-            dim += sg * d.v_im;
-          }
-        }
+        double dre, dim;
+        diagonal<CV>(T, p.n_diag, b, dre, dim);
         const E xi = load_x<CE>(p.x, i);
         if (CE) out = v_make(dre * v_re(xi) - dim * v_im(xi), dre * v_im(xi) + dim * v_re(xi), (E *)nullptr);
         else out = v_make(dre * v_re(xi), 0.0, (E *)nullptr);
