@@ -126,26 +126,114 @@ struct HostTables {
   std::vector<LutGroup> groups;
   std::vector<double> lut_re, lut_c;   // real parts only / interleaved complex
   std::vector<OffTerm> terms;
+  std::vector<BpWord> bp;               // non-empty: bit-parallel emit test (see BpWord)
   bool any_generic = false, any_s_out = false;
 };
 struct DevTables {
   DevBuf<LutGroup> groups;
   DevBuf<double> lut_re, lut_c;
   DevBuf<OffTerm> terms;
+  DevBuf<BpWord> bp;
   void upload(const HostTables &h, cudaStream_t s) {
     groups.upload(h.groups, s); lut_re.upload(h.lut_re, s); lut_c.upload(h.lut_c, s); terms.upload(h.terms, s);
+    bp.upload(h.bp, s);
   }
 };
 
+// support of a group: union of the masks of its terms
+uint64_t support_of(const std::vector<OffTerm> &terms) {
+  uint64_t m = 0;
+  for (const auto &t : terms) m |= t.m;
+  return m;
+}
+
 HostTables build_tables(const std::map<uint64_t, std::vector<OffTerm>> &by_x) {
   HostTables H;
+  // ---- can the whole operator use the bit-parallel emit test?  (every group: support <= 2 bits and a
+  // common sign mask outside the support)
+  struct Item { uint64_t x; const std::vector<OffTerm> *terms; int p0, p1; };
+  std::vector<Item> items;
+  bool bp_ok = !by_x.empty();
+  for (const auto &kv : by_x) {
+    const uint64_t sup = support_of(kv.second);
+    const int k = __builtin_popcountll(sup);
+    Item it{kv.first, &kv.second, 0, 0};
+    if (k > 2) bp_ok = false;
+    if (k >= 1) it.p0 = __builtin_ctzll(sup);
+    it.p1 = (k == 2) ? 63 - __builtin_clzll(sup) : it.p0;
+    const uint64_t s_out = kv.second.front().s & ~sup;
+    for (const auto &t : kv.second) if ((t.s & ~sup) != s_out) bp_ok = false;
+    items.push_back(it);
+  }
+  if (bp_ok) {
+    // order the groups so that few distinct shifts (group index - bit position) occur
+    std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+      if (a.p1 - a.p0 != b.p1 - b.p0) return a.p1 - a.p0 < b.p1 - b.p0;
+      return a.p0 < b.p0;
+    });
+    const int n_words = (int)((items.size() + 63) / 64);
+    std::vector<BpWord> words((size_t)n_words);
+    for (auto &w : words) memset(&w, 0, sizeof(w));
+    for (size_t g = 0; g < items.size() && bp_ok; ++g) {
+      BpWord &W = words[g / 64];
+      const int gl = (int)(g % 64);
+      auto add = [&](int pos, uint64_t *m, uint8_t *l, uint8_t *r, int32_t &n) {
+        const int d = gl - pos;
+        const uint8_t sl = d >= 0 ? (uint8_t)d : 0, sr = d >= 0 ? 0 : (uint8_t)(-d);
+        for (int k = 0; k < n; ++k)
+          if (l[k] == sl && r[k] == sr) { m[k] |= 1ull << gl; return; }
+        if (n == 8) { bp_ok = false; return; }
+        l[n] = sl; r[n] = sr; m[n] = 1ull << gl; ++n;
+      };
+      add(items[g].p0, W.m0, W.l0, W.r0, W.n0);
+      add(items[g].p1, W.m1, W.l1, W.r1, W.n1);
+    }
+    if (bp_ok) {
+      for (size_t g = 0; g < items.size(); ++g) {
+        const Item &it = items[g];
+        LutGroup grp{};
+        grp.x = it.x;
+        grp.first = (int32_t)H.terms.size();
+        grp.count = (int32_t)it.terms->size();
+        const uint64_t sup = support_of(*it.terms);
+        grp.s_out = it.terms->front().s & ~sup;
+        if (grp.s_out) H.any_s_out = true;
+        grp.posk = (2ull << 48) | ((uint64_t)it.p1 << 8) | (uint64_t)it.p0;
+        grp.lut_offset = (uint32_t)(4 * g);
+        for (const auto &t : *it.terms) H.terms.push_back(t);
+        for (int idx = 0; idx < 4; ++idx) {
+          const int b0 = idx & 1, b1 = idx >> 1;
+          double re = 0.0, im = 0.0;
+          bool hit = false;
+          if (!(it.p0 == it.p1 && b0 != b1)) {
+            const uint64_t a = ((uint64_t)b0 << it.p0) | ((uint64_t)b1 << it.p1);
+            for (const auto &t : *it.terms)
+              if ((a & t.m) == t.r) {
+                const double sg = (__builtin_popcountll(a & t.s & sup) & 1) ? -1.0 : 1.0;
+                re += sg * t.v_re; im += sg * t.v_im; hit = true;
+              }
+          }
+          if (hit && (re != 0.0 || im != 0.0)) {
+            grp.emit_bits |= 1ull << idx;
+            words[g / 64].tt[idx] |= 1ull << (g % 64);
+          }
+          H.lut_re.push_back(re);
+          H.lut_c.push_back(re); H.lut_c.push_back(im);
+        }
+        H.groups.push_back(grp);
+      }
+      H.bp = words;
+      return H;
+    }
+  }
+  // ---- general layout: one LUT of 2^k entries per group (k <= 6), term-by-term evaluation otherwise
   for (const auto &kv : by_x) {
     LutGroup g{};
     g.x = kv.first;
     g.first = (int32_t)H.terms.size();
     g.count = (int32_t)kv.second.size();
-    uint64_t support = 0;
-    for (const auto &t : kv.second) { H.terms.push_back(t); support |= t.m; }
+    for (const auto &t : kv.second) H.terms.push_back(t);
+    const uint64_t support = support_of(kv.second);
     const int k = __builtin_popcountll(support);
     bool lutable = k <= 6;
     const uint64_t s_out = kv.second.front().s & ~support;
@@ -205,6 +293,7 @@ struct dmv_context {
   // options
   int opt_mode = -1;    // -1 auto (pull when one rank owns the basis), 0 push (scatter), 1 pull (gather)
   int opt_index = -1;   // -1 auto, 0 directory search, 2 combinadic rank
+  int opt_bitparallel = 1;  // 0: walk the groups one by one even when the bit-parallel test applies
   int index_mode = INDEX_DIRECTORY;
   DevBuf<uint32_t> d_binom;
   int binom_stride = 0;
@@ -290,6 +379,7 @@ void select_tables(dmv_context *ctx, KernelParams &p, bool pull, bool complex_va
   p.terms = d.terms.ptr; p.n_terms = (int)h.terms.size();
   p.any_generic = h.any_generic ? 1 : 0;
   p.any_s_out = h.any_s_out ? 1 : 0;
+  p.bp = d.bp.ptr; p.n_bp = (ctx->opt_bitparallel != 0) ? (int)h.bp.size() : 0;
 }
 
 void require_states(const dmv_context *ctx) {
@@ -678,6 +768,9 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
     if (value != -1 && value != 0 && value != 2) throw std::runtime_error("index: -1 auto, 0 directory, 2 rank");
     ctx->opt_index = (int)value;
     if (ctx->n_states >= 0) { CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); select_index_mode(ctx); }
+  } else if (key == "bitparallel") {
+    ctx->opt_bitparallel = value != 0;
+    ctx->planned = false;
   } else {
     throw std::runtime_error("unknown option '" + key + "'");
   }
@@ -691,6 +784,8 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
   if (key == "pull") return use_pull(ctx) ? 1 : 0;
   if (key == "projection") return (int64_t)ctx->proj;
   if (key == "n_groups") return (int64_t)ctx->h_push.groups.size();
+  if (key == "bp_words") return (int64_t)ctx->h_push.bp.size();
+  if (key == "bp_pairs") { int64_t n = 0; for (auto &w : ctx->h_push.bp) n += w.n0 + w.n1; return n; }
   if (key == "orbit_n_q") return ctx->host_orbit.n_q;
   if (key == "orbit_n_t") return ctx->host_orbit.n_t;
   if (key == "orbit_n_stages") return ctx->host_orbit.n_stages;

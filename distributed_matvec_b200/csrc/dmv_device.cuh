@@ -40,6 +40,19 @@ struct LutGroup {
 };
 static_assert(sizeof(LutGroup) == 48, "LutGroup layout");
 
+// Bit-parallel emit test for operators whose groups all have a support of <= 2 bits (every two-body
+// spin Hamiltonian): for a word of <= 64 groups, A_b = "support bit b of every group" is gathered from
+// the state by a few masked shifts (the host orders the groups so that few distinct shifts occur: a
+// chain needs 2 per operand), and the groups that emit are
+//     mask = (~A0 & ~A1 & tt[0]) | (A0 & ~A1 & tt[1]) | (~A0 & A1 & tt[2]) | (A0 & A1 & tt[3]).
+struct BpWord {
+  uint64_t tt[4];
+  uint64_t m0[8], m1[8];   // masks over group bits (output positions)
+  uint8_t l0[8], r0[8], l1[8], r1[8];   // A_b |= ((a << l) >> r) & m   (one of l, r is zero)
+  int32_t n0, n1;
+};
+static_assert(sizeof(BpWord) == 32 + 128 + 32 + 8, "BpWord layout");
+
 __host__ __device__ __forceinline__ unsigned lut_index(uint64_t posk, uint64_t a) {
   const unsigned k = (unsigned)(posk >> 48) & 0xffu;
   unsigned idx = 0;

@@ -41,6 +41,7 @@ struct KernelParams {
   const double *lut;       int32_t n_lut;     // real table (CV = false) or interleaved complex (CV = true)
   const OffTerm *terms;    int32_t n_terms;   // only read by groups with the generic flag
   int32_t any_generic, any_s_out;
+  const BpWord *bp; int32_t n_bp;   // bit-parallel emit test (n_bp == 0: walk the groups one by one)
   uint64_t rank_total;        // INDEX_RANK: C(n_sites, weight)
   const DiagTerm *diag;    int32_t n_diag;
   // symmetry

@@ -74,13 +74,18 @@ __device__ __forceinline__ double v_im(double2 a) { return a.y; }
 
 // ---- shared-memory staging of the operator / orbit tables ---------------------------------------
 struct SmemLayout {
-  size_t groups, lut, terms, diag, orbit64, orbit32, binom, queues, total;
+  size_t groups, gx, bp, lut, terms, diag, orbit64, orbit32, binom, queues, total;
 };
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int proj, size_t val_bytes) {
   SmemLayout L;
   size_t off = 0;
-  L.groups = off; off += sizeof(LutGroup) * p.n_groups;
+  // bit-parallel mode keeps only the flip masks (compact) and the word descriptors; the full group
+  // records are needed when groups are walked one by one or carry an outside sign mask
+  const bool full_groups = p.n_bp == 0 || p.any_s_out;
+  L.groups = off; off += full_groups ? sizeof(LutGroup) * p.n_groups : 0;
+  L.gx = off; off += 8 * (size_t)p.n_groups;
+  L.bp = off; off += sizeof(BpWord) * p.n_bp;
   off = align_up(off, 16);
   L.lut = off; off += val_bytes * p.n_lut;
   off = align_up(off, 8);
@@ -114,6 +119,9 @@ template <bool CV>
 struct Tables {
   using V = typename ValT<CV>::type;
   const LutGroup *groups;
+  const uint64_t *gx;   // flip mask of every group
+  const BpWord *bp;
+  int n_bp;
   const V *lut;
   const OffTerm *terms;
   const DiagTerm *diag;
@@ -129,7 +137,13 @@ __device__ __forceinline__ Tables<CV> stage_tables(const KernelParams &p, unsign
   V *s_lut = reinterpret_cast<V *>(smem + L.lut);
   OffTerm *s_terms = reinterpret_cast<OffTerm *>(smem + L.terms);
   DiagTerm *s_diag = reinterpret_cast<DiagTerm *>(smem + L.diag);
-  stage(s_groups, p.groups, p.n_groups);
+  uint64_t *s_gx = reinterpret_cast<uint64_t *>(smem + L.gx);
+  BpWord *s_bp = reinterpret_cast<BpWord *>(smem + L.bp);
+  if (p.n_bp == 0 || p.any_s_out) stage(s_groups, p.groups, p.n_groups);
+  for (int i = threadIdx.x; i < p.n_groups; i += blockDim.x) s_gx[i] = p.groups[i].x;
+  stage(reinterpret_cast<uint64_t *>(s_bp), reinterpret_cast<const uint64_t *>(p.bp),
+        p.n_bp * (int)(sizeof(BpWord) / 8));
+  T.gx = s_gx; T.bp = s_bp; T.n_bp = p.n_bp;
   stage(s_lut, reinterpret_cast<const V *>(p.lut), p.n_lut);
   if (p.any_generic) stage(s_terms, p.terms, p.n_terms);
   stage(s_diag, p.diag, p.n_diag);
@@ -178,11 +192,25 @@ __device__ __noinline__ typename ValT<CV>::type generic_coefficient(const OffTer
   return c;
 }
 
-// Bit g - g0 of the result is set iff group g emits a term for state a (g0 <= g < g1 <= g0 + 64).
-// All lanes walk the groups in lock step: the group header reads are shared-memory broadcasts.
+// The terms one row emits within a word of <= 64 groups.
+struct RowTerms {
+  uint64_t mask;     // bit g - g0 set <=> group g emits
+  uint64_t a0, a1;   // bit-parallel mode: the two support bits of every group (for the LUT index)
+};
+
+// All lanes evaluate the same word in lock step (table reads are shared-memory broadcasts).
 template <bool CV>
-__device__ __forceinline__ uint64_t emit_mask(const Tables<CV> &T, int g0, int g1, uint64_t a, bool count_only) {
-  uint64_t mask = 0;
+__device__ __forceinline__ RowTerms row_terms(const Tables<CV> &T, int w, int g0, int g1, uint64_t a) {
+  RowTerms rt;
+  rt.mask = 0; rt.a0 = 0; rt.a1 = 0;
+  if (T.n_bp > 0) {
+    const BpWord &W = T.bp[w];
+    for (int k = 0; k < W.n0; ++k) rt.a0 |= ((a << W.l0[k]) >> W.r0[k]) & W.m0[k];
+    for (int k = 0; k < W.n1; ++k) rt.a1 |= ((a << W.l1[k]) >> W.r1[k]) & W.m1[k];
+    rt.mask = (~rt.a0 & ~rt.a1 & W.tt[0]) | (rt.a0 & ~rt.a1 & W.tt[1]) | (~rt.a0 & rt.a1 & W.tt[2]) |
+              (rt.a0 & rt.a1 & W.tt[3]);
+    return rt;
+  }
   for (int g = g0; g < g1; ++g) {
     const uint64_t posk = T.groups[g].posk;
     bool emit;
@@ -193,21 +221,33 @@ __device__ __forceinline__ uint64_t emit_mask(const Tables<CV> &T, int g0, int g
     } else {
       emit = (T.groups[g].emit_bits >> lut_index(posk, a)) & 1ull;
     }
-    mask |= (uint64_t)emit << (g - g0);
+    rt.mask |= (uint64_t)emit << (g - g0);
   }
-  return mask;
+  return rt;
 }
 
-// coefficient of group g for state a (the caller knows it emits)
+// Pops the lowest emitting group of the row: returns its flip mask and coefficient for state a.
 template <bool CV>
-__device__ __forceinline__ typename ValT<CV>::type group_coefficient(const Tables<CV> &T, const LutGroup &grp,
-                                                                      uint64_t a, bool any_s_out) {
+__device__ __forceinline__ typename ValT<CV>::type pop_term(const Tables<CV> &T, RowTerms &rt, int g0, uint64_t a,
+                                                             bool any_s_out, uint64_t &flip) {
   using V = typename ValT<CV>::type;
+  const int gl = __ffsll((long long)rt.mask) - 1;
+  rt.mask &= rt.mask - 1;
+  const int g = g0 + gl;
+  flip = T.gx[g];
+  V c;
+  if (T.n_bp > 0) {
+    const unsigned idx = (unsigned)((rt.a0 >> gl) & 1ull) | ((unsigned)((rt.a1 >> gl) & 1ull) << 1);
+    c = T.lut[4 * g + idx];
+    if (any_s_out && (__popcll(a & T.groups[g].s_out) & 1)) c = v_scale(c, -1.0);
+    return c;
+  }
+  const LutGroup grp = T.groups[g];
   if (grp.posk >> 56) {
     bool hit;
     return generic_coefficient<CV>(T.terms, grp.first, grp.count, a, &hit);
   }
-  V c = T.lut[grp.lut_offset + lut_index(grp.posk, a)];
+  c = T.lut[grp.lut_offset + lut_index(grp.posk, a)];
   if (any_s_out && (__popcll(a & grp.s_out) & 1)) c = v_scale(c, -1.0);
   return c;
 }
@@ -366,20 +406,20 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
       xi = v_scale(xi, 1.0 / __ldg(p.norms + i));   // 1 / norm(alpha): BO:200
 
     // ---- off-diagonal: which groups emit (bit mask), then compact the emitted terms into the ring
-    for (int g0 = 0; g0 < p.n_groups; g0 += 64) {
+    for (int g0 = 0, w = 0; g0 < p.n_groups; g0 += 64, ++w) {
       const int g1 = min(g0 + 64, p.n_groups);
-      uint64_t mask = valid ? emit_mask<CV>(T, g0, g1, alpha, COUNT_ONLY) : 0ull;
+      RowTerms rt = row_terms<CV>(T, w, g0, g1, alpha);
+      if (!valid) rt.mask = 0;
       for (;;) {
-        const bool has = mask != 0;
+        const bool has = rt.mask != 0;
         const unsigned m = __ballot_sync(0xffffffffu, has);
         if (m == 0) break;
         if (has) {
-          const int g = g0 + __ffsll((long long)mask) - 1;
-          mask &= mask - 1;
-          const LutGroup grp = T.groups[g];
+          uint64_t flip;
+          const V c = pop_term<CV>(T, rt, g0, alpha, any_s_out, flip);
           const unsigned pos = (head + count + __popc(m & ((1u << lane) - 1u))) & (kQueue - 1);
-          qb[pos] = alpha ^ grp.x;
-          if (!COUNT_ONLY) qc[pos] = v_mul(group_coefficient<CV>(T, grp, alpha, any_s_out), xi);
+          qb[pos] = alpha ^ flip;
+          if (!COUNT_ONLY) qc[pos] = v_mul(c, xi);
         }
         count += __popc(m);
         if (count >= 32) {
@@ -485,17 +525,16 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
     double inv_nb = 1.0;
     if (PROJ == PROJ_GROUP && valid) inv_nb = 1.0 / __ldg(p.norms + i);
 
-    for (int g0 = 0; g0 < p.n_groups; g0 += 64) {
+    for (int g0 = 0, w = 0; g0 < p.n_groups; g0 += 64, ++w) {
       const int g1 = min(g0 + 64, p.n_groups);
-      uint64_t mask = valid ? emit_mask<CV>(T, g0, g1, b, false) : 0ull;
+      RowTerms rt = row_terms<CV>(T, w, g0, g1, b);
+      if (!valid) rt.mask = 0;
       if (PROJ != PROJ_GROUP) {
         // every lane walks the set bits of ITS row: no lane idles on a bond that does not emit
-        while (mask) {
-          const int g = g0 + __ffsll((long long)mask) - 1;
-          mask &= mask - 1;
-          const LutGroup grp = T.groups[g];
-          V h = group_coefficient<CV>(T, grp, b, any_s_out);
-          uint64_t a = b ^ grp.x;
+        while (rt.mask) {
+          uint64_t flip;
+          V h = pop_term<CV>(T, rt, g0, b, any_s_out, flip);
+          uint64_t a = b ^ flip;
           bool flipped = false;
           if (PROJ == PROJ_INVERSION) {
             const uint64_t inv = a ^ p.site_mask;
@@ -505,8 +544,8 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
           int64_t idx;
           if (index.mode == INDEX_RANK) {
             // rank over the full fixed-weight set, incrementally from rank(b) = i
-            const int lo = __ffsll((long long)grp.x) - 1;
-            const int hi = 63 - __clzll((long long)grp.x);
+            const int lo = __ffsll((long long)flip) - 1;
+            const int hi = 63 - __clzll((long long)flip);
             const uint64_t span = ((hi == 63) ? ~0ull : ((1ull << (hi + 1)) - 1)) & ~((1ull << lo) - 1);
             const uint64_t ob = b & span, nb = a & span;
             idx = -1;
@@ -528,16 +567,15 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
         }
       } else {
         for (;;) {
-          const bool has = mask != 0;
+          const bool has = rt.mask != 0;
           const unsigned m = __ballot_sync(0xffffffffu, has);
           if (m == 0) break;
           if (has) {
-            const int g = g0 + __ffsll((long long)mask) - 1;
-            mask &= mask - 1;
-            const LutGroup grp = T.groups[g];
+            uint64_t flip;
+            const V c = pop_term<CV>(T, rt, g0, b, any_s_out, flip);
             const unsigned pos = (head + count + __popc(m & ((1u << lane) - 1u))) & (kQueue - 1);
-            qb[pos] = b ^ grp.x;
-            qc[pos] = v_scale(group_coefficient<CV>(T, grp, b, any_s_out), inv_nb);
+            qb[pos] = b ^ flip;
+            qc[pos] = v_scale(c, inv_nb);
             ql[pos] = (unsigned char)lane;
           }
           count += __popc(m);

@@ -267,3 +267,78 @@ def test_hermiticity_and_linearity_at_size(need_cuda):
         results.append(Hu)
     assert torch.allclose(results[0], results[1], rtol=1e-12, atol=1e-12)   # push == pull
     op.close()
+
+
+def _custom(n, hw, terms, **basis_kw):
+    from distributed_matvec_b200.config import basis_from_dict, operator_from_dict
+    basis = basis_from_dict({"number_spins": n, "hamming_weight": hw, **basis_kw})
+    return basis, operator_from_dict({"terms": terms}, basis)
+
+
+GENERAL_MODELS = {
+    # 3-site terms: support of 3 bits -> general LUT path (not bit-parallel)
+    "three_site": lambda: _custom(10, None, [
+        {"expression": "σˣ₀ σˣ₁ σᶻ₂", "sites": [[i, (i + 1) % 10, (i + 2) % 10] for i in range(10)]},
+        {"expression": "0.7 × σᶻ₀ σᶻ₁", "sites": [[i, (i + 1) % 10] for i in range(10)]}]),
+    # 7-site string: support of 7 bits -> term-by-term (generic) path; sigma^y makes coefficients complex
+    "seven_site_complex": lambda: _custom(9, None, [
+        {"expression": "σʸ₀ σᶻ₁ σᶻ₂ σᶻ₃ σᶻ₄ σᶻ₅ σˣ₆", "sites": [[(i + k) % 9 for k in range(7)] for i in range(9)]},
+        {"expression": "σˣ₀", "sites": [[i] for i in range(9)]}]),
+    # single-site field + hopping, fixed magnetisation, complex hopping amplitude
+    "complex_hopping": lambda: _custom(10, 5, [
+        {"expression": "σ⁺₀ σ⁻₁", "sites": [[i, (i + 1) % 10] for i in range(10)]},
+        {"expression": "σ⁻₀ σ⁺₁", "sites": [[i, (i + 1) % 10] for i in range(10)]},
+        {"expression": "0.3j × σ⁺₀ σ⁻₁", "sites": [[i, (i + 2) % 10] for i in range(10)]},
+        {"expression": "-0.3j × σ⁻₀ σ⁺₁", "sites": [[i, (i + 2) % 10] for i in range(10)]},
+        {"expression": "σᶻ₀", "sites": [[0], [3]]}]),
+    # translation symmetry with a complex character (momentum sector 1)
+    "momentum_sector": lambda: _custom(10, 5, [
+        {"expression": "σˣ₀ σˣ₁", "sites": [[i, (i + 1) % 10] for i in range(10)]},
+        {"expression": "σʸ₀ σʸ₁", "sites": [[i, (i + 1) % 10] for i in range(10)]},
+        {"expression": "σᶻ₀ σᶻ₁", "sites": [[i, (i + 1) % 10] for i in range(10)]}],
+        symmetries=[{"permutation": [(i + 1) % 10 for i in range(10)], "sector": 1}]),
+}
+
+
+@pytest.mark.parametrize("model", sorted(GENERAL_MODELS))
+def test_general_operators_all_paths(need_cuda, model):
+    """Operators beyond two-body real Heisenberg: every generation path (bit-parallel, LUT walk, term by
+    term), push and pull, real and complex vectors, 1 and 3 ranks."""
+    basis, matrix = GENERAL_MODELS[model]()
+    reps, _ = po.enumerate_states(basis)
+    for cplx in (False, True):
+        x = _x(reps.shape[0], cplx, seed=17)
+        y_ref = po.matvec_global(matrix, reps, x, 1)
+        for mode in (0, 1):
+            for bitparallel in (1, 0):
+                op = Operator(matrix)
+                op.set_option("mode", mode)
+                op.set_option("bitparallel", bitparallel)
+                op.basis.build()
+                assert np.array_equal(op.basis.representatives(), reps)
+                y = op.matvec(x)
+                assert _close(y, y_ref), (model, cplx, mode, bitparallel, np.abs(y - y_ref).max())
+                op.close()
+        masks, blocks = po.partition_by_hash(reps, 3)
+        cl = EmulatedCluster(matrix, 3).build()
+        yb = cl.matvec([torch.from_numpy(b).cuda() for b in block_to_hashed(x, masks, 3)])
+        torch.cuda.synchronize()
+        assert _close(hashed_to_block([t.cpu().numpy() for t in yb], masks), y_ref)
+        cl.close()
+
+
+def test_bitparallel_matches_group_walk(need_cuda):
+    basis, matrix = _load("heisenberg_kagome_16")
+    op = Operator(matrix)
+    op.basis.build()
+    assert op.info("bp_words") == 1
+    x = _x(op.basis.numberStates(), True)
+    ys = []
+    for mode in (0, 1):
+        for bp in (1, 0):
+            op.set_option("mode", mode)
+            op.set_option("bitparallel", bp)
+            ys.append(op.matvec(x))
+    for y in ys[1:]:
+        assert _close(y, ys[0])
+    op.close()
