@@ -182,7 +182,7 @@ HostTables build_tables(const std::map<uint64_t, std::vector<OffTerm>> &by_x) {
         const uint8_t sl = d >= 0 ? (uint8_t)d : 0, sr = d >= 0 ? 0 : (uint8_t)(-d);
         for (int k = 0; k < n; ++k)
           if (l[k] == sl && r[k] == sr) { m[k] |= 1ull << gl; return; }
-        if (n == 8) { bp_ok = false; return; }
+        if (n == kBpPairs) { bp_ok = false; return; }
         l[n] = sl; r[n] = sr; m[n] = 1ull << gl; ++n;
       };
       add(items[g].p0, W.m0, W.l0, W.r0, W.n0);
@@ -463,7 +463,7 @@ void install_directory(dmv_context *ctx) {
   int shift = bits > want ? bits - want : 0;
   ctx->dir_shift = shift;
   ctx->n_buckets = (max_rep >> shift) + 1;
-  ctx->d_dir.alloc(ctx->n_buckets + 2);
+  ctx->d_dir.alloc(2 * ctx->n_buckets + 2);
   launch_build_directory(ctx->d_reps.ptr, n, ctx->d_dir.ptr, ctx->n_buckets, shift, ctx->stream);
   ctx->planned = false;
   select_index_mode(ctx);

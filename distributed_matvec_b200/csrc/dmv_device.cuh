@@ -45,13 +45,14 @@ static_assert(sizeof(LutGroup) == 48, "LutGroup layout");
 // the state by a few masked shifts (the host orders the groups so that few distinct shifts occur: a
 // chain needs 2 per operand), and the groups that emit are
 //     mask = (~A0 & ~A1 & tt[0]) | (A0 & ~A1 & tt[1]) | (~A0 & A1 & tt[2]) | (A0 & A1 & tt[3]).
+constexpr int kBpPairs = 24;   // distinct shifts per operand and word; more -> walk the groups
 struct BpWord {
   uint64_t tt[4];
-  uint64_t m0[8], m1[8];   // masks over group bits (output positions)
-  uint8_t l0[8], r0[8], l1[8], r1[8];   // A_b |= ((a << l) >> r) & m   (one of l, r is zero)
+  uint64_t m0[kBpPairs], m1[kBpPairs];   // masks over group bits (output positions)
+  uint8_t l0[kBpPairs], r0[kBpPairs], l1[kBpPairs], r1[kBpPairs];   // A_b |= ((a << l) >> r) & m
   int32_t n0, n1;
 };
-static_assert(sizeof(BpWord) == 32 + 128 + 32 + 8, "BpWord layout");
+static_assert(sizeof(BpWord) == 32 + 16 * kBpPairs + 4 * kBpPairs + 8, "BpWord layout");
 
 __host__ __device__ __forceinline__ unsigned lut_index(uint64_t posk, uint64_t a) {
   const unsigned k = (unsigned)(posk >> 48) & 0xffu;
@@ -114,7 +115,7 @@ enum IndexMode { INDEX_DIRECTORY = 0, INDEX_IDENTITY = 1, INDEX_RANK = 2 };
 struct StateIndex {
   const uint64_t *reps;   // ascending, this rank's block
   int64_t n;
-  const uint32_t *dir;    // dir[b] = lower_bound(reps, b << shift), n_buckets + 1 entries
+  const uint32_t *dir;    // pairs: dir[2b] = lower_bound(reps, b << shift), dir[2b+1] = lower_bound(reps, (b+1) << shift)
   uint64_t n_buckets;
   int32_t shift;
   int32_t mode;           // IndexMode
@@ -127,15 +128,15 @@ struct StateIndex {
 __device__ __forceinline__ int64_t locate_directory(const StateIndex &ix, uint64_t key) {
   const uint64_t b = key >> ix.shift;
   if (b >= ix.n_buckets) return -1;
-  // dir entries are 4 bytes: dir[b] and dir[b+1] normally share one 32-byte sector
-  uint32_t lo = __ldg(ix.dir + b), hi = __ldg(ix.dir + b + 1);
-  const uint32_t end = hi;
+  // one 8-byte load: (first, one-past-last) position of the bucket
+  const uint2 range = __ldg(reinterpret_cast<const uint2 *>(ix.dir) + b);
+  uint32_t lo = range.x, hi = range.y;
   while (lo < hi) {
     const uint32_t mid = (lo + hi) >> 1;
     const uint64_t v = __ldg(ix.reps + mid);
+    if (v == key) return (int64_t)mid;   // states are unique: stop at the first hit
     if (v < key) lo = mid + 1; else hi = mid;
   }
-  if (lo < end && __ldg(ix.reps + lo) == key) return (int64_t)lo;
   return -1;
 }
 

@@ -642,19 +642,21 @@ __global__ void __launch_bounds__(kThreads) k_accumulate(const KernelParams p, i
   }
 }
 
-// dir[b] = lower_bound(reps, b << shift) for b in [0, n_buckets]
+// dir[2b] = lower_bound(reps, b << shift), dir[2b+1] = lower_bound(reps, (b+1) << shift) for b in [0, n_buckets)
 __global__ void k_build_directory(const uint64_t *__restrict__ reps, int64_t n, uint32_t *dir,
                                   uint64_t n_buckets, int shift) {
-  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > n_buckets) return;
-  const uint64_t key = (b == n_buckets) ? ~0ull : (b << shift);
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * n_buckets) return;
+  const uint64_t b = (t >> 1) + (t & 1);
   int64_t lo = 0, hi = n;
-  if (b == n_buckets) lo = n;
+  const bool past_end = shift > 0 ? (b > (~0ull >> shift)) : false;
+  if (past_end) lo = n;
+  const uint64_t key = b << shift;
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
     if (reps[mid] < key) lo = mid + 1; else hi = mid;
   }
-  dir[b] = (uint32_t)lo;
+  dir[t] = (uint32_t)lo;
 }
 
 __global__ void k_state_index(const StateIndex ix, int64_t count, const uint64_t *__restrict__ spins,
@@ -883,7 +885,7 @@ void launch_accumulate(const KernelParams &p, Projection proj, bool cv, bool ce,
 
 void launch_build_directory(const uint64_t *reps, int64_t n, uint32_t *dir, uint64_t n_buckets, int shift,
                             cudaStream_t stream) {
-  const int64_t items = (int64_t)n_buckets + 1;
+  const int64_t items = 2 * (int64_t)n_buckets;
   k_build_directory<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(reps, n, dir, n_buckets, shift);
   DMV_CUDA_CHECK(cudaGetLastError());
   g_launches++;
