@@ -424,7 +424,8 @@ void select_index_mode(dmv_context *ctx) {
   ctx->index_mode = INDEX_DIRECTORY;
   if (ctx->identity_index && ctx->num_ranks == 1) { ctx->index_mode = INDEX_IDENTITY; return; }
   const int n = ctx->n_sites, w = ctx->hamming_weight;
-  const bool eligible = ctx->num_ranks == 1 && w >= 0 && ctx->proj != PROJ_GROUP && ctx->opt_index != 0;
+  // auto = directory search: the combinadic rank trades L1 traffic for issue slots and measured slower
+  const bool eligible = ctx->num_ranks == 1 && w >= 0 && ctx->proj != PROJ_GROUP && ctx->opt_index == 2;
   if (!eligible) return;
   const uint64_t total = binom().c[n][w];
   const uint64_t expect = (ctx->proj == PROJ_INVERSION) ? total / 2 : total;
@@ -575,7 +576,9 @@ void do_plan(dmv_context *ctx) {
 }
 
 bool use_pull(const dmv_context *ctx) {
-  return ctx->num_ranks == 1 && ctx->opt_mode != 0;
+  // auto = push: with the warp-queue drain the scatter form is the faster one on B200 (measured, see
+  // DESIGN.md "Kernels"); the row-gather form stays selectable ("mode" = 1) and deterministic.
+  return ctx->num_ranks == 1 && ctx->opt_mode == 1;
 }
 
 void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev) {

@@ -38,7 +38,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kQueue = 64;  // ring capacity per warp (>= 31 pending + 32 appended)
+constexpr int kQueue = 128;  // ring capacity per warp (>= 63 pending + 32 appended)
 
 // ---- value helpers: V = double (real coefficients and real x) or double2 (complex) -------------
 template <bool CV> struct ValT { using type = double; };
@@ -266,12 +266,12 @@ __device__ __forceinline__ void diagonal(const Tables<CV> &T, int n_diag, uint64
 }
 
 // ---- the consumer side: one record per lane -----------------------------------------------------
-// Projects beta (inversion / full group), and either accumulates it locally or appends it to the
-// bucket of its owner.  `active` lanes carry a record; all 32 lanes must call this (warp collectives).
+// route(): projects beta (inversion / full group) and appends the record to the bucket of its owner when
+// that is another rank.  Returns true when the record is this rank's own (to be searched + accumulated).
+// All 32 lanes must call it (warp collectives); `active` lanes carry a record.
 template <int PROJ, bool CV, bool CE, bool COUNT_ONLY>
-__device__ __forceinline__ void consume(const KernelParams &p, const OrbitProgram &orbit,
-                                        const StateIndex &index, bool active, uint64_t beta,
-                                        typename ValT<CV>::type c) {
+__device__ __forceinline__ bool route(const KernelParams &p, const OrbitProgram &orbit, bool active,
+                                      uint64_t &beta, typename ValT<CV>::type &c) {
   using V = typename ValT<CV>::type;
   const unsigned lane = threadIdx.x & 31u;
   if (PROJ == PROJ_INVERSION) {
@@ -306,7 +306,7 @@ __device__ __forceinline__ void consume(const KernelParams &p, const OrbitProgra
         p.out_keys[pos] = (uint8_t)owner;
       }
     }
-    return;
+    return false;
   }
 
   if (p.num_ranks > 1) {
@@ -331,29 +331,88 @@ __device__ __forceinline__ void consume(const KernelParams &p, const OrbitProgra
         }
       }
     }
-    if (COUNT_ONLY) return;
-    active = active && owner == p.rank;
+    if (COUNT_ONLY) return false;
+    return active && owner == p.rank;
   } else if (COUNT_ONLY) {
     const unsigned m = __ballot_sync(0xffffffffu, active);
     if (lane == 0 && m) atomicAdd(p.out_count, (unsigned long long)__popc(m));
-    return;
+    return false;
   }
+  return active;
+}
 
-  // ---- local records: localProcess (reference DMV:73-127)
-  if (active) {
-    const int64_t idx = locate(index, beta);
-    if (idx >= 0) {
-      if (PROJ == PROJ_GROUP) c = v_scale(c, __ldg(p.norms + idx));
-      if (v_nonzero(c)) atomic_accumulate<CE>(p.y, idx, v_re(c), v_im(c));   // DMV:110: skip c == 0
-    } else if (v_nonzero(c)) {
-      bool fatal = true;
-      if (PROJ == PROJ_GROUP && !orbit.trivial_characters)
-        fatal = orbit_stabiliser_sum(orbit, beta) > 1e-12 * (double)orbit.group_order;  // zero-norm orbit
-      if (fatal) {                                                             // DMV:115-118
-        if (atomicAdd(p.status, 1ull) == 0) p.status[1] = beta;
-      }
+// finish(): localProcess (reference DMV:73-127) for one located record
+template <int PROJ, bool CV, bool CE>
+__device__ __forceinline__ void finish(const KernelParams &p, const OrbitProgram &orbit, bool active,
+                                       uint64_t beta, typename ValT<CV>::type c, int64_t idx) {
+  if (!active) return;
+  if (idx >= 0) {
+    if (PROJ == PROJ_GROUP) c = v_scale(c, __ldg(p.norms + idx));
+    if (v_nonzero(c)) atomic_accumulate<CE>(p.y, idx, v_re(c), v_im(c));   // DMV:110: skip c == 0
+  } else if (v_nonzero(c)) {
+    bool fatal = true;
+    if (PROJ == PROJ_GROUP && !orbit.trivial_characters)
+      fatal = orbit_stabiliser_sum(orbit, beta) > 1e-12 * (double)orbit.group_order;  // zero-norm orbit
+    if (fatal) {                                                             // DMV:115-118
+      if (atomicAdd(p.status, 1ull) == 0) p.status[1] = beta;
     }
   }
+}
+
+// Two independent searches advanced in lock step: both directory loads, then both probes of every
+// level, are in flight together (the search is a chain of dependent L2 accesses; this doubles the
+// memory-level parallelism of a warp).
+__device__ __forceinline__ void locate2(const StateIndex &ix, bool a0, uint64_t k0, bool a1, uint64_t k1,
+                                        int64_t &i0, int64_t &i1) {
+  if (ix.mode != INDEX_DIRECTORY) {
+    i0 = a0 ? locate(ix, k0) : -1;
+    i1 = a1 ? locate(ix, k1) : -1;
+    return;
+  }
+  i0 = -1; i1 = -1;
+  const uint64_t b0 = k0 >> ix.shift, b1 = k1 >> ix.shift;
+  a0 = a0 && b0 < ix.n_buckets;
+  a1 = a1 && b1 < ix.n_buckets;
+  uint2 r0 = make_uint2(0, 0), r1 = make_uint2(0, 0);
+  if (a0) r0 = __ldg(reinterpret_cast<const uint2 *>(ix.dir) + b0);
+  if (a1) r1 = __ldg(reinterpret_cast<const uint2 *>(ix.dir) + b1);
+  uint32_t lo0 = r0.x, hi0 = r0.y, lo1 = r1.x, hi1 = r1.y;
+  while (lo0 < hi0 || lo1 < hi1) {
+    const bool s0 = lo0 < hi0, s1 = lo1 < hi1;
+    const uint32_t m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
+    uint64_t v0 = 0, v1 = 0;
+    if (s0) v0 = __ldg(ix.reps + m0);
+    if (s1) v1 = __ldg(ix.reps + m1);
+    if (s0) {
+      if (v0 == k0) { i0 = m0; lo0 = hi0; }
+      else if (v0 < k0) lo0 = m0 + 1; else hi0 = m0;
+    }
+    if (s1) {
+      if (v1 == k1) { i1 = m1; lo1 = hi1; }
+      else if (v1 < k1) lo1 = m1 + 1; else hi1 = m1;
+    }
+  }
+}
+
+// Drain up to 64 queued records of this warp: lane handles entries `lane` and `lane + 32`.
+template <int PROJ, bool CV, bool CE, bool COUNT_ONLY>
+__device__ __forceinline__ void drain(const KernelParams &p, const OrbitProgram &orbit, const StateIndex &index,
+                                      const uint64_t *qb, const typename ValT<CV>::type *qc, unsigned head,
+                                      unsigned n) {
+  using V = typename ValT<CV>::type;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned p0 = (head + lane) & (kQueue - 1), p1 = (head + lane + 32) & (kQueue - 1);
+  bool a0 = lane < n, a1 = lane + 32 < n;
+  uint64_t k0 = a0 ? qb[p0] : 0ull, k1 = a1 ? qb[p1] : 0ull;
+  V c0 = a0 ? qc[p0] : v_make(0.0, 0.0, (V *)nullptr), c1 = a1 ? qc[p1] : v_make(0.0, 0.0, (V *)nullptr);
+  a0 = route<PROJ, CV, CE, COUNT_ONLY>(p, orbit, a0, k0, c0);
+  if (n > 32) a1 = route<PROJ, CV, CE, COUNT_ONLY>(p, orbit, a1, k1, c1);   // n is warp-uniform
+  else a1 = false;
+  if (COUNT_ONLY) return;
+  int64_t i0, i1;
+  locate2(index, a0, k0, a1, k1, i0, i1);
+  finish<PROJ, CV, CE>(p, orbit, a0, k0, c0, i0);
+  finish<PROJ, CV, CE>(p, orbit, a1, k1, c1, i1);
 }
 
 template <int PROJ, bool CV, bool CE, bool COUNT_ONLY>
@@ -422,12 +481,11 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
           if (!COUNT_ONLY) qc[pos] = v_mul(c, xi);
         }
         count += __popc(m);
-        if (count >= 32) {
+        if (count >= 64) {
           __syncwarp();
-          const unsigned pos = (head + lane) & (kQueue - 1);
-          consume<PROJ, CV, CE, COUNT_ONLY>(p, T.orbit, T.index, true, qb[pos], qc[pos]);
-          head = (head + 32) & (kQueue - 1);
-          count -= 32;
+          drain<PROJ, CV, CE, COUNT_ONLY>(p, T.orbit, T.index, qb, qc, head, 64);
+          head = (head + 64) & (kQueue - 1);
+          count -= 64;
           __syncwarp();
         }
       }
@@ -435,10 +493,7 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
   }
   if (count > 0) {
     __syncwarp();
-    const unsigned pos = (head + lane) & (kQueue - 1);
-    const bool active = lane < count;
-    consume<PROJ, CV, CE, COUNT_ONLY>(p, T.orbit, T.index, active, active ? qb[pos] : 0ull,
-                                      active ? qc[pos] : v_make(0.0, 0.0, (V *)nullptr));
+    drain<PROJ, CV, CE, COUNT_ONLY>(p, T.orbit, T.index, qb, qc, head, count);
   }
 }
 

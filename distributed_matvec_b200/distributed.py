@@ -120,3 +120,44 @@ def matrix_vector_product(matrix, x, y=None):
     """``matrixVectorProduct(matrix, x, y, representatives)`` (DMV:1072-1075) on this rank's blocks;
     `matrix` is an Operator (one rank) or a DistributedOperator."""
     return matrix.matvec(x, y)
+
+
+class HostExchangedProduct:
+    """``matrixVectorProduct`` with the exchange owned by the HOST through torch.distributed
+    (``all_to_all_single``), driving the stepwise C ABI (dmv_plan / dmv_generate / dmv_outgoing /
+    dmv_accumulate) -- what a Chapel host doing its own PUTs (DMV:361-371) would do.  Works with any
+    torch.distributed backend; `rank_ops` is this rank's Operator (or, in the CPU tests, a stand-in with
+    the same methods built on the oracle, so that the exchange logic is covered without a GPU).
+
+    Protocol per product (all ranks):
+      1. counts[r][q] (records r sends q) are fixed by the plan; exchanged once with all_gather
+      2. generate: own records are accumulated locally, the rest land in per-destination buckets
+      3. all_to_all_single of betas (int64 view of uint64) and coefficients (float64, `width` per record)
+      4. accumulate the received records
+    """
+
+    def __init__(self, rank_ops, width_of=None):
+        import torch
+        import torch.distributed as dist
+        self.ops = rank_ops
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        send = torch.from_numpy(np.asarray(self.ops.plan(), dtype=np.int64).copy())
+        send[self.rank] = 0
+        gathered = [torch.zeros_like(send) for _ in range(self.world)]
+        dist.all_gather(gathered, send)
+        self.send_counts = send.tolist()
+        self.recv_counts = [int(gathered[q][self.rank]) for q in range(self.world)]
+
+    def matvec(self, x, y):
+        import torch
+        import torch.distributed as dist
+        width = self.ops.record_width(x)
+        self.ops.generate(x, y)
+        betas_out, coeffs_out = self.ops.outgoing_tensors(width)   # concatenated over destinations
+        betas_in = torch.empty(sum(self.recv_counts), dtype=torch.int64, device=betas_out.device)
+        coeffs_in = torch.empty(sum(self.recv_counts) * width, dtype=torch.float64, device=betas_out.device)
+        dist.all_to_all_single(betas_in, betas_out, self.recv_counts, self.send_counts)
+        dist.all_to_all_single(coeffs_in, coeffs_out, [c * width for c in self.recv_counts],
+                               [c * width for c in self.send_counts])
+        self.ops.accumulate_tensors(x, betas_in, coeffs_in, y)
+        return y

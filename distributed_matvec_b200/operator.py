@@ -244,10 +244,49 @@ class Operator:
     def accumulate(self, elt: int, count: int, betas_ptr, coeffs_ptr, y):
         nat.check(nat.lib().dmv_accumulate(self._ctx, elt, count, C.c_void_p(betas_ptr), C.c_void_p(coeffs_ptr), _ptr(y)))
 
+    # -- tensor views for hosts that own the exchange (HostExchangedProduct) ----------------------
+    def record_width(self, x) -> int:
+        """doubles per coefficient of the records generated for vectors like x"""
+        return 2 if (_elt_of(x) == nat.DMV_C128 or not self.spec.is_real() or
+                     not self.spec.basis.group.all_characters_trivial) else 1
+
+    def outgoing_tensors(self, width: int):
+        """(betas int64, coeffs float64) torch views of all outgoing buckets, concatenated by destination."""
+        import torch
+        first = None
+        total = 0
+        for q in range(self.num_ranks):
+            b, c, n = self.outgoing(q)
+            if q != self.rank:
+                if first is None:
+                    first = (b, c)
+                total += n
+        if total == 0:
+            dev = torch.device("cuda", self.device)
+            return torch.empty(0, dtype=torch.int64, device=dev), torch.empty(0, dtype=torch.float64, device=dev)
+        betas = _device_tensor(first[0], total, torch.int64, self.device)
+        coeffs = _device_tensor(first[1], total * width, torch.float64, self.device)
+        return betas, coeffs
+
+    def accumulate_tensors(self, x, betas, coeffs, y):
+        if betas.numel() > 0:
+            self.accumulate(_elt_of(x), int(betas.numel()), betas.data_ptr(), coeffs.data_ptr(), y)
+
     def timings(self) -> dict:
         buf = (C.c_double * 8)()
         n = nat.lib().dmv_last_timings(self._ctx, buf, 8)
         return {nat.lib().dmv_timing_name(i).decode(): buf[i] for i in range(n)}
+
+
+def _device_tensor(ptr: int, count: int, dtype, device: int):
+    """Zero-copy torch view of library-owned device memory (valid until the next generate)."""
+    import torch
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+
+    class _Holder:
+        __cuda_array_interface__ = {"shape": (count,), "typestr": "<i8" if dtype == torch.int64 else "<f8",
+                                    "data": (ptr, False), "version": 2, "strides": (itemsize,)}
+    return torch.as_tensor(_Holder(), device=torch.device("cuda", device))
 
 
 class BatchedOperator:

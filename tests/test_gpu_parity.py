@@ -133,7 +133,7 @@ def test_local_matvec_matches_oracle(need_cuda, name, cplx, mode):
     reps = op.basis.representatives()
     x = _x(reps.shape[0], cplx)
     y_ref = po.matvec_global(matrix, reps, x, 1)
-    for index in (-1, 0):          # auto (rank / identity where they apply) and forced directory search
+    for index in (2, 0):           # combinadic rank / identity where they apply, and forced directory search
         op.set_option("index", index)
         y = op.matvec(x)
         assert _close(y, y_ref), (index, op.info("index_mode"), np.abs(y - y_ref).max())
@@ -152,6 +152,7 @@ def test_rank_index_is_selected_and_bit_exact(need_cuda):
                          ("heisenberg_kagome_12_symm", 0)):
         basis, matrix = _load(name)
         op = Operator(matrix)
+        op.set_option("index", 2)
         op.basis.build()
         assert op.info("index_mode") == expect, name
         reps = op.basis.representatives()

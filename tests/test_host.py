@@ -1,0 +1,126 @@
+"""Host logic and the C-ABI library without a GPU: expression compile, symmetry groups, model inputs,
+the group compiler of libdmv_b200 (host-side self-check entry), exported symbols, loud failure."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import yaml
+
+from distributed_matvec_b200 import _native as nat
+from distributed_matvec_b200.config import basis_from_dict, load_config_from_yaml
+from distributed_matvec_b200.expr import compile_terms, parse_expression
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = os.path.join(ROOT, "data")
+
+
+def test_expression_parser():
+    p = parse_expression("0.8 × σˣ₀ σˣ₁")
+    assert len(p) == 1 and p[0].coeff == 0.8 and [f.comp for f in p[0].factors] == ["x", "x"]
+    p = parse_expression("σ⁺₀ σ⁻₁ + σ⁻₀ σ⁺₁")
+    assert len(p) == 2 and [f.site for f in p[1].factors] == [0, 1]
+    p = parse_expression("-0.3j × Sᶻ₁₂")
+    assert p[0].coeff == -0.3j and p[0].factors[0].site == 12 and p[0].factors[0].kind == "S"
+    with pytest.raises(ValueError):
+        parse_expression("σˣ")
+
+
+def test_heisenberg_bond_compiles_to_two_terms_per_bond():
+    off, diag = compile_terms([{"expression": "σˣ₀ σˣ₁", "sites": [[0, 1]]}, {"expression": "σʸ₀ σʸ₁", "sites": [[0, 1]]},
+                               {"expression": "σᶻ₀ σᶻ₁", "sites": [[0, 1]]}], 2)
+    # sigma^x sigma^x + sigma^y sigma^y = 2 (s+ s- + s- s+): parallel spins cancel exactly
+    assert len(off) == 2 and set(off.r.tolist()) == {1, 2} and np.all(off.v == 2) and np.all(off.x == 3)
+    assert len(diag) == 1 and diag.s[0] == 3 and diag.v[0] == 1
+    off, diag = compile_terms([{"expression": "Sˣ₀ Sˣ₁", "sites": [[0, 1]]}, {"expression": "Sʸ₀ Sʸ₁", "sites": [[0, 1]]},
+                               {"expression": "Sᶻ₀ Sᶻ₁", "sites": [[0, 1]]}], 2)
+    assert np.allclose(off.v, 0.5) and np.allclose(diag.v, 0.25)
+
+
+@pytest.mark.parametrize("name,order", [("heisenberg_chain_24_symm", 96), ("heisenberg_chain_32_symm", 128),
+                                        ("heisenberg_square_4x4", 256), ("heisenberg_square_6x6", 576),
+                                        ("heisenberg_chain_36_symm", 144), ("heisenberg_kagome_12_symm", 2),
+                                        ("heisenberg_chain_10", 2)])
+def test_group_orders(name, order):
+    basis, _ = load_config_from_yaml(os.path.join(DATA, name + ".yaml"))
+    assert len(basis.group) == order
+
+
+def test_inconsistent_sectors_are_rejected():
+    b = basis_from_dict({"number_spins": 4, "symmetries": [{"permutation": [1, 2, 3, 0], "sector": 1},
+                                                            {"permutation": [2, 3, 0, 1], "sector": 0}]})
+    with pytest.raises(ValueError):
+        b.group
+
+
+def test_model_inputs_equal_the_reference_inputs():
+    """data/*.yaml are normalised copies of the reference's model inputs (tools/gen_models.py)."""
+    ref_dir = "/root/reference/data"
+    if not os.path.isdir(ref_dir):
+        pytest.skip("reference tree not present (GPU box)")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from gen_models import normalise
+    names = sorted(f for f in os.listdir(ref_dir) if f.endswith(".yaml"))
+    assert len(names) == 22
+    for f in names:
+        with open(os.path.join(ref_dir, f), encoding="utf-8") as fh:
+            ref = normalise(yaml.safe_load(fh))
+        with open(os.path.join(DATA, f), encoding="utf-8") as fh:
+            ours = yaml.safe_load(fh)
+        assert yaml.safe_load(yaml.safe_dump(ref, allow_unicode=True)) == ours, f
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports every function include/dmv_b200.h declares."""
+    with open(os.path.join(ROOT, "include", "dmv_b200.h"), encoding="utf-8") as f:
+        header = f.read()
+    declared = set(re.findall(r"\b((?:dmv|ls_chpl)_[a-z0-9_]+)\s*\(", header))
+    declared -= {"dmv_context", "dmv_basis_desc", "dmv_operator_desc"}
+    lib = nat.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(nat.EXPORTED_SYMBOLS), declared ^ set(nat.EXPORTED_SYMBOLS)
+    assert lib.dmv_version() >= 100
+    lib.ls_chpl_init()
+    lib.ls_chpl_finalize()
+
+
+def test_no_silent_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from distributed_matvec_b200 import Operator
+    _, matrix = load_config_from_yaml(os.path.join(DATA, "heisenberg_chain_10.yaml"))
+    with pytest.raises(nat.DmvError, match="no CPU fallback"):
+        Operator(matrix)
+
+
+@pytest.mark.parametrize("name", ["heisenberg_kagome_12_symm", "issue_01", "heisenberg_chain_24_symm",
+                                  "heisenberg_square_4x4", "heisenberg_chain_32_symm", "heisenberg_chain_36_symm",
+                                  "heisenberg_square_6x6", "heisenberg_chain_40_symm"])
+def test_group_compiler_matches_oracle(name):
+    """The orbit program (coset networks x shift chain) that the GPU kernels execute, evaluated on the host
+    by the library's self-check entry, gives the oracle's orbit representatives and stabiliser sizes."""
+    basis, _ = load_config_from_yaml(os.path.join(DATA, name + ".yaml"))
+    g = basis.group
+    bd = nat.BasisDesc()
+    bd.number_sites, bd.hamming_weight, bd.spin_inversion, bd.has_permutations = (
+        basis.number_sites, -1 if basis.hamming_weight is None else basis.hamming_weight, basis.spin_inversion, 1)
+    perms, flips, chars = (np.ascontiguousarray(g.perms), np.ascontiguousarray(g.flips),
+                           np.ascontiguousarray(g.characters))
+    bd.group_order, bd.perms, bd.flips, bd.characters = len(g), perms.ctypes.data, flips.ctypes.data, chars.ctypes.data
+    rng = np.random.default_rng(0)
+    states = rng.integers(0, 2**basis.number_sites, size=3000, dtype=np.uint64)
+    info = np.zeros(6, dtype=np.int64)
+    reps = np.zeros_like(states)
+    stab = np.zeros(states.shape[0], dtype=np.int32)
+    nat.check(nat.lib().dmv_debug_compile_group(C.byref(bd), info.ctypes.data, states.shape[0], states.ctypes.data,
+                                                reps.ctypes.data, stab.ctypes.data))
+    o_reps, _, o_norms = po.state_info(basis, states)
+    assert np.array_equal(reps, o_reps)
+    assert info[0] * info[2] * (2 if info[5] else 1) == len(g)      # n_q * n_t * flip = |G|
+    if g.all_characters_trivial:
+        assert np.allclose(np.sqrt(stab / len(g)), o_norms, atol=1e-15)
