@@ -37,7 +37,7 @@ DEFAULT_WORKLOAD = "heisenberg_chain_24"   # BASELINE.json configs[1]
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("DMV_WORKLOAD", DEFAULT_WORKLOAD))
@@ -48,31 +48,53 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every 2 ms; the nvidia-smi
+    query of B200_PROFILING.md polls too slowly for a region of a few tens of milliseconds)."""
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.sm, self.reasons, self.sm_max = [], set(), None
         self._stop = threading.Event()
         self._thread = None
 
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if visible:
+                try:
+                    idx = int(visible.split(",")[self.index])
+                except ValueError:
+                    pass
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            while not self._stop.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self._stop.wait(0.002)
+        except Exception as e:  # NVML missing: fall back to one nvidia-smi query
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                parts = [p.strip() for p in out.stdout.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
+                a, b = [float(v) for v in out.stdout.strip().split(",")]
+                self.sm.append(a)
+                self.sm_max = b
             except Exception:
-                pass
-            self._stop.wait(0.2)
+                self.reasons.add(f"unsampled ({type(e).__name__})")
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
+        time.sleep(0.01)
         return self
 
     def __exit__(self, *a):
@@ -80,13 +102,27 @@ class ClockSampler:
         self._thread.join(timeout=10)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons) or ["unsampled"]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+def measured_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(kernel)
+    return None
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def measured_peaks():
@@ -100,6 +136,7 @@ def measured_peaks():
 def cpu_reference_run(matrix, reps, x, seconds: float, max_iters: int = 5):
     """Time the oracle (OpenMP, all host threads) on the full workload; returns (states/s, iters, threads, y)."""
     from oracle import pyoracle as po
+    po.set_num_threads(host_threads())   # torchrun exports OMP_NUM_THREADS=1: use all the host threads anyway
     threads = po.num_threads()
     t_first = time.perf_counter()
     y = po.matvec_blocks(matrix, [reps], [x], num_tasks=threads)[0]
@@ -130,6 +167,7 @@ def run_reference(args):
     x = rng.random(reps.shape[0]) - 0.5
     if cplx:
         x = x + 1j * (rng.random(reps.shape[0]) - 0.5)
+    po.set_num_threads(host_threads())
     threads = po.num_threads()
     times = []
     for i in range(args.warmup + args.steps):
@@ -308,7 +346,8 @@ def main():
                 "stages_ms": stage},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_kind": peak_kind, "kernel": "k_generate", "kernel_ms": kernel_ms,
+                     "traffic": measured_traffic(f"k_generate:{args.workload}:{args.dtype}") if world == 1 else None,
+                     "peak_kind": peak_kind, "kernel": "k_generate", "kernel_ms": kernel_ms,
                      "algorithmic_bytes": int(bytes_alg_local),
                      "note": "working set of chain_24 fits the 126 MB L2: bound is L2 atomics/random access"},
         "clocks": clocks.summary(),

@@ -177,16 +177,16 @@ HostTables build_tables(const std::map<uint64_t, std::vector<OffTerm>> &by_x) {
     for (size_t g = 0; g < items.size() && bp_ok; ++g) {
       BpWord &W = words[g / 64];
       const int gl = (int)(g % 64);
-      auto add = [&](int pos, uint64_t *m, uint8_t *l, uint8_t *r, int32_t &n) {
+      auto add = [&](int pos, BpPair *pairs, int32_t &n) {
         const int d = gl - pos;
-        const uint8_t sl = d >= 0 ? (uint8_t)d : 0, sr = d >= 0 ? 0 : (uint8_t)(-d);
+        const uint32_t sl = d >= 0 ? (uint32_t)d : 0u, sr = d >= 0 ? 0u : (uint32_t)(-d);
         for (int k = 0; k < n; ++k)
-          if (l[k] == sl && r[k] == sr) { m[k] |= 1ull << gl; return; }
+          if (pairs[k].l == sl && pairs[k].r == sr) { pairs[k].m |= 1ull << gl; return; }
         if (n == kBpPairs) { bp_ok = false; return; }
-        l[n] = sl; r[n] = sr; m[n] = 1ull << gl; ++n;
+        pairs[n].l = sl; pairs[n].r = sr; pairs[n].m = 1ull << gl; ++n;
       };
-      add(items[g].p0, W.m0, W.l0, W.r0, W.n0);
-      add(items[g].p1, W.m1, W.l1, W.r1, W.n1);
+      add(items[g].p0, W.p0, W.n0);
+      add(items[g].p1, W.p1, W.n1);
     }
     if (bp_ok) {
       for (size_t g = 0; g < items.size(); ++g) {
@@ -320,7 +320,9 @@ struct dmv_context {
   int64_t number_terms = 0;
   DevBuf<unsigned long long> d_status;
   // streams
-  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+  static constexpr int kCopyChunks = 8;
+  cudaEvent_t ev_chunk[kCopyChunks] = {};
   cudaEvent_t ev[T_COUNT + 2] = {};
   double timings[T_COUNT] = {};
   // communicator
@@ -329,11 +331,19 @@ struct dmv_context {
   ~dmv_context() {
     if (comm) nccl().CommDestroy(comm);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ev_chunk) if (e) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
 };
 
 namespace {
+
+bool use_pull(const dmv_context *ctx) {
+  // auto = push: with the warp-queue drain the scatter form is the faster one on B200 (measured, see
+  // DESIGN.md "Kernels"); the row-gather form stays selectable ("mode" = 1) and deterministic.
+  return ctx->num_ranks == 1 && ctx->opt_mode == 1;
+}
 
 void use_device(const dmv_context *ctx) { CUDA_CHECK(cudaSetDevice(ctx->device)); }
 
@@ -520,6 +530,7 @@ void zero_y_if_diag(dmv_context *ctx, int elt, void *y) {
 
 struct VecStage {  // x / y either used in place (device pointers) or staged through context buffers
   const void *x_dev; void *y_dev; bool y_host; void *y_user; size_t bytes;
+  const void *x_host_pending;   // host x whose upload is pipelined with generation (push traversal)
 };
 VecStage stage_vectors(dmv_context *ctx, int elt, const void *x, void *y) {
   VecStage v{};
@@ -528,8 +539,11 @@ VecStage stage_vectors(dmv_context *ctx, int elt, const void *x, void *y) {
   if (is_device_pointer(x)) v.x_dev = x;
   else {
     ctx->d_x.alloc((size_t)ctx->n_states * elt);
-    CUDA_CHECK(cudaMemcpyAsync(ctx->d_x.ptr, x, v.bytes, cudaMemcpyHostToDevice, ctx->stream));
     v.x_dev = ctx->d_x.ptr;
+    // the column traversal only reads x[i] of the rows it is generating: upload in row chunks on a copy
+    // stream and start generating as soon as the first chunk has landed (see do_generate)
+    if (!use_pull(ctx) && ctx->n_states >= (1 << 16)) v.x_host_pending = x;
+    else CUDA_CHECK(cudaMemcpyAsync(ctx->d_x.ptr, x, v.bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
   if (is_device_pointer(y)) { v.y_dev = y; v.y_host = false; }
   else {
@@ -575,13 +589,8 @@ void do_plan(dmv_context *ctx) {
   ctx->planned = true;
 }
 
-bool use_pull(const dmv_context *ctx) {
-  // auto = push: with the warp-queue drain the scatter form is the faster one on B200 (measured, see
-  // DESIGN.md "Kernels"); the row-gather form stays selectable ("mode" = 1) and deterministic.
-  return ctx->num_ranks == 1 && ctx->opt_mode == 1;
-}
-
-void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev) {
+void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev,
+                 const void *x_host_pending = nullptr) {
   if (use_pull(ctx)) {   // one rank owns the basis: traverse by rows (gather), see k_pull
     KernelParams p = base_params(ctx);
     p.x = x_dev;
@@ -600,7 +609,28 @@ void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev) {
   const bool cv = complex_values(ctx, elt);
   ctx->record_width = cv ? 2 : 1;
   select_tables(ctx, p, false, cv);
-  launch_generate(p, ctx->proj, cv, elt == DMV_C128, false, ctx->stream);
+  if (!x_host_pending) {
+    launch_generate(p, ctx->proj, cv, elt == DMV_C128, false, ctx->stream);
+    return;
+  }
+  // pipelined: chunk k of x is copied while chunk k-1 is being generated
+  const int chunks = dmv_context::kCopyChunks;
+  const int64_t n = ctx->n_states, per = ((n + chunks - 1) / chunks + 31) / 32 * 32;
+  const size_t esz = (size_t)8 * elt;
+  CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[0], ctx->stream));       // copy stream starts after prior work
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[0], 0));
+  for (int k = 0; k < chunks; ++k) {
+    const int64_t b = std::min<int64_t>(n, (int64_t)k * per), e = std::min<int64_t>(n, b + per);
+    if (e <= b) break;
+    CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char *>(ctx->d_x.ptr) + b * esz,
+                               reinterpret_cast<const char *>(x_host_pending) + b * esz, (size_t)(e - b) * esz,
+                               cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
+    p.row_begin = b;
+    p.row_end = e;
+    launch_generate(p, ctx->proj, cv, elt == DMV_C128, false, ctx->stream);
+  }
 }
 
 void do_accumulate(dmv_context *ctx, int elt, int64_t count, const uint64_t *betas, const double *coeffs,
@@ -677,7 +707,9 @@ int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op,
   use_device(ctx.get());
   CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (auto &e : ctx->ev) CUDA_CHECK(cudaEventCreate(&e));
+  for (auto &e : ctx->ev_chunk) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   ctx->n_sites = basis->number_sites;
   ctx->hamming_weight = basis->hamming_weight;
   ctx->spin_inversion = basis->spin_inversion;
@@ -1002,7 +1034,7 @@ int dmv_local_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
   if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
   if (x == y) throw std::runtime_error("x and y must not alias");
   VecStage v = stage_vectors(ctx, elt, x, y);
-  do_generate(ctx, elt, v.x_dev, v.y_dev);
+  do_generate(ctx, elt, v.x_dev, v.y_dev, v.x_host_pending);
   CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
   CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
   finish_vectors(ctx, v);
@@ -1064,7 +1096,7 @@ int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
     ctx->d_in_coeffs.alloc((size_t)total_in * 2);
   }
   VecStage v = stage_vectors(ctx, elt, x, y);
-  do_generate(ctx, elt, v.x_dev, v.y_dev);
+  do_generate(ctx, elt, v.x_dev, v.y_dev, v.x_host_pending);
   CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
   const int width = ctx->record_width;
   int64_t total_in = 0;

@@ -46,13 +46,16 @@ static_assert(sizeof(LutGroup) == 48, "LutGroup layout");
 // chain needs 2 per operand), and the groups that emit are
 //     mask = (~A0 & ~A1 & tt[0]) | (A0 & ~A1 & tt[1]) | (~A0 & A1 & tt[2]) | (A0 & A1 & tt[3]).
 constexpr int kBpPairs = 24;   // distinct shifts per operand and word; more -> walk the groups
+struct BpPair {            // A |= ((a << l) >> r) & m   (one of l, r is zero); one 16-byte load
+  uint64_t m;
+  uint32_t l, r;
+};
 struct BpWord {
   uint64_t tt[4];
-  uint64_t m0[kBpPairs], m1[kBpPairs];   // masks over group bits (output positions)
-  uint8_t l0[kBpPairs], r0[kBpPairs], l1[kBpPairs], r1[kBpPairs];   // A_b |= ((a << l) >> r) & m
+  BpPair p0[kBpPairs], p1[kBpPairs];
   int32_t n0, n1;
 };
-static_assert(sizeof(BpWord) == 32 + 16 * kBpPairs + 4 * kBpPairs + 8, "BpWord layout");
+static_assert(sizeof(BpWord) == 32 + 32 * kBpPairs + 8, "BpWord layout");
 
 __host__ __device__ __forceinline__ unsigned lut_index(uint64_t posk, uint64_t a) {
   const unsigned k = (unsigned)(posk >> 48) & 0xffu;

@@ -205,8 +205,10 @@ __device__ __forceinline__ RowTerms row_terms(const Tables<CV> &T, int w, int g0
   rt.mask = 0; rt.a0 = 0; rt.a1 = 0;
   if (T.n_bp > 0) {
     const BpWord &W = T.bp[w];
-    for (int k = 0; k < W.n0; ++k) rt.a0 |= ((a << W.l0[k]) >> W.r0[k]) & W.m0[k];
-    for (int k = 0; k < W.n1; ++k) rt.a1 |= ((a << W.l1[k]) >> W.r1[k]) & W.m1[k];
+#pragma unroll 1
+    for (int k = 0; k < W.n0; ++k) { const BpPair q = W.p0[k]; rt.a0 |= ((a << q.l) >> q.r) & q.m; }
+#pragma unroll 1
+    for (int k = 0; k < W.n1; ++k) { const BpPair q = W.p1[k]; rt.a1 |= ((a << q.l) >> q.r) & q.m; }
     rt.mask = (~rt.a0 & ~rt.a1 & W.tt[0]) | (rt.a0 & ~rt.a1 & W.tt[1]) | (~rt.a0 & rt.a1 & W.tt[2]) |
               (rt.a0 & rt.a1 & W.tt[3]);
     return rt;
