@@ -484,6 +484,13 @@ void upload_orbit(dmv_context *ctx) {
   const HostOrbitProgram &H = ctx->host_orbit;
   std::vector<uint64_t> h64 = H.benes_mask;
   h64.insert(h64.end(), H.step_mask.begin(), H.step_mask.end());
+  if (h64.size() & 1) h64.push_back(0);   // 16-byte alignment of the packed 32-bit steps
+  const size_t off_pack64 = h64.size();
+  h64.insert(h64.end(), H.step_pack64.begin(), H.step_pack64.end());
+  if (h64.size() & 1) h64.push_back(0);
+  const size_t off_pack32 = h64.size();
+  for (size_t i = 0; i + 1 < H.step_pack32.size(); i += 2)
+    h64.push_back((uint64_t)H.step_pack32[i] | ((uint64_t)H.step_pack32[i + 1] << 32));
   std::vector<int32_t> h32 = H.benes_delta;
   h32.insert(h32.end(), H.step_shift.begin(), H.step_shift.end());
   ctx->d_orbit64.upload(h64, ctx->stream);
@@ -495,6 +502,9 @@ void upload_orbit(dmv_context *ctx) {
   P.benes_delta = ctx->d_orbit32.ptr;
   P.step_shift = ctx->d_orbit32.ptr + H.benes_delta.size();
   P.characters = reinterpret_cast<const double2 *>(ctx->d_chars.ptr);
+  P.simple = H.simple;
+  P.step_pack64 = ctx->d_orbit64.ptr + off_pack64;
+  P.step_pack32 = H.step_pack32.empty() ? nullptr : reinterpret_cast<const uint4 *>(ctx->d_orbit64.ptr + off_pack32);
   ctx->orbit = P;
 }
 

@@ -83,6 +83,12 @@ struct OrbitProgram {
   const int32_t *step_shift;   // [n_t-1][n_left + n_right]
   const double2 *characters;   // [n_q][n_t][2]  character of (t_j . q_i, flip); conj NOT applied
   int64_t group_order;         // n_q * n_t * (has_flip ? 2 : 1)
+  // fast paths for chains whose every step is one left + one right masked shift (translations):
+  //   step_pack32[j] = {mask_left, mask_right, shift_left, shift_right}   (n_sites <= 32: 32-bit arithmetic)
+  //   step_pack64[3j..3j+2] = {mask_left, mask_right, shift_left | shift_right << 32}
+  int32_t simple;              // 0: general; 1: packed steps are valid
+  const uint4 *step_pack32;    // [n_t - 1] or nullptr
+  const uint64_t *step_pack64; // [3 (n_t - 1)]
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -198,6 +204,50 @@ struct OrbitResult {
   int32_t stab;     // number of elements with g(s) == s   (only filled by orbit_scan<.., true>)
 };
 
+// min_g g(s) for trivial characters (no argmin needed), translation-like chains, <= 32 sites:
+// everything in 32-bit registers, one 16-byte shared-memory load per group element.
+__device__ __forceinline__ uint64_t orbit_min_narrow(const OrbitProgram &P, uint64_t s64) {
+  const uint32_t s = (uint32_t)s64, site_mask = (uint32_t)P.site_mask;
+  uint32_t best = 0xffffffffu;
+  for (int q = 0; q < P.n_q; ++q) {
+    uint32_t cur = s;
+    const uint64_t *bm = P.benes_mask + (int64_t)q * P.n_stages;
+    for (int st = 0; st < P.n_stages; ++st) {
+      const int d = P.benes_delta[st];
+      const uint32_t t = ((cur >> d) ^ cur) & (uint32_t)bm[st];
+      cur ^= t ^ (t << d);
+    }
+    best = min(best, P.has_flip ? min(cur, cur ^ site_mask) : cur);
+#pragma unroll 4
+    for (int j = 0; j < P.n_t - 1; ++j) {
+      const uint4 st = P.step_pack32[j];
+      cur = ((cur << st.z) & st.x) | ((cur >> st.w) & st.y);
+      best = min(best, P.has_flip ? min(cur, cur ^ site_mask) : cur);
+    }
+  }
+  return (uint64_t)best;
+}
+
+__device__ __forceinline__ uint64_t orbit_min_wide(const OrbitProgram &P, uint64_t s) {
+  uint64_t best = ~0ull;
+  for (int q = 0; q < P.n_q; ++q) {
+    uint64_t cur = s;
+    const uint64_t *bm = P.benes_mask + (int64_t)q * P.n_stages;
+    for (int st = 0; st < P.n_stages; ++st) cur = butterfly(cur, bm[st], P.benes_delta[st]);
+    best = min(best, P.has_flip ? min(cur, cur ^ P.site_mask) : cur);
+#pragma unroll 2
+    for (int j = 0; j < P.n_t - 1; ++j) {
+      const uint64_t ml = P.step_pack64[3 * j], mr = P.step_pack64[3 * j + 1], sh = P.step_pack64[3 * j + 2];
+      cur = ((cur << (uint32_t)sh) & ml) | ((cur >> (uint32_t)(sh >> 32)) & mr);
+      best = min(best, P.has_flip ? min(cur, cur ^ P.site_mask) : cur);
+    }
+  }
+  return best;
+}
+
+// representative only (characters trivial): picks the fastest applicable scan
+__device__ __forceinline__ uint64_t orbit_representative(const OrbitProgram &P, uint64_t s);
+
 // Scan the whole group.  COUNT_STAB additionally counts stabiliser elements (needs the full scan).
 // EARLY_EXIT returns as soon as a candidate smaller than `s` is seen (is_representative test).
 template <bool COUNT_STAB, bool EARLY_EXIT>
@@ -236,6 +286,11 @@ __host__ __device__ __forceinline__ OrbitResult orbit_scan(const OrbitProgram &P
     }
   }
   return out;
+}
+
+__device__ __forceinline__ uint64_t orbit_representative(const OrbitProgram &P, uint64_t s) {
+  if (P.simple) return P.step_pack32 ? orbit_min_narrow(P, s) : orbit_min_wide(P, s);
+  return orbit_scan<false, false>(P, s).rep;
 }
 
 // Full-precision stabiliser sum  sum_{g : g(s) = s} Re chi(g)  (only needed with non-trivial characters)

@@ -271,6 +271,20 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
     }
   }
   (void)n_pairs;
+  // packed steps for the translation-like fast paths (exactly one left and one right shift per step)
+  if (H.n_left == 1 && H.n_right == 1) {
+    H.simple = 1;
+    for (size_t j = 0; j < best.steps.size(); ++j) {
+      const uint64_t ml = H.step_mask[2 * j], mr = H.step_mask[2 * j + 1];
+      const uint32_t sl = (uint32_t)H.step_shift[2 * j], sr = (uint32_t)H.step_shift[2 * j + 1];
+      H.step_pack64.push_back(ml); H.step_pack64.push_back(mr);
+      H.step_pack64.push_back((uint64_t)sl | ((uint64_t)sr << 32));
+      if (n_sites <= 32) {
+        H.step_pack32.push_back((uint32_t)ml); H.step_pack32.push_back((uint32_t)mr);
+        H.step_pack32.push_back(sl); H.step_pack32.push_back(sr);
+      }
+    }
+  }
 
   H.characters.resize((size_t)H.n_q * H.n_t * 2 * 2, 0.0);
   for (int q = 0; q < H.n_q; ++q)
@@ -324,6 +338,9 @@ OrbitProgram HostOrbitProgram::view() const {
   P.step_shift = step_shift.data();
   P.characters = reinterpret_cast<const double2 *>(characters.data());
   P.group_order = group_order;
+  P.simple = simple;
+  P.step_pack32 = step_pack32.empty() ? nullptr : reinterpret_cast<const uint4 *>(step_pack32.data());
+  P.step_pack64 = step_pack64.data();
   return P;
 }
 

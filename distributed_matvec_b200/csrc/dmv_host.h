@@ -20,6 +20,9 @@ struct HostOrbitProgram {
   std::vector<uint64_t> step_mask;
   std::vector<int32_t> step_shift;
   std::vector<double> characters;  // interleaved, [n_q][n_t][2][2]
+  std::vector<uint32_t> step_pack32;  // 4 words per step (empty unless simple and n_sites <= 32)
+  std::vector<uint64_t> step_pack64;  // 3 words per step (empty unless simple)
+  int32_t simple = 0;
   OrbitProgram view() const;       // pointers into the host vectors
 };
 

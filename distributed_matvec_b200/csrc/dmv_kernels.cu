@@ -95,8 +95,12 @@ __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int pro
   size_t n64 = 0, n32 = 0;
   if (proj == PROJ_GROUP) {
     const int np = p.orbit.n_left + p.orbit.n_right;
-    n64 = (size_t)p.orbit.n_q * p.orbit.n_stages + (size_t)(p.orbit.n_t - 1) * np;
-    n32 = (size_t)p.orbit.n_stages + (size_t)(p.orbit.n_t - 1) * np;
+    const size_t steps = (size_t)(p.orbit.n_t - 1);
+    n64 = (size_t)p.orbit.n_q * p.orbit.n_stages;
+    if (n64 & 1) ++n64;   // keep the packed steps 16-byte aligned
+    n32 = (size_t)p.orbit.n_stages;
+    if (p.orbit.simple) n64 += p.orbit.step_pack32 ? 2 * steps : 3 * steps;   // packed steps only
+    else { n64 += steps * np; n32 += steps * np; }
   }
   off += 8 * n64;
   L.orbit32 = off; off += 4 * n32;
@@ -153,15 +157,27 @@ __device__ __forceinline__ Tables<CV> stage_tables(const KernelParams &p, unsign
     const int np = T.orbit.n_left + T.orbit.n_right;
     uint64_t *s64 = reinterpret_cast<uint64_t *>(smem + L.orbit64);
     int32_t *s32 = reinterpret_cast<int32_t *>(smem + L.orbit32);
-    const int nb = T.orbit.n_q * T.orbit.n_stages, ns = (T.orbit.n_t - 1) * np;
+    const int nb = T.orbit.n_q * T.orbit.n_stages, steps = T.orbit.n_t - 1;
+    const int nb_pad = nb + (nb & 1);
     stage(s64, p.orbit.benes_mask, nb);
-    stage(s64 + nb, p.orbit.step_mask, ns);
     stage(s32, p.orbit.benes_delta, T.orbit.n_stages);
-    stage(s32 + T.orbit.n_stages, p.orbit.step_shift, ns);
     T.orbit.benes_mask = s64;
-    T.orbit.step_mask = s64 + nb;
     T.orbit.benes_delta = s32;
-    T.orbit.step_shift = s32 + T.orbit.n_stages;
+    if (T.orbit.simple) {
+      // only the packed steps live in shared memory; the general arrays (rare paths) stay in global
+      if (p.orbit.step_pack32) {
+        stage(s64 + nb_pad, reinterpret_cast<const uint64_t *>(p.orbit.step_pack32), 2 * steps);
+        T.orbit.step_pack32 = reinterpret_cast<const uint4 *>(s64 + nb_pad);
+      } else {
+        stage(s64 + nb_pad, p.orbit.step_pack64, 3 * steps);
+        T.orbit.step_pack64 = s64 + nb_pad;
+      }
+    } else {
+      stage(s64 + nb_pad, p.orbit.step_mask, steps * np);
+      stage(s32 + T.orbit.n_stages, p.orbit.step_shift, steps * np);
+      T.orbit.step_mask = s64 + nb_pad;
+      T.orbit.step_shift = s32 + T.orbit.n_stages;
+    }
   }
   T.index = p.index;
   if (T.index.mode == INDEX_RANK) {
@@ -282,9 +298,11 @@ __device__ __forceinline__ bool route(const KernelParams &p, const OrbitProgram 
     if (inv < beta) { beta = inv; c = v_scale(c, p.inversion_character); }
   } else if (PROJ == PROJ_GROUP) {
     if (active) {
-      const OrbitResult r = orbit_scan<false, false>(orbit, beta);
-      beta = r.rep;
-      if (!orbit.trivial_characters) {
+      if (orbit.trivial_characters) {
+        beta = orbit_representative(orbit, beta);
+      } else {
+        const OrbitResult r = orbit_scan<false, false>(orbit, beta);
+        beta = r.rep;
         const double2 chi = __ldg(orbit.characters + r.arg);   // state_info returns conj(chi)
         c = v_mul(c, v_make(chi.x, -chi.y, (V *)nullptr));
       }
@@ -552,8 +570,11 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
       const uint64_t raw = qb[pos];
       V h = qc[pos];
       const unsigned src = ql[pos];
-      const OrbitResult r = orbit_scan<false, false>(orbit, raw);
-      if (!orbit.trivial_characters) {
+      OrbitResult r;
+      if (orbit.trivial_characters) {
+        r.rep = orbit_representative(orbit, raw);
+      } else {
+        r = orbit_scan<false, false>(orbit, raw);
         const double2 chi = __ldg(orbit.characters + r.arg);   // chi(g), not conjugated (see header)
         h = v_mul(h, v_make(chi.x, chi.y, (V *)nullptr));
       }
