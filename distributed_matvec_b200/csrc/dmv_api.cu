@@ -317,6 +317,15 @@ struct dmv_context {
   DevBuf<uint64_t> d_out_betas, d_in_betas;
   DevBuf<double> d_out_coeffs, d_in_coeffs;
   int record_width = 2;                    // doubles per coefficient of the current buckets
+  int plan_grid = 0;                       // CTAs of the planned launches (exact warp-private regions)
+  bool peer_direct = false;                // records are stored straight into the peers' incoming buffers
+  int ptr_width = 0;                       // record width the destination pointer table was built for
+  DevBuf<unsigned long long> d_warp_counts;
+  DevBuf<int64_t> d_warp_offsets, d_out_capacity;
+  DevBuf<uint64_t *> d_out_betas_ptr;
+  DevBuf<double *> d_out_coeffs_ptr;
+  std::vector<uint64_t *> h_out_betas_ptr;   // where the records for every destination go (local bucket or peer)
+  std::vector<double *> h_out_coeffs_ptr;
   int64_t number_terms = 0;
   DevBuf<unsigned long long> d_status;
   // streams
@@ -374,6 +383,12 @@ KernelParams base_params(dmv_context *ctx) {
   p.out_coeffs = ctx->d_out_coeffs.ptr;
   p.out_offset = ctx->d_out_offset.ptr;
   p.out_count = ctx->d_out_count.ptr;
+  p.grid_blocks = ctx->num_ranks > 1 ? ctx->plan_grid : 0;
+  p.warp_offsets = ctx->d_warp_offsets.ptr;
+  p.warp_counts = ctx->d_warp_counts.ptr;
+  p.out_betas_ptr = ctx->d_out_betas_ptr.ptr;
+  p.out_coeffs_ptr = ctx->d_out_coeffs_ptr.ptr;
+  p.out_capacity = ctx->d_out_capacity.ptr;
   p.status = ctx->d_status.ptr;
   p.row_begin = 0;
   p.row_end = ctx->n_states;
@@ -552,7 +567,7 @@ VecStage stage_vectors(dmv_context *ctx, int elt, const void *x, void *y) {
     v.x_dev = ctx->d_x.ptr;
     // the column traversal only reads x[i] of the rows it is generating: upload in row chunks on a copy
     // stream and start generating as soon as the first chunk has landed (see do_generate)
-    if (!use_pull(ctx) && ctx->n_states >= (1 << 16)) v.x_host_pending = x;
+    if (!use_pull(ctx) && ctx->num_ranks == 1 && ctx->n_states >= (1 << 16)) v.x_host_pending = x;
     else CUDA_CHECK(cudaMemcpyAsync(ctx->d_x.ptr, x, v.bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
   if (is_device_pointer(y)) { v.y_dev = y; v.y_host = false; }
@@ -571,29 +586,68 @@ void finish_vectors(dmv_context *ctx, const VecStage &v) {
   CUDA_CHECK(cudaEventRecord(ctx->ev[5], ctx->stream));
 }
 
+void upload_out_pointers(dmv_context *ctx) {
+  ctx->d_out_betas_ptr.upload(ctx->h_out_betas_ptr, ctx->stream);
+  ctx->d_out_coeffs_ptr.upload(ctx->h_out_coeffs_ptr, ctx->stream);
+}
+
+// One counting pass.  Record counts do not depend on x, and the grid-stride tile loop is deterministic,
+// so the pass yields (a) the exact number of records for every destination and (b) for num_ranks <= 32
+// the exact share of every warp, from which each warp gets a private, exactly sized slice of every
+// destination region (prefix sums): the real pass needs no slot-claim atomics at all.
 void do_plan(dmv_context *ctx) {
   require_states(ctx);
   const int P = ctx->num_ranks;
+  const bool exact_regions = P <= 32;
+  ctx->plan_grid = planned_grid(ctx->n_states);
+  const size_t n_warps = (size_t)ctx->plan_grid * kWarpsPerCta;
   ctx->d_out_count.alloc(P);
+  ctx->d_warp_counts.alloc(n_warps * P);
   CUDA_CHECK(cudaMemsetAsync(ctx->d_out_count.ptr, 0, sizeof(unsigned long long) * P, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_warp_counts.ptr, 0, sizeof(unsigned long long) * n_warps * P, ctx->stream));
   KernelParams p = base_params(ctx);
+  p.grid_blocks = ctx->plan_grid;
   select_tables(ctx, p, false, ctx->complex_coefficients);
   // counting pass: element type does not matter
   launch_generate(p, ctx->proj, ctx->complex_coefficients, false, /*count_only=*/true, ctx->stream);
-  std::vector<unsigned long long> counts(P);
-  CUDA_CHECK(cudaMemcpyAsync(counts.data(), ctx->d_out_count.ptr, sizeof(unsigned long long) * P,
-                             cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  std::vector<unsigned long long> counts(P, 0);
+  std::vector<int64_t> warp_offsets(n_warps * P, 0);
+  if (exact_regions) {
+    std::vector<unsigned long long> wc(n_warps * P);
+    CUDA_CHECK(cudaMemcpyAsync(wc.data(), ctx->d_warp_counts.ptr, sizeof(unsigned long long) * wc.size(),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int d = 0; d < P; ++d)
+      for (size_t w = 0; w < n_warps; ++w) {
+        warp_offsets[w * P + d] = (int64_t)counts[d];
+        counts[d] += wc[w * P + d];
+      }
+  } else {
+    CUDA_CHECK(cudaMemcpyAsync(counts.data(), ctx->d_out_count.ptr, sizeof(unsigned long long) * P,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->d_warp_offsets.upload(warp_offsets, ctx->stream);
   ctx->send_counts.assign(P, 0);
   ctx->number_terms = 0;
   for (int d = 0; d < P; ++d) { ctx->send_counts[d] = (int64_t)counts[d]; ctx->number_terms += (int64_t)counts[d]; }
   ctx->h_out_offset.assign(P + 1, 0);
-  for (int d = 0; d < P; ++d)
-    ctx->h_out_offset[d + 1] = ctx->h_out_offset[d] + (d == ctx->rank ? 0 : ctx->send_counts[d]);
+  std::vector<int64_t> capacity(P, 0);
+  for (int d = 0; d < P; ++d) {
+    capacity[d] = (d == ctx->rank) ? 0 : ctx->send_counts[d];
+    ctx->h_out_offset[d + 1] = ctx->h_out_offset[d] + capacity[d];
+  }
   ctx->d_out_offset.upload(ctx->h_out_offset, ctx->stream);
+  ctx->d_out_capacity.upload(capacity, ctx->stream);
   const int64_t total_out = ctx->h_out_offset[P];
   ctx->d_out_betas.alloc((size_t)total_out);
   ctx->d_out_coeffs.alloc((size_t)total_out * 2);
+  // by default the records of destination d go to the local bucket d (sent with NCCL afterwards);
+  // the coefficient base assumes the widest record (re-derived per product, see do_generate)
+  ctx->h_out_betas_ptr.assign(P, nullptr);
+  ctx->h_out_coeffs_ptr.assign(P, nullptr);
+  ctx->peer_direct = false;
+  ctx->ptr_width = 0;
   ctx->recv_counts.assign(P, -1);
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   ctx->planned = true;
@@ -617,6 +671,18 @@ void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev,
   p.x = x_dev;
   p.y = y_dev;
   const bool cv = complex_values(ctx, elt);
+  if (ctx->num_ranks > 1 && !ctx->peer_direct && ctx->ptr_width != (cv ? 2 : 1)) {
+    // local buckets: destination d's records start at out_offset[d] (coefficients: width doubles each)
+    const int width = cv ? 2 : 1;
+    for (int d = 0; d < ctx->num_ranks; ++d) {
+      ctx->h_out_betas_ptr[d] = ctx->d_out_betas.ptr + ctx->h_out_offset[d];
+      ctx->h_out_coeffs_ptr[d] = ctx->d_out_coeffs.ptr + ctx->h_out_offset[d] * width;
+    }
+    upload_out_pointers(ctx);
+    p.out_betas_ptr = ctx->d_out_betas_ptr.ptr;
+    p.out_coeffs_ptr = ctx->d_out_coeffs_ptr.ptr;
+    ctx->ptr_width = width;
+  }
   ctx->record_width = cv ? 2 : 1;
   select_tables(ctx, p, false, cv);
   if (!x_host_pending) {

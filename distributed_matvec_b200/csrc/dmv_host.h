@@ -59,6 +59,15 @@ struct KernelParams {
   uint64_t *out_betas; double *out_coeffs;
   const int64_t *out_offset;      // [num_ranks + 1] device
   unsigned long long *out_count;  // [num_ranks] device, reset before each generate
+  // exact warp-private regions (num_ranks <= 32): the grid-stride tile loop is deterministic, so the
+  // counting pass records how many records every warp emits per destination and the real pass starts
+  // each warp at the prefix sum -- no slot-claim atomics, no slack, deterministic bucket layout.
+  int32_t grid_blocks;              // 0: size the grid from occupancy; else exactly this many CTAs
+  const int64_t *warp_offsets;      // [grid_blocks * 8][num_ranks]
+  unsigned long long *warp_counts;  // counting pass output, same shape
+  uint64_t *const *out_betas_ptr;   // [num_ranks]: base of MY region in the destination's record buffer
+  double *const *out_coeffs_ptr;    //              (a local bucket, or the peer's incoming buffer over NVLink)
+  const int64_t *out_capacity;      // [num_ranks]
   // emit_all: computeOffDiag mode -- every record goes to one flat output with its locale key
   int32_t emit_all; uint8_t *out_keys;
   // error reporting: status[0] = number of bad records, status[1] = first bad state, status[2] = overflow
@@ -94,5 +103,7 @@ void launch_enumerate(const OrbitProgram &P, Projection proj, uint64_t site_mask
                       const unsigned long long *chunk_offset, uint64_t *out, double *out_norms,
                       bool write_pass, cudaStream_t stream);
 int64_t launch_counter();
+int planned_grid(int64_t rows);
+constexpr int kWarpsPerCta = 8;
 
 }  // namespace dmv

@@ -289,7 +289,7 @@ __device__ __forceinline__ void diagonal(const Tables<CV> &T, int n_diag, uint64
 // All 32 lanes must call it (warp collectives); `active` lanes carry a record.
 template <int PROJ, bool CV, bool CE, bool COUNT_ONLY>
 __device__ __forceinline__ bool route(const KernelParams &p, const OrbitProgram &orbit, bool active,
-                                      uint64_t &beta, typename ValT<CV>::type &c) {
+                                      uint64_t &beta, typename ValT<CV>::type &c, unsigned long long &cur) {
   using V = typename ValT<CV>::type;
   const unsigned lane = threadIdx.x & 31u;
   if (PROJ == PROJ_INVERSION) {
@@ -329,8 +329,32 @@ __device__ __forceinline__ bool route(const KernelParams &p, const OrbitProgram 
     return false;
   }
 
+  if (p.num_ranks <= 32 && (p.num_ranks > 1 || COUNT_ONLY)) {
+    // ---- remote records: lane d keeps this warp's cursor into destination d's region (exact regions
+    // from the plan: no atomics).  In the counting pass every record (own ones too) is counted.
+    const bool remote = active && (COUNT_ONLY || owner != p.rank);
+    for (int d = 0; d < p.num_ranks; ++d) {   // warp-uniform
+      const bool mine = remote && owner == d;
+      const unsigned m = __ballot_sync(0xffffffffu, mine);
+      if (m) {
+        const unsigned long long base = __shfl_sync(0xffffffffu, cur, d);
+        if (!COUNT_ONLY && mine) {
+          const int64_t slot = (int64_t)base + __popc(m & ((1u << lane) - 1u));
+          if (slot < p.out_capacity[d]) {
+            p.out_betas_ptr[d][slot] = beta;
+            reinterpret_cast<V *>(p.out_coeffs_ptr[d])[slot] = c;
+          } else {
+            atomicAdd(p.status + 2, 1ull);
+          }
+        }
+        if ((int)lane == d) cur += __popc(m);
+      }
+    }
+    if (COUNT_ONLY) return false;
+    return active && owner == p.rank;
+  }
   if (p.num_ranks > 1) {
-    // ---- remote records: warp-aggregated slot claim per destination, then scattered 8/16-byte stores
+    // ---- more than 32 ranks: warp-aggregated slot claim per destination with global atomics
     const bool remote = active && (COUNT_ONLY || owner != p.rank);
     const unsigned remote_mask = __ballot_sync(0xffffffffu, remote);
     if (remote) {
@@ -353,10 +377,6 @@ __device__ __forceinline__ bool route(const KernelParams &p, const OrbitProgram 
     }
     if (COUNT_ONLY) return false;
     return active && owner == p.rank;
-  } else if (COUNT_ONLY) {
-    const unsigned m = __ballot_sync(0xffffffffu, active);
-    if (lane == 0 && m) atomicAdd(p.out_count, (unsigned long long)__popc(m));
-    return false;
   }
   return active;
 }
@@ -418,15 +438,15 @@ __device__ __forceinline__ void locate2(const StateIndex &ix, bool a0, uint64_t 
 template <int PROJ, bool CV, bool CE, bool COUNT_ONLY>
 __device__ __forceinline__ void drain(const KernelParams &p, const OrbitProgram &orbit, const StateIndex &index,
                                       const uint64_t *qb, const typename ValT<CV>::type *qc, unsigned head,
-                                      unsigned n) {
+                                      unsigned n, unsigned long long &cur) {
   using V = typename ValT<CV>::type;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned p0 = (head + lane) & (kQueue - 1), p1 = (head + lane + 32) & (kQueue - 1);
   bool a0 = lane < n, a1 = lane + 32 < n;
   uint64_t k0 = a0 ? qb[p0] : 0ull, k1 = a1 ? qb[p1] : 0ull;
   V c0 = a0 ? qc[p0] : v_make(0.0, 0.0, (V *)nullptr), c1 = a1 ? qc[p1] : v_make(0.0, 0.0, (V *)nullptr);
-  a0 = route<PROJ, CV, CE, COUNT_ONLY>(p, orbit, a0, k0, c0);
-  if (n > 32) a1 = route<PROJ, CV, CE, COUNT_ONLY>(p, orbit, a1, k1, c1);   // n is warp-uniform
+  a0 = route<PROJ, CV, CE, COUNT_ONLY>(p, orbit, a0, k0, c0, cur);
+  if (n > 32) a1 = route<PROJ, CV, CE, COUNT_ONLY>(p, orbit, a1, k1, c1, cur);   // n is warp-uniform
   else a1 = false;
   if (COUNT_ONLY) return;
   int64_t i0, i1;
@@ -449,6 +469,11 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
   V *qc = reinterpret_cast<V *>(smem + L.queues + (size_t)kWarps * kQueue * 8) + warp * kQueue;
   unsigned head = 0, count = 0;  // warp-uniform
   const bool any_s_out = p.any_s_out != 0;
+  // lane d: cursor of this warp in destination d's region (see route())
+  const int64_t gw = (int64_t)blockIdx.x * kWarps + warp;
+  unsigned long long cur = 0;
+  if (!COUNT_ONLY && p.num_ranks > 1 && p.num_ranks <= 32 && (int)lane < p.num_ranks)
+    cur = (unsigned long long)p.warp_offsets[gw * p.num_ranks + lane];
 
   const int64_t n_rows = p.row_end - p.row_begin;
   const int64_t n_tiles = (n_rows + 31) / 32;
@@ -503,7 +528,7 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
         count += __popc(m);
         if (count >= 64) {
           __syncwarp();
-          drain<PROJ, CV, CE, COUNT_ONLY>(p, T.orbit, T.index, qb, qc, head, 64);
+          drain<PROJ, CV, CE, COUNT_ONLY>(p, T.orbit, T.index, qb, qc, head, 64, cur);
           head = (head + 64) & (kQueue - 1);
           count -= 64;
           __syncwarp();
@@ -513,8 +538,10 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
   }
   if (count > 0) {
     __syncwarp();
-    drain<PROJ, CV, CE, COUNT_ONLY>(p, T.orbit, T.index, qb, qc, head, count);
+    drain<PROJ, CV, CE, COUNT_ONLY>(p, T.orbit, T.index, qb, qc, head, count, cur);
   }
+  if (COUNT_ONLY && p.num_ranks <= 32 && (int)lane < p.num_ranks)
+    p.warp_counts[gw * p.num_ranks + lane] = cur;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -851,6 +878,19 @@ int grid_for(int64_t work_items, int per_block, int max_blocks) {
   return (int)b;
 }
 
+}  // namespace
+int planned_grid(int64_t rows) {   // grid of the planned (multi-rank) launches: fixed, not occupancy-derived
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  int64_t b = ((rows + 31) / 32 + kWarps - 1) / kWarps;
+  if (b < 1) b = 1;
+  if (b > (int64_t)n * 4) b = (int64_t)n * 4;
+  return (int)b;
+}
+namespace {
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -874,7 +914,7 @@ void launch_generate_t(const KernelParams &p, cudaStream_t stream) {
   if (per_sm < 1) per_sm = 1;
   const int64_t tiles = (p.row_end - p.row_begin + 31) / 32;
   // grid = a whole number of waves of resident CTAs (148 SMs x per_sm), or fewer when the work is small
-  const int blocks = grid_for(tiles, kWarps, sm_count() * per_sm);
+  const int blocks = p.grid_blocks > 0 ? p.grid_blocks : grid_for(tiles, kWarps, sm_count() * per_sm);
   kernel<<<blocks, kThreads, L.total, stream>>>(p);
   DMV_CUDA_CHECK(cudaGetLastError());
   g_launches++;
