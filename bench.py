@@ -238,6 +238,8 @@ def main():
         op = dop.op
     else:
         op = Operator(matrix, device=local_rank)
+    if os.environ.get("DMV_EXCHANGE"):
+        op.set_option("exchange", int(os.environ["DMV_EXCHANGE"]))
     op.basis.build()
     n_local = op.basis.numberStates()
     op.use_torch_stream()
@@ -338,7 +340,8 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "c128" if cplx else "f64", "data": "synthetic",
         "config": {"workload": args.workload, "basis_states": n_total, "off_diag_terms": nnz_total,
-                   "terms_per_s": nnz_total / (ms_per_step * 1e-3), "partition": f"hash{world}",
+                   "terms_per_s": nnz_total / (ms_per_step * 1e-3), "partition": f"hash{world}", "exchange": ("peer-direct NVLink stores" if op.info("peer_direct") else
+                                                               ("nccl send/recv" if world > 1 else "none")),
                    "x": "uniform(-0.5,0.5) seed 42", "l2": "flushed between timed iterations (256 MB write)",
                    "ms_best_step": ms_best, "basis_build_s": build_s},
         "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "states/s", "ms_per_step": e2e_ms,

@@ -86,6 +86,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi &nccl() {
@@ -100,7 +101,7 @@ NcclApi &nccl() {
     if (!api.handle) return;
 #define LOAD(sym) api.sym = reinterpret_cast<decltype(api.sym)>(dlsym(api.handle, "nccl" #sym))
     LOAD(GetUniqueId); LOAD(CommInitRank); LOAD(CommDestroy); LOAD(GroupStart); LOAD(GroupEnd);
-    LOAD(Send); LOAD(Recv); LOAD(AllGather); LOAD(GetErrorString);
+    LOAD(Send); LOAD(Recv); LOAD(AllGather); LOAD(AllReduce); LOAD(GetErrorString);
 #undef LOAD
   });
   if (!api.handle || !api.Send) throw std::runtime_error("NCCL (libnccl.so.2) is not available");
@@ -320,6 +321,10 @@ struct dmv_context {
   int plan_grid = 0;                       // CTAs of the planned launches (exact warp-private regions)
   bool peer_direct = false;                // records are stored straight into the peers' incoming buffers
   int ptr_width = 0;                       // record width the destination pointer table was built for
+  int opt_exchange = -1;                   // -1 auto (peer-direct when possible), 0 NCCL send/recv, 1 peer-direct
+  std::vector<void *> peer_betas, peer_coeffs;   // IPC-mapped incoming buffers of the peers
+  std::vector<int64_t> my_offset_in_peer;         // first slot of MY region in every peer's incoming buffer
+  DevBuf<int> d_barrier;
   DevBuf<unsigned long long> d_warp_counts;
   DevBuf<int64_t> d_warp_offsets, d_out_capacity;
   DevBuf<uint64_t *> d_out_betas_ptr;
@@ -338,6 +343,8 @@ struct dmv_context {
   ncclComm_t comm = nullptr;
 
   ~dmv_context() {
+    for (void *q : peer_betas) if (q) cudaIpcCloseMemHandle(q);
+    for (void *q : peer_coeffs) if (q) cudaIpcCloseMemHandle(q);
     if (comm) nccl().CommDestroy(comm);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
     for (auto &e : ev_chunk) if (e) cudaEventDestroy(e);
@@ -671,6 +678,19 @@ void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev,
   p.x = x_dev;
   p.y = y_dev;
   const bool cv = complex_values(ctx, elt);
+  if (ctx->num_ranks > 1 && ctx->peer_direct && ctx->ptr_width != (cv ? 2 : 1)) {
+    // peer-direct: destination d's records are stored straight into d's incoming buffer over NVLink
+    const int width = cv ? 2 : 1;
+    for (int d = 0; d < ctx->num_ranks; ++d) {
+      if (d == ctx->rank) { ctx->h_out_betas_ptr[d] = nullptr; ctx->h_out_coeffs_ptr[d] = nullptr; continue; }
+      ctx->h_out_betas_ptr[d] = reinterpret_cast<uint64_t *>(ctx->peer_betas[d]) + ctx->my_offset_in_peer[d];
+      ctx->h_out_coeffs_ptr[d] = reinterpret_cast<double *>(ctx->peer_coeffs[d]) + ctx->my_offset_in_peer[d] * width;
+    }
+    upload_out_pointers(ctx);
+    p.out_betas_ptr = ctx->d_out_betas_ptr.ptr;
+    p.out_coeffs_ptr = ctx->d_out_coeffs_ptr.ptr;
+    ctx->ptr_width = width;
+  }
   if (ctx->num_ranks > 1 && !ctx->peer_direct && ctx->ptr_width != (cv ? 2 : 1)) {
     // local buckets: destination d's records start at out_offset[d] (coefficients: width doubles each)
     const int width = cv ? 2 : 1;
@@ -754,6 +774,87 @@ struct OutArg {  // device view of an output array, copied back by finish()
 };
 }  // namespace
 
+
+
+// One-time exchange of the plan: every rank learns how many records each peer sends it; then, when
+// possible, the peers' incoming buffers are mapped (CUDA IPC over NVLink) so that k_generate can store
+// remote records directly where the owner will read them.
+void setup_exchange(dmv_context *ctx) {
+  NcclApi &N = nccl();
+  const int P = ctx->num_ranks;
+  for (auto &q : ctx->peer_betas) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+  for (auto &q : ctx->peer_coeffs) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+  DevBuf<int64_t> d_send, d_all;
+  d_send.upload(ctx->send_counts, ctx->stream);
+  d_all.alloc((size_t)P * P);
+  NCCL_CHECK(N.AllGather(d_send.ptr, d_all.ptr, (size_t)P, ncclInt64, ctx->comm, ctx->stream));
+  std::vector<int64_t> all((size_t)P * P);   // all[r * P + q]: records r emits for q (own ones included)
+  CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.ptr, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  int64_t total_in = 0;
+  for (int q = 0; q < P; ++q) {
+    ctx->recv_counts[q] = (q == ctx->rank) ? 0 : all[(size_t)q * P + ctx->rank];
+    total_in += ctx->recv_counts[q];
+  }
+  ctx->d_in_betas.alloc((size_t)total_in);
+  ctx->d_in_coeffs.alloc((size_t)total_in * 2);
+  ctx->d_barrier.alloc(1);
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_barrier.ptr, 0, sizeof(int), ctx->stream));
+  ctx->peer_direct = false;
+  if (ctx->opt_exchange == 0 || P > 32) return;
+
+  // ---- try to map the peers' incoming buffers
+  struct Handles { cudaIpcMemHandle_t betas, coeffs; int ok; int pad[15]; };
+  static_assert(sizeof(Handles) % 8 == 0, "handle block");
+  Handles mine{};
+  mine.ok = (cudaIpcGetMemHandle(&mine.betas, ctx->d_in_betas.ptr) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine.coeffs, ctx->d_in_coeffs.ptr) == cudaSuccess) ? 1 : 0;
+  cudaGetLastError();
+  DevBuf<char> d_mine, d_handles;
+  d_mine.alloc(sizeof(Handles));
+  d_handles.alloc(sizeof(Handles) * P);
+  CUDA_CHECK(cudaMemcpyAsync(d_mine.ptr, &mine, sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_CHECK(N.AllGather(d_mine.ptr, d_handles.ptr, sizeof(Handles), ncclChar, ctx->comm, ctx->stream));
+  std::vector<Handles> handles(P);
+  CUDA_CHECK(cudaMemcpyAsync(handles.data(), d_handles.ptr, sizeof(Handles) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  int ok = 1;
+  for (int q = 0; q < P; ++q) ok &= handles[q].ok;
+  ctx->peer_betas.assign(P, nullptr);
+  ctx->peer_coeffs.assign(P, nullptr);
+  if (ok) {
+    for (int q = 0; q < P && ok; ++q) {
+      if (q == ctx->rank) continue;
+      if (cudaIpcOpenMemHandle(&ctx->peer_betas[q], handles[q].betas, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&ctx->peer_coeffs[q], handles[q].coeffs, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        ok = 0;
+        cudaGetLastError();
+      }
+    }
+  }
+  // everybody must agree
+  int agree = ok;
+  CUDA_CHECK(cudaMemcpyAsync(ctx->d_barrier.ptr, &agree, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_CHECK(N.AllReduce(ctx->d_barrier.ptr, ctx->d_barrier.ptr, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(&agree, ctx->d_barrier.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (!agree) {
+    for (auto &q : ctx->peer_betas) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    for (auto &q : ctx->peer_coeffs) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    if (ctx->opt_exchange == 1) throw std::runtime_error("peer-direct exchange requested but CUDA IPC mapping failed");
+    return;
+  }
+  // my region inside peer q's incoming buffer: after the regions of the ranks before me (q itself sends nothing)
+  ctx->my_offset_in_peer.assign(P, 0);
+  for (int q = 0; q < P; ++q) {
+    int64_t off = 0;
+    for (int r = 0; r < ctx->rank; ++r)
+      if (r != q) off += all[(size_t)r * P + q];
+    ctx->my_offset_in_peer[q] = off;
+  }
+  ctx->peer_direct = true;
+  ctx->ptr_width = 0;
+}
 
 // =================================================================================================
 extern "C" {
@@ -879,6 +980,10 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
     if (value != -1 && value != 0 && value != 2) throw std::runtime_error("index: -1 auto, 0 directory, 2 rank");
     ctx->opt_index = (int)value;
     if (ctx->n_states >= 0) { CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); select_index_mode(ctx); }
+  } else if (key == "exchange") {
+    if (value < -1 || value > 1) throw std::runtime_error("exchange: -1 auto, 0 NCCL send/recv, 1 peer-direct");
+    ctx->opt_exchange = (int)value;
+    ctx->planned = false;
   } else if (key == "bitparallel") {
     ctx->opt_bitparallel = value != 0;
     ctx->planned = false;
@@ -893,6 +998,7 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
   if (!ctx) return -1;
   if (key == "index_mode") return ctx->index_mode;
   if (key == "pull") return use_pull(ctx) ? 1 : 0;
+  if (key == "peer_direct") return ctx->peer_direct ? 1 : 0;
   if (key == "projection") return (int64_t)ctx->proj;
   if (key == "n_groups") return (int64_t)ctx->h_push.groups.size();
   if (key == "bp_words") return (int64_t)ctx->h_push.bp.size();
@@ -1154,28 +1260,23 @@ int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
   if (!ctx->comm) throw std::runtime_error("dmv_matvec on several ranks needs dmv_comm_init");
   NcclApi &N = nccl();
   if (!ctx->planned) do_plan(ctx);
-  if (ctx->recv_counts[0] < 0) {
-    // one-time exchange of the plan: every rank learns how many records each peer will send it
-    DevBuf<int64_t> d_send, d_all;
-    d_send.upload(ctx->send_counts, ctx->stream);
-    d_all.alloc((size_t)P * P);
-    NCCL_CHECK(N.AllGather(d_send.ptr, d_all.ptr, (size_t)P, ncclInt64, ctx->comm, ctx->stream));
-    std::vector<int64_t> all((size_t)P * P);
-    CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.ptr, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    int64_t total_in = 0;
-    for (int q = 0; q < P; ++q) {
-      ctx->recv_counts[q] = (q == ctx->rank) ? 0 : all[(size_t)q * P + ctx->rank];
-      total_in += ctx->recv_counts[q];
-    }
-    ctx->d_in_betas.alloc((size_t)total_in);
-    ctx->d_in_coeffs.alloc((size_t)total_in * 2);
-  }
+  if (ctx->recv_counts[0] < 0) setup_exchange(ctx);
+  auto barrier = [&]() {
+    NCCL_CHECK(N.AllReduce(ctx->d_barrier.ptr, ctx->d_barrier.ptr, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
+  };
+  // peer-direct: nobody may overwrite my incoming buffer before I have consumed the previous product
+  if (ctx->peer_direct) barrier();
   VecStage v = stage_vectors(ctx, elt, x, y);
   do_generate(ctx, elt, v.x_dev, v.y_dev, v.x_host_pending);
   CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
   const int width = ctx->record_width;
   int64_t total_in = 0;
+  if (ctx->peer_direct) {
+    // the records are already in the peers' incoming buffers (NVLink stores issued by k_generate, overlapped
+    // with generation); the all-reduce is the "every sender has finished" fence
+    barrier();
+    for (int q = 0; q < P; ++q) total_in += ctx->recv_counts[q];
+  } else {
   NCCL_CHECK(N.GroupStart());
   {
     int64_t in_off = 0;
@@ -1196,6 +1297,7 @@ int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
     total_in = in_off;
   }
   NCCL_CHECK(N.GroupEnd());
+  }
   CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
   do_accumulate(ctx, elt, total_in, ctx->d_in_betas.ptr, ctx->d_in_coeffs.ptr, v.y_dev);
   finish_vectors(ctx, v);

@@ -27,6 +27,7 @@ def main():
     for name in names:
         basis, matrix = load_config_from_yaml(os.path.join(ROOT, "data", name + ".yaml"))
         dop = DistributedOperator(matrix, device=local)
+        dop.op.set_option("exchange", int(os.environ.get("DMV_EXCHANGE", "-1")))
         dop.basis.build()
         mine = dop.basis.representatives()
         o_reps, _ = po.enumerate_states(basis)
@@ -54,7 +55,8 @@ def main():
             dist.all_reduce(flag)
             if rank == 0:
                 print(f"{name:28s} P={world} {'c128' if cplx else 'f64 '} N={o_reps.shape[0]} basis_ok={ok_basis} "
-                      f"err_host={e1:.1e} err_dev={e2:.1e} {'OK' if int(flag) == 0 else 'FAIL'}", flush=True)
+                      f"err_host={e1:.1e} err_dev={e2:.1e} peer_direct={dop.op.info('peer_direct')} "
+                      f"{'OK' if int(flag) == 0 else 'FAIL'}", flush=True)
             failures += int(flag)
         dop.op.close()
     dist.barrier()
