@@ -296,7 +296,8 @@ struct dmv_context {
   int opt_index = -1;   // -1 auto, 0 directory search, 2 combinadic rank
   int opt_bitparallel = 1;  // 0: walk the groups one by one even when the bit-parallel test applies
   int index_mode = INDEX_DIRECTORY;
-  DevBuf<uint32_t> d_binom;
+  DevBuf<uint32_t> d_binom, d_lin_a, d_lin_b;
+  int lin_bits = 0;
   int binom_stride = 0;
   uint64_t rank_total = 0;
   // representatives of this rank
@@ -378,6 +379,9 @@ KernelParams base_params(dmv_context *ctx) {
   p.index.n_sites = ctx->n_sites;
   p.index.weight = ctx->hamming_weight;
   p.index.site_mask = ctx->site_mask;
+  p.index.lin_a = ctx->d_lin_a.ptr;
+  p.index.lin_b = ctx->d_lin_b.ptr;
+  p.index.lin_bits = ctx->lin_bits;
   p.rank_total = ctx->rank_total;
   p.norms = ctx->d_norms.ptr;
   p.diag = ctx->d_diag.ptr;     p.n_diag = (int)ctx->h_diag.size();
@@ -452,35 +456,57 @@ struct Binomials {
 const Binomials &binom() { static Binomials b; return b; }
 
 // Which state -> index kernel applies (the reference's per-basis `state_index_kernel`, FFI:90-93).
+//   auto (-1): identity when it applies; two-table Lin lookup for full fixed-Hamming bases on one rank
+//   (<= 40 sites); directory search otherwise.  0 forces the directory, 2 the combinadic rank, 3 Lin.
 void select_index_mode(dmv_context *ctx) {
   ctx->index_mode = INDEX_DIRECTORY;
   if (ctx->identity_index && ctx->num_ranks == 1) { ctx->index_mode = INDEX_IDENTITY; return; }
   const int n = ctx->n_sites, w = ctx->hamming_weight;
-  // auto = directory search: the combinadic rank trades L1 traffic for issue slots and measured slower
-  const bool eligible = ctx->num_ranks == 1 && w >= 0 && ctx->proj != PROJ_GROUP && ctx->opt_index == 2;
+  const int want = ctx->opt_index;
+  if (want == 0) return;
+  const bool eligible = ctx->num_ranks == 1 && w >= 0 && ctx->proj != PROJ_GROUP;
   if (!eligible) return;
   const uint64_t total = binom().c[n][w];
   const uint64_t expect = (ctx->proj == PROJ_INVERSION) ? total / 2 : total;
   if ((uint64_t)ctx->n_states != expect || total >= (1ull << 32)) return;
-  const int stride = w + 2;
-  std::vector<uint32_t> table((size_t)n * stride);
-  for (int pos = 0; pos < n; ++pos)
-    for (int k = 0; k < stride; ++k)
-      table[(size_t)pos * stride + k] = (uint32_t)std::min<uint64_t>(binom().c[pos][k], 0xffffffffull);
-  ctx->d_binom.upload(table, ctx->stream);
-  ctx->binom_stride = stride;
-  ctx->rank_total = total;
-  // the block must be exactly the first `expect` fixed-weight states: rank(reps[i]) == i for all i
   StateIndex ix{};
-  ix.reps = ctx->d_reps.ptr; ix.n = ctx->n_states; ix.mode = INDEX_RANK; ix.binom = ctx->d_binom.ptr;
-  ix.stride = stride; ix.n_sites = n; ix.weight = w; ix.site_mask = ctx->site_mask;
+  ix.reps = ctx->d_reps.ptr; ix.n = ctx->n_states; ix.n_sites = n; ix.weight = w; ix.site_mask = ctx->site_mask;
+  if (want == 2) {
+    const int stride = w + 2;
+    std::vector<uint32_t> table((size_t)n * stride);
+    for (int pos = 0; pos < n; ++pos)
+      for (int k = 0; k < stride; ++k)
+        table[(size_t)pos * stride + k] = (uint32_t)std::min<uint64_t>(binom().c[pos][k], 0xffffffffull);
+    ctx->d_binom.upload(table, ctx->stream);
+    ctx->binom_stride = stride;
+    ix.mode = INDEX_RANK; ix.binom = ctx->d_binom.ptr; ix.stride = stride;
+  } else {
+    if (n > 40) return;
+    // Lin tables: states ascending = (hi, lo) lexicographic; index = Ja[hi] + Jb[lo]
+    const int lb = n / 2, hb = n - lb;
+    std::vector<uint32_t> ja((size_t)1 << hb), jb((size_t)1 << lb);
+    uint64_t running = 0;
+    for (uint64_t hi = 0; hi < (1ull << hb); ++hi) {
+      const int k = w - __builtin_popcountll(hi);
+      ja[hi] = (uint32_t)std::min<uint64_t>(running, 0xffffffffull);
+      if (k >= 0 && k <= lb) running += binom().c[lb][k];
+    }
+    std::vector<uint32_t> counter(lb + 1, 0);
+    for (uint64_t lo = 0; lo < (1ull << lb); ++lo) jb[lo] = counter[__builtin_popcountll(lo)]++;
+    ctx->d_lin_a.upload(ja, ctx->stream);
+    ctx->d_lin_b.upload(jb, ctx->stream);
+    ctx->lin_bits = lb;
+    ix.mode = INDEX_LIN; ix.lin_a = ctx->d_lin_a.ptr; ix.lin_b = ctx->d_lin_b.ptr; ix.lin_bits = lb;
+  }
+  ctx->rank_total = total;
+  // the block must be exactly the first `expect` fixed-weight states: index(reps[i]) == i for all i
   CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
   launch_verify_rank(ix, ctx->d_status.ptr, ctx->stream);
   unsigned long long bad = 0;
   CUDA_CHECK(cudaMemcpyAsync(&bad, ctx->d_status.ptr, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
-  if (bad == 0) ctx->index_mode = INDEX_RANK;
+  if (bad == 0) ctx->index_mode = ix.mode;
 }
 
 void install_directory(dmv_context *ctx) {
@@ -977,7 +1003,8 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
     if (value < -1 || value > 1) throw std::runtime_error("mode: -1 auto, 0 push, 1 pull");
     ctx->opt_mode = (int)value;
   } else if (key == "index") {
-    if (value != -1 && value != 0 && value != 2) throw std::runtime_error("index: -1 auto, 0 directory, 2 rank");
+    if (value != -1 && value != 0 && value != 2 && value != 3)
+      throw std::runtime_error("index: -1 auto, 0 directory, 2 combinadic rank, 3 Lin tables");
     ctx->opt_index = (int)value;
     if (ctx->n_states >= 0) { CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); select_index_mode(ctx); }
   } else if (key == "exchange") {

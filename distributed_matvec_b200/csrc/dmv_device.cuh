@@ -119,7 +119,9 @@ __host__ __device__ __forceinline__ int locale_idx_of(uint64_t state, int num_ra
 //                     memory traffic to the representatives (ls_hs_fixed_hamming_state_to_index,
 //                     reference src/FFI.chpl:165).  Results are bit-identical to the search.
 // ---------------------------------------------------------------------------------------------
-enum IndexMode { INDEX_DIRECTORY = 0, INDEX_IDENTITY = 1, INDEX_RANK = 2 };
+//   INDEX_LIN       : same bases as INDEX_RANK: two-table (Lin) lookup  index = Ja[s >> h] + Jb[s & mask]:
+//                     two independent small-table loads, no dependent probe chain, bit-identical results.
+enum IndexMode { INDEX_DIRECTORY = 0, INDEX_IDENTITY = 1, INDEX_RANK = 2, INDEX_LIN = 3 };
 
 struct StateIndex {
   const uint64_t *reps;   // ascending, this rank's block
@@ -132,6 +134,9 @@ struct StateIndex {
   const uint32_t *binom;  // [n_sites][weight + 2]: binom[pos * stride + k] = C(pos, k) (saturated)
   int32_t stride, n_sites, weight;
   uint64_t site_mask;
+  // INDEX_LIN
+  const uint32_t *lin_a, *lin_b;   // Ja[2^(n - h)], Jb[2^h]
+  int32_t lin_bits;                // h: number of low bits
 };
 
 __device__ __forceinline__ int64_t locate_directory(const StateIndex &ix, uint64_t key) {
@@ -183,7 +188,15 @@ __device__ __forceinline__ int64_t locate_rank_incremental(const StateIndex &ix,
   return r < ix.n ? r : -1;
 }
 
+__device__ __forceinline__ int64_t locate_lin(const StateIndex &ix, uint64_t key) {
+  if ((key & ~ix.site_mask) != 0 || __popcll(key) != ix.weight) return -1;
+  const uint32_t lo = (uint32_t)(key & ((1ull << ix.lin_bits) - 1)), hi = (uint32_t)(key >> ix.lin_bits);
+  const int64_t r = (int64_t)__ldg(ix.lin_a + hi) + (int64_t)__ldg(ix.lin_b + lo);
+  return r < ix.n ? r : -1;   // with spin inversion only the first half are representatives
+}
+
 __device__ __forceinline__ int64_t locate(const StateIndex &ix, uint64_t key) {
+  if (ix.mode == INDEX_LIN) return locate_lin(ix, key);
   if (ix.mode == INDEX_IDENTITY) return (key < (uint64_t)ix.n) ? (int64_t)key : -1;
   if (ix.mode == INDEX_RANK) return locate_rank(ix, ix.binom, key);
   return locate_directory(ix, key);

@@ -772,7 +772,7 @@ __global__ void k_state_index(const StateIndex ix, int64_t count, const uint64_t
 
 __global__ void k_verify_rank(const StateIndex ix, unsigned long long *status) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < ix.n && locate_rank(ix, ix.binom, ix.reps[k]) != k) atomicAdd(status, 1ull);
+  if (k < ix.n && locate(ix, ix.reps[k]) != k) atomicAdd(status, 1ull);
 }
 
 __global__ void k_locale_idx(int64_t count, const uint64_t *__restrict__ states, int num_ranks, uint8_t *keys) {

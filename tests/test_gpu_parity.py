@@ -133,7 +133,7 @@ def test_local_matvec_matches_oracle(need_cuda, name, cplx, mode):
     reps = op.basis.representatives()
     x = _x(reps.shape[0], cplx)
     y_ref = po.matvec_global(matrix, reps, x, 1)
-    for index in (2, 0):           # combinadic rank / identity where they apply, and forced directory search
+    for index in (-1, 2, 0):       # auto (Lin tables / identity where they apply), combinadic rank, directory search
         op.set_option("index", index)
         y = op.matvec(x)
         assert _close(y, y_ref), (index, op.info("index_mode"), np.abs(y - y_ref).max())
@@ -148,20 +148,23 @@ def test_local_matvec_matches_oracle(need_cuda, name, cplx, mode):
 
 def test_rank_index_is_selected_and_bit_exact(need_cuda):
     """The combinadic-rank index kernel must agree bit for bit with the sorted-array search."""
-    for name, expect in (("heisenberg_chain_16", 2), ("heisenberg_chain_10", 2), ("heisenberg_chain_12", 1),
-                         ("heisenberg_kagome_12_symm", 0)):
-        basis, matrix = _load(name)
-        op = Operator(matrix)
-        op.set_option("index", 2)
-        op.basis.build()
-        assert op.info("index_mode") == expect, name
-        reps = op.basis.representatives()
-        rng = np.random.default_rng(5)
-        probe = np.concatenate([reps, reps ^ np.uint64(3), rng.integers(0, 2**(basis.number_sites + 1), 4000,
-                                                                        dtype=np.uint64)])
-        got = op.basis.stateIndex(probe)
-        assert np.array_equal(got, po.state_index(reps, probe)), name
-        op.close()
+    for option, expected in ((2, {"heisenberg_chain_16": 2, "heisenberg_chain_10": 2, "heisenberg_chain_12": 1,
+                                  "heisenberg_kagome_12_symm": 0}),
+                             (-1, {"heisenberg_chain_16": 3, "heisenberg_chain_10": 3, "heisenberg_chain_12": 1,
+                                   "heisenberg_kagome_12_symm": 0, "heisenberg_kagome_16": 3})):
+        for name, expect in expected.items():
+            basis, matrix = _load(name)
+            op = Operator(matrix)
+            op.set_option("index", option)
+            op.basis.build()
+            assert op.info("index_mode") == expect, (name, option)
+            reps = op.basis.representatives()
+            rng = np.random.default_rng(5)
+            probe = np.concatenate([reps, reps ^ np.uint64(3), rng.integers(0, 2**(basis.number_sites + 1), 4000,
+                                                                            dtype=np.uint64)])
+            got = op.basis.stateIndex(probe)
+            assert np.array_equal(got, po.state_index(reps, probe)), (name, option)
+            op.close()
 
 
 @pytest.mark.parametrize("cplx", [False, True])

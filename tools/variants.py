@@ -35,10 +35,10 @@ def main():
             yd = torch.zeros_like(xd)
             ref = None
             for mode in (0, 1):
-                for index in (0, 2):
+                for index in (0, -1):
                     op.set_option("mode", mode)
                     op.set_option("index", index)
-                    if index == 2 and op.info("index_mode") == 0:
+                    if index == -1 and op.info("index_mode") == 0:
                         continue
                     for _ in range(3):
                         op.matvec(xd, yd)
