@@ -291,6 +291,10 @@ struct dmv_context {
   HostTables h_push, h_pull;          // column-traversal (scatter) / row-traversal (gather) tables
   DevTables d_push, d_pull;
   DevBuf<DiagTerm> d_diag;
+  std::vector<DiagClass> h_diag_classes;  // bit-parallel part of the diagonal; h_diag is reordered: rest first
+  DevBuf<DiagClass> d_diag_classes;
+  int n_diag_rest = 0;
+  size_t h_diag_kept = 0;   // number of diagonal terms of the operator (h_diag itself only keeps the non-class rest)
   // options
   int opt_mode = -1;    // -1 auto (pull when one rank owns the basis), 0 push (scatter), 1 pull (gather)
   int opt_index = -1;   // -1 auto, 0 directory search, 2 combinadic rank
@@ -384,7 +388,9 @@ KernelParams base_params(dmv_context *ctx) {
   p.index.lin_bits = ctx->lin_bits;
   p.rank_total = ctx->rank_total;
   p.norms = ctx->d_norms.ptr;
-  p.diag = ctx->d_diag.ptr;     p.n_diag = (int)ctx->h_diag.size();
+  p.diag = ctx->d_diag.ptr;     p.n_diag = (int)ctx->h_diag_kept;
+  p.diag_classes = ctx->d_diag_classes.ptr; p.n_diag_classes = (int)ctx->h_diag_classes.size();
+  p.n_diag_rest = ctx->n_diag_rest;
   p.orbit = ctx->orbit;
   p.site_mask = ctx->site_mask;
   p.inversion_character = (double)ctx->spin_inversion;
@@ -404,6 +410,62 @@ KernelParams base_params(dmv_context *ctx) {
   p.row_begin = 0;
   p.row_end = ctx->n_states;
   return p;
+}
+
+// Split the diagonal into bit-parallel classes (m == 0, two sign bits, equal coefficient) and the rest.
+void build_diag_classes(dmv_context *ctx) {
+  std::vector<DiagTerm> rest;
+  std::map<std::pair<double, double>, std::vector<DiagTerm>> by_v;
+  for (const auto &d : ctx->h_diag) {
+    if (d.m == 0 && d.r == 0 && __builtin_popcountll(d.s) == 2) by_v[{d.v_re, d.v_im}].push_back(d);
+    else rest.push_back(d);
+  }
+  for (auto &kv : by_v) {
+    auto &terms = kv.second;
+    std::stable_sort(terms.begin(), terms.end(), [](const DiagTerm &a, const DiagTerm &b) {
+      const int a0 = __builtin_ctzll(a.s), a1 = 63 - __builtin_clzll(a.s);
+      const int b0 = __builtin_ctzll(b.s), b1 = 63 - __builtin_clzll(b.s);
+      if (a1 - a0 != b1 - b0) return a1 - a0 < b1 - b0;
+      return a0 < b0;
+    });
+    for (size_t first = 0; first < terms.size(); first += 64) {
+      const size_t n = std::min<size_t>(64, terms.size() - first);
+      DiagClass D;
+      memset(&D, 0, sizeof(D));
+      D.v_re = kv.first.first; D.v_im = kv.first.second;
+      bool ok = true;
+      for (size_t t = 0; t < n && ok; ++t) {
+        const uint64_t sbits = terms[first + t].s;
+        const int pos[2] = {__builtin_ctzll(sbits), 63 - __builtin_clzll(sbits)};
+        BpPair *pairs[2] = {D.p0, D.p1};
+        int32_t *cnt[2] = {&D.n0, &D.n1};
+        for (int b = 0; b < 2 && ok; ++b) {
+          const int d = (int)t - pos[b];
+          const uint32_t sl = d >= 0 ? (uint32_t)d : 0u, sr = d >= 0 ? 0u : (uint32_t)(-d);
+          int k = 0;
+          for (; k < *cnt[b]; ++k)
+            if (pairs[b][k].l == sl && pairs[b][k].r == sr) break;
+          if (k == *cnt[b]) {
+            if (k == kBpPairs) { ok = false; break; }
+            pairs[b][k].l = sl; pairs[b][k].r = sr; pairs[b][k].m = 0; ++*cnt[b];
+          }
+          pairs[b][k].m |= 1ull << t;
+        }
+      }
+      if (ok) {
+        D.count = (int32_t)n;
+        D.mask = n == 64 ? ~0ull : ((1ull << n) - 1);
+        ctx->h_diag_classes.push_back(D);
+      } else {
+        for (size_t t = 0; t < n; ++t) rest.push_back(terms[first + t]);
+      }
+    }
+  }
+  // reorder: the terms evaluated one by one come first
+  ctx->n_diag_rest = (int)rest.size();
+  std::vector<DiagTerm> reordered = rest;
+  ctx->h_diag_kept = ctx->h_diag.size();
+  ctx->h_diag = reordered;
 }
 
 // point the kernel at the column-traversal (push) or row-traversal (pull) tables
@@ -582,7 +644,7 @@ uint64_t fixed_hamming_unrank(uint64_t r, int weight) {  // ls_hs_fixed_hamming_
 
 void zero_y_if_diag(dmv_context *ctx, int elt, void *y) {
   // DMV:1062-1063: with diagonal terms y is overwritten by D x, otherwise it is accumulated into
-  if (!ctx->h_diag.empty())
+  if (ctx->h_diag_kept > 0)
     CUDA_CHECK(cudaMemsetAsync(y, 0, (size_t)ctx->n_states * 8 * elt, ctx->stream));
 }
 
@@ -607,7 +669,7 @@ VecStage stage_vectors(dmv_context *ctx, int elt, const void *x, void *y) {
   else {
     ctx->d_y.alloc((size_t)ctx->n_states * elt);
     v.y_dev = ctx->d_y.ptr; v.y_host = true; v.y_user = y;
-    if (ctx->h_diag.empty())  // y is accumulated into: bring the caller's y over
+    if (ctx->h_diag_kept == 0)  // y is accumulated into: bring the caller's y over
       CUDA_CHECK(cudaMemcpyAsync(ctx->d_y.ptr, y, v.bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
   CUDA_CHECK(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -947,6 +1009,8 @@ int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op,
     if (d.v_im != 0.0) cplx = true;
     ctx->h_diag.push_back(d);
   }
+  build_diag_classes(ctx.get());
+  ctx->d_diag_classes.upload(ctx->h_diag_classes, ctx->stream);
   ctx->d_push.upload(ctx->h_push, ctx->stream);
   ctx->d_pull.upload(ctx->h_pull, ctx->stream);
   ctx->d_diag.upload(ctx->h_diag, ctx->stream);

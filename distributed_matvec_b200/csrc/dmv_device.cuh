@@ -57,6 +57,16 @@ struct BpWord {
 };
 static_assert(sizeof(BpWord) == 32 + 32 * kBpPairs + 8, "BpWord layout");
 
+// Diagonal terms of the form v (-1)^(bit_i ^ bit_j) (every sigma^z sigma^z coupling) grouped by coefficient:
+//   sum over the class = v * (count - 2 popc((A0 ^ A1) & mask)),   A_b gathered by masked shifts as in BpWord.
+struct DiagClass {
+  double v_re, v_im;
+  int32_t count, n0, n1, pad;
+  uint64_t mask;
+  BpPair p0[kBpPairs], p1[kBpPairs];
+};
+static_assert(sizeof(DiagClass) == 40 + 32 * kBpPairs, "DiagClass layout");
+
 __host__ __device__ __forceinline__ unsigned lut_index(uint64_t posk, uint64_t a) {
   const unsigned k = (unsigned)(posk >> 48) & 0xffu;
   unsigned idx = 0;

@@ -46,7 +46,9 @@ struct KernelParams {
   int32_t any_generic, any_s_out;
   const BpWord *bp; int32_t n_bp;   // bit-parallel emit test (n_bp == 0: walk the groups one by one)
   uint64_t rank_total;        // INDEX_RANK: C(n_sites, weight)
-  const DiagTerm *diag;    int32_t n_diag;
+  const DiagTerm *diag;    int32_t n_diag;       // all diagonal terms (n_diag > 0 <=> the operator has a diagonal)
+  const DiagClass *diag_classes; int32_t n_diag_classes;   // bit-parallel part
+  int32_t n_diag_rest;        // terms diag[0 .. n_diag_rest) are NOT covered by the classes (evaluated one by one)
   // symmetry
   OrbitProgram orbit;         // device pointers (PROJ_GROUP)
   uint64_t site_mask;

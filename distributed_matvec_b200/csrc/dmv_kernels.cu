@@ -74,7 +74,7 @@ __device__ __forceinline__ double v_im(double2 a) { return a.y; }
 
 // ---- shared-memory staging of the operator / orbit tables ---------------------------------------
 struct SmemLayout {
-  size_t groups, gx, bp, lut, terms, diag, orbit64, orbit32, binom, queues, total;
+  size_t groups, gx, bp, lut, terms, diag, dclass, orbit64, orbit32, binom, queues, total;
 };
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int proj, size_t val_bytes) {
@@ -90,7 +90,8 @@ __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int pro
   L.lut = off; off += val_bytes * p.n_lut;
   off = align_up(off, 8);
   L.terms = off; off += p.any_generic ? sizeof(OffTerm) * p.n_terms : 0;
-  L.diag = off; off += sizeof(DiagTerm) * p.n_diag;
+  L.diag = off; off += sizeof(DiagTerm) * p.n_diag_rest;
+  L.dclass = off; off += sizeof(DiagClass) * p.n_diag_classes;
   L.orbit64 = off;
   size_t n64 = 0, n32 = 0;
   if (proj == PROJ_GROUP) {
@@ -129,6 +130,8 @@ struct Tables {
   const V *lut;
   const OffTerm *terms;
   const DiagTerm *diag;
+  const DiagClass *dclass;
+  int n_diag_rest, n_dclass;
   OrbitProgram orbit;
   StateIndex index;
 };
@@ -150,8 +153,12 @@ __device__ __forceinline__ Tables<CV> stage_tables(const KernelParams &p, unsign
   T.gx = s_gx; T.bp = s_bp; T.n_bp = p.n_bp;
   stage(s_lut, reinterpret_cast<const V *>(p.lut), p.n_lut);
   if (p.any_generic) stage(s_terms, p.terms, p.n_terms);
-  stage(s_diag, p.diag, p.n_diag);
+  stage(s_diag, p.diag, p.n_diag_rest);
+  DiagClass *s_dclass = reinterpret_cast<DiagClass *>(smem + L.dclass);
+  stage(reinterpret_cast<uint64_t *>(s_dclass), reinterpret_cast<const uint64_t *>(p.diag_classes),
+        p.n_diag_classes * (int)(sizeof(DiagClass) / 8));
   T.groups = s_groups; T.lut = s_lut; T.terms = s_terms; T.diag = s_diag;
+  T.dclass = s_dclass; T.n_diag_rest = p.n_diag_rest; T.n_dclass = p.n_diag_classes;
   T.orbit = p.orbit;
   if (PROJ == PROJ_GROUP) {
     const int np = T.orbit.n_left + T.orbit.n_right;
@@ -271,9 +278,21 @@ __device__ __forceinline__ typename ValT<CV>::type pop_term(const Tables<CV> &T,
 }
 
 template <bool CV>
-__device__ __forceinline__ void diagonal(const Tables<CV> &T, int n_diag, uint64_t a, double &dre, double &dim) {
+__device__ __forceinline__ void diagonal(const Tables<CV> &T, int /*n_diag*/, uint64_t a, double &dre, double &dim) {
   dre = 0.0; dim = 0.0;
-  for (int t = 0; t < n_diag; ++t) {
+  // zz-like couplings, one class per distinct coefficient: count - 2 popc(antiparallel bonds)
+  for (int c = 0; c < T.n_dclass; ++c) {
+    const DiagClass &D = T.dclass[c];
+    uint64_t a0 = 0, a1 = 0;
+#pragma unroll 1
+    for (int k = 0; k < D.n0; ++k) { const BpPair q = D.p0[k]; a0 |= ((a << q.l) >> q.r) & q.m; }
+#pragma unroll 1
+    for (int k = 0; k < D.n1; ++k) { const BpPair q = D.p1[k]; a1 |= ((a << q.l) >> q.r) & q.m; }
+    const double w = (double)(D.count - 2 * __popcll((a0 ^ a1) & D.mask));
+    dre += w * D.v_re;
+    dim += w * D.v_im;
+  }
+  for (int t = 0; t < T.n_diag_rest; ++t) {
     const DiagTerm d = T.diag[t];
     if ((a & d.m) == d.r) {
       const double sg = (__popcll(a & d.s) & 1) ? -1.0 : 1.0;
