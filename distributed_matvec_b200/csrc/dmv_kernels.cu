@@ -92,6 +92,7 @@ __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int pro
   L.terms = off; off += p.any_generic ? sizeof(OffTerm) * p.n_terms : 0;
   L.diag = off; off += sizeof(DiagTerm) * p.n_diag_rest;
   L.dclass = off; off += sizeof(DiagClass) * p.n_diag_classes;
+  off = align_up(off, 16);   // packed orbit steps are read with 16-byte loads
   L.orbit64 = off;
   size_t n64 = 0, n32 = 0;
   if (proj == PROJ_GROUP) {
