@@ -324,6 +324,7 @@ struct dmv_context {
   DevBuf<double> d_out_coeffs, d_in_coeffs;
   int record_width = 2;                    // doubles per coefficient of the current buckets
   int plan_grid = 0;                       // CTAs of the planned launches (exact warp-private regions)
+  int row_split = 1;                       // lanes per source state (chosen at plan time from the block size)
   bool peer_direct = false;                // records are stored straight into the peers' incoming buffers
   int ptr_width = 0;                       // record width the destination pointer table was built for
   int opt_exchange = -1;                   // -1 auto (peer-direct when possible), 0 NCCL send/recv, 1 peer-direct
@@ -401,6 +402,7 @@ KernelParams base_params(dmv_context *ctx) {
   p.out_offset = ctx->d_out_offset.ptr;
   p.out_count = ctx->d_out_count.ptr;
   p.grid_blocks = ctx->num_ranks > 1 ? ctx->plan_grid : 0;
+  p.row_split = ctx->row_split;
   p.warp_offsets = ctx->d_warp_offsets.ptr;
   p.warp_counts = ctx->d_warp_counts.ptr;
   p.out_betas_ptr = ctx->d_out_betas_ptr.ptr;
@@ -694,7 +696,8 @@ void do_plan(dmv_context *ctx) {
   require_states(ctx);
   const int P = ctx->num_ranks;
   const bool exact_regions = P <= 32;
-  ctx->plan_grid = planned_grid(ctx->n_states);
+  ctx->row_split = choose_row_split(ctx->n_states, (int)ctx->h_push.groups.size());
+  ctx->plan_grid = planned_grid(ctx->n_states, ctx->row_split);
   const size_t n_warps = (size_t)ctx->plan_grid * kWarpsPerCta;
   ctx->d_out_count.alloc(P);
   ctx->d_warp_counts.alloc(n_warps * P);

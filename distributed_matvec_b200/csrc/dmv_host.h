@@ -65,6 +65,7 @@ struct KernelParams {
   // counting pass records how many records every warp emits per destination and the real pass starts
   // each warp at the prefix sum -- no slot-claim atomics, no slack, deterministic bucket layout.
   int32_t grid_blocks;              // 0: size the grid from occupancy; else exactly this many CTAs
+  int32_t row_split;                // lanes sharing one source state (1, 2, 4, ... 32), see k_generate
   const int64_t *warp_offsets;      // [grid_blocks * 8][num_ranks]
   unsigned long long *warp_counts;  // counting pass output, same shape
   uint64_t *const *out_betas_ptr;   // [num_ranks]: base of MY region in the destination's record buffer
@@ -105,7 +106,8 @@ void launch_enumerate(const OrbitProgram &P, Projection proj, uint64_t site_mask
                       const unsigned long long *chunk_offset, uint64_t *out, double *out_norms,
                       bool write_pass, cudaStream_t stream);
 int64_t launch_counter();
-int planned_grid(int64_t rows);
+int planned_grid(int64_t rows, int row_split);
+int choose_row_split(int64_t rows, int n_groups);
 constexpr int kWarpsPerCta = 8;
 
 }  // namespace dmv

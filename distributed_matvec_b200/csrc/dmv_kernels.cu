@@ -495,11 +495,21 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
   if (!COUNT_ONLY && p.num_ranks > 1 && p.num_ranks <= 32 && (int)lane < p.num_ranks)
     cur = (unsigned long long)p.warp_offsets[gw * p.num_ranks + lane];
 
+  // row_split = S lanes share one source state (each takes every S-th flip-mask group): small bases get
+  // S times more warps and S times shorter per-warp latency chains; large ones run with S = 1
+  const int S = p.row_split > 1 ? p.row_split : 1;
+  const int rows_per_tile = 32 / S;
+  const unsigned slice = lane & (unsigned)(S - 1);
+  uint64_t slice_mask = ~0ull;
+  if (S > 1) {
+    slice_mask = 0;
+    for (int g = (int)slice; g < 64; g += S) slice_mask |= 1ull << g;
+  }
   const int64_t n_rows = p.row_end - p.row_begin;
-  const int64_t n_tiles = (n_rows + 31) / 32;
+  const int64_t n_tiles = (n_rows + rows_per_tile - 1) / rows_per_tile;
   const int64_t warps_total = (int64_t)gridDim.x * kWarps;
   for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += warps_total) {
-    const int64_t i = p.row_begin + tile * 32 + lane;
+    const int64_t i = p.row_begin + tile * rows_per_tile + lane / S;
     const bool valid = i < p.row_end;
     uint64_t alpha = 0;
     V xi = v_make(0.0, 0.0, (V *)nullptr);
@@ -515,7 +525,7 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
       }
     }
     // ---- diagonal: y[i] += x[i] * sum_t v_t [alpha & m == r] (-1)^popc(alpha & s)   (DMV:36-53)
-    if (!COUNT_ONLY && !p.emit_all && p.n_diag > 0 && valid) {
+    if (!COUNT_ONLY && !p.emit_all && p.n_diag > 0 && valid && slice == 0) {
       double dre, dim;
       diagonal<CV>(T, p.n_diag, alpha, dre, dim);
       if (CE) {
@@ -533,6 +543,7 @@ __global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
     for (int g0 = 0, w = 0; g0 < p.n_groups; g0 += 64, ++w) {
       const int g1 = min(g0 + 64, p.n_groups);
       RowTerms rt = row_terms<CV>(T, w, g0, g1, alpha);
+      rt.mask &= slice_mask;
       if (!valid) rt.mask = 0;
       for (;;) {
         const bool has = rt.mask != 0;
@@ -745,25 +756,24 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
 }
 
 // localProcess for records that arrived from other ranks: already projected and hashed by the sender.
+// Two records per thread with their searches advanced in lock step (see locate2).
 template <int PROJ, bool CV, bool CE>
 __global__ void __launch_bounds__(kThreads) k_accumulate(const KernelParams p, int64_t count,
                                                          const uint64_t *__restrict__ betas,
                                                          const double *__restrict__ coeffs) {
   using V = typename ValT<CV>::type;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
-    const uint64_t beta = __ldg(betas + k);
-    V c = __ldg(reinterpret_cast<const V *>(coeffs) + k);
-    const int64_t idx = locate(p.index, beta);
-    if (idx >= 0) {
-      if (PROJ == PROJ_GROUP) c = v_scale(c, __ldg(p.norms + idx));
-      if (v_nonzero(c)) atomic_accumulate<CE>(p.y, idx, v_re(c), v_im(c));
-    } else if (v_nonzero(c)) {
-      bool fatal = true;
-      if (PROJ == PROJ_GROUP && !p.orbit.trivial_characters)
-        fatal = orbit_stabiliser_sum(p.orbit, beta) > 1e-12 * (double)p.orbit.group_order;
-      if (fatal && atomicAdd(p.status, 1ull) == 0) p.status[1] = beta;
-    }
+  const int64_t half = (count + 1) / 2;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < half; k += stride) {
+    const int64_t k1 = k + half;
+    const bool a1 = k1 < count;
+    const uint64_t b0 = __ldg(betas + k), b1 = a1 ? __ldg(betas + k1) : 0ull;
+    const V c0 = __ldg(reinterpret_cast<const V *>(coeffs) + k);
+    const V c1 = a1 ? __ldg(reinterpret_cast<const V *>(coeffs) + k1) : v_make(0.0, 0.0, (V *)nullptr);
+    int64_t i0, i1;
+    locate2(p.index, true, b0, a1, b1, i0, i1);
+    finish<PROJ, CV, CE>(p, p.orbit, true, b0, c0, i0);
+    finish<PROJ, CV, CE>(p, p.orbit, a1, b1, c1, i1);
   }
 }
 
@@ -899,12 +909,25 @@ int grid_for(int64_t work_items, int per_block, int max_blocks) {
 }
 
 }  // namespace
-int planned_grid(int64_t rows) {   // grid of the planned (multi-rank) launches: fixed, not occupancy-derived
+// lanes per source state: enough warps to fill the machine (>= 8 per SM) on small bases, never more than the
+// number of flip-mask groups
+int choose_row_split(int64_t rows, int n_groups) {
   int dev = 0, n = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   if (n <= 0) n = 148;
-  int64_t b = ((rows + 31) / 32 + kWarps - 1) / kWarps;
+  int s = 1;
+  while (s < 32 && 2 * s <= n_groups && (rows * s) / 32 < (int64_t)n * 16) s *= 2;
+  return s;
+}
+
+int planned_grid(int64_t rows, int row_split) {   // grid of the planned launches: fixed, not occupancy-derived
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  const int rows_per_tile = 32 / (row_split > 1 ? row_split : 1);
+  int64_t b = ((rows + rows_per_tile - 1) / rows_per_tile + kWarps - 1) / kWarps;
   if (b < 1) b = 1;
   if (b > (int64_t)n * 4) b = (int64_t)n * 4;
   return (int)b;
@@ -932,7 +955,8 @@ void launch_generate_t(const KernelParams &p, cudaStream_t stream) {
   int per_sm = 0;
   DMV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, L.total));
   if (per_sm < 1) per_sm = 1;
-  const int64_t tiles = (p.row_end - p.row_begin + 31) / 32;
+  const int rpt = 32 / (p.row_split > 1 ? p.row_split : 1);
+  const int64_t tiles = (p.row_end - p.row_begin + rpt - 1) / rpt;
   // grid = a whole number of waves of resident CTAs (148 SMs x per_sm), or fewer when the work is small
   const int blocks = p.grid_blocks > 0 ? p.grid_blocks : grid_for(tiles, kWarps, sm_count() * per_sm);
   kernel<<<blocks, kThreads, L.total, stream>>>(p);
@@ -981,7 +1005,7 @@ void launch_pull_p(const KernelParams &p, bool cv, bool ce, cudaStream_t s) {
 template <int PROJ>
 void launch_accumulate_p(const KernelParams &p, bool cv, bool ce, int64_t count, const uint64_t *b,
                          const double *c, cudaStream_t s) {
-  const int blocks = grid_for(count, kThreads, sm_count() * 8);
+  const int blocks = grid_for((count + 1) / 2, kThreads, sm_count() * 8);
   if (!cv && !ce) k_accumulate<PROJ, false, false><<<blocks, kThreads, 0, s>>>(p, count, b, c);
   else if (cv && ce) k_accumulate<PROJ, true, true><<<blocks, kThreads, 0, s>>>(p, count, b, c);
   else if (cv && !ce) k_accumulate<PROJ, true, false><<<blocks, kThreads, 0, s>>>(p, count, b, c);
