@@ -299,6 +299,10 @@ struct dmv_context {
   int opt_mode = -1;    // -1 auto (pull when one rank owns the basis), 0 push (scatter), 1 pull (gather)
   int opt_index = -1;   // -1 auto, 0 directory search, 2 combinadic rank
   int opt_bitparallel = 1;  // 0: walk the groups one by one even when the bit-parallel test applies
+  int opt_gather = -1;      // row traversal kernel: -1 auto (k_gather when it applies), 0 always the queued k_pull
+  // k_gather applicability (set at context creation from the row-traversal tables)
+  bool gather_ok = false, gather_narrow = false, gather_uniform = false;
+  double gather_uni[2] = {0.0, 0.0};
   int index_mode = INDEX_DIRECTORY;
   DevBuf<uint32_t> d_binom, d_lin_a, d_lin_b;
   int lin_bits = 0;
@@ -361,10 +365,16 @@ struct dmv_context {
 
 namespace {
 
+bool use_gather(const dmv_context *ctx) {   // the lean row-gather kernel applies and is not switched off
+  return ctx->gather_ok && ctx->opt_gather != 0 && ctx->opt_bitparallel != 0 && ctx->proj != PROJ_GROUP;
+}
 bool use_pull(const dmv_context *ctx) {
-  // auto = push: with the warp-queue drain the scatter form is the faster one on B200 (measured, see
-  // DESIGN.md "Kernels"); the row-gather form stays selectable ("mode" = 1) and deterministic.
-  return ctx->num_ranks == 1 && ctx->opt_mode == 1;
+  // auto: one rank, bit-parallel operator, no permutation symmetries -> k_gather (rows, no atomics, see
+  // dmv_gather.cu); everything else -> push (k_generate).  "mode" = 1 forces the row traversal (k_gather
+  // when it applies, else the queued k_pull), "mode" = 0 the scatter form.
+  if (ctx->num_ranks != 1) return false;
+  if (ctx->opt_mode == 1) return true;
+  return ctx->opt_mode == -1 && use_gather(ctx);
 }
 
 void use_device(const dmv_context *ctx) { CUDA_CHECK(cudaSetDevice(ctx->device)); }
@@ -752,11 +762,20 @@ void do_plan(dmv_context *ctx) {
 }
 
 void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev,
-                 const void *x_host_pending = nullptr) {
-  if (use_pull(ctx)) {   // one rank owns the basis: traverse by rows (gather), see k_pull
+                 const void *x_host_pending = nullptr, int64_t row_begin = 0, int64_t row_end = 0) {
+  if (use_pull(ctx)) {   // one rank owns the basis: traverse by rows (gather), see k_gather / k_pull
     KernelParams p = base_params(ctx);
     p.x = x_dev;
     p.y = y_dev;
+    if (row_end > row_begin) { p.row_begin = row_begin; p.row_end = row_end; }
+    if (use_gather(ctx)) {
+      select_tables(ctx, p, true, ctx->complex_coefficients);
+      p.row_split = choose_row_split(ctx->n_states, (int)ctx->h_pull.groups.size());
+      p.uni_re = ctx->gather_uni[0]; p.uni_im = ctx->gather_uni[1];
+      launch_gather(p, ctx->proj == PROJ_INVERSION, ctx->complex_coefficients, elt == DMV_C128,
+                    ctx->gather_narrow, ctx->index_mode == INDEX_LIN, ctx->gather_uniform, ctx->stream);
+      return;
+    }
     select_tables(ctx, p, true, complex_values(ctx, elt));
     launch_pull(p, ctx->proj, complex_values(ctx, elt), elt == DMV_C128, ctx->stream);
     return;
@@ -1012,6 +1031,23 @@ int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op,
     if (d.v_im != 0.0) cplx = true;
     ctx->h_diag.push_back(d);
   }
+  {
+    // k_gather needs the bit-parallel emit test on the row tables and coefficients that depend on the support
+    // bits only; it runs in 32-bit registers when sites and groups fit, and skips the LUT when every emitting
+    // (group, support bits) pair carries the same coefficient (every Heisenberg-type operator)
+    const HostTables &H = ctx->h_pull;
+    ctx->gather_ok = !H.bp.empty() && !H.any_s_out && !H.any_generic;
+    ctx->gather_narrow = basis->number_sites <= 32 && H.groups.size() <= 32;
+    bool first = true, uniform = ctx->gather_ok;
+    for (size_t g = 0; g < H.groups.size() && uniform; ++g)
+      for (int idx = 0; idx < 4; ++idx)
+        if ((H.groups[g].emit_bits >> idx) & 1ull) {
+          const double re = H.lut_c[2 * (4 * g + idx)], im = H.lut_c[2 * (4 * g + idx) + 1];
+          if (first) { ctx->gather_uni[0] = re; ctx->gather_uni[1] = im; first = false; }
+          else if (re != ctx->gather_uni[0] || im != ctx->gather_uni[1]) { uniform = false; break; }
+        }
+    ctx->gather_uniform = uniform && !first;
+  }
   build_diag_classes(ctx.get());
   ctx->d_diag_classes.upload(ctx->h_diag_classes, ctx->stream);
   ctx->d_push.upload(ctx->h_push, ctx->stream);
@@ -1078,6 +1114,9 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
     if (value < -1 || value > 1) throw std::runtime_error("exchange: -1 auto, 0 NCCL send/recv, 1 peer-direct");
     ctx->opt_exchange = (int)value;
     ctx->planned = false;
+  } else if (key == "gather") {
+    if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
+    ctx->opt_gather = (int)value;
   } else if (key == "bitparallel") {
     ctx->opt_bitparallel = value != 0;
     ctx->planned = false;
@@ -1092,6 +1131,9 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
   if (!ctx) return -1;
   if (key == "index_mode") return ctx->index_mode;
   if (key == "pull") return use_pull(ctx) ? 1 : 0;
+  if (key == "gather") return (use_pull(ctx) && use_gather(ctx)) ? 1 : 0;
+  if (key == "gather_narrow") return ctx->gather_narrow ? 1 : 0;
+  if (key == "gather_uniform") return ctx->gather_uniform ? 1 : 0;
   if (key == "peer_direct") return ctx->peer_direct ? 1 : 0;
   if (key == "projection") return (int64_t)ctx->proj;
   if (key == "n_groups") return (int64_t)ctx->h_push.groups.size();
@@ -1310,11 +1352,36 @@ int dmv_local_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
   if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
   if (x == y) throw std::runtime_error("x and y must not alias");
   VecStage v = stage_vectors(ctx, elt, x, y);
+  const bool host_result = v.y_host;
+  if (use_pull(ctx) && use_gather(ctx) && v.y_host && ctx->n_states >= (1 << 16)) {
+    // row traversal into a host y: every row chunk is final as soon as its launch ends, so its D2H copy
+    // (copy stream) overlaps the gather of the next chunk
+    const int chunks = dmv_context::kCopyChunks;
+    const int64_t n = ctx->n_states, per = ((n + chunks - 1) / chunks + 31) / 32 * 32;
+    const size_t esz = (size_t)8 * elt;
+    for (int k = 0; k < chunks; ++k) {
+      const int64_t b = std::min<int64_t>(n, (int64_t)k * per), e = std::min<int64_t>(n, b + per);
+      if (e <= b) break;
+      do_generate(ctx, elt, v.x_dev, v.y_dev, nullptr, b, e);
+      CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[k], ctx->stream));
+      CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[k], 0));
+      CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char *>(v.y_user) + b * esz,
+                                 reinterpret_cast<const char *>(v.y_dev) + b * esz, (size_t)(e - b) * esz,
+                                 cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CUDA_CHECK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[0], ctx->copy_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[0], 0));
+    CUDA_CHECK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  } else {
   do_generate(ctx, elt, v.x_dev, v.y_dev, v.x_host_pending);
   CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
   CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
   finish_vectors(ctx, v);
-  if (v.y_host || !is_device_pointer(x)) {
+  }
+  if (host_result || !is_device_pointer(x)) {
     // host callers get a finished result (and the error check) on return
     check_status(ctx);
     collect_timings(ctx);

@@ -1,0 +1,318 @@
+// dmv_gather.cu -- k_gather: the single-rank product traversed by ROWS, specialised for operators whose
+// flip-mask groups all pass the bit-parallel emit test (every two-body spin Hamiltonian) on bases without
+// permutation symmetries (BatchedOperator branches a and b, reference src/BatchedOperator.chpl:89-161).
+//
+//   y[b] = D(b) x[b] + sum_{g emits on row b} c_g(b) x[index(b ^ x_g)]
+//
+// The same arithmetic as localDiagonal + computeOffDiag + localProcess (reference
+// src/DistributedMatrixVector.chpl:36-127), but every y element is produced by ONE lane and stored once:
+// no (beta, c) records, no shared-memory queue, no FP64 atomics (the L2 atomic unit is the busiest unit of
+// the scatter form, profiles/r01_push_chain24_c128_final.md), and the result is bit-reproducible.
+// One lane owns one row: 8/16-byte coalesced loads of sigma_b and x_b, the emit mask of all groups from a few
+// masked shifts (BpWord), then a walk over the set bits two at a time -- two index look-ups and two x gathers
+// in flight per lane.  With <= 32 sites and <= 32 groups the whole row runs in 32-bit registers (NARROW).
+// Only used when one rank owns the basis (the distributed product needs the scatter form: the owner of a
+// row does not hold the x of its neighbours).
+#include <cuda_runtime.h>
+
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+
+#include "dmv_host.h"
+
+namespace dmv {
+
+void count_launch();
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <bool C> struct Val { using type = double; };
+template <> struct Val<true> { using type = double2; };
+
+__device__ __forceinline__ int popc_w(uint32_t v) { return __popc(v); }
+__device__ __forceinline__ int popc_w(uint64_t v) { return __popcll(v); }
+__device__ __forceinline__ int ffs_w(uint32_t v) { return __ffs((int)v); }
+__device__ __forceinline__ int ffs_w(uint64_t v) { return __ffsll((long long)v); }
+
+// acc += c * s * x for the four (coefficient, element) type combinations
+__device__ __forceinline__ void fma_to(double &acc, double c, double x) { acc = fma(c, x, acc); }
+__device__ __forceinline__ void fma_to(double2 &acc, double c, double2 x) {
+  acc.x = fma(c, x.x, acc.x); acc.y = fma(c, x.y, acc.y);
+}
+__device__ __forceinline__ void fma_to(double2 &acc, double2 c, double2 x) {
+  acc.x = fma(c.x, x.x, fma(-c.y, x.y, acc.x));
+  acc.y = fma(c.x, x.y, fma(c.y, x.x, acc.y));
+}
+__device__ __forceinline__ void fma_to(double2 &acc, double2 c, double x) {
+  acc.x = fma(c.x, x, acc.x); acc.y = fma(c.y, x, acc.y);
+}
+__device__ __forceinline__ double scale(double c, double s) { return c * s; }
+__device__ __forceinline__ double2 scale(double2 c, double s) { return make_double2(c.x * s, c.y * s); }
+__device__ __forceinline__ bool nonzero(double c) { return c != 0.0; }
+__device__ __forceinline__ bool nonzero(double2 c) { return c.x != 0.0 || c.y != 0.0; }
+__device__ __forceinline__ double ldx(const double *x, uint32_t i) { return __ldg(x + i); }
+__device__ __forceinline__ double2 ldx(const double2 *x, uint32_t i) { return __ldg(x + i); }
+__device__ __forceinline__ double make_v(double re, double, double *) { return re; }
+__device__ __forceinline__ double2 make_v(double re, double im, double2 *) { return make_double2(re, im); }
+__device__ __forceinline__ double zero_of(double *) { return 0.0; }
+__device__ __forceinline__ double2 zero_of(double2 *) { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ double shfl_xor_v(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double2 shfl_xor_v(double2 v, int m) {
+  return make_double2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+__device__ __forceinline__ void add_to(double &a, double b) { a += b; }
+__device__ __forceinline__ void add_to(double2 &a, double2 b) { a.x += b.x; a.y += b.y; }
+
+struct GatherLayout { size_t bp, dclass, diag, lut, gx, total; };
+__host__ __device__ inline GatherLayout gather_layout(const KernelParams &p, size_t word_bytes, size_t val_bytes,
+                                                      bool uniform) {
+  GatherLayout L;
+  size_t off = 0;
+  L.bp = off; off += sizeof(BpWord) * (size_t)p.n_bp;
+  L.dclass = off; off += sizeof(DiagClass) * (size_t)p.n_diag_classes;
+  L.diag = off; off += sizeof(DiagTerm) * (size_t)p.n_diag_rest;
+  off = (off + 15) / 16 * 16;
+  L.lut = off; off += uniform ? 0 : val_bytes * (size_t)p.n_lut;
+  L.gx = off; off += word_bytes * (size_t)p.n_groups;
+  L.total = (off + 15) / 16 * 16;
+  return L;
+}
+
+// masked-shift gather of one support bit of every group (see BpWord)
+template <typename W>
+__device__ __forceinline__ W bp_gather(const BpPair *pairs, int n, W a) {
+  W out = 0;
+#pragma unroll 1
+  for (int k = 0; k < n; ++k) {
+    const BpPair q = pairs[k];
+    out |= (W)((a << q.l) >> q.r) & (W)q.m;
+  }
+  return out;
+}
+
+// state -> index for a full fixed-Hamming-weight block: Lin tables (see StateIndex).  kNone = not a basis state.
+// Blocks hold fewer than 2^32 states (dmv_set_representatives / dmv_basis_build enforce it).
+constexpr uint32_t kNone = 0xffffffffu;
+template <typename W>
+__device__ __forceinline__ uint32_t lin_index(const uint32_t *__restrict__ lin_a, const uint32_t *__restrict__ lin_b,
+                                              int lin_bits, W lo_mask, int weight, uint32_t n, W key) {
+  // key = (row state) ^ (flip mask): always inside the site mask, only the weight can be wrong
+  if (popc_w(key) != weight) return kNone;
+  const uint32_t r = __ldg(lin_a + (uint32_t)(key >> lin_bits)) + __ldg(lin_b + (uint32_t)(key & lo_mask));
+  return r < n ? r : kNone;   // with spin inversion only the first half are representatives
+}
+
+template <bool INV, bool CV, bool CE, bool NARROW, bool LIN, bool UNI>
+__global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
+  using V = typename Val<CV>::type;            // coefficient type
+  using E = typename Val<CE>::type;            // vector element type
+  using A = typename Val<CV || CE>::type;      // row accumulator
+  using W = typename std::conditional<NARROW, uint32_t, uint64_t>::type;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const GatherLayout L = gather_layout(p, sizeof(W), sizeof(V), UNI);
+  BpWord *s_bp = reinterpret_cast<BpWord *>(smem + L.bp);
+  DiagClass *s_dclass = reinterpret_cast<DiagClass *>(smem + L.dclass);
+  DiagTerm *s_diag = reinterpret_cast<DiagTerm *>(smem + L.diag);
+  V *s_lut = reinterpret_cast<V *>(smem + L.lut);
+  W *s_gx = reinterpret_cast<W *>(smem + L.gx);
+  {
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(p.bp);
+    uint64_t *dst = reinterpret_cast<uint64_t *>(s_bp);
+    for (int i = threadIdx.x; i < p.n_bp * (int)(sizeof(BpWord) / 8); i += blockDim.x) dst[i] = src[i];
+    src = reinterpret_cast<const uint64_t *>(p.diag_classes);
+    dst = reinterpret_cast<uint64_t *>(s_dclass);
+    for (int i = threadIdx.x; i < p.n_diag_classes * (int)(sizeof(DiagClass) / 8); i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < p.n_diag_rest; i += blockDim.x) s_diag[i] = p.diag[i];
+    if (!UNI)
+      for (int i = threadIdx.x; i < p.n_lut; i += blockDim.x) s_lut[i] = reinterpret_cast<const V *>(p.lut)[i];
+    for (int i = threadIdx.x; i < p.n_groups; i += blockDim.x) s_gx[i] = (W)p.groups[i].x;
+  }
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const int warps_per_cta = kThreads / 32;
+  const W site = (W)p.site_mask;
+  const E *xv = reinterpret_cast<const E *>(p.x);
+  const V uni = make_v(p.uni_re, p.uni_im, (V *)nullptr);
+  const uint32_t *__restrict__ lin_a = p.index.lin_a, *__restrict__ lin_b = p.index.lin_b;
+  const int lin_bits = p.index.lin_bits, weight = p.index.weight;
+  const W lo_mask = (W)((1ull << lin_bits) - 1);
+  const uint32_t n_states = (uint32_t)p.index.n;
+
+  // row_split = S lanes share one row (each walks every S-th group), combined with S-1 shuffles: small bases
+  const int S = p.row_split > 1 ? p.row_split : 1;
+  const int rows_per_tile = 32 / S;
+  const unsigned slice = lane & (unsigned)(S - 1);
+  W slice_mask = ~(W)0;
+  if (S > 1) {
+    slice_mask = 0;
+    for (int g = (int)slice; g < (int)(8 * sizeof(W)); g += S) slice_mask |= (W)1 << g;
+  }
+  const int64_t n_rows = p.row_end - p.row_begin;
+  const int64_t n_tiles = (n_rows + rows_per_tile - 1) / rows_per_tile;
+  const int64_t warps_total = (int64_t)gridDim.x * warps_per_cta;
+  unsigned long long bad = 0, bad_state = 0;
+
+  for (int64_t tile = (int64_t)blockIdx.x * warps_per_cta + warp; tile < n_tiles; tile += warps_total) {
+    const int64_t i = p.row_begin + tile * rows_per_tile + lane / S;
+    const bool valid = i < p.row_end;
+    const W b = valid ? (W)__ldg(p.index.reps + i) : (W)0;
+    A acc = zero_of((A *)nullptr);
+
+    for (int w = 0; w < p.n_bp; ++w) {
+      const BpWord &Wd = s_bp[w];
+      const W a0 = bp_gather<W>(Wd.p0, Wd.n0, b), a1 = bp_gather<W>(Wd.p1, Wd.n1, b);
+      W mask = (~a0 & ~a1 & (W)Wd.tt[0]) | (a0 & ~a1 & (W)Wd.tt[1]) | (~a0 & a1 & (W)Wd.tt[2]) |
+               (a0 & a1 & (W)Wd.tt[3]);
+      mask &= slice_mask;
+      if (!valid) mask = 0;
+      const int g_base = 64 * w;
+      while (mask) {
+        // two terms per trip: both index look-ups, then both gathers, are in flight together
+        const int g0 = ffs_w(mask) - 1;
+        mask &= mask - 1;
+        const bool two = mask != 0;
+        const int g1 = two ? ffs_w(mask) - 1 : g0;
+        mask &= mask - 1;   // no-op when mask is already empty
+        W k0 = b ^ s_gx[g_base + g0], k1 = b ^ s_gx[g_base + g1];
+        double s0 = 1.0, s1 = 1.0;
+        if (INV) {   // reference src/BatchedOperator.chpl:145-152
+          const W f0 = k0 ^ site, f1 = k1 ^ site;
+          if (f0 < k0) { k0 = f0; s0 = p.inversion_character; }
+          if (f1 < k1) { k1 = f1; s1 = p.inversion_character; }
+        }
+        uint32_t i0, i1;
+        if (LIN) {
+          i0 = lin_index<W>(lin_a, lin_b, lin_bits, lo_mask, weight, n_states, k0);
+          i1 = lin_index<W>(lin_a, lin_b, lin_bits, lo_mask, weight, n_states, k1);
+        } else {
+          i0 = (uint32_t)locate(p.index, (uint64_t)k0);   // -1 -> kNone
+          i1 = (uint32_t)locate(p.index, (uint64_t)k1);
+        }
+        V c0, c1;
+        if (UNI) { c0 = uni; c1 = uni; }
+        else {
+          c0 = s_lut[4 * (g_base + g0) + ((unsigned)((a0 >> g0) & 1) | ((unsigned)((a1 >> g0) & 1) << 1))];
+          c1 = s_lut[4 * (g_base + g1) + ((unsigned)((a0 >> g1) & 1) | ((unsigned)((a1 >> g1) & 1) << 1))];
+        }
+        E x0 = zero_of((E *)nullptr), x1 = zero_of((E *)nullptr);
+        if (i0 != kNone) x0 = ldx(xv, i0);
+        if (two && i1 != kNone) x1 = ldx(xv, i1);
+        if (INV) { c0 = scale(c0, s0); c1 = scale(c1, s1); }
+        fma_to(acc, c0, x0);
+        if (two) fma_to(acc, c1, x1);
+        if ((i0 == kNone) | (two & (i1 == kNone))) {   // DMV:115-118 (rare)
+          if (i0 == kNone && nonzero(c0)) { ++bad; bad_state = (unsigned long long)k0; }
+          if (two && i1 == kNone && nonzero(c1)) { ++bad; bad_state = (unsigned long long)k1; }
+        }
+      }
+    }
+    if (S > 1)
+      for (int m = 1; m < S; m <<= 1) add_to(acc, shfl_xor_v(acc, m));
+
+    if (valid && slice == 0) {
+      // diagonal (DMV:36-53) and the single store of y[i]; without diagonal terms y is accumulated into
+      E out;
+      if (p.n_diag > 0) {
+        double dre = 0.0, dim = 0.0;
+        for (int c = 0; c < p.n_diag_classes; ++c) {
+          const DiagClass &D = s_dclass[c];
+          const W d0 = bp_gather<W>(D.p0, D.n0, b), d1 = bp_gather<W>(D.p1, D.n1, b);
+          const double wgt = (double)(D.count - 2 * popc_w((W)((d0 ^ d1) & (W)D.mask)));
+          dre += wgt * D.v_re;
+          dim += wgt * D.v_im;
+        }
+        for (int t = 0; t < p.n_diag_rest; ++t) {
+          const DiagTerm d = s_diag[t];
+          if (((uint64_t)b & d.m) == d.r) {
+            const double sg = (__popcll((uint64_t)b & d.s) & 1) ? -1.0 : 1.0;
+            dre += sg * d.v_re;
+            dim += sg * d.v_im;
+          }
+        }
+        const E xi = ldx(xv, (uint32_t)i);
+        if constexpr (CE) out = make_double2(dre * xi.x - dim * xi.y, dre * xi.y + dim * xi.x);
+        else out = dre * xi;   // real vectors take the real part of the diagonal
+      } else {
+        out = reinterpret_cast<const E *>(p.y)[i];
+      }
+      if constexpr (CE) { out.x += acc.x; out.y += acc.y; }
+      else if constexpr (CV) out += acc.x;
+      else out += acc;
+      reinterpret_cast<E *>(p.y)[i] = out;
+    }
+  }
+  if (bad) {
+    if (atomicAdd(p.status, bad) == 0) p.status[1] = bad_state;
+  }
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <bool INV, bool CV, bool CE, bool NARROW, bool LIN, bool UNI>
+void launch_t(const KernelParams &p, cudaStream_t stream) {
+  using V = typename Val<CV>::type;
+  const GatherLayout L = gather_layout(p, NARROW ? 4 : 8, sizeof(V), UNI);
+  auto kernel = k_gather<INV, CV, CE, NARROW, LIN, UNI>;
+  if (L.total > 48 * 1024) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess)
+      throw std::runtime_error("k_gather: operator tables do not fit in shared memory");
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, L.total) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  const int rpt = 32 / (p.row_split > 1 ? p.row_split : 1);
+  const int64_t tiles = (p.row_end - p.row_begin + rpt - 1) / rpt;
+  int64_t blocks = (tiles + kThreads / 32 - 1) / (kThreads / 32);
+  const int64_t resident = (int64_t)sm_count() * per_sm;
+  if (blocks > resident) blocks = resident;   // whole waves of resident CTAs, grid-stride over the tiles
+  if (blocks < 1) blocks = 1;
+  kernel<<<(unsigned)blocks, kThreads, L.total, stream>>>(p);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_gather launch: ") + cudaGetErrorString(e));
+  count_launch();
+}
+
+template <bool INV, bool CV, bool CE, bool NARROW>
+void launch_n(const KernelParams &p, bool lin, bool uni, cudaStream_t s) {
+  if (lin) { if (uni) launch_t<INV, CV, CE, NARROW, true, true>(p, s); else launch_t<INV, CV, CE, NARROW, true, false>(p, s); }
+  else { if (uni) launch_t<INV, CV, CE, NARROW, false, true>(p, s); else launch_t<INV, CV, CE, NARROW, false, false>(p, s); }
+}
+template <bool INV, bool CV, bool CE>
+void launch_w(const KernelParams &p, bool narrow, bool lin, bool uni, cudaStream_t s) {
+  if (narrow) launch_n<INV, CV, CE, true>(p, lin, uni, s);
+  else launch_n<INV, CV, CE, false>(p, lin, uni, s);
+}
+template <bool INV>
+void launch_v(const KernelParams &p, bool cv, bool ce, bool narrow, bool lin, bool uni, cudaStream_t s) {
+  if (!cv && !ce) launch_w<INV, false, false>(p, narrow, lin, uni, s);
+  else if (!cv && ce) launch_w<INV, false, true>(p, narrow, lin, uni, s);
+  else if (cv && ce) launch_w<INV, true, true>(p, narrow, lin, uni, s);
+  else launch_w<INV, true, false>(p, narrow, lin, uni, s);
+}
+
+}  // namespace
+
+// p.groups / p.lut / p.bp must point at the ROW-traversal tables (see k_pull); complex_values says whether the
+// LUT is the interleaved complex one.
+void launch_gather(const KernelParams &p, bool inversion, bool complex_values, bool complex_elements,
+                   bool narrow, bool lin, bool uniform, cudaStream_t stream) {
+  if (p.row_end <= p.row_begin) return;
+  if (inversion) launch_v<true>(p, complex_values, complex_elements, narrow, lin, uniform, stream);
+  else launch_v<false>(p, complex_values, complex_elements, narrow, lin, uniform, stream);
+}
+
+}  // namespace dmv

@@ -77,6 +77,8 @@ struct KernelParams {
   unsigned long long *status;
   // source range of this launch
   int64_t row_begin, row_end;
+  // k_gather: the coefficient shared by every emitting (group, support bits) pair, when there is one
+  double uni_re, uni_im;
 };
 
 // launchers (dmv_kernels.cu)
@@ -85,6 +87,9 @@ void launch_generate(const KernelParams &p, Projection proj, bool complex_values
                      bool count_only, cudaStream_t stream);
 void launch_pull(const KernelParams &p, Projection proj, bool complex_values, bool complex_elements,
                  cudaStream_t stream);
+// row traversal without queue / atomics for bit-parallel operators on unprojected or inversion-only bases
+void launch_gather(const KernelParams &p, bool inversion, bool complex_values, bool complex_elements,
+                   bool narrow, bool lin, bool uniform, cudaStream_t stream);
 void launch_accumulate(const KernelParams &p, Projection proj, bool complex_values, bool complex_elements,
                        int64_t count, const uint64_t *betas, const double *coeffs, cudaStream_t stream);
 void launch_build_directory(const uint64_t *reps, int64_t n, uint32_t *dir, uint64_t n_buckets, int shift,

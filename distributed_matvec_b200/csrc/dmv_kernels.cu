@@ -26,6 +26,7 @@ namespace dmv {
 
 static std::atomic<int64_t> g_launches{0};
 int64_t launch_counter() { return g_launches.load(); }
+void count_launch() { g_launches++; }
 
 #define DMV_CUDA_CHECK(expr)                                                                    \
   do {                                                                                          \

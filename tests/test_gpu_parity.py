@@ -121,14 +121,17 @@ def test_state_info_matches_oracle(need_cuda, name):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
-@pytest.mark.parametrize("mode", ["push", "pull"])
+@pytest.mark.parametrize("mode", ["auto", "push", "pull", "pull_queued"])
 @pytest.mark.parametrize("name", SMALL + MEDIUM)
 def test_local_matvec_matches_oracle(need_cuda, name, cplx, mode):
     """test/TestMatrixVectorProduct.chpl on one locale: host vectors through the C ABI.
-    push = the reference's traversal (scatter with atomics), pull = by rows (gather); both index kernels."""
+    push = the reference's traversal (scatter with atomics), pull = by rows (k_gather where it applies, else
+    the queued k_pull), pull_queued = k_pull everywhere; all index kernels."""
     basis, matrix = _load(name)
     op = Operator(matrix)
-    op.set_option("mode", 0 if mode == "push" else 1)
+    op.set_option("mode", {"auto": -1, "push": 0, "pull": 1, "pull_queued": 1}[mode])
+    if mode == "pull_queued":
+        op.set_option("gather", 0)
     op.basis.build()
     reps = op.basis.representatives()
     x = _x(reps.shape[0], cplx)
@@ -142,7 +145,12 @@ def test_local_matvec_matches_oracle(need_cuda, name, cplx, mode):
         yd = op.matvec(xd)
         torch.cuda.synchronize()
         assert _close(yd.cpu().numpy(), y_ref)
-    assert op.info("pull") == (1 if mode == "pull" else 0)
+    gather_applies = not basis.has_permutation_symmetries()    # two-body operators: bit-parallel emit test
+    if mode == "auto":
+        assert op.info("pull") == op.info("gather") == (1 if gather_applies else 0)
+    else:
+        assert op.info("pull") == (0 if mode == "push" else 1)
+        assert op.info("gather") == (1 if (mode == "pull" and gather_applies) else 0)
     op.close()
 
 
@@ -295,6 +303,23 @@ GENERAL_MODELS = {
         {"expression": "0.3j × σ⁺₀ σ⁻₁", "sites": [[i, (i + 2) % 10] for i in range(10)]},
         {"expression": "-0.3j × σ⁻₀ σ⁺₁", "sites": [[i, (i + 2) % 10] for i in range(10)]},
         {"expression": "σᶻ₀", "sites": [[0], [3]]}]),
+    # two-body, bond-dependent couplings: bit-parallel emit test with a non-uniform coefficient table
+    "anisotropic_bonds": lambda: _custom(12, 6, [
+        {"expression": "σ⁺₀ σ⁻₁", "sites": [[i, (i + 1) % 12] for i in range(12)]},
+        {"expression": "σ⁻₀ σ⁺₁", "sites": [[i, (i + 1) % 12] for i in range(12)]},
+        {"expression": "0.37 × σ⁺₀ σ⁻₁", "sites": [[i, (i + 3) % 12] for i in range(0, 12, 2)]},
+        {"expression": "0.37 × σ⁻₀ σ⁺₁", "sites": [[i, (i + 3) % 12] for i in range(0, 12, 2)]},
+        {"expression": "1.3 × σᶻ₀ σᶻ₁", "sites": [[i, (i + 1) % 12] for i in range(12)]}]),
+    # more than 32 sites / groups: the 64-bit row path of k_gather (two magnons on a 34-site ring)
+    "wide_two_magnon": lambda: _custom(34, 2, [
+        {"expression": "σˣ₀ σˣ₁", "sites": [[i, (i + 1) % 34] for i in range(34)]},
+        {"expression": "σʸ₀ σʸ₁", "sites": [[i, (i + 1) % 34] for i in range(34)]},
+        {"expression": "σᶻ₀ σᶻ₁", "sites": [[i, (i + 1) % 34] for i in range(34)]}]),
+    # spin inversion (BatchedOperator branch b) with a next-nearest-neighbour zz coupling, odd sector
+    "inversion_two_body": lambda: _custom(12, 6, [
+        {"expression": "σˣ₀ σˣ₁", "sites": [[i, (i + 1) % 12] for i in range(12)]},
+        {"expression": "σʸ₀ σʸ₁", "sites": [[i, (i + 1) % 12] for i in range(12)]},
+        {"expression": "0.5 × σᶻ₀ σᶻ₁", "sites": [[i, (i + 2) % 12] for i in range(12)]}], spin_inversion=-1),
     # translation symmetry with a complex character (momentum sector 1)
     "momentum_sector": lambda: _custom(10, 5, [
         {"expression": "σˣ₀ σˣ₁", "sites": [[i, (i + 1) % 10] for i in range(10)]},
@@ -329,6 +354,50 @@ def test_general_operators_all_paths(need_cuda, model):
         torch.cuda.synchronize()
         assert _close(hashed_to_block([t.cpu().numpy() for t in yb], masks), y_ref)
         cl.close()
+
+
+def test_gather_kernel_variants(need_cuda):
+    """Which k_gather specialisation each operator gets (32-bit rows, LUT-free uniform coefficient), and that
+    every one of them reproduces the oracle for real and complex vectors, host and device pointers."""
+    expect = {   # name: (gather applies, narrow, uniform coefficient)
+        "anisotropic_bonds": (1, 1, 0), "wide_two_magnon": (1, 0, 1), "inversion_two_body": (1, 1, 1),
+        "complex_hopping": (1, 1, 0), "three_site": (0, 1, 0)}
+    for model, (applies, narrow, uniform) in expect.items():
+        basis, matrix = GENERAL_MODELS[model]()
+        reps, _ = po.enumerate_states(basis)
+        op = Operator(matrix)
+        op.basis.build()
+        assert (op.info("gather"), op.info("gather_narrow")) == (applies, narrow), model
+        if applies:
+            assert op.info("gather_uniform") == uniform, model
+        for cplx in (False, True):
+            x = _x(reps.shape[0], cplx, seed=23)
+            y_ref = po.matvec_global(matrix, reps, x, 1)
+            y = op.matvec(x)
+            assert _close(y, y_ref), (model, cplx, np.abs(y - y_ref).max())
+            yd = op.matvec(torch.from_numpy(x).cuda()).cpu().numpy()
+            if applies:
+                assert np.array_equal(yd, y), model    # no atomics: bit-reproducible
+            else:
+                assert _close(yd, y_ref), model
+        op.close()
+
+
+def test_gather_is_bit_reproducible_and_chunked_d2h(need_cuda):
+    """k_gather writes every y element once: repeated products are bit-identical, and the host-pointer call
+    (row chunks with overlapped D2H copies) returns exactly the device result."""
+    basis, matrix = _load("heisenberg_chain_20")
+    op = Operator(matrix)
+    op.basis.build()
+    n = op.basis.numberStates()
+    assert n >= 1 << 16 and op.info("gather") == 1
+    x = _x(n, True, 3)
+    xd = torch.from_numpy(x).cuda()
+    y1 = op.matvec(xd).cpu().numpy()
+    y2 = op.matvec(xd).cpu().numpy()
+    y_host = op.matvec(x)
+    assert np.array_equal(y1, y2) and np.array_equal(y1, y_host)
+    op.close()
 
 
 def test_bitparallel_matches_group_walk(need_cuda):
