@@ -351,8 +351,9 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "c128" if cplx else "f64", "data": "synthetic",
         "config": {"workload": args.workload, "basis_states": n_total, "off_diag_terms": nnz_total,
-                   "terms_per_s": nnz_total / (ms_per_step * 1e-3), "partition": f"hash{world}", "exchange": ("peer-direct NVLink stores" if op.info("peer_direct") else
-                                                               ("nccl send/recv" if world > 1 else "none")),
+                   "terms_per_s": nnz_total / (ms_per_step * 1e-3), "partition": f"hash{world}", "exchange": ("replicated x: NCCL all-gather + row gather" if op.info("replicated") else
+                                "peer-direct NVLink stores" if op.info("peer_direct") else
+                                ("nccl send/recv" if world > 1 else "none")),
                    "x": "uniform(-0.5,0.5) seed 42", "l2": "flushed between timed iterations (256 MB write)",
                    "ms_best_step": ms_best, "basis_build_s": build_s},
         "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "states/s", "ms_per_step": e2e_ms,

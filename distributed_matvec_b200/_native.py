@@ -22,6 +22,10 @@ class BasisDesc(C.Structure):
     ]
 
 
+class ExternalArray(C.Structure):   # chpl_external_array
+    _fields_ = [("elts", C.c_void_p), ("num_elts", C.c_uint64), ("freer", C.CFUNCTYPE(None, C.c_void_p))]
+
+
 class OperatorDesc(C.Structure):
     _fields_ = [
         ("n_off", C.c_int64), ("off_v", C.c_void_p), ("off_m", C.c_void_p), ("off_r", C.c_void_p),
@@ -64,6 +68,8 @@ _SIGNATURES = [
     ("dmv_outgoing", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                C.POINTER(C.c_int64)]),
     ("dmv_accumulate", C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("dmv_replicated_setup", C.c_int, [C.c_void_p]),
+    ("dmv_replicated_product", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("dmv_comm_unique_id", C.c_int, [C.c_void_p]),
     ("dmv_comm_init", C.c_int, [C.c_void_p, C.c_void_p]),
     ("dmv_last_timings", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
@@ -71,6 +77,12 @@ _SIGNATURES = [
     ("dmv_number_terms", C.c_int64, [C.c_void_p]),
     ("dmv_bind_operator", C.c_int, [C.c_void_p, C.c_void_p]),
     ("ls_chpl_matrix_vector_product", None, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    ("dmv_apply_diag", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    ("dmv_apply_off_diag", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("ls_chpl_operator_apply_diag", None, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(ExternalArray), C.c_int64]),
+    ("ls_chpl_operator_apply_off_diag", None, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(ExternalArray),
+                                               C.POINTER(ExternalArray), C.POINTER(ExternalArray), C.c_int64]),
+    ("ls_chpl_enumerate_representatives", None, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ExternalArray)]),
     ("dmv_debug_compile_group", C.c_int, [C.POINTER(BasisDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                           C.c_void_p]),
 ]

@@ -351,8 +351,18 @@ struct dmv_context {
   double timings[T_COUNT] = {};
   // communicator
   ncclComm_t comm = nullptr;
+  // replicated-x product (exchange = 2, see setup_replicated): a single-rank twin context holding the WHOLE basis,
+  // the slot of every global state in the all-gathered x, and the gathered x itself
+  std::vector<double> k_off_v, k_diag_v;                      // copies of the creation arguments
+  std::vector<uint64_t> k_off_m, k_off_r, k_off_x, k_off_s, k_diag_m, k_diag_r, k_diag_s;
+  dmv_context *global = nullptr;
+  DevBuf<uint32_t> d_pos;
+  int64_t repl_block = 0;        // slot size per rank in the gathered x (the largest block)
+  DevBuf<double> d_xcat;
+  bool replicated = false, exchange_decided = false, timeline_replicated = false;
 
   ~dmv_context() {
+    delete global;
     for (void *q : peer_betas) if (q) cudaIpcCloseMemHandle(q);
     for (void *q : peer_coeffs) if (q) cudaIpcCloseMemHandle(q);
     if (comm) nccl().CommDestroy(comm);
@@ -849,9 +859,15 @@ void do_accumulate(dmv_context *ctx, int elt, int64_t count, const uint64_t *bet
 void collect_timings(dmv_context *ctx) {
   auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]); return (double)t; };
   ctx->timings[T_H2D] = ms(0, 1);
+  if (ctx->timeline_replicated) {   // the exchange (all-gather of x) comes first, then the row gather
+    ctx->timings[T_EXCHANGE] = ms(1, 6);
+    ctx->timings[T_GENERATE] = ms(6, 2);
+    ctx->timings[T_ACCUMULATE] = 0.0;
+  } else {
   ctx->timings[T_GENERATE] = ms(1, 2);
   ctx->timings[T_EXCHANGE] = ms(2, 3);
   ctx->timings[T_ACCUMULATE] = ms(3, 4);
+  }
   ctx->timings[T_D2H] = ms(4, 5);
   ctx->timings[T_TOTAL] = ms(0, 5);
 }
@@ -966,6 +982,117 @@ void setup_exchange(dmv_context *ctx) {
   ctx->ptr_width = 0;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Replicated-x product.  With 180 GB of HBM per GPU every basis of BASELINE.json fits on ONE device many times
+// over, so for operators k_gather applies to, the ranks can trade the reference's record exchange (24 bytes per
+// off-diagonal term over NVLink, DMV:313-436) for one all-gather of x (E bytes per STATE): every rank keeps the
+// whole sorted basis (a single-rank twin context), gathers x from all ranks into slots of equal size, and computes
+// ITS rows by the atomics-free row traversal.  The hash partition of x, y and the representatives -- the layout the
+// callers see (SE:129-156) -- is unchanged.  Local part of the set-up; no communication here.
+void setup_replicated(dmv_context *ctx) {
+  require_states(ctx);
+  const int P = ctx->num_ranks;
+  if (P > 32) throw std::runtime_error("replicated-x product supports at most 32 ranks");
+  if (!ctx->gather_ok || ctx->proj == PROJ_GROUP || ctx->opt_bitparallel == 0)
+    throw std::runtime_error("replicated-x product needs an operator k_gather applies to");
+  if (!ctx->global) {
+    dmv_basis_desc b{};
+    b.number_sites = ctx->n_sites; b.hamming_weight = ctx->hamming_weight; b.spin_inversion = ctx->spin_inversion;
+    dmv_operator_desc o{};
+    o.n_off = (int64_t)ctx->k_off_m.size(); o.off_v = ctx->k_off_v.data();
+    o.off_m = ctx->k_off_m.data(); o.off_r = ctx->k_off_r.data(); o.off_x = ctx->k_off_x.data(); o.off_s = ctx->k_off_s.data();
+    o.n_diag = (int64_t)ctx->k_diag_m.size(); o.diag_v = ctx->k_diag_v.data();
+    o.diag_m = ctx->k_diag_m.data(); o.diag_r = ctx->k_diag_r.data(); o.diag_s = ctx->k_diag_s.data();
+    // rough size check before enumerating: reps + directory + positions + gathered x
+    double states = 1.0;
+    if (ctx->hamming_weight >= 0) states = (double)binom().c[ctx->n_sites][ctx->hamming_weight];
+    else states = std::ldexp(1.0, ctx->n_sites);
+    if (ctx->spin_inversion != 0) states *= 0.5;
+    size_t free_b = 0, total_b = 0;
+    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    if (states * 40.0 > 0.5 * (double)free_b) throw std::runtime_error("replicated-x product: the whole basis does not fit");
+    dmv_context *g = nullptr;
+    if (dmv_context_create(&b, &o, ctx->device, 0, 1, &g) != 0) throw std::runtime_error(g_last_error);
+    ctx->global = g;
+    if (dmv_basis_build(g) != 0) throw std::runtime_error(g_last_error);
+  }
+  dmv_context *g = ctx->global;
+  CUDA_CHECK(cudaStreamSynchronize(g->stream));
+  const int64_t n = g->n_states;
+  // ---- slot of every global state: owner r = hash % P (SE:129-136), index inside r's ascending block
+  const int64_t chunk = 256, n_chunks = (n + chunk - 1) / chunk;
+  DevBuf<unsigned long long> d_counts, d_base;
+  d_counts.alloc((size_t)n_chunks * P);
+  d_base.alloc((size_t)n_chunks * P);
+  ctx->d_pos.alloc((size_t)n);
+  launch_owner_positions(g->d_reps.ptr, n, P, chunk, false, d_counts.ptr, nullptr, 0, nullptr, ctx->stream);
+  std::vector<unsigned long long> counts((size_t)n_chunks * P), base((size_t)n_chunks * P);
+  CUDA_CHECK(cudaMemcpyAsync(counts.data(), d_counts.ptr, counts.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  std::vector<unsigned long long> total(P, 0);
+  for (int64_t c = 0; c < n_chunks; ++c)
+    for (int r = 0; r < P; ++r) { base[(size_t)c * P + r] = total[r]; total[r] += counts[(size_t)c * P + r]; }
+  if ((int64_t)total[ctx->rank] != ctx->n_states)
+    throw std::runtime_error("replicated-x product: this rank's block is not the hash partition of the full basis");
+  int64_t block = 0;
+  for (int r = 0; r < P; ++r) block = std::max<int64_t>(block, (int64_t)total[r]);
+  block = (block + 1) / 2 * 2;
+  if ((double)block * P >= 4294967295.0) throw std::runtime_error("replicated-x product: more than 2^32 slots");
+  d_base.upload(base, ctx->stream);
+  launch_owner_positions(g->d_reps.ptr, n, P, chunk, true, d_counts.ptr, d_base.ptr, block, ctx->d_pos.ptr, ctx->stream);
+  ctx->repl_block = block;
+  ctx->d_xcat.alloc((size_t)block * P * 2);
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_xcat.ptr, 0, (size_t)block * P * 2 * sizeof(double), ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+// y (this rank's block) <- rows of H applied to the gathered x (slot r * repl_block holds rank r's block)
+void replicated_rows(dmv_context *ctx, int elt, const void *x_cat, void *y_dev) {
+  dmv_context *g = ctx->global;
+  KernelParams p = base_params(g);
+  p.x = x_cat;
+  p.y = y_dev;
+  p.status = ctx->d_status.ptr;
+  p.row_states = ctx->d_reps.ptr;
+  p.row_begin = 0;
+  p.row_end = ctx->n_states;
+  p.pos = ctx->d_pos.ptr;
+  p.x_row_offset = (int64_t)ctx->rank * ctx->repl_block;
+  select_tables(g, p, true, g->complex_coefficients);
+  p.row_split = choose_row_split(ctx->n_states, (int)g->h_pull.groups.size());
+  p.uni_re = g->gather_uni[0]; p.uni_im = g->gather_uni[1];
+  launch_gather(p, g->proj == PROJ_INVERSION, g->complex_coefficients, elt == DMV_C128, g->gather_narrow,
+                g->index_mode == INDEX_LIN, g->gather_uniform, ctx->stream);
+}
+
+// Collective: which exchange the distributed product uses.  exchange = -1 (auto) prefers the replicated-x product
+// when k_gather applies and the whole basis fits, else the record exchange (peer-direct / NCCL, see setup_exchange).
+void decide_exchange(dmv_context *ctx) {
+  NcclApi &N = nccl();
+  int ok = 0;
+  std::string why;
+  const bool want = (ctx->opt_exchange == 2 || ctx->opt_exchange == -1) && ctx->opt_mode != 0;
+  if (want && ctx->gather_ok && ctx->proj != PROJ_GROUP && ctx->opt_bitparallel != 0 && ctx->num_ranks <= 32) {
+    try { setup_replicated(ctx); ok = 1; } catch (const std::exception &e) { why = e.what(); ok = 0; }
+  } else {
+    why = "k_gather does not apply to this operator / basis";
+  }
+  ctx->d_barrier.alloc(1);
+  CUDA_CHECK(cudaMemcpyAsync(ctx->d_barrier.ptr, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_CHECK(N.AllReduce(ctx->d_barrier.ptr, ctx->d_barrier.ptr, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+  int agree = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&agree, ctx->d_barrier.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->replicated = agree != 0;
+  ctx->exchange_decided = true;
+  if (!ctx->replicated) {
+    delete ctx->global; ctx->global = nullptr;
+    ctx->d_pos.release(); ctx->d_xcat.release();
+    if (ctx->opt_exchange == 2)
+      throw std::runtime_error("replicated-x exchange requested but not possible on every rank: " + why);
+  }
+}
+
 // =================================================================================================
 extern "C" {
 
@@ -1007,6 +1134,12 @@ int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op,
   else ctx->proj = PROJ_NONE;                                          // BO:89
   ctx->identity_index = (ctx->proj == PROJ_NONE && ctx->hamming_weight < 0);
 
+  ctx->k_off_v.assign(op->off_v, op->off_v + 2 * op->n_off);
+  ctx->k_off_m.assign(op->off_m, op->off_m + op->n_off); ctx->k_off_r.assign(op->off_r, op->off_r + op->n_off);
+  ctx->k_off_x.assign(op->off_x, op->off_x + op->n_off); ctx->k_off_s.assign(op->off_s, op->off_s + op->n_off);
+  ctx->k_diag_v.assign(op->diag_v, op->diag_v + 2 * op->n_diag);
+  ctx->k_diag_m.assign(op->diag_m, op->diag_m + op->n_diag); ctx->k_diag_r.assign(op->diag_r, op->diag_r + op->n_diag);
+  ctx->k_diag_s.assign(op->diag_s, op->diag_s + op->n_diag);
   bool cplx = false;
   // ---- operator: group off-diagonal terms by flip mask
   std::map<uint64_t, std::vector<OffTerm>> by_x;
@@ -1111,9 +1244,12 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
     ctx->opt_index = (int)value;
     if (ctx->n_states >= 0) { CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); select_index_mode(ctx); }
   } else if (key == "exchange") {
-    if (value < -1 || value > 1) throw std::runtime_error("exchange: -1 auto, 0 NCCL send/recv, 1 peer-direct");
+    if (value < -1 || value > 2)
+      throw std::runtime_error("exchange: -1 auto, 0 NCCL send/recv, 1 peer-direct records, 2 replicated x (all-gather)");
     ctx->opt_exchange = (int)value;
     ctx->planned = false;
+    ctx->exchange_decided = false;
+    ctx->replicated = false;
   } else if (key == "gather") {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
@@ -1131,10 +1267,13 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
   if (!ctx) return -1;
   if (key == "index_mode") return ctx->index_mode;
   if (key == "pull") return use_pull(ctx) ? 1 : 0;
-  if (key == "gather") return (use_pull(ctx) && use_gather(ctx)) ? 1 : 0;
+  if (key == "gather") return ((use_pull(ctx) && use_gather(ctx)) || ctx->replicated) ? 1 : 0;
   if (key == "gather_narrow") return ctx->gather_narrow ? 1 : 0;
   if (key == "gather_uniform") return ctx->gather_uniform ? 1 : 0;
   if (key == "peer_direct") return ctx->peer_direct ? 1 : 0;
+  if (key == "replicated") return ctx->replicated ? 1 : 0;
+  if (key == "replicated_block") return ctx->repl_block;
+  if (key == "global_states") return ctx->global ? ctx->global->n_states : -1;
   if (key == "projection") return (int64_t)ctx->proj;
   if (key == "n_groups") return (int64_t)ctx->h_push.groups.size();
   if (key == "bp_words") return (int64_t)ctx->h_push.bp.size();
@@ -1420,6 +1559,38 @@ int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
   }
   if (!ctx->comm) throw std::runtime_error("dmv_matvec on several ranks needs dmv_comm_init");
   NcclApi &N = nccl();
+  if (!ctx->exchange_decided) decide_exchange(ctx);
+  if (ctx->replicated) {
+    // ---- replicated-x product: all-gather x into equal slots, then this rank's rows by the row traversal
+    if (x == y) throw std::runtime_error("x and y must not alias");
+    const size_t esz = (size_t)8 * elt, bytes = (size_t)ctx->n_states * esz;
+    char *slot = reinterpret_cast<char *>(ctx->d_xcat.ptr) + (size_t)ctx->rank * ctx->repl_block * esz;
+    CUDA_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(slot, x, bytes, cudaMemcpyDefault, ctx->stream));   // host or device x
+    void *y_dev = y;
+    const bool y_host = !is_device_pointer(y);
+    if (y_host) {
+      ctx->d_y.alloc((size_t)ctx->n_states * elt);
+      y_dev = ctx->d_y.ptr;
+      if (ctx->h_diag_kept == 0) CUDA_CHECK(cudaMemcpyAsync(y_dev, y, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CUDA_CHECK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    NCCL_CHECK(N.AllGather(slot, ctx->d_xcat.ptr, (size_t)ctx->repl_block * elt, ncclDouble, ctx->comm, ctx->stream));
+    CUDA_CHECK(cudaEventRecord(ctx->ev[6], ctx->stream));
+    replicated_rows(ctx, elt, ctx->d_xcat.ptr, y_dev);
+    CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CUDA_CHECK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (y_host) CUDA_CHECK(cudaMemcpyAsync(y, y_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->timeline_replicated = true;
+    if (y_host || !is_device_pointer(x)) {
+      check_status(ctx);
+      collect_timings(ctx);
+    }
+    return 0;
+  }
+  ctx->timeline_replicated = false;
   if (!ctx->planned) do_plan(ctx);
   if (ctx->recv_counts[0] < 0) setup_exchange(ctx);
   auto barrier = [&]() {
@@ -1466,6 +1637,27 @@ int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
     check_status(ctx);
     collect_timings(ctx);
   }
+  API_END
+}
+
+// Replicated-x product without a communicator (the host owns the all-gather): set-up, then rows of H applied to
+// a caller-assembled x_cat (rank r's block at r * dmv_get_info("replicated_block") elements).  Device pointers.
+int dmv_replicated_setup(dmv_context *ctx) {
+  API_BEGIN
+  use_device(ctx);
+  setup_replicated(ctx);
+  API_END
+}
+
+int dmv_replicated_product(dmv_context *ctx, int elt, const void *x_cat, void *y) {
+  API_BEGIN
+  use_device(ctx);
+  require_states(ctx);
+  if (!ctx->global || ctx->repl_block <= 0) throw std::runtime_error("dmv_replicated_setup has not run");
+  if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
+  if (!is_device_pointer(x_cat) || !is_device_pointer(y)) throw std::runtime_error("dmv_replicated_product needs device pointers");
+  replicated_rows(ctx, elt, x_cat, y);
+  check_status(ctx);
   API_END
 }
 
@@ -1523,6 +1715,111 @@ int dmv_compute_off_diag(dmv_context *ctx, int64_t count, const uint64_t *alphas
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   if (n) *n = (int64_t)total;
   API_END
+}
+
+// ---- plugin kernels: ls_chpl_operator_apply_diag / _apply_off_diag (reference src/BatchedOperator.chpl:217-275)
+int dmv_apply_diag(dmv_context *ctx, int64_t count, const uint64_t *alphas, double *coeffs) {
+  API_BEGIN
+  use_device(ctx);
+  if (ctx->proj != PROJ_NONE) throw std::runtime_error("bases that require projection are not yet supported");  // BO:226-227
+  if (count < 0) throw std::runtime_error("negative count");
+  InArg<uint64_t> a(alphas, (size_t)count, ctx->stream);
+  OutArg<double> out(coeffs, (size_t)count);
+  KernelParams p = base_params(ctx);
+  select_tables(ctx, p, false, true);
+  launch_apply_diag(p, count, a.ptr, out.ptr, ctx->stream);
+  out.finish(ctx->stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+int dmv_apply_off_diag(dmv_context *ctx, int64_t count, const uint64_t *alphas, uint64_t *betas, double *coeffs,
+                       int64_t *offsets) {
+  API_BEGIN
+  use_device(ctx);
+  if (ctx->proj != PROJ_NONE) throw std::runtime_error("bases that require projection are not yet supported");  // BO:247-248
+  if (count < 0) throw std::runtime_error("negative count");
+  const size_t cap = (size_t)count * std::max<size_t>(1, ctx->h_push.groups.size());
+  InArg<uint64_t> a(alphas, (size_t)count, ctx->stream);
+  OutArg<uint64_t> ob(betas, cap);
+  OutArg<double> oc(coeffs, cap * 2);
+  OutArg<int64_t> oo(offsets, (size_t)count + 1);
+  DevBuf<int64_t> d_counts;
+  d_counts.alloc((size_t)count + 1);
+  KernelParams p = base_params(ctx);
+  select_tables(ctx, p, false, true);
+  launch_apply_off_diag(p, count, a.ptr, nullptr, d_counts.ptr, nullptr, nullptr, false, ctx->stream);
+  std::vector<int64_t> h((size_t)count + 1, 0);
+  if (count > 0)
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), d_counts.ptr, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  int64_t acc = 0;
+  for (int64_t i = 0; i < count; ++i) { const int64_t c = h[i]; h[i] = acc; acc += c; }   // CSR row pointer (BO:109)
+  h[count] = acc;
+  CUDA_CHECK(cudaMemcpyAsync(oo.ptr, h.data(), ((size_t)count + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  launch_apply_off_diag(p, count, a.ptr, oo.ptr, nullptr, ob.ptr, oc.ptr, true, ctx->stream);
+  ob.finish(ctx->stream, (size_t)acc); oc.finish(ctx->stream, (size_t)acc * 2); oo.finish(ctx->stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+extern "C++" {
+namespace {
+dmv_context *bound_context(const void *key, const char *who) {
+  dmv_context *ctx = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_bind_mutex);
+    auto it = g_bindings.find(key);
+    if (it != g_bindings.end()) ctx = it->second;
+  }
+  if (!ctx) { fprintf(stderr, "%s: handle is not bound to a dmv context (dmv_bind_operator)\n", who); abort(); }
+  return ctx;
+}
+template <typename T>
+dmv_external_array external_array(size_t n) {   // convertToExternalArray (BO:232): callee allocates, caller frees
+  dmv_external_array a;
+  a.elts = n ? malloc(n * sizeof(T)) : nullptr;
+  a.num_elts = n;
+  a.freer = n ? &free : nullptr;
+  if (n && !a.elts) { fprintf(stderr, "out of memory\n"); abort(); }
+  return a;
+}
+}  // namespace
+}  // extern "C++"
+
+void ls_chpl_operator_apply_diag(const void *ls_hs_operator_ptr, int64_t count, const uint64_t *alphas,
+                                 dmv_external_array *coeffs, int64_t /*num_tasks*/) {
+  dmv_context *ctx = bound_context(ls_hs_operator_ptr, "ls_chpl_operator_apply_diag");
+  *coeffs = external_array<double>((size_t)count);
+  if (dmv_apply_diag(ctx, count, alphas, (double *)coeffs->elts) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
+}
+
+void ls_chpl_operator_apply_off_diag(const void *ls_hs_operator_ptr, int64_t count, const uint64_t *alphas,
+                                     dmv_external_array *betas, dmv_external_array *coeffs,
+                                     dmv_external_array *offsets, int64_t /*num_tasks*/) {
+  dmv_context *ctx = bound_context(ls_hs_operator_ptr, "ls_chpl_operator_apply_off_diag");
+  const size_t T = (size_t)dmv_max_number_off_diag(ctx);
+  *offsets = external_array<int64_t>((size_t)count + 1);
+  if (T == 0) {   // BO:269-273
+    betas->elts = nullptr; betas->num_elts = 0; betas->freer = nullptr;
+    coeffs->elts = nullptr; coeffs->num_elts = 0; coeffs->freer = nullptr;
+    memset(offsets->elts, 0, ((size_t)count + 1) * sizeof(int64_t));
+    return;
+  }
+  *betas = external_array<uint64_t>((size_t)count * T);
+  *coeffs = external_array<double>((size_t)count * T * 2);
+  if (dmv_apply_off_diag(ctx, count, alphas, (uint64_t *)betas->elts, (double *)coeffs->elts,
+                         (int64_t *)offsets->elts) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
+}
+
+// reference src/StatesEnumeration.chpl:588-603: the bounds are accepted and ignored there too (the whole range of the
+// basis is enumerated); returns this locale's block
+void ls_chpl_enumerate_representatives(const void *ls_hs_basis_ptr, uint64_t /*lower*/, uint64_t /*upper*/,
+                                       dmv_external_array *dest) {
+  dmv_context *ctx = bound_context(ls_hs_basis_ptr, "ls_chpl_enumerate_representatives");
+  if (dmv_number_states(ctx) < 0 && dmv_basis_build(ctx) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
+  *dest = external_array<uint64_t>((size_t)dmv_number_states(ctx));
+  if (dmv_get_representatives(ctx, (uint64_t *)dest->elts, nullptr) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
 }
 
 int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t count,

@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
   const int lin_bits = p.index.lin_bits, weight = p.index.weight;
   const W lo_mask = (W)((1ull << lin_bits) - 1);
   const uint32_t n_states = (uint32_t)p.index.n;
+  const uint64_t *__restrict__ row_states = p.row_states ? p.row_states : p.index.reps;
+  const uint32_t *__restrict__ pos = p.pos;   // replicated-x product: global index -> slot of the gathered x
 
   // row_split = S lanes share one row (each walks every S-th group), combined with S-1 shuffles: small bases
   const int S = p.row_split > 1 ? p.row_split : 1;
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
   for (int64_t tile = (int64_t)blockIdx.x * warps_per_cta + warp; tile < n_tiles; tile += warps_total) {
     const int64_t i = p.row_begin + tile * rows_per_tile + lane / S;
     const bool valid = i < p.row_end;
-    const W b = valid ? (W)__ldg(p.index.reps + i) : (W)0;
+    const W b = valid ? (W)__ldg(row_states + i) : (W)0;
     A acc = zero_of((A *)nullptr);
 
     for (int w = 0; w < p.n_bp; ++w) {
@@ -199,6 +201,10 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
           c0 = s_lut[4 * (g_base + g0) + ((unsigned)((a0 >> g0) & 1) | ((unsigned)((a1 >> g0) & 1) << 1))];
           c1 = s_lut[4 * (g_base + g1) + ((unsigned)((a0 >> g1) & 1) | ((unsigned)((a1 >> g1) & 1) << 1))];
         }
+        if (pos) {
+          if (i0 != kNone) i0 = __ldg(pos + i0);
+          if (two && i1 != kNone) i1 = __ldg(pos + i1);
+        }
         E x0 = zero_of((E *)nullptr), x1 = zero_of((E *)nullptr);
         if (i0 != kNone) x0 = ldx(xv, i0);
         if (two && i1 != kNone) x1 = ldx(xv, i1);
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
             dim += sg * d.v_im;
           }
         }
-        const E xi = ldx(xv, (uint32_t)i);
+        const E xi = ldx(xv, (uint32_t)(p.x_row_offset + i));
         if constexpr (CE) out = make_double2(dre * xi.x - dim * xi.y, dre * xi.y + dim * xi.x);
         else out = dre * xi;   // real vectors take the real part of the diagonal
       } else {
@@ -249,6 +255,35 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
   if (bad) {
     if (atomicAdd(p.status, bad) == 0) p.status[1] = bad_state;
   }
+}
+
+// one thread per chunk of consecutive global states (set-up only)
+template <bool WRITE>
+__global__ void k_owner_positions(const uint64_t *__restrict__ states, int64_t n, int num_ranks, int64_t chunk,
+                                  unsigned long long *chunk_counts, const unsigned long long *__restrict__ chunk_base,
+                                  int64_t block, uint32_t *pos) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t first = c * chunk;
+  if (first >= n) return;
+  const int64_t last = min(n, first + chunk);
+  uint32_t cnt[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) cnt[r] = 0;
+  for (int64_t g = first; g < last; ++g) {
+    const int r = locale_idx_of(states[g], num_ranks);
+    uint32_t k = 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q)   // register-resident counters: no dynamic indexing
+      if (q == r) { k = cnt[q]; cnt[q] = k + 1; }
+    if (WRITE) pos[g] = (uint32_t)((int64_t)r * block + (int64_t)chunk_base[c * num_ranks + r] + k);
+  }
+  if (!WRITE)
+    for (int r = 0; r < num_ranks; ++r) {
+      uint32_t k = 0;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) if (q == r) k = cnt[q];
+      chunk_counts[c * num_ranks + r] = k;
+    }
 }
 
 int sm_count() {
@@ -305,6 +340,20 @@ void launch_v(const KernelParams &p, bool cv, bool ce, bool narrow, bool lin, bo
 }
 
 }  // namespace
+
+void launch_owner_positions(const uint64_t *states, int64_t n, int num_ranks, int64_t chunk, bool write_pass,
+                            unsigned long long *chunk_counts, const unsigned long long *chunk_base, int64_t block,
+                            uint32_t *pos, cudaStream_t stream) {
+  if (n <= 0) return;
+  if (num_ranks > 32) throw std::runtime_error("replicated-x product supports at most 32 ranks");
+  const int64_t n_chunks = (n + chunk - 1) / chunk;
+  const unsigned blocks = (unsigned)((n_chunks + 127) / 128);
+  if (write_pass) k_owner_positions<true><<<blocks, 128, 0, stream>>>(states, n, num_ranks, chunk, chunk_counts, chunk_base, block, pos);
+  else k_owner_positions<false><<<blocks, 128, 0, stream>>>(states, n, num_ranks, chunk, chunk_counts, chunk_base, block, pos);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_owner_positions launch: ") + cudaGetErrorString(e));
+  count_launch();
+}
 
 // p.groups / p.lut / p.bp must point at the ROW-traversal tables (see k_pull); complex_values says whether the
 // LUT is the interleaved complex one.

@@ -79,6 +79,12 @@ struct KernelParams {
   int64_t row_begin, row_end;
   // k_gather: the coefficient shared by every emitting (group, support bits) pair, when there is one
   double uni_re, uni_im;
+  // k_gather, replicated-x product (several ranks, every rank holds the whole basis and an all-gathered x):
+  //   rows come from row_states (this rank's block) while `index` describes the GLOBAL basis; global index g lives
+  //   at x[pos[g]]; the row's own element is x[x_row_offset + i].  All null / zero on one rank.
+  const uint64_t *row_states;
+  const uint32_t *pos;
+  int64_t x_row_offset;
 };
 
 // launchers (dmv_kernels.cu)
@@ -92,6 +98,10 @@ void launch_gather(const KernelParams &p, bool inversion, bool complex_values, b
                    bool narrow, bool lin, bool uniform, cudaStream_t stream);
 void launch_accumulate(const KernelParams &p, Projection proj, bool complex_values, bool complex_elements,
                        int64_t count, const uint64_t *betas, const double *coeffs, cudaStream_t stream);
+// plugin kernels (BO:217-275): diagonal coefficients / CSR list of off-diagonal terms of caller-given states
+void launch_apply_diag(const KernelParams &p, int64_t count, const uint64_t *alphas, double *coeffs, cudaStream_t stream);
+void launch_apply_off_diag(const KernelParams &p, int64_t count, const uint64_t *alphas, const int64_t *offsets,
+                           int64_t *counts, uint64_t *betas, double *coeffs, bool write_pass, cudaStream_t stream);
 void launch_build_directory(const uint64_t *reps, int64_t n, uint32_t *dir, uint64_t n_buckets, int shift,
                             cudaStream_t stream);
 void launch_state_index(const StateIndex &ix, int64_t count, const uint64_t *spins, int64_t *indices,
@@ -110,6 +120,11 @@ void launch_enumerate(const OrbitProgram &P, Projection proj, uint64_t site_mask
                       const uint64_t *chunk_last, unsigned long long *chunk_count,
                       const unsigned long long *chunk_offset, uint64_t *out, double *out_norms,
                       bool write_pass, cudaStream_t stream);
+// replicated-x set-up: owner and position of every global state in the all-gathered x.
+//   pass 0: chunk_counts[c * P + r] = states of chunk c owned by r;  pass 1: pos[g] = r * block + chunk_base[c * P + r] + k
+void launch_owner_positions(const uint64_t *states, int64_t n, int num_ranks, int64_t chunk, bool write_pass,
+                            unsigned long long *chunk_counts, const unsigned long long *chunk_base, int64_t block,
+                            uint32_t *pos, cudaStream_t stream);
 int64_t launch_counter();
 int planned_grid(int64_t rows, int row_split);
 int choose_row_split(int64_t rows, int n_groups);

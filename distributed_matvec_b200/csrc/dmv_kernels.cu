@@ -778,6 +778,55 @@ __global__ void __launch_bounds__(kThreads) k_accumulate(const KernelParams p, i
   }
 }
 
+// ls_chpl_operator_apply_diag / ls_chpl_operator_apply_off_diag (reference src/BatchedOperator.chpl:217-275):
+// the term kernels applied to caller-given states with xs = nil ("times one", BO:230,263), no projection.
+//   apply_diag:     coeffs[i] = Re sum_t v_t [alpha_i & m == r] (-1)^popc(alpha_i & s)
+//   apply_off_diag: CSR by row -- pass 0 counts the emitting groups of every row, the host turns the counts into
+//                   the row pointer `offsets`, pass 1 writes (beta, coefficient) of row i at offsets[i]...
+// One lane per state; tables in shared memory as in k_generate.
+__global__ void __launch_bounds__(kThreads) k_apply_diag(const KernelParams p, int64_t count,
+                                                         const uint64_t *__restrict__ alphas, double *coeffs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(p, PROJ_NONE, sizeof(double2));
+  const Tables<true> T = stage_tables<PROJ_NONE, true>(p, smem, L);
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    double dre, dim;
+    diagonal<true>(T, p.n_diag, alphas[i], dre, dim);
+    coeffs[i] = dre;
+  }
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kThreads) k_apply_off_diag(const KernelParams p, int64_t count,
+                                                             const uint64_t *__restrict__ alphas,
+                                                             const int64_t *__restrict__ offsets, int64_t *counts,
+                                                             uint64_t *betas, double2 *coeffs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(p, PROJ_NONE, sizeof(double2));
+  const Tables<true> T = stage_tables<PROJ_NONE, true>(p, smem, L);
+  __syncthreads();
+  const bool any_s_out = p.any_s_out != 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const uint64_t alpha = alphas[i];
+    int64_t o = WRITE ? offsets[i] : 0;
+    for (int g0 = 0, w = 0; g0 < p.n_groups; g0 += 64, ++w) {
+      RowTerms rt = row_terms<true>(T, w, g0, min(g0 + 64, p.n_groups), alpha);
+      if (!WRITE) { o += __popcll(rt.mask); continue; }
+      while (rt.mask) {
+        uint64_t flip;
+        const double2 c = pop_term<true>(T, rt, g0, alpha, any_s_out, flip);
+        betas[o] = alpha ^ flip;
+        coeffs[o] = c;
+        ++o;
+      }
+    }
+    if (!WRITE) counts[i] = o;
+  }
+}
+
 // dir[2b] = lower_bound(reps, b << shift), dir[2b+1] = lower_bound(reps, (b+1) << shift) for b in [0, n_buckets)
 __global__ void k_build_directory(const uint64_t *__restrict__ reps, int64_t n, uint32_t *dir,
                                   uint64_t n_buckets, int shift) {
@@ -1044,6 +1093,37 @@ void launch_accumulate(const KernelParams &p, Projection proj, bool cv, bool ce,
     case PROJ_INVERSION: launch_accumulate_p<PROJ_INVERSION>(p, cv, ce, count, betas, coeffs, stream); break;
     case PROJ_GROUP: launch_accumulate_p<PROJ_GROUP>(p, cv, ce, count, betas, coeffs, stream); break;
   }
+}
+
+void launch_apply_diag(const KernelParams &p, int64_t count, const uint64_t *alphas, double *coeffs,
+                       cudaStream_t stream) {
+  if (count <= 0) return;
+  const SmemLayout L = smem_layout(p, PROJ_NONE, sizeof(double2));
+  if (L.total > 48 * 1024)
+    DMV_CUDA_CHECK(cudaFuncSetAttribute(k_apply_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  k_apply_diag<<<grid_for(count, kThreads, sm_count() * 4), kThreads, L.total, stream>>>(p, count, alphas, coeffs);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
+void launch_apply_off_diag(const KernelParams &p, int64_t count, const uint64_t *alphas, const int64_t *offsets,
+                           int64_t *counts, uint64_t *betas, double *coeffs, bool write_pass, cudaStream_t stream) {
+  if (count <= 0) return;
+  const SmemLayout L = smem_layout(p, PROJ_NONE, sizeof(double2));
+  const int blocks = grid_for(count, kThreads, sm_count() * 4);
+  if (write_pass) {
+    if (L.total > 48 * 1024)
+      DMV_CUDA_CHECK(cudaFuncSetAttribute(k_apply_off_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    k_apply_off_diag<true><<<blocks, kThreads, L.total, stream>>>(p, count, alphas, offsets, counts, betas,
+                                                                   reinterpret_cast<double2 *>(coeffs));
+  } else {
+    if (L.total > 48 * 1024)
+      DMV_CUDA_CHECK(cudaFuncSetAttribute(k_apply_off_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    k_apply_off_diag<false><<<blocks, kThreads, L.total, stream>>>(p, count, alphas, offsets, counts, betas,
+                                                                    reinterpret_cast<double2 *>(coeffs));
+  }
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
 }
 
 void launch_build_directory(const uint64_t *reps, int64_t n, uint32_t *dir, uint64_t n_buckets, int shift,

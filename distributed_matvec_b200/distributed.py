@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _native as nat
 from .config import OperatorSpec
-from .operator import Operator, _elt_of, locale_idx_of
+from .operator import Operator, _elt_of, _ptr, locale_idx_of
 
 
 def masks_of(op: Operator, states: np.ndarray, num_ranks: int) -> np.ndarray:
@@ -82,6 +82,26 @@ class EmulatedCluster:
                 betas, coeffs, n = src.outgoing(q)
                 if n > 0:
                     dst.accumulate(elt, n, betas, coeffs, ys[q])
+        for op in self.ops:
+            op.synchronize()
+        return ys
+
+    def matvec_replicated(self, x_blocks):
+        """The replicated-x form (dmv_replicated_*): the host plays the all-gather -- every logical rank gets the
+        same gathered x (rank r's block in slot r) and computes its own rows."""
+        import torch
+        elt = _elt_of(x_blocks[0])
+        for op in self.ops:
+            nat.check(nat.lib().dmv_replicated_setup(op._ctx))
+        block = self.ops[0].info("replicated_block")
+        assert all(op.info("replicated_block") == block for op in self.ops)
+        x_cat = torch.zeros(block * self.num_ranks, dtype=x_blocks[0].dtype, device=x_blocks[0].device)
+        for r, x in enumerate(x_blocks):
+            x_cat[r * block:r * block + x.shape[0]] = x
+        ys = [torch.zeros_like(x) for x in x_blocks]
+        torch.cuda.synchronize()
+        for r, op in enumerate(self.ops):
+            nat.check(nat.lib().dmv_replicated_product(op._ctx, elt, _ptr(x_cat), _ptr(ys[r])))
         for op in self.ops:
             op.synchronize()
         return ys

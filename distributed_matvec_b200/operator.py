@@ -312,6 +312,62 @@ class BatchedOperator:
         return n, betas[:n], coeffs[:n], keys[:n]
 
 
+def _take(arr, ctype, dtype):
+    """Copy a callee-allocated chpl_external_array out and release it through its freer (BO:232 contract)."""
+    n = int(arr.num_elts)
+    if n == 0 or not arr.elts:
+        return np.zeros(0, dtype=dtype)
+    out = np.ctypeslib.as_array(C.cast(arr.elts, C.POINTER(ctype)), shape=(n,)).copy()
+    if arr.freer:
+        arr.freer(arr.elts)
+    return out.view(dtype) if dtype is not None and out.dtype != np.dtype(dtype) else out
+
+
+class ChapelKernels:
+    """The reference's plugin table ``ls_chpl_kernels`` (src/FFI.chpl:233-239) on top of one Operator: the four
+    entry points take the opaque ``ls_hs_operator*`` / ``ls_hs_basis*`` handle, which is bound to the context
+    with dmv_bind_operator (any unique address works as the handle here)."""
+
+    def __init__(self, matrix: Operator):
+        self.matrix = matrix
+        self._handle = C.c_void_p(id(self))          # stands in for the ls_hs_operator* / ls_hs_basis*
+        nat.check(nat.lib().dmv_bind_operator(self._handle, matrix._ctx))
+
+    def close(self):
+        nat.lib().dmv_bind_operator(self._handle, None)
+
+    def operator_apply_diag(self, alphas, num_tasks: int = 1) -> np.ndarray:
+        """ls_chpl_operator_apply_diag (BO:217-234)."""
+        alphas = np.ascontiguousarray(alphas, dtype=np.uint64)
+        out = nat.ExternalArray()
+        nat.lib().ls_chpl_operator_apply_diag(self._handle, alphas.shape[0], alphas.ctypes.data, C.byref(out), num_tasks)
+        return _take(out, C.c_double, np.float64)
+
+    def operator_apply_off_diag(self, alphas, num_tasks: int = 1):
+        """ls_chpl_operator_apply_off_diag (BO:236-275) -> (betas, coeffs, offsets); entries [0, offsets[-1]) used."""
+        alphas = np.ascontiguousarray(alphas, dtype=np.uint64)
+        b, c, o = nat.ExternalArray(), nat.ExternalArray(), nat.ExternalArray()
+        nat.lib().ls_chpl_operator_apply_off_diag(self._handle, alphas.shape[0], alphas.ctypes.data, C.byref(b),
+                                                  C.byref(c), C.byref(o), num_tasks)
+        offsets = _take(o, C.c_int64, np.int64)
+        betas = _take(b, C.c_uint64, np.uint64)
+        coeffs = _take(c, C.c_double, np.float64).view(np.complex128)
+        return betas, coeffs, offsets
+
+    def enumerate_representatives(self, lower: int = 0, upper: int = 2**64 - 1) -> np.ndarray:
+        """ls_chpl_enumerate_representatives (SE:588-603)."""
+        out = nat.ExternalArray()
+        nat.lib().ls_chpl_enumerate_representatives(self._handle, lower, upper, C.byref(out))
+        return _take(out, C.c_uint64, np.uint64)
+
+    def matrix_vector_product(self, x: np.ndarray) -> np.ndarray:
+        """ls_chpl_matrix_vector_product (DMV:1095-1110): real(64), one vector."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        nat.lib().ls_chpl_matrix_vector_product(self._handle, 1, x.ctypes.data, y.ctypes.data)
+        return y
+
+
 def local_matrix_vector(matrix: Operator, x, y=None):
     """``localMatrixVector(matrix, x, y, representatives)`` (DMV:1055-1070)."""
     return matrix.matvec(x, y)

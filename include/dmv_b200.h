@@ -118,7 +118,8 @@ int dmv_compute_off_diag(dmv_context *ctx, int64_t count, const uint64_t *alphas
  *   (DMV:1062-1069: without diagonal terms y is not cleared).  x, y: host or device pointers of
  *   dmv_number_states() elements of type `elt`.
  * dmv_matvec: matrixVectorProduct (DMV:1072-1093), collective over the communicator: generation,
- *   hash bucketing, all-to-all exchange (NCCL) and owner-side search + accumulate. */
+ *   hash bucketing, all-to-all exchange (peer-direct NVLink stores or NCCL) and owner-side search +
+ *   accumulate -- or the replicated-x form below when it applies. */
 int dmv_local_matvec(dmv_context *ctx, int elt, const void *x, void *y);
 int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y);
 
@@ -139,6 +140,18 @@ int dmv_outgoing(dmv_context *ctx, int dest, const uint64_t **betas, const doubl
 int dmv_accumulate(dmv_context *ctx, int elt, int64_t count, const uint64_t *betas,
                    const double *coeffs, void *y);
 
+/* ---- replicated-x form of the distributed product (B200-first alternative to the record exchange of DMV:313-436,
+ * chosen automatically by dmv_matvec -- option "exchange" = -1 / 2 -- when the operator passes the bit-parallel emit
+ * test, the basis has no permutation symmetries and the whole basis fits on one device): every rank keeps the whole
+ * sorted basis, x is all-gathered (E bytes per state instead of 8 + E bytes per off-diagonal term over NVLink) into
+ * slots of dmv_get_info(ctx, "replicated_block") elements per rank, and each rank computes ITS rows without atomics.
+ * The hash partition of x, y and the representatives seen by the caller (SE:129-156) is unchanged.
+ *   dmv_replicated_setup:   local set-up (whole basis, slot table); no communication.
+ *   dmv_replicated_product: y <- rows of this rank applied to a caller-assembled gathered x (device pointers); for
+ *                           hosts that own the all-gather themselves (several logical ranks on one GPU, tests). */
+int dmv_replicated_setup(dmv_context *ctx);
+int dmv_replicated_product(dmv_context *ctx, int elt, const void *x_cat, void *y);
+
 /* ---- communicator (NCCL over NVLink): 128-byte unique id made on rank 0, shared by the host */
 int dmv_comm_unique_id(void *id128);
 int dmv_comm_init(dmv_context *ctx, const void *id128);
@@ -155,6 +168,35 @@ int64_t dmv_number_terms(const dmv_context *ctx);
  * dmv_bind_operator (see INTEGRATION.md for the shim that extracts the flat tables). */
 int dmv_bind_operator(const void *ls_hs_operator_ptr, dmv_context *ctx);
 void ls_chpl_matrix_vector_product(const void *ls_hs_operator_ptr, int num_vectors, double *x, double *y);
+
+/* The other three entries of `ls_chpl_kernels` (src/FFI.chpl:233-239).  Outputs are returned the way Chapel's
+ * convertToExternalArray does (BO:232,265-272): allocated by the callee, released by the caller through `freer`.
+ * Layout of chpl_external_array (Chapel runtime, chpl-external-array.h): {void *elts; uint64_t num_elts; void *freer}.
+ *   ls_chpl_operator_apply_diag      BO:217-234: coeffs[i] = <alpha_i|H|alpha_i> (real(64)), no projection
+ *   ls_chpl_operator_apply_off_diag  BO:236-275: CSR by row: betas / coeffs (complex128) hold count * T entries of
+ *                                    which offsets[count] are used, offsets = row pointer; terms with the same flip
+ *                                    mask are merged into one entry; within a row entries are ordered by flip-mask
+ *                                    group (the third-party kernel's order is not specified in the reference tree)
+ *   ls_chpl_enumerate_representatives SE:588-603: this rank's block of representatives; `handle` is the ls_hs_basis*
+ *                                    (bound with dmv_bind_operator like an operator handle); bounds are ignored
+ *                                    exactly as in the reference
+ * dmv_apply_diag / dmv_apply_off_diag are the same kernels on caller-owned arrays (host or device pointers;
+ * betas: count * dmv_max_number_off_diag entries, coeffs: twice that many doubles, offsets: count + 1). */
+typedef struct {
+  void *elts;
+  uint64_t num_elts;
+  void (*freer)(void *);
+} dmv_external_array;
+int dmv_apply_diag(dmv_context *ctx, int64_t count, const uint64_t *alphas, double *coeffs);
+int dmv_apply_off_diag(dmv_context *ctx, int64_t count, const uint64_t *alphas, uint64_t *betas, double *coeffs,
+                       int64_t *offsets);
+void ls_chpl_operator_apply_diag(const void *ls_hs_operator_ptr, int64_t count, const uint64_t *alphas,
+                                 dmv_external_array *coeffs, int64_t num_tasks);
+void ls_chpl_operator_apply_off_diag(const void *ls_hs_operator_ptr, int64_t count, const uint64_t *alphas,
+                                     dmv_external_array *betas, dmv_external_array *coeffs,
+                                     dmv_external_array *offsets, int64_t num_tasks);
+void ls_chpl_enumerate_representatives(const void *ls_hs_basis_ptr, uint64_t lower, uint64_t upper,
+                                       dmv_external_array *dest);
 
 /* ---- self-check of the host-side group compiler (no device needed; NOT on the product path).
  * Compiles the symmetry group of `basis` into the device orbit program, verifies it against bit-by-bit

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 
-from distributed_matvec_b200 import (BatchedOperator, EmulatedCluster, Operator, block_to_hashed,  # noqa: E402
+from distributed_matvec_b200 import (BatchedOperator, ChapelKernels, EmulatedCluster, Operator, block_to_hashed,  # noqa: E402
                                      hashed_to_block, load_config_from_yaml, locale_idx_of)
 from oracle import pyoracle as po  # noqa: E402
 
@@ -224,6 +224,64 @@ def test_compute_off_diag_matches_oracle(need_cuda, name):
     op.close()
 
 
+def _rows_merged(betas, coeffs, offsets):
+    """CSR rows as sorted (beta, coefficient) lists with equal betas merged and zero sums dropped."""
+    rows = []
+    for i in range(offsets.shape[0] - 1):
+        acc = {}
+        for b, c in zip(betas[offsets[i]:offsets[i + 1]], coeffs[offsets[i]:offsets[i + 1]]):
+            acc[int(b)] = acc.get(int(b), 0.0) + complex(c)
+        rows.append(sorted((b, c) for b, c in acc.items() if abs(c) > 1e-15))
+    return rows
+
+
+@pytest.mark.parametrize("name", ["heisenberg_chain_12", "heisenberg_kagome_16", "heisenberg_chain_16",
+                                  "three_site", "seven_site_complex", "complex_hopping", "wide_two_magnon"])
+def test_chapel_plugin_kernels_match_oracle(need_cuda, name):
+    """The reference's plugin table (src/FFI.chpl:233-239): ls_chpl_operator_apply_diag / _apply_off_diag
+    (BO:217-275), ls_chpl_enumerate_representatives (SE:588-603), ls_chpl_matrix_vector_product (DMV:1095-1110)
+    against the oracle's restatement of the term kernels, enumeration and product."""
+    basis, matrix = GENERAL_MODELS[name]() if name in GENERAL_MODELS else _load(name)
+    reps, _ = po.enumerate_states(basis)
+    op = Operator(matrix)
+    k = ChapelKernels(op)
+    assert np.array_equal(k.enumerate_representatives(), reps)
+    rng = np.random.default_rng(13)
+    alphas = np.concatenate([reps[:4000], rng.integers(0, 2**basis.number_sites, 500, dtype=np.uint64)])
+    # diagonal: real part of the diagonal matrix element (real(64) output, BO:229-230)
+    d = k.operator_apply_diag(alphas)
+    d_ref = po.apply_diag(matrix, alphas, np.ones(alphas.shape[0], dtype=np.complex128)).real
+    assert np.allclose(d, d_ref, rtol=1e-14, atol=1e-14)
+    # off-diagonal: CSR by row; same row pointer semantics, rows compared as merged multisets
+    betas, coeffs, offsets = k.operator_apply_off_diag(alphas)
+    ob, oc, oo = po.apply_off_diag(matrix, alphas)
+    assert offsets.shape == (alphas.shape[0] + 1,) and offsets[0] == 0 and np.all(np.diff(offsets) >= 0)
+    assert betas.shape[0] == alphas.shape[0] * op.numberOffDiagTerms()        # full-capacity arrays (BO:250-252)
+    got, want = _rows_merged(betas, coeffs, offsets), _rows_merged(ob, oc, oo)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert [b for b, _ in g] == [b for b, _ in w]
+        assert np.allclose([c for _, c in g], [c for _, c in w], rtol=1e-14, atol=1e-15)
+    # the product entry point (real(64), one vector) when the operator is real
+    if not np.iscomplexobj(po.matvec_global(matrix, reps, np.ones(reps.shape[0]), 1)):
+        x = _x(reps.shape[0], False, 19)
+        assert _close(k.matrix_vector_product(x), po.matvec_global(matrix, reps, x, 1))
+    k.close()
+    op.close()
+
+
+def test_chapel_plugin_kernels_refuse_projected_bases(need_cuda):
+    """BO:224-227, 245-248: bases that require projection are not supported by the apply kernels."""
+    basis, matrix = _load("heisenberg_chain_10")
+    op = Operator(matrix)
+    from distributed_matvec_b200 import _native as nat
+    a = np.array([3], dtype=np.uint64)
+    out = np.zeros(1)
+    assert nat.lib().dmv_apply_diag(op._ctx, 1, a.ctypes.data, out.ctypes.data) != 0
+    assert b"projection" in nat.lib().dmv_last_error()
+    op.close()
+
+
 def test_missing_state_is_an_error(need_cuda):
     """DMV:115-118: a generated state that is not in the basis halts."""
     basis, matrix = _load("heisenberg_chain_10")
@@ -398,6 +456,40 @@ def test_gather_is_bit_reproducible_and_chunked_d2h(need_cuda):
     y_host = op.matvec(x)
     assert np.array_equal(y1, y2) and np.array_equal(y1, y_host)
     op.close()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("num_ranks", [2, 3, 8])
+@pytest.mark.parametrize("name", ["heisenberg_chain_10", "heisenberg_chain_12", "heisenberg_kagome_16",
+                                  "heisenberg_chain_16", "anisotropic_bonds", "wide_two_magnon",
+                                  "complex_hopping"])
+def test_replicated_x_product_matches_oracle(need_cuda, name, num_ranks, cplx):
+    """The replicated-x form of the distributed product (all-gather of x + rows without atomics) on P logical
+    ranks: same hash partition, same result as the oracle's P-rank product."""
+    basis, matrix = GENERAL_MODELS[name]() if name in GENERAL_MODELS else _load(name)
+    o_reps, _ = po.enumerate_states(basis)
+    masks, blocks = po.partition_by_hash(o_reps, num_ranks)
+    x = _x(o_reps.shape[0], cplx, seed=31)
+    y_ref = po.matvec_global(matrix, o_reps, x, num_ranks)
+    cl = EmulatedCluster(matrix, num_ranks).build()
+    xb = [torch.from_numpy(b).cuda() for b in block_to_hashed(x, masks, num_ranks)]
+    yb = cl.matvec_replicated(xb)
+    y = hashed_to_block([t.cpu().numpy() for t in yb], masks)
+    assert _close(y, y_ref), np.abs(y - y_ref).max()
+    assert cl.ops[0].info("global_states") == o_reps.shape[0]
+    # same answer as the record-exchange form on the same ranks
+    y_push = hashed_to_block([t.cpu().numpy() for t in cl.matvec(xb)], masks)
+    assert _close(y, y_push)
+    cl.close()
+
+
+def test_replicated_x_needs_an_applicable_operator(need_cuda):
+    basis, matrix = _load("heisenberg_kagome_12_symm")      # permutation symmetries: record exchange only
+    cl = EmulatedCluster(matrix, 2).build()
+    with pytest.raises(Exception, match="k_gather"):
+        cl.matvec_replicated([torch.zeros(op.basis.numberStates(), dtype=torch.float64, device="cuda")
+                              for op in cl.ops])
+    cl.close()
 
 
 def test_bitparallel_matches_group_walk(need_cuda):

@@ -55,7 +55,7 @@ def main():
             dist.all_reduce(flag)
             if rank == 0:
                 print(f"{name:28s} P={world} {'c128' if cplx else 'f64 '} N={o_reps.shape[0]} basis_ok={ok_basis} "
-                      f"err_host={e1:.1e} err_dev={e2:.1e} peer_direct={dop.op.info('peer_direct')} "
+                      f"err_host={e1:.1e} err_dev={e2:.1e} exchange={'replicated-x' if dop.op.info('replicated') else ('peer-direct' if dop.op.info('peer_direct') else 'nccl')} "
                       f"{'OK' if int(flag) == 0 else 'FAIL'}", flush=True)
             failures += int(flag)
         dop.op.close()
