@@ -1025,7 +1025,7 @@ void setup_replicated(dmv_context *ctx) {
   d_counts.alloc((size_t)n_chunks * P);
   d_base.alloc((size_t)n_chunks * P);
   ctx->d_pos.alloc((size_t)n);
-  launch_owner_positions(g->d_reps.ptr, n, P, chunk, false, d_counts.ptr, nullptr, 0, nullptr, ctx->stream);
+  launch_owner_positions(g->d_reps.ptr, nullptr, n, P, chunk, false, d_counts.ptr, nullptr, 0, nullptr, ctx->stream);
   std::vector<unsigned long long> counts((size_t)n_chunks * P), base((size_t)n_chunks * P);
   CUDA_CHECK(cudaMemcpyAsync(counts.data(), d_counts.ptr, counts.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -1039,7 +1039,7 @@ void setup_replicated(dmv_context *ctx) {
   block = (block + 1) / 2 * 2;
   if ((double)block * P >= 4294967295.0) throw std::runtime_error("replicated-x product: more than 2^32 slots");
   d_base.upload(base, ctx->stream);
-  launch_owner_positions(g->d_reps.ptr, n, P, chunk, true, d_counts.ptr, d_base.ptr, block, ctx->d_pos.ptr, ctx->stream);
+  launch_owner_positions(g->d_reps.ptr, nullptr, n, P, chunk, true, d_counts.ptr, d_base.ptr, block, ctx->d_pos.ptr, ctx->stream);
   ctx->repl_block = block;
   ctx->d_xcat.alloc((size_t)block * P * 2);
   CUDA_CHECK(cudaMemsetAsync(ctx->d_xcat.ptr, 0, (size_t)block * P * 2 * sizeof(double), ctx->stream));
@@ -1091,6 +1091,51 @@ void decide_exchange(dmv_context *ctx) {
     if (ctx->opt_exchange == 2)
       throw std::runtime_error("replicated-x exchange requested but not possible on every rank: " + why);
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Block <-> hashed redistribution of vectors (arrFromBlockToHashed, reference src/BlockToHashed.chpl:87-208;
+// arrFromHashedToBlock, src/HashedToBlock.chpl:67-153).  "Block" = the global array in sorted-state order cut into
+// contiguous chunks, one per rank; "hashed" = every rank holds the elements of the states it owns, ascending.
+// positions: slot of element i of a chunk in the ordering "grouped by owner, stable": offsets[mask[i]] + #{j < i :
+// mask[j] == mask[i]}; counts[r] = elements owned by r.  One counting pass, host prefix sums, one writing pass.
+void hashed_positions(dmv_context *ctx, int64_t count, const uint8_t *d_masks, int P, std::vector<int64_t> &counts,
+                      uint32_t *d_pos) {
+  if (P > 32) throw std::runtime_error("block <-> hashed redistribution supports at most 32 ranks");
+  counts.assign(P, 0);
+  if (count <= 0) return;
+  if (count >= (1ll << 32)) throw std::runtime_error("chunks of more than 2^32 elements are not supported");
+  const int64_t chunk = 256, n_chunks = (count + chunk - 1) / chunk;
+  DevBuf<unsigned long long> d_counts, d_base;
+  d_counts.alloc((size_t)n_chunks * P);
+  launch_owner_positions(nullptr, d_masks, count, P, chunk, false, d_counts.ptr, nullptr, 0, nullptr, ctx->stream);
+  std::vector<unsigned long long> c((size_t)n_chunks * P), base((size_t)n_chunks * P);
+  CUDA_CHECK(cudaMemcpyAsync(c.data(), d_counts.ptr, c.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  for (int64_t k = 0; k < n_chunks; ++k)
+    for (int r = 0; r < P; ++r) counts[r] += (int64_t)c[(size_t)k * P + r];
+  std::vector<unsigned long long> run(P, 0);
+  unsigned long long off = 0;
+  for (int r = 0; r < P; ++r) { run[r] = off; off += (unsigned long long)counts[r]; }
+  for (int64_t k = 0; k < n_chunks; ++k)
+    for (int r = 0; r < P; ++r) { base[(size_t)k * P + r] = run[r]; run[r] += c[(size_t)k * P + r]; }
+  d_base.upload(base, ctx->stream);
+  launch_owner_positions(nullptr, d_masks, count, P, chunk, true, d_counts.ptr, d_base.ptr, 0, d_pos, ctx->stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // d_base is released on return
+}
+
+// all[r * P + q] = what rank r reported for q (collective)
+std::vector<int64_t> all_gather_counts(dmv_context *ctx, const std::vector<int64_t> &mine) {
+  NcclApi &N = nccl();
+  const int P = ctx->num_ranks;
+  DevBuf<int64_t> d_mine, d_all;
+  d_mine.upload(mine, ctx->stream);
+  d_all.alloc((size_t)P * P);
+  NCCL_CHECK(N.AllGather(d_mine.ptr, d_all.ptr, (size_t)P, ncclInt64, ctx->comm, ctx->stream));
+  std::vector<int64_t> all((size_t)P * P);
+  CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.ptr, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return all;
 }
 
 // =================================================================================================
@@ -1637,6 +1682,132 @@ int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
     check_status(ctx);
     collect_timings(ctx);
   }
+  API_END
+}
+
+// ---- block <-> hashed redistribution ("next" row f2)
+int dmv_hashed_positions(dmv_context *ctx, int64_t count, const uint8_t *masks, int num_ranks, int64_t *counts,
+                         uint32_t *positions) {
+  API_BEGIN
+  use_device(ctx);
+  if (count < 0 || num_ranks < 1) throw std::runtime_error("bad arguments");
+  InArg<uint8_t> m(masks, (size_t)count, ctx->stream);
+  OutArg<uint32_t> out(positions, (size_t)count);
+  std::vector<int64_t> c;
+  hashed_positions(ctx, count, m.ptr, num_ranks, c, out.ptr);
+  if (counts) std::copy(c.begin(), c.end(), counts);
+  out.finish(ctx->stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+int dmv_permute(dmv_context *ctx, int elt, int64_t count, const uint32_t *positions, const void *in, void *out,
+                int gather) {
+  API_BEGIN
+  use_device(ctx);
+  if (elt != 1 && elt != 2) throw std::runtime_error("elt must be 1 (8-byte) or 2 (16-byte elements)");
+  if (in == out) throw std::runtime_error("in and out must not alias");
+  InArg<uint32_t> p(positions, (size_t)count, ctx->stream);
+  InArg<double> i(reinterpret_cast<const double *>(in), (size_t)count * elt, ctx->stream);
+  OutArg<double> o(reinterpret_cast<double *>(out), (size_t)count * elt);
+  launch_permute(count, elt, p.ptr, i.ptr, o.ptr, gather != 0, ctx->stream);
+  o.finish(ctx->stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+int dmv_block_to_hashed(dmv_context *ctx, int elt, int64_t chunk_count, const uint8_t *masks_chunk,
+                        const void *block_chunk, void *hashed, int64_t hashed_count) {
+  API_BEGIN
+  use_device(ctx);
+  if (elt != 1 && elt != 2) throw std::runtime_error("elt must be 1 (8-byte) or 2 (16-byte elements)");
+  const int P = ctx->num_ranks;
+  InArg<uint8_t> m(masks_chunk, (size_t)chunk_count, ctx->stream);
+  InArg<double> in(reinterpret_cast<const double *>(block_chunk), (size_t)chunk_count * elt, ctx->stream);
+  OutArg<double> out(reinterpret_cast<double *>(hashed), (size_t)hashed_count * elt);
+  DevBuf<uint32_t> d_pos;
+  DevBuf<double> d_grouped;
+  d_pos.alloc((size_t)chunk_count);
+  d_grouped.alloc((size_t)chunk_count * elt);
+  std::vector<int64_t> counts;
+  hashed_positions(ctx, chunk_count, m.ptr, P, counts, d_pos.ptr);
+  launch_permute(chunk_count, elt, d_pos.ptr, in.ptr, d_grouped.ptr, false, ctx->stream);
+  if (P == 1) {
+    if (hashed_count != chunk_count) throw std::runtime_error("hashed block size does not match the masks");
+    CUDA_CHECK(cudaMemcpyAsync(out.ptr, d_grouped.ptr, (size_t)chunk_count * elt * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    if (!ctx->comm) throw std::runtime_error("dmv_block_to_hashed on several ranks needs dmv_comm_init");
+    NcclApi &N = nccl();
+    const std::vector<int64_t> all = all_gather_counts(ctx, counts);   // all[r * P + q]: chunk r holds for owner q
+    int64_t incoming = 0;
+    for (int r = 0; r < P; ++r) incoming += all[(size_t)r * P + ctx->rank];
+    if (incoming != hashed_count) throw std::runtime_error("hashed block size does not match the masks");
+    NCCL_CHECK(N.GroupStart());
+    int64_t send_off = 0, recv_off = 0;
+    for (int q = 0; q < P; ++q) {
+      const int64_t sc = counts[q], rc = all[(size_t)q * P + ctx->rank];
+      if (q == ctx->rank) {
+        if (sc > 0) CUDA_CHECK(cudaMemcpyAsync(out.ptr + recv_off * elt, d_grouped.ptr + send_off * elt, (size_t)sc * elt * 8,
+                                               cudaMemcpyDeviceToDevice, ctx->stream));
+      } else {
+        if (sc > 0) NCCL_CHECK(N.Send(d_grouped.ptr + send_off * elt, (size_t)sc * elt, ncclDouble, q, ctx->comm, ctx->stream));
+        if (rc > 0) NCCL_CHECK(N.Recv(out.ptr + recv_off * elt, (size_t)rc * elt, ncclDouble, q, ctx->comm, ctx->stream));
+      }
+      send_off += sc;
+      recv_off += rc;
+    }
+    NCCL_CHECK(N.GroupEnd());
+  }
+  out.finish(ctx->stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+int dmv_hashed_to_block(dmv_context *ctx, int elt, int64_t chunk_count, const uint8_t *masks_chunk,
+                        const void *hashed, int64_t hashed_count, void *block_chunk) {
+  API_BEGIN
+  use_device(ctx);
+  if (elt != 1 && elt != 2) throw std::runtime_error("elt must be 1 (8-byte) or 2 (16-byte elements)");
+  const int P = ctx->num_ranks;
+  InArg<uint8_t> m(masks_chunk, (size_t)chunk_count, ctx->stream);
+  InArg<double> in(reinterpret_cast<const double *>(hashed), (size_t)hashed_count * elt, ctx->stream);
+  OutArg<double> out(reinterpret_cast<double *>(block_chunk), (size_t)chunk_count * elt);
+  DevBuf<uint32_t> d_pos;
+  DevBuf<double> d_grouped;
+  d_pos.alloc((size_t)chunk_count);
+  d_grouped.alloc((size_t)chunk_count * elt);
+  std::vector<int64_t> counts;   // counts[q]: positions of MY chunk owned by q = what q sends me
+  hashed_positions(ctx, chunk_count, m.ptr, P, counts, d_pos.ptr);
+  if (P == 1) {
+    if (hashed_count != chunk_count) throw std::runtime_error("hashed block size does not match the masks");
+    CUDA_CHECK(cudaMemcpyAsync(d_grouped.ptr, in.ptr, (size_t)chunk_count * elt * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    if (!ctx->comm) throw std::runtime_error("dmv_hashed_to_block on several ranks needs dmv_comm_init");
+    NcclApi &N = nccl();
+    const std::vector<int64_t> all = all_gather_counts(ctx, counts);   // all[r * P + q]: chunk r needs from owner q
+    int64_t outgoing = 0;
+    for (int r = 0; r < P; ++r) outgoing += all[(size_t)r * P + ctx->rank];
+    if (outgoing != hashed_count) throw std::runtime_error("hashed block size does not match the masks");
+    NCCL_CHECK(N.GroupStart());
+    int64_t send_off = 0, recv_off = 0;
+    for (int q = 0; q < P; ++q) {
+      // my hashed block is ascending in global position: the part for chunk q follows the parts for chunks < q
+      const int64_t sc = all[(size_t)q * P + ctx->rank], rc = counts[q];
+      if (q == ctx->rank) {
+        if (sc > 0) CUDA_CHECK(cudaMemcpyAsync(d_grouped.ptr + recv_off * elt, in.ptr + send_off * elt, (size_t)sc * elt * 8,
+                                               cudaMemcpyDeviceToDevice, ctx->stream));
+      } else {
+        if (sc > 0) NCCL_CHECK(N.Send(in.ptr + send_off * elt, (size_t)sc * elt, ncclDouble, q, ctx->comm, ctx->stream));
+        if (rc > 0) NCCL_CHECK(N.Recv(d_grouped.ptr + recv_off * elt, (size_t)rc * elt, ncclDouble, q, ctx->comm, ctx->stream));
+      }
+      send_off += sc;
+      recv_off += rc;
+    }
+    NCCL_CHECK(N.GroupEnd());
+  }
+  launch_permute(chunk_count, elt, d_pos.ptr, d_grouped.ptr, out.ptr, true, ctx->stream);
+  out.finish(ctx->stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   API_END
 }
 

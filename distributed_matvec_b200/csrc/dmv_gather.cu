@@ -15,6 +15,7 @@
 // row does not hold the x of its neighbours).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -259,9 +260,9 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
 
 // one thread per chunk of consecutive global states (set-up only)
 template <bool WRITE>
-__global__ void k_owner_positions(const uint64_t *__restrict__ states, int64_t n, int num_ranks, int64_t chunk,
-                                  unsigned long long *chunk_counts, const unsigned long long *__restrict__ chunk_base,
-                                  int64_t block, uint32_t *pos) {
+__global__ void k_owner_positions(const uint64_t *__restrict__ states, const uint8_t *__restrict__ masks, int64_t n,
+                                  int num_ranks, int64_t chunk, unsigned long long *chunk_counts,
+                                  const unsigned long long *__restrict__ chunk_base, int64_t block, uint32_t *pos) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t first = c * chunk;
   if (first >= n) return;
@@ -270,7 +271,7 @@ __global__ void k_owner_positions(const uint64_t *__restrict__ states, int64_t n
 #pragma unroll
   for (int r = 0; r < 32; ++r) cnt[r] = 0;
   for (int64_t g = first; g < last; ++g) {
-    const int r = locale_idx_of(states[g], num_ranks);
+    const int r = masks ? (int)masks[g] : locale_idx_of(states[g], num_ranks);
     uint32_t k = 0;
 #pragma unroll
     for (int q = 0; q < 32; ++q)   // register-resident counters: no dynamic indexing
@@ -339,17 +340,42 @@ void launch_v(const KernelParams &p, bool cv, bool ce, bool narrow, bool lin, bo
   else launch_w<INV, true, false>(p, narrow, lin, uni, s);
 }
 
+// out[pos[i]] = in[i] (scatter) or out[i] = in[pos[i]] (gather) for 8- or 16-byte elements
+template <typename T, bool GATHER>
+__global__ void k_permute(int64_t n, const uint32_t *__restrict__ pos, const T *__restrict__ in, T *__restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (GATHER) out[i] = in[pos[i]];
+    else out[pos[i]] = in[i];
+  }
+}
+
 }  // namespace
 
-void launch_owner_positions(const uint64_t *states, int64_t n, int num_ranks, int64_t chunk, bool write_pass,
-                            unsigned long long *chunk_counts, const unsigned long long *chunk_base, int64_t block,
-                            uint32_t *pos, cudaStream_t stream) {
+void launch_permute(int64_t n, int elt, const uint32_t *pos, const void *in, void *out, bool gather, cudaStream_t stream) {
+  if (n <= 0) return;
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 16);
+  if (elt == 1) {
+    if (gather) k_permute<double, true><<<blocks, 256, 0, stream>>>(n, pos, (const double *)in, (double *)out);
+    else k_permute<double, false><<<blocks, 256, 0, stream>>>(n, pos, (const double *)in, (double *)out);
+  } else {
+    if (gather) k_permute<double2, true><<<blocks, 256, 0, stream>>>(n, pos, (const double2 *)in, (double2 *)out);
+    else k_permute<double2, false><<<blocks, 256, 0, stream>>>(n, pos, (const double2 *)in, (double2 *)out);
+  }
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_permute launch: ") + cudaGetErrorString(e));
+  count_launch();
+}
+
+void launch_owner_positions(const uint64_t *states, const uint8_t *masks, int64_t n, int num_ranks, int64_t chunk,
+                            bool write_pass, unsigned long long *chunk_counts, const unsigned long long *chunk_base,
+                            int64_t block, uint32_t *pos, cudaStream_t stream) {
   if (n <= 0) return;
   if (num_ranks > 32) throw std::runtime_error("replicated-x product supports at most 32 ranks");
   const int64_t n_chunks = (n + chunk - 1) / chunk;
   const unsigned blocks = (unsigned)((n_chunks + 127) / 128);
-  if (write_pass) k_owner_positions<true><<<blocks, 128, 0, stream>>>(states, n, num_ranks, chunk, chunk_counts, chunk_base, block, pos);
-  else k_owner_positions<false><<<blocks, 128, 0, stream>>>(states, n, num_ranks, chunk, chunk_counts, chunk_base, block, pos);
+  if (write_pass) k_owner_positions<true><<<blocks, 128, 0, stream>>>(states, masks, n, num_ranks, chunk, chunk_counts, chunk_base, block, pos);
+  else k_owner_positions<false><<<blocks, 128, 0, stream>>>(states, masks, n, num_ranks, chunk, chunk_counts, chunk_base, block, pos);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("k_owner_positions launch: ") + cudaGetErrorString(e));
   count_launch();

@@ -122,9 +122,12 @@ void launch_enumerate(const OrbitProgram &P, Projection proj, uint64_t site_mask
                       bool write_pass, cudaStream_t stream);
 // replicated-x set-up: owner and position of every global state in the all-gathered x.
 //   pass 0: chunk_counts[c * P + r] = states of chunk c owned by r;  pass 1: pos[g] = r * block + chunk_base[c * P + r] + k
-void launch_owner_positions(const uint64_t *states, int64_t n, int num_ranks, int64_t chunk, bool write_pass,
-                            unsigned long long *chunk_counts, const unsigned long long *chunk_base, int64_t block,
-                            uint32_t *pos, cudaStream_t stream);
+// (owners from hash64_01(states[g]) % P, or from masks[g] when masks != nullptr)
+void launch_owner_positions(const uint64_t *states, const uint8_t *masks, int64_t n, int num_ranks, int64_t chunk,
+                            bool write_pass, unsigned long long *chunk_counts, const unsigned long long *chunk_base,
+                            int64_t block, uint32_t *pos, cudaStream_t stream);
+// out[pos[i]] = in[i] (gather == false) or out[i] = in[pos[i]]; elt = 8-byte words per element (1 or 2)
+void launch_permute(int64_t n, int elt, const uint32_t *pos, const void *in, void *out, bool gather, cudaStream_t stream);
 int64_t launch_counter();
 int planned_grid(int64_t rows, int row_split);
 int choose_row_split(int64_t rows, int n_groups);

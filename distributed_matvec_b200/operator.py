@@ -180,6 +180,60 @@ class Operator:
         """emitted off-diagonal terms of this rank in one product (from the last plan)"""
         return int(nat.lib().dmv_number_terms(self._ctx))
 
+    # -- block <-> hashed redistribution (arrFromBlockToHashed / arrFromHashedToBlock) ----------------------
+    def hashed_positions(self, masks: np.ndarray, num_ranks: int):
+        """-> (counts[num_ranks], positions): slot of every chunk element in "grouped by owner, stable" order."""
+        masks = np.ascontiguousarray(masks, dtype=np.uint8)
+        counts = np.zeros(num_ranks, dtype=np.int64)
+        pos = np.zeros(masks.shape[0], dtype=np.uint32)
+        nat.check(nat.lib().dmv_hashed_positions(self._ctx, masks.shape[0], masks.ctypes.data, num_ranks,
+                                                 counts.ctypes.data, pos.ctypes.data))
+        return counts, pos
+
+    def permute(self, arr: np.ndarray, positions: np.ndarray, gather: bool) -> np.ndarray:
+        arr = np.ascontiguousarray(arr)
+        assert arr.dtype.itemsize in (8, 16)
+        out = np.zeros_like(arr)
+        positions = np.ascontiguousarray(positions, dtype=np.uint32)
+        nat.check(nat.lib().dmv_permute(self._ctx, arr.dtype.itemsize // 8, arr.shape[0], positions.ctypes.data,
+                                        arr.ctypes.data, out.ctypes.data, 1 if gather else 0))
+        return out
+
+    def block_to_hashed(self, block_chunk, masks_chunk: np.ndarray, hashed_count: int | None = None):
+        """arrFromBlockToHashed (src/BlockToHashed.chpl:87): this rank's chunk of a vector in sorted-state order ->
+        this rank's hashed block.  Collective when num_ranks > 1.  numpy or torch CUDA arrays."""
+        masks_chunk = np.ascontiguousarray(masks_chunk, dtype=np.uint8)
+        n_out = self.basis.numberStates() if hashed_count is None else hashed_count
+        if _is_torch(block_chunk):
+            import torch
+            self.use_torch_stream()
+            out = torch.zeros(n_out, dtype=block_chunk.dtype, device=block_chunk.device)
+            itemsize = block_chunk.element_size()
+        else:
+            block_chunk = np.ascontiguousarray(block_chunk)
+            out = np.zeros(n_out, dtype=block_chunk.dtype)
+            itemsize = block_chunk.dtype.itemsize
+        nat.check(nat.lib().dmv_block_to_hashed(self._ctx, itemsize // 8, masks_chunk.shape[0], masks_chunk.ctypes.data,
+                                                _ptr(block_chunk), _ptr(out), n_out))
+        return out
+
+    def hashed_to_block(self, hashed, masks_chunk: np.ndarray):
+        """arrFromHashedToBlock (src/HashedToBlock.chpl:67): inverse of block_to_hashed."""
+        masks_chunk = np.ascontiguousarray(masks_chunk, dtype=np.uint8)
+        n_out = masks_chunk.shape[0]
+        if _is_torch(hashed):
+            import torch
+            self.use_torch_stream()
+            out = torch.zeros(n_out, dtype=hashed.dtype, device=hashed.device)
+            itemsize = hashed.element_size()
+        else:
+            hashed = np.ascontiguousarray(hashed)
+            out = np.zeros(n_out, dtype=hashed.dtype)
+            itemsize = hashed.dtype.itemsize
+        nat.check(nat.lib().dmv_hashed_to_block(self._ctx, itemsize // 8, n_out, masks_chunk.ctypes.data, _ptr(hashed),
+                                                int(hashed.shape[0]), _ptr(out)))
+        return out
+
     def set_option(self, name: str, value: int):
         """"mode": -1 auto / 0 push (scatter + atomics) / 1 pull (gather); "index": -1 auto / 0 directory / 2 rank"""
         nat.check(nat.lib().dmv_set_option(self._ctx, name.encode(), int(value)))

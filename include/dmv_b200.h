@@ -152,6 +152,25 @@ int dmv_accumulate(dmv_context *ctx, int elt, int64_t count, const uint64_t *bet
 int dmv_replicated_setup(dmv_context *ctx);
 int dmv_replicated_product(dmv_context *ctx, int elt, const void *x_cat, void *y);
 
+/* ---- block <-> hashed redistribution of vectors (arrFromBlockToHashed, reference src/BlockToHashed.chpl:87-208;
+ * arrFromHashedToBlock, src/HashedToBlock.chpl:67-153): how vectors in file (sorted-state) order enter and leave the
+ * hash partition (test/TestMatrixVectorProduct.chpl:35,45).  "Block": the global array cut into contiguous chunks,
+ * one per rank, with masks[i] = owner of element i (SE:138-156); "hashed": each rank holds the elements it owns,
+ * ascending.  elt = 8-byte words per element (1: real(64) / uint(64), 2: complex128).  Host or device pointers.
+ *   dmv_hashed_positions: positions[i] = slot of chunk element i in the ordering "grouped by owner, stable";
+ *                         counts[r] = elements owned by r.  Building block of the two conversions.
+ *   dmv_permute:          out[positions[i]] = in[i] (gather == 0) or out[i] = in[positions[i]] (gather != 0).
+ *   dmv_block_to_hashed / dmv_hashed_to_block: the conversions, collective over the communicator (NCCL
+ *                         all-to-all-v of the grouped chunks); with one rank they are the permutation alone. */
+int dmv_hashed_positions(dmv_context *ctx, int64_t count, const uint8_t *masks, int num_ranks, int64_t *counts,
+                         uint32_t *positions);
+int dmv_permute(dmv_context *ctx, int elt, int64_t count, const uint32_t *positions, const void *in, void *out,
+                int gather);
+int dmv_block_to_hashed(dmv_context *ctx, int elt, int64_t chunk_count, const uint8_t *masks_chunk,
+                        const void *block_chunk, void *hashed, int64_t hashed_count);
+int dmv_hashed_to_block(dmv_context *ctx, int elt, int64_t chunk_count, const uint8_t *masks_chunk,
+                        const void *hashed, int64_t hashed_count, void *block_chunk);
+
 /* ---- communicator (NCCL over NVLink): 128-byte unique id made on rank 0, shared by the host */
 int dmv_comm_unique_id(void *id128);
 int dmv_comm_init(dmv_context *ctx, const void *id128);

@@ -282,6 +282,53 @@ def test_chapel_plugin_kernels_refuse_projected_bases(need_cuda):
     op.close()
 
 
+@pytest.mark.parametrize("num_ranks", [1, 2, 3, 8])
+def test_block_hashed_redistribution_kernels(need_cuda, num_ranks):
+    """arrFromBlockToHashed / arrFromHashedToBlock (src/BlockToHashed.chpl:87, src/HashedToBlock.chpl:67): the
+    GPU position + permutation kernels, with the all-to-all played by the host, against the numpy statement."""
+    basis, matrix = _load("heisenberg_chain_16")
+    op = Operator(matrix)
+    reps, _ = po.enumerate_states(basis)
+    masks = po.locale_idx_of(reps, num_ranks)
+    for dtype in (np.float64, np.complex128, np.uint64):
+        arr = reps.copy() if dtype == np.uint64 else _x(reps.shape[0], dtype == np.complex128, 5).astype(dtype)
+        want = block_to_hashed(arr, masks, num_ranks)
+        bounds = np.linspace(0, reps.shape[0], num_ranks + 1).astype(int)      # contiguous chunks, one per rank
+        grouped, counts = [], []
+        for r in range(num_ranks):
+            m = masks[bounds[r]:bounds[r + 1]]
+            c, pos = op.hashed_positions(m, num_ranks)
+            assert np.array_equal(c, np.bincount(m, minlength=num_ranks))
+            grouped.append(op.permute(arr[bounds[r]:bounds[r + 1]], pos, gather=False))
+            counts.append(c)
+        got = []
+        for q in range(num_ranks):      # the "all-to-all": owner q concatenates its share of every chunk, in chunk order
+            parts = [grouped[r][counts[r][:q].sum():counts[r][:q + 1].sum()] for r in range(num_ranks)]
+            got.append(np.concatenate(parts))
+        for q in range(num_ranks):
+            assert np.array_equal(got[q], want[q]), (dtype, q)
+        # and back: chunk r takes, from every owner, the elements that fall into it, then un-groups them
+        back = np.zeros_like(arr)
+        taken = [0] * num_ranks
+        for r in range(num_ranks):
+            m = masks[bounds[r]:bounds[r + 1]]
+            c, pos = op.hashed_positions(m, num_ranks)
+            parts = []
+            for q in range(num_ranks):
+                parts.append(got[q][taken[q]:taken[q] + c[q]])
+                taken[q] += c[q]
+            back[bounds[r]:bounds[r + 1]] = op.permute(np.concatenate(parts), pos, gather=True)
+        assert np.array_equal(back, arr)
+    if num_ranks == 1:      # the collective entry points degenerate to the permutation alone
+        op.basis.build()
+        x = _x(reps.shape[0], True, 7)
+        assert np.array_equal(op.block_to_hashed(x, masks), x)
+        assert np.array_equal(op.hashed_to_block(x, masks), x)
+        xd = torch.from_numpy(x).cuda()
+        assert torch.equal(op.hashed_to_block(op.block_to_hashed(xd, masks), masks), xd)
+    op.close()
+
+
 def test_missing_state_is_an_error(need_cuda):
     """DMV:115-118: a generated state that is not in the basis halts."""
     basis, matrix = _load("heisenberg_chain_10")

@@ -33,6 +33,14 @@ def main():
         o_reps, _ = po.enumerate_states(basis)
         masks, blocks = po.partition_by_hash(o_reps, world)
         ok_basis = np.array_equal(mine, blocks[rank])
+        # block <-> hashed redistribution (collective, NCCL all-to-all-v inside the library)
+        bounds = np.linspace(0, o_reps.shape[0], world + 1).astype(int)
+        m_chunk = masks[bounds[rank]:bounds[rank + 1]]
+        for arr in (o_reps, (np.arange(o_reps.shape[0]) * (1 + 2j)).astype(np.complex128)):
+            hashed = dop.op.block_to_hashed(arr[bounds[rank]:bounds[rank + 1]], m_chunk)
+            ok_basis &= bool(np.array_equal(hashed, arr[masks == rank]))
+            back = dop.op.hashed_to_block(torch.from_numpy(hashed).cuda(), m_chunk)
+            ok_basis &= bool(np.array_equal(back.cpu().numpy(), arr[bounds[rank]:bounds[rank + 1]]))
         for cplx in (False, True):
             rng = np.random.default_rng(42)
             x = rng.random(o_reps.shape[0]) - 0.5
