@@ -285,6 +285,9 @@ struct dmv_context {
   DevBuf<uint64_t> d_orbit64;
   DevBuf<int32_t> d_orbit32;
   DevBuf<double> d_chars;
+  DevBuf<uint16_t> d_canon_lut;
+  DevBuf<uint64_t> d_canon_masks;
+  int opt_canon = -1;    // -1 auto (block-rotation canonical form when the chain subgroup allows it), 0 walk the chain
   OrbitProgram orbit{};  // device view
   // operator
   std::vector<DiagTerm> h_diag;
@@ -637,6 +640,11 @@ void upload_orbit(dmv_context *ctx) {
   P.simple = H.simple;
   P.step_pack64 = ctx->d_orbit64.ptr + off_pack64;
   P.step_pack32 = H.step_pack32.empty() ? nullptr : reinterpret_cast<const uint4 *>(ctx->d_orbit64.ptr + off_pack32);
+  ctx->d_canon_lut.upload(H.canon_lut, ctx->stream);
+  ctx->d_canon_masks.upload(H.canon_masks, ctx->stream);
+  P.canon_lut = ctx->d_canon_lut.ptr;
+  P.canon_masks = ctx->d_canon_masks.ptr;
+  if (ctx->opt_canon == 0) P.canon_mode = 0;
   ctx->orbit = P;
 }
 
@@ -1298,6 +1306,9 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
   } else if (key == "gather") {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
+  } else if (key == "canon") {
+    ctx->opt_canon = value == 0 ? 0 : -1;
+    if (ctx->proj == PROJ_GROUP) { CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); upload_orbit(ctx); }
   } else if (key == "bitparallel") {
     ctx->opt_bitparallel = value != 0;
     ctx->planned = false;
@@ -1323,6 +1334,8 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
   if (key == "n_groups") return (int64_t)ctx->h_push.groups.size();
   if (key == "bp_words") return (int64_t)ctx->h_push.bp.size();
   if (key == "bp_pairs") { int64_t n = 0; for (auto &w : ctx->h_push.bp) n += w.n0 + w.n1; return n; }
+  if (key == "canon_mode") return ctx->orbit.canon_mode;
+  if (key == "canon_k") return ctx->host_orbit.canon_k;
   if (key == "orbit_n_q") return ctx->host_orbit.n_q;
   if (key == "orbit_n_t") return ctx->host_orbit.n_t;
   if (key == "orbit_n_stages") return ctx->host_orbit.n_stages;
@@ -2001,10 +2014,13 @@ int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t 
   if (info) {
     info[0] = H.n_q; info[1] = H.n_stages; info[2] = H.n_t; info[3] = H.n_left; info[4] = H.n_right;
     info[5] = H.has_flip;
+    if (count < 0) { info[6] = H.canon_mode; info[7] = H.canon_k; info[8] = H.canon_r; }   // extended query (count = -1)
   }
   OrbitProgram P = H.view();
   for (int64_t k = 0; k < count; ++k) {
     const OrbitResult r = orbit_scan<true, false>(P, states[k]);
+    if (P.canon_mode && orbit_min_canon(P, states[k]) != r.rep)
+      throw std::runtime_error("block-rotation canonical form disagrees with the chain walk");
     if (reps) reps[k] = r.rep;
     if (stab) stab[k] = r.stab;
   }

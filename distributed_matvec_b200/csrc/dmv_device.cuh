@@ -99,6 +99,15 @@ struct OrbitProgram {
   int32_t simple;              // 0: general; 1: packed steps are valid
   const uint4 *step_pack32;    // [n_t - 1] or nullptr
   const uint64_t *step_pack64; // [3 (n_t - 1)]
+  // canonical form under the chain subgroup WITHOUT walking it, when that subgroup is the group of block rotations
+  //   { rotate the bits inside every k-bit block by a, rotate the R blocks by b },  n_sites = k R
+  // (translations of a chain: R = 1; of an R x k torus numbered row by row): see translation_canon()
+  //   1: k <= 8, R <= 8: the top block of the minimum is the smallest rotation of any block (LUT over 2^k block
+  //      values); only the few (block, amount) pairs reaching it are expanded
+  //   2: R = 1: the minimum rotation starts with the longest cyclic run of zeros; runs are found by iterated AND
+  int32_t canon_mode, canon_k, canon_r;
+  const uint16_t *canon_lut;   // [2^k]: (set of amounts reaching the minimum) << 8 | minimum rotation of the block value
+  const uint64_t *canon_masks; // [2 k]: masks of rotating every block right by a: (low part, wrapped part)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -268,6 +277,145 @@ __device__ __forceinline__ uint64_t orbit_min_wide(const OrbitProgram &P, uint64
   return best;
 }
 
+// ---- minimum over all rotations of an n-bit word: it starts with the longest cyclic run of zeros ----------------
+__host__ __device__ __forceinline__ int top_bit(uint64_t v) {
+#ifdef __CUDA_ARCH__
+  return 63 - __clzll((long long)v);
+#else
+  return 63 - __builtin_clzll(v);
+#endif
+}
+__host__ __device__ __forceinline__ int low_bit(uint32_t v) {
+#ifdef __CUDA_ARCH__
+  return __ffs((int)v) - 1;
+#else
+  return __builtin_ffs((int)v) - 1;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t rotl_n(uint64_t v, int sh, int n, uint64_t mask) {
+  return sh ? (((v << sh) | (v >> (n - sh))) & mask) : v;
+}
+__host__ __device__ __forceinline__ uint64_t min_rotation_runs(uint64_t w, int n, uint64_t mask) {
+  const uint64_t z = ~w & mask;
+  if (w == 0 || z == 0) return w;          // all zeros / all ones: every rotation is the word itself
+  // r = positions p such that bits p, p-1, ..., p-L+1 (cyclically) are all zero; grow L while some run survives
+  uint64_t r = z, zr = z;
+  for (;;) {
+    zr = ((zr << 1) | (zr >> (n - 1))) & mask;     // zr bit p = z bit (p - L)
+    const uint64_t r2 = r & zr;
+    if (r2 == 0) break;
+    r = r2;
+  }
+  uint64_t best = ~0ull;
+  while (r) {                               // one candidate per maximal run: put its top end at the MSB
+    const int p = top_bit(r);
+    r &= ~(1ull << p);
+    const uint64_t c = rotl_n(w, n - 1 - p, n, mask);
+    best = c < best ? c : best;
+  }
+  return best;
+}
+
+// the same in 32-bit registers (n <= 32)
+__host__ __device__ __forceinline__ uint32_t min_rotation_runs32(uint32_t w, int n, uint32_t mask) {
+  const uint32_t z = ~w & mask;
+  if (w == 0 || z == 0) return w;
+  uint32_t r = z, zr = z;
+  for (;;) {
+    zr = ((zr << 1) | (zr >> (n - 1))) & mask;
+    const uint32_t r2 = r & zr;
+    if (r2 == 0) break;
+    r = r2;
+  }
+  uint32_t best = 0xffffffffu;
+  while (r) {
+#ifdef __CUDA_ARCH__
+    const int p = 31 - __clz((int)r);
+#else
+    const int p = 31 - __builtin_clz(r);
+#endif
+    r &= ~(1u << p);
+    const int sh = n - 1 - p;
+    const uint32_t c = sh ? (((w << sh) | (w >> (n - sh))) & mask) : w;
+    best = c < best ? c : best;
+  }
+  return best;
+}
+
+// minimum over { rotate inside every k-bit block by a, rotate the R blocks by b }
+__host__ __device__ __forceinline__ uint64_t min_rotation_blocks(const uint16_t *lut, const uint64_t *masks, int k,
+                                                                 int R, int n, uint64_t mask, uint64_t w) {
+  const uint32_t bm = (1u << k) - 1u;
+  uint64_t pack_m = 0, pack_a = 0;          // per block: minimum rotation / set of amounts reaching it (k, R <= 8)
+  uint32_t mstar = 0xffu;
+  for (int y = 0; y < R; ++y) {
+#ifdef __CUDA_ARCH__
+    const uint32_t e = __ldg(lut + ((uint32_t)(w >> (k * y)) & bm));
+#else
+    const uint32_t e = lut[(uint32_t)(w >> (k * y)) & bm];
+#endif
+    pack_m |= (uint64_t)(e & 0xffu) << (8 * y);
+    pack_a |= (uint64_t)(e >> 8) << (8 * y);
+    mstar = (e & 0xffu) < mstar ? (e & 0xffu) : mstar;
+  }
+  uint64_t best = ~0ull;
+  for (int y = 0; y < R; ++y) {
+    if (((uint32_t)(pack_m >> (8 * y)) & 0xffu) != mstar) continue;
+    uint32_t aset = (uint32_t)(pack_a >> (8 * y)) & 0xffu;
+    const int sh = (R - 1 - y) * k;         // bring block y to the top
+    while (aset) {
+      const int a = low_bit(aset);
+      aset &= aset - 1;
+      const uint64_t wa = a ? (((w >> a) & masks[2 * a]) | ((w << (k - a)) & masks[2 * a + 1])) : w;
+      const uint64_t c = rotl_n(wa, sh, n, mask);
+      best = c < best ? c : best;
+    }
+  }
+  return best;
+}
+
+__host__ __device__ __forceinline__ uint64_t translation_canon(const OrbitProgram &P, uint64_t w) {
+  if (P.canon_mode == 2) return min_rotation_runs(w, P.n_sites, P.site_mask);
+  return min_rotation_blocks(P.canon_lut, P.canon_masks, P.canon_k, P.canon_r, P.n_sites, P.site_mask, w);
+}
+
+// min_g g(s) through the canonical form of every coset representative (trivial characters)
+__host__ __device__ __forceinline__ uint64_t orbit_min_canon(const OrbitProgram &P, uint64_t s) {
+  if (P.canon_mode == 2 && P.n_sites <= 32) {   // chains of up to 32 sites: everything in 32-bit registers
+    const uint32_t site = (uint32_t)P.site_mask;
+    uint32_t best32 = 0xffffffffu;
+    for (int q = 0; q < P.n_q; ++q) {
+      uint32_t cur = (uint32_t)s;
+      const uint64_t *bm = P.benes_mask + (int64_t)q * P.n_stages;
+      for (int st = 0; st < P.n_stages; ++st) {
+        const int d = P.benes_delta[st];
+        const uint32_t t = ((cur >> d) ^ cur) & (uint32_t)bm[st];
+        cur ^= t ^ (t << d);
+      }
+      uint32_t c = min_rotation_runs32(cur, P.n_sites, site);
+      best32 = c < best32 ? c : best32;
+      if (P.has_flip) {
+        c = min_rotation_runs32(cur ^ site, P.n_sites, site);
+        best32 = c < best32 ? c : best32;
+      }
+    }
+    return (uint64_t)best32;
+  }
+  uint64_t best = ~0ull;
+  for (int q = 0; q < P.n_q; ++q) {
+    uint64_t cur = s;
+    const uint64_t *bm = P.benes_mask + (int64_t)q * P.n_stages;
+    for (int st = 0; st < P.n_stages; ++st) cur = butterfly(cur, bm[st], P.benes_delta[st]);
+    uint64_t c = translation_canon(P, cur);
+    best = c < best ? c : best;
+    if (P.has_flip) {
+      c = translation_canon(P, cur ^ P.site_mask);
+      best = c < best ? c : best;
+    }
+  }
+  return best;
+}
+
 // representative only (characters trivial): picks the fastest applicable scan
 __device__ __forceinline__ uint64_t orbit_representative(const OrbitProgram &P, uint64_t s);
 
@@ -312,6 +460,7 @@ __host__ __device__ __forceinline__ OrbitResult orbit_scan(const OrbitProgram &P
 }
 
 __device__ __forceinline__ uint64_t orbit_representative(const OrbitProgram &P, uint64_t s) {
+  if (P.canon_mode) return orbit_min_canon(P, s);
   if (P.simple) return P.step_pack32 ? orbit_min_narrow(P, s) : orbit_min_wide(P, s);
   return orbit_scan<false, false>(P, s).rep;
 }

@@ -173,11 +173,7 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
   Candidate best;
   bool have_best = false;
   const double butterfly_cost = (W == 64) ? 8.0 : 4.0, pair_cost_instr = (W == 64) ? 4.0 : 2.0;
-  for (int kmax : {0, 2, 3, 4, 6, 8}) {
-    Candidate c;
-    std::vector<Perm> gens;
-    for (int i = 0; i < Gp; ++i)
-      if (!is_identity(plist[i]) && pair_cost[i] <= kmax) gens.push_back(plist[i]);
+  auto build_candidate = [&](const std::vector<Perm> &gens, Candidate &c) -> bool {
     // subgroup generated by gens
     std::set<Perm> T{ident};
     std::vector<Perm> frontier{ident};
@@ -231,12 +227,45 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
       c.transversal.push_back(p);
       for (auto &t : c.chain) covered.insert(compose(t, p));
     }
-    if ((int)covered.size() != Gp || (int)(c.transversal.size() * c.chain.size()) != Gp) continue;
+    if ((int)covered.size() != Gp || (int)(c.transversal.size() * c.chain.size()) != Gp) return false;
     c.cost = c.transversal.size() * full_stages * butterfly_cost +
              (double)Gp * ((c.n_left + c.n_right) * pair_cost_instr + 8.0);
+    return true;
+  };
+  for (int kmax : {0, 2, 3, 4, 6, 8}) {
+    Candidate c;
+    std::vector<Perm> gens;
+    for (int i = 0; i < Gp; ++i)
+      if (!is_identity(plist[i]) && pair_cost[i] <= kmax) gens.push_back(plist[i]);
+    if (!build_candidate(gens, c)) continue;
     if (!have_best || c.cost < best.cost) { best = c; have_best = true; }
   }
   if (!have_best) throw std::runtime_error("could not factor the symmetry group");
+
+  // ---- does the group contain the block rotations { rotate the bits inside every k-bit block, rotate the R blocks }
+  // (translations of a chain: one block; of an R x k torus numbered row by row)?  Then factor G over THAT subgroup:
+  // its orbit minimum needs no walk (translation_canon in dmv_device.cuh), only the coset networks remain.
+  if (H.trivial_characters && n_sites >= 2) {
+    for (int k = n_sites; k >= 2 && H.canon_mode == 0; --k) {
+      if (n_sites % k) continue;
+      const int R = n_sites / k;
+      if (!(R == 1 || (k <= 8 && R <= 8))) continue;
+      Perm A(n_sites), B(n_sites);
+      for (int i = 0; i < n_sites; ++i) {
+        A[i] = k * (i / k) + ((i % k + 1) % k);   // rotate inside every block
+        B[i] = (i + k) % n_sites;                 // rotate the blocks
+      }
+      if (!perm_index.count(A) || (R > 1 && !perm_index.count(B))) continue;
+      Candidate c;
+      std::vector<Perm> gens{A};
+      if (R > 1) gens.push_back(B);
+      if (!build_candidate(gens, c) || (int)c.chain.size() != n_sites) continue;
+      best = c;
+      H.canon_mode = R == 1 ? 2 : 1;
+      H.canon_k = k;
+      H.canon_r = R;
+    }
+  }
 
   // prefer the identity as the first coset representative (cheaper network: all-zero masks)
   H.n_q = (int)best.transversal.size();
@@ -286,6 +315,31 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
     }
   }
 
+  if (H.canon_mode == 1) {   // tables of the block-rotation canonical form
+    const int k = H.canon_k, R = H.canon_r;
+    const uint32_t bm = (1u << k) - 1u;
+    H.canon_lut.resize((size_t)1 << k);
+    for (uint32_t v = 0; v <= bm; ++v) {
+      uint32_t best_v = ~0u, aset = 0;
+      for (int a = 0; a < k; ++a) {
+        const uint32_t r = a ? (((v >> a) | (v << (k - a))) & bm) : v;
+        if (r < best_v) { best_v = r; aset = 1u << a; }
+        else if (r == best_v) aset |= 1u << a;
+      }
+      H.canon_lut[v] = (uint16_t)((aset << 8) | best_v);
+    }
+    H.canon_masks.assign((size_t)2 * k, 0);
+    for (int a = 1; a < k; ++a) {
+      uint64_t lo = 0, hi = 0;
+      for (int y = 0; y < R; ++y) {
+        lo |= (uint64_t)((1u << (k - a)) - 1u) << (k * y);
+        hi |= (uint64_t)(bm & ~((1u << (k - a)) - 1u)) << (k * y);
+      }
+      H.canon_masks[2 * a] = lo;
+      H.canon_masks[2 * a + 1] = hi;
+    }
+  }
+
   H.characters.resize((size_t)H.n_q * H.n_t * 2 * 2, 0.0);
   for (int q = 0; q < H.n_q; ++q)
     for (int j = 0; j < H.n_t; ++j) {
@@ -304,8 +358,18 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
   // self-check against bit-by-bit application on random states
   OrbitProgram P = H.view();
   std::mt19937_64 rng(12345);
-  for (int trial = 0; trial < 64; ++trial) {
-    const uint64_t s = rng() & H.site_mask;
+  // random states plus patterns with many tied rotations (uniform, alternating, repeated blocks, single bits)
+  std::vector<uint64_t> probes = {0ull, H.site_mask, 0x5555555555555555ull & H.site_mask,
+                                  0xaaaaaaaaaaaaaaaaull & H.site_mask, 1ull, H.site_mask >> 1,
+                                  0x3333333333333333ull & H.site_mask, 0x0f0f0f0f0f0f0f0full & H.site_mask,
+                                  0x249249249249249ull & H.site_mask, 0x1041041041041041ull & H.site_mask};
+  for (int trial = 0; trial < 256; ++trial) {
+    uint64_t v = rng() & H.site_mask;
+    if (trial & 1) v &= rng();            // sparse and dense words: long runs
+    if ((trial & 3) == 3) v = ~v & H.site_mask;
+    probes.push_back(v);
+  }
+  for (const uint64_t s : probes) {
     uint64_t expect = ~0ull;
     int stab = 0;
     for (int i = 0; i < Gp; ++i) {
@@ -316,6 +380,8 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
     }
     OrbitResult r = orbit_scan<true, false>(P, s);
     if (r.rep != expect || r.stab != stab) throw std::runtime_error("orbit program self-check failed");
+    if (H.canon_mode && orbit_min_canon(P, s) != expect)
+      throw std::runtime_error("orbit program self-check failed (block-rotation canonical form)");
     // the element reported as minimising must really map s to rep
     const int e = r.arg >> 1;
     const Perm g = compose(best.chain[e % H.n_t], best.transversal[e / H.n_t]);
@@ -341,6 +407,9 @@ OrbitProgram HostOrbitProgram::view() const {
   P.simple = simple;
   P.step_pack32 = step_pack32.empty() ? nullptr : reinterpret_cast<const uint4 *>(step_pack32.data());
   P.step_pack64 = step_pack64.data();
+  P.canon_mode = canon_mode; P.canon_k = canon_k; P.canon_r = canon_r;
+  P.canon_lut = canon_lut.data();
+  P.canon_masks = canon_masks.data();
   return P;
 }
 

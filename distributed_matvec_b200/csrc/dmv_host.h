@@ -23,6 +23,9 @@ struct HostOrbitProgram {
   std::vector<uint32_t> step_pack32;  // 4 words per step (empty unless simple and n_sites <= 32)
   std::vector<uint64_t> step_pack64;  // 3 words per step (empty unless simple)
   int32_t simple = 0;
+  int32_t canon_mode = 0, canon_k = 0, canon_r = 0;   // block-rotation canonical form of the chain subgroup
+  std::vector<uint16_t> canon_lut;
+  std::vector<uint64_t> canon_masks;
   OrbitProgram view() const;       // pointers into the host vectors
 };
 

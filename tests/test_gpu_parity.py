@@ -539,6 +539,39 @@ def test_replicated_x_needs_an_applicable_operator(need_cuda):
     cl.close()
 
 
+@pytest.mark.parametrize("name,mode", [("heisenberg_chain_24_symm", 2), ("heisenberg_square_4x4", 1),
+                                       ("heisenberg_kagome_12_symm", 0), ("heisenberg_chain_32_symm", 2),
+                                       ("heisenberg_square_6x6", 1)])
+def test_block_rotation_canonical_form(need_cuda, name, mode):
+    """Orbit minima through the canonical form of the translation subgroup (no walk over its elements) are bit-identical
+    to the chain walk: state_info against the oracle, and the product with the canonical form on and off."""
+    basis, matrix = _load(name)
+    op = Operator(matrix)
+    assert op.info("canon_mode") == mode
+    rng = np.random.default_rng(29)
+    alphas = rng.integers(0, 2**basis.number_sites, 4000, dtype=np.uint64)
+    alphas[:4] = [0, 2**basis.number_sites - 1, 0x5555555555555555 & (2**basis.number_sites - 1), 1]
+    want = po.state_info(basis, alphas)[0]
+    if basis.number_sites <= 24:
+        op.basis.build()
+        x = _x(op.basis.numberStates(), True, 3)
+        y_on = op.matvec(x)
+        op.set_option("canon", 0)
+        assert op.info("canon_mode") == 0
+        y_off = op.matvec(x)
+        assert _close(y_on, y_off)
+        y_ref = po.matvec_global(matrix, op.basis.representatives(), x, 1)
+        assert _close(y_on, y_ref)
+        op.set_option("canon", -1)
+    # computeOffDiag goes through orbit_representative for every emitted state: compare the projected states
+    bo = BatchedOperator(op, 512)
+    n, betas, coeffs, keys = bo.computeOffDiag(512, po.state_info(basis, alphas[:512])[0], np.ones(512))
+    ob, oc, ok, _ = po.compute_off_diag(matrix, 1, po.state_info(basis, alphas[:512])[0], np.ones(512))
+    assert np.array_equal(np.sort(betas), np.sort(ob))
+    assert np.array_equal(op.basis.stateInfo(alphas)[0], want)
+    op.close()
+
+
 def test_bitparallel_matches_group_walk(need_cuda):
     basis, matrix = _load("heisenberg_kagome_16")
     op = Operator(matrix)

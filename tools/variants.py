@@ -18,6 +18,8 @@ def main():
     for name in workloads:
         basis, matrix = load_config_from_yaml(os.path.join(ROOT, "data", name + ".yaml"))
         op = Operator(matrix)
+        if os.environ.get("DMV_CANON"):
+            op.set_option("canon", int(os.environ["DMV_CANON"]))
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record(); op.basis.build(); t1.record(); torch.cuda.synchronize()
         n = op.basis.numberStates()
@@ -25,7 +27,8 @@ def main():
         op.set_option("mode", 0)
         nnz = int(op.plan().sum())
         print(f"== {name}: N={n} nnz={nnz} build {t0.elapsed_time(t1):.1f} ms "
-              f"orbit(q,t,stages)=({op.info('orbit_n_q')},{op.info('orbit_n_t')},{op.info('orbit_n_stages')})", flush=True)
+              f"orbit(q,t,stages)=({op.info('orbit_n_q')},{op.info('orbit_n_t')},{op.info('orbit_n_stages')}) "
+              f"canon_mode={op.info('canon_mode')}", flush=True)
         rng = np.random.default_rng(42)
         for cplx in (True, False):
             x = rng.random(n) - 0.5
