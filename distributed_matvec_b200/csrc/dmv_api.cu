@@ -286,7 +286,9 @@ struct dmv_context {
   DevBuf<int32_t> d_orbit32;
   DevBuf<double> d_chars;
   DevBuf<uint16_t> d_canon_lut;
-  DevBuf<uint64_t> d_canon_masks;
+  DevBuf<uint64_t> d_canon_masks, d_cc_mask;
+  DevBuf<uint32_t> d_canon_lut2;
+  DevBuf<int32_t> d_cc_begin, d_cc_delta;
   int opt_canon = -1;    // -1 auto (block-rotation canonical form when the chain subgroup allows it), 0 walk the chain
   OrbitProgram orbit{};  // device view
   // operator
@@ -644,6 +646,15 @@ void upload_orbit(dmv_context *ctx) {
   ctx->d_canon_masks.upload(H.canon_masks, ctx->stream);
   P.canon_lut = ctx->d_canon_lut.ptr;
   P.canon_masks = ctx->d_canon_masks.ptr;
+  ctx->d_canon_lut2.upload(H.canon_lut2, ctx->stream);
+  ctx->d_cc_begin.upload(H.cc_begin, ctx->stream);
+  ctx->d_cc_mask.upload(H.cc_mask, ctx->stream);
+  ctx->d_cc_delta.upload(H.cc_delta, ctx->stream);
+  P.canon_lut2 = H.canon_lut2.empty() ? nullptr : ctx->d_canon_lut2.ptr;
+  P.cc_begin = ctx->d_cc_begin.ptr;
+  P.cc_mask = ctx->d_cc_mask.ptr;
+  P.cc_delta = ctx->d_cc_delta.ptr;
+  if (ctx->opt_canon == 2) { P.canon_lut2 = nullptr; P.cc_n = 0; P.cc_stages = 0; }   // first version: single-block LUT, independent networks
   if (ctx->opt_canon == 0) P.canon_mode = 0;
   ctx->orbit = P;
 }
@@ -1307,7 +1318,7 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
   } else if (key == "canon") {
-    ctx->opt_canon = value == 0 ? 0 : -1;
+    ctx->opt_canon = (value == 0 || value == 2) ? (int)value : -1;
     if (ctx->proj == PROJ_GROUP) { CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); upload_orbit(ctx); }
   } else if (key == "bitparallel") {
     ctx->opt_bitparallel = value != 0;
@@ -2014,7 +2025,12 @@ int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t 
   if (info) {
     info[0] = H.n_q; info[1] = H.n_stages; info[2] = H.n_t; info[3] = H.n_left; info[4] = H.n_right;
     info[5] = H.has_flip;
-    if (count < 0) { info[6] = H.canon_mode; info[7] = H.canon_k; info[8] = H.canon_r; }   // extended query (count = -1)
+    if (count < 0) {   // extended query (count = -1): info must hold 12 entries
+      info[6] = H.canon_mode; info[7] = H.canon_k; info[8] = H.canon_r;
+      info[9] = H.canon_lut2.empty() ? 0 : 1;
+      info[10] = H.cc_begin.empty() ? 0 : (int64_t)H.cc_begin.size() - 1;
+      info[11] = (int64_t)H.cc_mask.size();
+    }
   }
   OrbitProgram P = H.view();
   for (int64_t k = 0; k < count; ++k) {

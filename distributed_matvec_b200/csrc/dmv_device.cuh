@@ -108,6 +108,17 @@ struct OrbitProgram {
   int32_t canon_mode, canon_k, canon_r;
   const uint16_t *canon_lut;   // [2^k]: (set of amounts reaching the minimum) << 8 | minimum rotation of the block value
   const uint64_t *canon_masks; // [2 k]: masks of rotating every block right by a: (low part, wrapped part)
+  //   mode 1 with 2 k <= 12: the LUT runs over PAIRS of adjacent blocks (top two blocks of a candidate), which leaves
+  //   one candidate for all but symmetric states:  canon_lut2[hi << k | lo] = amounts << 16 | minimum rotated pair
+  const uint32_t *canon_lut2;  // nullptr: single-block LUT
+  int32_t canon_div;           // floor(bit / k) = (bit * canon_div) >> 16 for bit < 64
+  // coset representatives for the canonical-form scan as a CHAIN: q_0 = identity, q_i = c_i . q_{i-1} with c_i a cheap
+  // involution of the group (reflections: a few delta-swaps) or, failing that, a full network
+  int32_t cc_n;                // number of cosets (0: use the independent networks above)
+  int32_t cc_stages;           // total number of stages = cc_begin[cc_n]
+  const int32_t *cc_begin;     // [cc_n + 1] stage ranges
+  const uint64_t *cc_mask;     // delta-swap stages
+  const int32_t *cc_delta;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -374,8 +385,86 @@ __host__ __device__ __forceinline__ uint64_t min_rotation_blocks(const uint16_t 
   return best;
 }
 
+// the same with a LUT over pairs of adjacent blocks; candidates are popped by bit index so that all lanes of a warp
+// evaluate their (usually single) candidate together
+__host__ __device__ __forceinline__ uint64_t min_rotation_pairs(const uint32_t *lut2, const uint64_t *masks, int k,
+                                                                int R, int n, uint64_t mask, int div, uint64_t w) {
+  const uint32_t bm = (1u << k) - 1u;
+  uint64_t wy = w, wr = rotl_n(w, k, n, mask);   // block y of wr = block y - 1 of w: the block below the top one
+  uint64_t cand = 0;                             // bit (k y + a): candidate "block y on top, rotated by a"
+  uint32_t mstar = 0xffffffffu;
+  for (int y = 0; y < R; ++y) {
+    const uint32_t e = lut2[(((uint32_t)wy & bm) << k) | ((uint32_t)wr & bm)];
+    const uint32_t m = e & 0xffffu;
+    const uint64_t a = (uint64_t)(e >> 16) << (k * y);
+    cand = m < mstar ? a : (m == mstar ? (cand | a) : cand);
+    mstar = m < mstar ? m : mstar;
+    wy >>= k;
+    wr >>= k;
+  }
+  uint64_t best = ~0ull;
+  while (cand) {
+#ifdef __CUDA_ARCH__
+    const int bit = __ffsll((long long)cand) - 1;
+#else
+    const int bit = __builtin_ffsll((long long)cand) - 1;
+#endif
+    cand &= cand - 1;
+    const int y = (bit * div) >> 16, a = bit - y * k;
+    const uint64_t wa = a ? (((w >> a) & masks[2 * a]) | ((w << (k - a)) & masks[2 * a + 1])) : w;
+    const uint64_t c = rotl_n(wa, (R - 1 - y) * k, n, mask);
+    best = c < best ? c : best;
+  }
+  return best;
+}
+
+// min over the block rotations of w AND of its spin-flipped image ~w: the blocks of ~w are the complements, so one
+// extraction per block pair serves both look-ups
+__host__ __device__ __forceinline__ uint64_t min_rotation_pairs_flip(const uint32_t *lut2, const uint64_t *masks, int k,
+                                                                     int R, int n, uint64_t mask, int div, uint64_t w) {
+  const uint32_t bm = (1u << k) - 1u, pm = (1u << (2 * k)) - 1u;
+  uint64_t wy = w, wr = rotl_n(w, k, n, mask);
+  uint64_t cand0 = 0, cand1 = 0;
+  uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu;
+  for (int y = 0; y < R; ++y) {
+    const uint32_t idx = (((uint32_t)wy & bm) << k) | ((uint32_t)wr & bm);
+    const uint32_t e0 = lut2[idx], e1 = lut2[idx ^ pm];
+    const uint32_t v0 = e0 & 0xffffu, v1 = e1 & 0xffffu;
+    const uint64_t a0 = (uint64_t)(e0 >> 16) << (k * y), a1 = (uint64_t)(e1 >> 16) << (k * y);
+    cand0 = v0 < m0 ? a0 : (v0 == m0 ? (cand0 | a0) : cand0);
+    cand1 = v1 < m1 ? a1 : (v1 == m1 ? (cand1 | a1) : cand1);
+    m0 = v0 < m0 ? v0 : m0;
+    m1 = v1 < m1 ? v1 : m1;
+    wy >>= k;
+    wr >>= k;
+  }
+  // only the image(s) with the smaller top pair can hold the minimum
+  uint64_t best = ~0ull;
+  const uint64_t wf = w ^ mask;
+  if (m1 < m0) cand0 = 0;
+  if (m0 < m1) cand1 = 0;
+  while (cand0 | cand1) {
+    const bool flipped = cand0 == 0;
+    uint64_t &cand = flipped ? cand1 : cand0;
+#ifdef __CUDA_ARCH__
+    const int bit = __ffsll((long long)cand) - 1;
+#else
+    const int bit = __builtin_ffsll((long long)cand) - 1;
+#endif
+    cand &= cand - 1;
+    const uint64_t src = flipped ? wf : w;
+    const int y = (bit * div) >> 16, a = bit - y * k;
+    const uint64_t wa = a ? (((src >> a) & masks[2 * a]) | ((src << (k - a)) & masks[2 * a + 1])) : src;
+    const uint64_t c = rotl_n(wa, (R - 1 - y) * k, n, mask);
+    best = c < best ? c : best;
+  }
+  return best;
+}
+
 __host__ __device__ __forceinline__ uint64_t translation_canon(const OrbitProgram &P, uint64_t w) {
   if (P.canon_mode == 2) return min_rotation_runs(w, P.n_sites, P.site_mask);
+  if (P.canon_lut2)
+    return min_rotation_pairs(P.canon_lut2, P.canon_masks, P.canon_k, P.canon_r, P.n_sites, P.site_mask, P.canon_div, w);
   return min_rotation_blocks(P.canon_lut, P.canon_masks, P.canon_k, P.canon_r, P.n_sites, P.site_mask, w);
 }
 
@@ -402,6 +491,25 @@ __host__ __device__ __forceinline__ uint64_t orbit_min_canon(const OrbitProgram 
     return (uint64_t)best32;
   }
   uint64_t best = ~0ull;
+  if (P.cc_n > 0) {   // coset representatives as a chain of cheap steps
+    uint64_t cur = s;
+    for (int q = 0; q < P.cc_n; ++q) {
+      for (int st = P.cc_begin[q]; st < P.cc_begin[q + 1]; ++st) cur = butterfly(cur, P.cc_mask[st], P.cc_delta[st]);
+      if (P.canon_lut2 && P.has_flip) {
+        const uint64_t c2 = min_rotation_pairs_flip(P.canon_lut2, P.canon_masks, P.canon_k, P.canon_r, P.n_sites,
+                                                    P.site_mask, P.canon_div, cur);
+        best = c2 < best ? c2 : best;
+        continue;
+      }
+      uint64_t c = translation_canon(P, cur);
+      best = c < best ? c : best;
+      if (P.has_flip) {
+        c = translation_canon(P, cur ^ P.site_mask);
+        best = c < best ? c : best;
+      }
+    }
+    return best;
+  }
   for (int q = 0; q < P.n_q; ++q) {
     uint64_t cur = s;
     const uint64_t *bm = P.benes_mask + (int64_t)q * P.n_stages;

@@ -340,6 +340,72 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
     }
   }
 
+  if (H.canon_mode == 1 && 2 * H.canon_k <= 12) {   // pair LUT: top two blocks of a candidate
+    const int k = H.canon_k;
+    const uint32_t bm = (1u << k) - 1u;
+    H.canon_lut2.resize((size_t)1 << (2 * k));
+    for (uint32_t hi = 0; hi <= bm; ++hi)
+      for (uint32_t lo = 0; lo <= bm; ++lo) {
+        uint32_t best_v = ~0u, aset = 0;
+        for (int a = 0; a < k; ++a) {
+          const uint32_t rh = a ? (((hi >> a) | (hi << (k - a))) & bm) : hi;
+          const uint32_t rl = a ? (((lo >> a) | (lo << (k - a))) & bm) : lo;
+          const uint32_t v = (rh << k) | rl;
+          if (v < best_v) { best_v = v; aset = 1u << a; }
+          else if (v == best_v) aset |= 1u << a;
+        }
+        H.canon_lut2[(hi << k) | lo] = (aset << 16) | best_v;
+      }
+    H.canon_div = 65536 / k + 1;
+    for (int bit = 0; bit < 64; ++bit)
+      if (((bit * H.canon_div) >> 16) != bit / k) throw std::runtime_error("canon_div is not exact");
+  }
+  if (H.canon_mode != 0 && best.transversal.size() > 1) {
+    // ---- coset representatives as a chain q_i = c_i . q_{i-1}: c_i a cheap involution of the group (disjoint
+    // transpositions grouped by distance = one delta-swap per distinct distance), else a full network
+    struct Involution { Perm p; std::map<int, uint64_t> stages; };
+    std::vector<Involution> invs;
+    for (auto &p : plist) {
+      if (is_identity(p) || !is_identity(compose(p, p))) continue;
+      Involution v{p, {}};
+      for (int i = 0; i < n_sites; ++i)
+        if (p[i] > i) v.stages[p[i] - i] |= 1ull << i;
+      if (v.stages.size() <= 6) invs.push_back(v);
+    }
+    std::stable_sort(invs.begin(), invs.end(),
+                     [](const Involution &a, const Involution &b) { return a.stages.size() < b.stages.size(); });
+    std::map<Perm, int> coset_of;
+    for (size_t i = 0; i < best.transversal.size(); ++i)
+      for (auto &t : best.chain) coset_of[compose(t, best.transversal[i])] = (int)i;
+    std::vector<char> visited(best.transversal.size(), 0);
+    Perm cur = ident;
+    visited[coset_of.at(ident)] = 1;
+    H.cc_begin = {0, 0};   // coset of the identity: no stages
+    size_t n_visited = 1;
+    while (n_visited < best.transversal.size()) {
+      bool moved = false;
+      for (auto &v : invs) {
+        const Perm x = compose(v.p, cur);
+        const int ci = coset_of.at(x);
+        if (visited[ci]) continue;
+        for (auto &st : v.stages) { H.cc_mask.push_back(st.second); H.cc_delta.push_back(st.first); }
+        cur = x; visited[ci] = 1; moved = true;
+        break;
+      }
+      if (!moved) {   // jump to any unvisited coset through a full network
+        size_t ci = 0;
+        while (visited[ci]) ++ci;
+        const Perm step = compose(best.transversal[ci], inverse(cur));
+        for (auto &st : benes_network(step, W))
+          if (st.first) { H.cc_mask.push_back(st.first); H.cc_delta.push_back(st.second); }
+        cur = best.transversal[ci];
+        visited[ci] = 1;
+      }
+      H.cc_begin.push_back((int32_t)H.cc_mask.size());
+      ++n_visited;
+    }
+  }
+
   H.characters.resize((size_t)H.n_q * H.n_t * 2 * 2, 0.0);
   for (int q = 0; q < H.n_q; ++q)
     for (int j = 0; j < H.n_t; ++j) {
@@ -410,6 +476,13 @@ OrbitProgram HostOrbitProgram::view() const {
   P.canon_mode = canon_mode; P.canon_k = canon_k; P.canon_r = canon_r;
   P.canon_lut = canon_lut.data();
   P.canon_masks = canon_masks.data();
+  P.canon_lut2 = canon_lut2.empty() ? nullptr : canon_lut2.data();
+  P.canon_div = canon_div;
+  P.cc_n = cc_begin.empty() ? 0 : (int32_t)cc_begin.size() - 1;
+  P.cc_stages = (int32_t)cc_mask.size();
+  P.cc_begin = cc_begin.data();
+  P.cc_mask = cc_mask.data();
+  P.cc_delta = cc_delta.data();
   return P;
 }
 

@@ -26,6 +26,10 @@ struct HostOrbitProgram {
   int32_t canon_mode = 0, canon_k = 0, canon_r = 0;   // block-rotation canonical form of the chain subgroup
   std::vector<uint16_t> canon_lut;
   std::vector<uint64_t> canon_masks;
+  std::vector<uint32_t> canon_lut2;      // pair LUT (empty: single-block LUT)
+  int32_t canon_div = 0;
+  std::vector<int32_t> cc_begin, cc_delta;   // coset chain of the canonical-form scan
+  std::vector<uint64_t> cc_mask;
   OrbitProgram view() const;       // pointers into the host vectors
 };
 

@@ -75,7 +75,7 @@ __device__ __forceinline__ double v_im(double2 a) { return a.y; }
 
 // ---- shared-memory staging of the operator / orbit tables ---------------------------------------
 struct SmemLayout {
-  size_t groups, gx, bp, lut, terms, diag, dclass, orbit64, orbit32, binom, queues, total;
+  size_t groups, gx, bp, lut, terms, diag, dclass, orbit64, orbit32, canon, binom, queues, total;
 };
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int proj, size_t val_bytes) {
@@ -107,6 +107,15 @@ __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int pro
   }
   off += 8 * n64;
   L.orbit32 = off; off += 4 * n32;
+  // canonical-form scan: coset chain (masks, then begin / delta) and the pair LUT
+  off = align_up(off, 8);
+  L.canon = off;
+  if (proj == PROJ_GROUP && p.orbit.canon_mode != 0) {
+    const size_t n_st = p.orbit.cc_n > 0 ? (size_t)p.orbit.cc_stages : 0;
+    off += 8 * n_st + 4 * (n_st + (p.orbit.cc_n > 0 ? (size_t)p.orbit.cc_n + 1 : 0));
+    off = align_up(off, 4);
+    if (p.orbit.canon_lut2) off += 4 * ((size_t)1 << (2 * p.orbit.canon_k));
+  }
   L.binom = off;
   if (p.index.mode == INDEX_RANK) off += 4 * (size_t)p.index.n_sites * p.index.stride;
   off = align_up(off, 16);
@@ -186,6 +195,26 @@ __device__ __forceinline__ Tables<CV> stage_tables(const KernelParams &p, unsign
       stage(s32 + T.orbit.n_stages, p.orbit.step_shift, steps * np);
       T.orbit.step_mask = s64 + nb_pad;
       T.orbit.step_shift = s32 + T.orbit.n_stages;
+    }
+  }
+  if (PROJ == PROJ_GROUP && T.orbit.canon_mode != 0) {
+    unsigned char *base = smem + L.canon;
+    if (T.orbit.cc_n > 0) {
+      const int n_st = T.orbit.cc_stages;
+      uint64_t *cm = reinterpret_cast<uint64_t *>(base);
+      int32_t *cb = reinterpret_cast<int32_t *>(base + 8 * (size_t)n_st);
+      int32_t *cd = cb + (T.orbit.cc_n + 1);
+      stage(cm, p.orbit.cc_mask, n_st);
+      stage(cb, p.orbit.cc_begin, T.orbit.cc_n + 1);
+      stage(cd, p.orbit.cc_delta, n_st);
+      T.orbit.cc_mask = cm; T.orbit.cc_begin = cb; T.orbit.cc_delta = cd;
+      base += 8 * (size_t)n_st + 4 * ((size_t)n_st + T.orbit.cc_n + 1);
+    }
+    base = smem + align_up((size_t)(base - smem), 4);
+    if (T.orbit.canon_lut2) {
+      uint32_t *l2 = reinterpret_cast<uint32_t *>(base);
+      stage(l2, p.orbit.canon_lut2, 1 << (2 * T.orbit.canon_k));
+      T.orbit.canon_lut2 = l2;
     }
   }
   T.index = p.index;
@@ -476,8 +505,10 @@ __device__ __forceinline__ void drain(const KernelParams &p, const OrbitProgram 
   finish<PROJ, CV, CE>(p, orbit, a1, k1, c1, i1);
 }
 
+// (symmetric bases: the orbit scan wants > 100 registers; three resident CTAs per SM hide its latencies better than
+// two, at the price of a few spills outside the scan)
 template <int PROJ, bool CV, bool CE, bool COUNT_ONLY>
-__global__ void __launch_bounds__(kThreads) k_generate(const KernelParams p) {
+__global__ void __launch_bounds__(kThreads, PROJ == PROJ_GROUP ? 3 : 1) k_generate(const KernelParams p) {
   using V = typename ValT<CV>::type;
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(p, PROJ, sizeof(V));
@@ -1002,6 +1033,8 @@ void launch_generate_t(const KernelParams &p, cudaStream_t stream) {
   auto kernel = k_generate<PROJ, CV, CE, COUNT_ONLY>;
   if (L.total > 48 * 1024)
     DMV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  if (L.total > 40 * 1024)   // let several CTAs with large tables share the SM
+    DMV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
   DMV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, L.total));
   if (per_sm < 1) per_sm = 1;

@@ -126,11 +126,14 @@ def test_group_compiler_matches_oracle(name):
         assert np.allclose(np.sqrt(stab / len(g)), o_norms, atol=1e-15)
     # which chain subgroups are recognised as block rotations (canonical form without walking the chain; the call
     # above has already checked it against the walk for every probe state): mode 2 = one block (chains), 1 = R x k
-    ext = np.zeros(9, dtype=np.int64)
+    ext = np.zeros(12, dtype=np.int64)
     nat.check(nat.lib().dmv_debug_compile_group(C.byref(bd), ext.ctypes.data, -1, None, None, None))
     expect = {"heisenberg_chain_24_symm": (2, 24, 1), "heisenberg_chain_32_symm": (2, 32, 1),
               "heisenberg_chain_36_symm": (2, 36, 1), "heisenberg_chain_40_symm": (2, 40, 1),
               "heisenberg_square_4x4": (1, 4, 4), "heisenberg_square_6x6": (1, 6, 6)}
     if name in expect:
         assert tuple(ext[6:9]) == expect[name], (name, ext)
-    print(name, "canon (mode, k, R) =", tuple(ext[6:9]), "orbit (n_q, n_stages, n_t) =", tuple(ext[:3]))
+    print(name, "canon (mode, k, R, pair LUT, chain cosets, chain stages) =", [int(v) for v in ext[6:12]],
+          "orbit (n_q, n_stages, n_t) =", [int(v) for v in ext[:3]])
+    if name == "heisenberg_square_6x6":      # D4 walked with three reflections (3 + 3 + 5 delta-swaps), no full network
+        assert ext[9] == 1 and ext[10] == 8 and ext[11] <= 7 * 5
