@@ -76,6 +76,8 @@ _SIGNATURES = [
     ("dmv_replicated_product", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("dmv_comm_unique_id", C.c_int, [C.c_void_p]),
     ("dmv_comm_init", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("dmv_lanczos", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_uint64, C.POINTER(C.c_double), C.c_void_p,
+                              C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     ("dmv_last_timings", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     ("dmv_timing_name", C.c_char_p, [C.c_int]),
     ("dmv_number_terms", C.c_int64, [C.c_void_p]),
@@ -87,6 +89,7 @@ _SIGNATURES = [
     ("ls_chpl_operator_apply_off_diag", None, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(ExternalArray),
                                                C.POINTER(ExternalArray), C.POINTER(ExternalArray), C.c_int64]),
     ("ls_chpl_enumerate_representatives", None, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ExternalArray)]),
+    ("dmv_debug_tridiagonal_lowest", C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     ("dmv_debug_compile_group", C.c_int, [C.POINTER(BasisDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                           C.c_void_p]),
 ]

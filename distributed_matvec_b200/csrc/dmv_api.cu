@@ -360,11 +360,18 @@ struct dmv_context {
   // the slot of every global state in the all-gathered x, and the gathered x itself
   std::vector<double> k_off_v, k_diag_v;                      // copies of the creation arguments
   std::vector<uint64_t> k_off_m, k_off_r, k_off_x, k_off_s, k_diag_m, k_diag_r, k_diag_s;
+  std::vector<int32_t> k_perms;
+  std::vector<uint8_t> k_flips;
+  std::vector<double> k_chars;
+  int64_t k_group_order = 0;
   dmv_context *global = nullptr;
   DevBuf<uint32_t> d_pos;
   int64_t repl_block = 0;        // slot size per rank in the gathered x (the largest block)
   DevBuf<double> d_xcat;
   bool replicated = false, exchange_decided = false, timeline_replicated = false;
+  // Lanczos work space (dmv_lanczos)
+  DevBuf<double> lz_v[4];
+  DevBuf<double> lz_scal;
 
   ~dmv_context() {
     delete global;
@@ -1012,11 +1019,13 @@ void setup_replicated(dmv_context *ctx) {
   require_states(ctx);
   const int P = ctx->num_ranks;
   if (P > 32) throw std::runtime_error("replicated-x product supports at most 32 ranks");
-  if (!ctx->gather_ok || ctx->proj == PROJ_GROUP || ctx->opt_bitparallel == 0)
-    throw std::runtime_error("replicated-x product needs an operator k_gather applies to");
   if (!ctx->global) {
     dmv_basis_desc b{};
     b.number_sites = ctx->n_sites; b.hamming_weight = ctx->hamming_weight; b.spin_inversion = ctx->spin_inversion;
+    if (ctx->proj == PROJ_GROUP) {
+      b.has_permutations = 1; b.group_order = ctx->k_group_order;
+      b.perms = ctx->k_perms.data(); b.flips = ctx->k_flips.data(); b.characters = ctx->k_chars.data();
+    }
     dmv_operator_desc o{};
     o.n_off = (int64_t)ctx->k_off_m.size(); o.off_v = ctx->k_off_v.data();
     o.off_m = ctx->k_off_m.data(); o.off_r = ctx->k_off_r.data(); o.off_x = ctx->k_off_x.data(); o.off_s = ctx->k_off_s.data();
@@ -1026,10 +1035,11 @@ void setup_replicated(dmv_context *ctx) {
     double states = 1.0;
     if (ctx->hamming_weight >= 0) states = (double)binom().c[ctx->n_sites][ctx->hamming_weight];
     else states = std::ldexp(1.0, ctx->n_sites);
-    if (ctx->spin_inversion != 0) states *= 0.5;
+    if (ctx->spin_inversion != 0 && ctx->proj != PROJ_GROUP) states *= 0.5;
+    if (ctx->proj == PROJ_GROUP) states = 1.5 * states / (double)std::max<int64_t>(1, ctx->k_group_order) + 1e4;
     size_t free_b = 0, total_b = 0;
     CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    if (states * 40.0 > 0.5 * (double)free_b) throw std::runtime_error("replicated-x product: the whole basis does not fit");
+    if (states * 48.0 > 0.5 * (double)free_b) throw std::runtime_error("replicated-x product: the whole basis does not fit");
     dmv_context *g = nullptr;
     if (dmv_context_create(&b, &o, ctx->device, 0, 1, &g) != 0) throw std::runtime_error(g_last_error);
     ctx->global = g;
@@ -1077,11 +1087,20 @@ void replicated_rows(dmv_context *ctx, int elt, const void *x_cat, void *y_dev) 
   p.row_end = ctx->n_states;
   p.pos = ctx->d_pos.ptr;
   p.x_row_offset = (int64_t)ctx->rank * ctx->repl_block;
-  select_tables(g, p, true, g->complex_coefficients);
-  p.row_split = choose_row_split(ctx->n_states, (int)g->h_pull.groups.size());
-  p.uni_re = g->gather_uni[0]; p.uni_im = g->gather_uni[1];
-  launch_gather(p, g->proj == PROJ_INVERSION, g->complex_coefficients, elt == DMV_C128, g->gather_narrow,
-                g->index_mode == INDEX_LIN, g->gather_uniform, ctx->stream);
+  if (use_gather(g)) {
+    select_tables(g, p, true, g->complex_coefficients);
+    p.row_split = choose_row_split(ctx->n_states, (int)g->h_pull.groups.size());
+    p.uni_re = g->gather_uni[0]; p.uni_im = g->gather_uni[1];
+    launch_gather(p, g->proj == PROJ_INVERSION, g->complex_coefficients, elt == DMV_C128, g->gather_narrow,
+                  g->index_mode == INDEX_LIN, g->gather_uniform, ctx->stream);
+    return;
+  }
+  // bases with permutation symmetries / operators outside the bit-parallel test: the queued row traversal
+  if (p.index.mode == INDEX_RANK) p.index.mode = INDEX_DIRECTORY;   // the incremental rank needs row index == rank
+  p.row_norms = ctx->d_norms.ptr;
+  p.row_split = 1;
+  select_tables(g, p, true, complex_values(g, elt));
+  launch_pull(p, g->proj, complex_values(g, elt), elt == DMV_C128, ctx->stream);
 }
 
 // Collective: which exchange the distributed product uses.  exchange = -1 (auto) prefers the replicated-x product
@@ -1091,10 +1110,10 @@ void decide_exchange(dmv_context *ctx) {
   int ok = 0;
   std::string why;
   const bool want = (ctx->opt_exchange == 2 || ctx->opt_exchange == -1) && ctx->opt_mode != 0;
-  if (want && ctx->gather_ok && ctx->proj != PROJ_GROUP && ctx->opt_bitparallel != 0 && ctx->num_ranks <= 32) {
+  if (want && ctx->num_ranks <= 32) {
     try { setup_replicated(ctx); ok = 1; } catch (const std::exception &e) { why = e.what(); ok = 0; }
   } else {
-    why = "k_gather does not apply to this operator / basis";
+    why = "switched off (exchange / mode options) or more than 32 ranks";
   }
   ctx->d_barrier.alloc(1);
   CUDA_CHECK(cudaMemcpyAsync(ctx->d_barrier.ptr, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -1157,6 +1176,82 @@ std::vector<int64_t> all_gather_counts(dmv_context *ctx, const std::vector<int64
   return all;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Lowest eigenpair of a symmetric tridiagonal matrix (diagonal a[0..k), off-diagonal b[0..k-1)): Sturm bisection for
+// the eigenvalue, inverse iteration for the vector.  Host side of dmv_lanczos; k is at most a few hundred.
+double tridiagonal_lowest(const std::vector<double> &a, const std::vector<double> &b, std::vector<double> &vec) {
+  const int k = (int)a.size();
+  double lo = a[0], hi = a[0];
+  for (int i = 0; i < k; ++i) {
+    const double r = (i > 0 ? std::fabs(b[i - 1]) : 0.0) + (i + 1 < k ? std::fabs(b[i]) : 0.0);
+    lo = std::min(lo, a[i] - r);
+    hi = std::max(hi, a[i] + r);
+  }
+  auto below = [&](double x) {   // number of eigenvalues < x
+    int count = 0;
+    double q = a[0] - x;
+    for (int i = 0;; ++i) {
+      if (q < 0.0) ++count;
+      if (i + 1 == k) break;
+      if (std::fabs(q) < 1e-300) q = q < 0 ? -1e-300 : 1e-300;
+      q = a[i + 1] - x - b[i] * b[i] / q;
+    }
+    return count;
+  };
+  for (int it = 0; it < 200 && hi - lo > 4e-16 * std::max(1.0, std::max(std::fabs(lo), std::fabs(hi))); ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (below(mid) >= 1) hi = mid; else lo = mid;
+  }
+  const double theta = 0.5 * (lo + hi);
+  // inverse iteration on (T - shift I): LU of a tridiagonal matrix with partial pivoting (the dgttrf / dgttrs scheme)
+  vec.assign(k, 1.0 / std::sqrt((double)k));
+  const double scale = std::max(1.0, std::max(std::fabs(lo), std::fabs(hi)));
+  const double shift = theta - 1e-13 * scale;
+  if (k > 1) {
+    std::vector<double> dl(k - 1), d(k), du(k - 1), du2(k > 2 ? k - 2 : 0, 0.0);
+    std::vector<int> piv(k - 1);
+    for (int i = 0; i < k; ++i) d[i] = a[i] - shift;
+    for (int i = 0; i + 1 < k; ++i) { dl[i] = b[i]; du[i] = b[i]; }
+    const double tiny = 1e-300;
+    for (int i = 0; i + 1 < k; ++i) {
+      if (std::fabs(d[i]) >= std::fabs(dl[i])) {
+        if (std::fabs(d[i]) < tiny) d[i] = tiny;
+        const double f = dl[i] / d[i];
+        dl[i] = f;
+        d[i + 1] -= f * du[i];
+        piv[i] = i;
+      } else {
+        const double f = d[i] / dl[i];
+        d[i] = dl[i];
+        dl[i] = f;
+        const double t = du[i];
+        du[i] = d[i + 1];
+        d[i + 1] = t - f * d[i + 1];
+        if (i + 2 < k) { du2[i] = du[i + 1]; du[i + 1] = -f * du[i + 1]; }
+        piv[i] = i + 1;
+      }
+    }
+    if (std::fabs(d[k - 1]) < tiny) d[k - 1] = tiny;
+    for (int rep = 0; rep < 4; ++rep) {
+      std::vector<double> x = vec;
+      for (int i = 0; i + 1 < k; ++i) {
+        if (piv[i] == i) x[i + 1] -= dl[i] * x[i];
+        else { const double t = x[i]; x[i] = x[i + 1]; x[i + 1] = t - dl[i] * x[i]; }
+      }
+      x[k - 1] /= d[k - 1];
+      if (k > 1) x[k - 2] = (x[k - 2] - du[k - 2] * x[k - 1]) / d[k - 2];
+      for (int i = k - 3; i >= 0; --i) x[i] = (x[i] - du[i] * x[i + 1] - du2[i] * x[i + 2]) / d[i];
+      double nrm = 0.0;
+      for (double v : x) nrm += v * v;
+      nrm = std::sqrt(nrm);
+      if (!(nrm > 0.0) || !std::isfinite(nrm)) break;
+      for (int i = 0; i < k; ++i) vec[i] = x[i] / nrm;
+    }
+  }
+  if (k == 1) vec[0] = 1.0;
+  return theta;
+}
+
 // =================================================================================================
 extern "C" {
 
@@ -1204,6 +1299,12 @@ int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op,
   ctx->k_diag_v.assign(op->diag_v, op->diag_v + 2 * op->n_diag);
   ctx->k_diag_m.assign(op->diag_m, op->diag_m + op->n_diag); ctx->k_diag_r.assign(op->diag_r, op->diag_r + op->n_diag);
   ctx->k_diag_s.assign(op->diag_s, op->diag_s + op->n_diag);
+  if (basis->has_permutations && basis->group_order > 0 && basis->perms && basis->flips && basis->characters) {
+    ctx->k_group_order = basis->group_order;
+    ctx->k_perms.assign(basis->perms, basis->perms + basis->group_order * basis->number_sites);
+    ctx->k_flips.assign(basis->flips, basis->flips + basis->group_order);
+    ctx->k_chars.assign(basis->characters, basis->characters + 2 * basis->group_order);
+  }
   bool cplx = false;
   // ---- operator: group off-diagonal terms by flip mask
   std::map<uint64_t, std::vector<OffTerm>> by_x;
@@ -1856,6 +1957,100 @@ int dmv_replicated_product(dmv_context *ctx, int elt, const void *x_cat, void *y
   API_END
 }
 
+// ---- Lanczos ground-state solver on the device ("next" row f3): the consumer of the product.  The reference hands its
+// matvec to PRIMME (src/Diagonalize.chpl:134-225); here the three-term recurrence, its dot products (NCCL all-reduce
+// across ranks) and the Ritz-vector accumulation all stay in HBM, only alpha_j / beta_j (two doubles) visit the host.
+int dmv_lanczos(dmv_context *ctx, int elt, int max_iters, double tol, uint64_t seed, double *eigenvalue,
+                void *eigenvector, int *iterations, double *residual) {
+  API_BEGIN
+  use_device(ctx);
+  require_states(ctx);
+  if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
+  if (max_iters < 1) throw std::runtime_error("max_iters must be positive");
+  const int P = ctx->num_ranks;
+  if (P > 1 && !ctx->comm) throw std::runtime_error("dmv_lanczos on several ranks needs dmv_comm_init");
+  const int64_t n = ctx->n_states;
+  const size_t words = (size_t)n * elt;
+  const bool ce = elt == DMV_C128;
+  for (auto &b : ctx->lz_v) b.alloc(words);
+  ctx->lz_scal.alloc(8);
+  double *scal = ctx->lz_scal.ptr;
+  cudaStream_t st = ctx->stream;
+  auto reduce = [&](int count) {   // sum the first `count` scalars over the ranks, bring them to the host
+    if (P > 1) NCCL_CHECK(nccl().AllReduce(scal, scal, (size_t)count, ncclDouble, ncclSum, ctx->comm, st));
+    double h[4] = {0, 0, 0, 0};
+    CUDA_CHECK(cudaMemcpyAsync(h, scal, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return std::vector<double>(h, h + count);
+  };
+  auto product = [&](const double *x, double *y) {
+    CUDA_CHECK(cudaMemsetAsync(y, 0, words * 8, st));   // operators without a diagonal accumulate into y (DMV:1062-1069)
+    const int rc = P == 1 ? dmv_local_matvec(ctx, elt, x, y) : dmv_matvec(ctx, elt, x, y);
+    if (rc) throw std::runtime_error(g_last_error);
+  };
+  auto start_vector = [&](double *v) {
+    launch_fill((int64_t)words, seed, (uint64_t)ctx->rank << 40, v, st);
+    CUDA_CHECK(cudaMemsetAsync(scal, 0, 8 * sizeof(double), st));
+    launch_dot(n, ce, v, v, scal, st);
+    const double nrm = std::sqrt(reduce(1)[0]);
+    if (!(nrm > 0.0)) throw std::runtime_error("empty basis");
+    launch_scale((int64_t)words, 1.0 / nrm, v, v, false, st);
+  };
+  std::vector<double> alphas, betas, ritz;
+  double theta = 0.0, res = 0.0;
+  {
+    double *v = ctx->lz_v[0].ptr, *u = ctx->lz_v[1].ptr, *w = ctx->lz_v[2].ptr;
+    start_vector(v);
+    double beta_prev = 0.0;
+    for (int j = 0; j < max_iters; ++j) {
+      product(v, w);
+      CUDA_CHECK(cudaMemsetAsync(scal, 0, 8 * sizeof(double), st));
+      launch_dot(n, ce, v, w, scal, st);
+      const double alpha = reduce(1)[0];
+      const double coef[2] = {alpha, beta_prev};
+      CUDA_CHECK(cudaMemcpyAsync(scal + 4, coef, sizeof(coef), cudaMemcpyHostToDevice, st));
+      CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double), st));
+      launch_lanczos_update(n, ce, w, v, j > 0 ? u : nullptr, scal + 4, scal, st);
+      const double beta = std::sqrt(std::max(0.0, reduce(1)[0]));
+      alphas.push_back(alpha);
+      theta = tridiagonal_lowest(alphas, betas, ritz);
+      res = std::fabs(beta * ritz.back());
+      const bool done = res <= tol * std::max(1.0, std::fabs(theta)) || beta <= 1e-14 * std::max(1.0, std::fabs(alpha)) ||
+                        (int64_t)alphas.size() >= n * (P > 1 ? (int64_t)P : 1);
+      if (done || j + 1 == max_iters) break;
+      betas.push_back(beta);
+      launch_scale((int64_t)words, 1.0 / beta, w, w, false, st);
+      double *t = u; u = v; v = w; w = t;   // v_prev <- v, v <- w / beta, old v_prev becomes scratch
+      beta_prev = beta;
+    }
+  }
+  if (eigenvalue) *eigenvalue = theta;
+  if (iterations) *iterations = (int)alphas.size();
+  if (residual) *residual = res;
+  if (eigenvector) {
+    // second pass with the stored alpha / beta (no dot products): Ritz vector = sum_j s_j v_j
+    double *v = ctx->lz_v[0].ptr, *u = ctx->lz_v[1].ptr, *w = ctx->lz_v[2].ptr, *acc = ctx->lz_v[3].ptr;
+    start_vector(v);
+    CUDA_CHECK(cudaMemsetAsync(acc, 0, words * 8, st));
+    const int k = (int)alphas.size();
+    for (int j = 0; j < k; ++j) {
+      launch_scale((int64_t)words, ritz[j], v, acc, true, st);
+      if (j + 1 == k) break;
+      product(v, w);
+      const double coef[2] = {alphas[j], j > 0 ? betas[j - 1] : 0.0};
+      CUDA_CHECK(cudaMemcpyAsync(scal + 4, coef, sizeof(coef), cudaMemcpyHostToDevice, st));
+      launch_lanczos_update(n, ce, w, v, j > 0 ? u : nullptr, scal + 4, scal, st);
+      CUDA_CHECK(cudaStreamSynchronize(st));   // coef lives on the host stack
+      launch_scale((int64_t)words, 1.0 / betas[j], w, w, false, st);
+      double *t = u; u = v; v = w; w = t;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(eigenvector, acc, words * 8, cudaMemcpyDefault, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  check_status(ctx);
+  API_END
+}
+
 int dmv_last_timings(dmv_context *ctx, double *ms, int capacity) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
@@ -2015,6 +2210,16 @@ void ls_chpl_enumerate_representatives(const void *ls_hs_basis_ptr, uint64_t /*l
   if (dmv_number_states(ctx) < 0 && dmv_basis_build(ctx) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
   *dest = external_array<uint64_t>((size_t)dmv_number_states(ctx));
   if (dmv_get_representatives(ctx, (uint64_t *)dest->elts, nullptr) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
+}
+
+// host-only self-check entry for the tridiagonal solver behind dmv_lanczos (no device needed)
+int dmv_debug_tridiagonal_lowest(int k, const double *diag, const double *offdiag, double *eigenvalue, double *vector) {
+  API_BEGIN
+  if (k < 1) throw std::runtime_error("empty matrix");
+  std::vector<double> a(diag, diag + k), b(offdiag, offdiag + (k - 1)), v;
+  *eigenvalue = tridiagonal_lowest(a, b, v);
+  if (vector) std::copy(v.begin(), v.end(), vector);
+  API_END
 }
 
 int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t count,

@@ -86,10 +86,11 @@ struct KernelParams {
   int64_t row_begin, row_end;
   // k_gather: the coefficient shared by every emitting (group, support bits) pair, when there is one
   double uni_re, uni_im;
-  // k_gather, replicated-x product (several ranks, every rank holds the whole basis and an all-gathered x):
+  // k_gather / k_pull, replicated-x product (several ranks, every rank holds the whole basis and an all-gathered x):
   //   rows come from row_states (this rank's block) while `index` describes the GLOBAL basis; global index g lives
   //   at x[pos[g]]; the row's own element is x[x_row_offset + i].  All null / zero on one rank.
   const uint64_t *row_states;
+  const double *row_norms;     // norms of the rows (k_pull on bases with permutation symmetries); `norms` is then global
   const uint32_t *pos;
   int64_t x_row_offset;
 };
@@ -135,6 +136,12 @@ void launch_owner_positions(const uint64_t *states, const uint8_t *masks, int64_
                             int64_t block, uint32_t *pos, cudaStream_t stream);
 // out[pos[i]] = in[i] (gather == false) or out[i] = in[pos[i]]; elt = 8-byte words per element (1 or 2)
 void launch_permute(int64_t n, int elt, const uint32_t *pos, const void *in, void *out, bool gather, cudaStream_t stream);
+// Lanczos vector kernels (dmv_solver.cu); n = elements, words = 8-byte words
+void launch_dot(int64_t n, bool complex_elements, const double *a, const double *b, double *out2, cudaStream_t s);
+void launch_lanczos_update(int64_t n, bool complex_elements, double *w, const double *v, const double *u,
+                           const double *coef2, double *out1, cudaStream_t s);
+void launch_scale(int64_t words, double scale, const double *x, double *y, bool accumulate, cudaStream_t s);
+void launch_fill(int64_t words, uint64_t seed, uint64_t offset, double *x, cudaStream_t s);
 int64_t launch_counter();
 int planned_grid(int64_t rows, int row_split);
 int choose_row_split(int64_t rows, int n_groups);

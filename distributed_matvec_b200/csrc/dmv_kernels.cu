@@ -651,6 +651,11 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
   __syncthreads();
   unsigned head = 0, count = 0;
   const bool any_s_out = p.any_s_out != 0;
+  // replicated-x product: rows are this rank's block, `index` / `norms` describe the global basis, global index g
+  // lives at x[pos[g]] (see dmv_host.h)
+  const uint64_t *__restrict__ row_states = p.row_states ? p.row_states : p.index.reps;
+  const double *__restrict__ row_norms = p.row_norms ? p.row_norms : p.norms;
+  const uint32_t *__restrict__ xslot = p.pos;
 
   // drains `k` queued entries (PROJ_GROUP): orbit scan, search, gather, add into the owner row's slot
   auto drain = [&](unsigned k) {
@@ -671,7 +676,8 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
       const int64_t idx = locate(index, r.rep);
       if (idx >= 0) {
         h = v_scale(h, __ldg(p.norms + idx));
-        const V val = v_mul(h, to_v(load_x<CE>(p.x, idx), (V *)nullptr));
+        const int64_t xi = xslot ? (int64_t)__ldg(xslot + idx) : idx;
+        const V val = v_mul(h, to_v(load_x<CE>(p.x, xi), (V *)nullptr));
         smem_add(acc_s + src, val);
       } else if (v_nonzero(h)) {
         bool fatal = true;
@@ -688,10 +694,10 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
   for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += warps_total) {
     const int64_t i = p.row_begin + tile * 32 + lane;
     const bool valid = i < p.row_end;
-    const uint64_t b = valid ? __ldg(p.index.reps + i) : 0ull;
+    const uint64_t b = valid ? __ldg(row_states + i) : 0ull;
     V acc = v_make(0.0, 0.0, (V *)nullptr);
     double inv_nb = 1.0;
-    if (PROJ == PROJ_GROUP && valid) inv_nb = 1.0 / __ldg(p.norms + i);
+    if (PROJ == PROJ_GROUP && valid) inv_nb = 1.0 / __ldg(row_norms + i);
 
     for (int g0 = 0, w = 0; g0 < p.n_groups; g0 += 64, ++w) {
       const int g1 = min(g0 + 64, p.n_groups);
@@ -728,7 +734,8 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
             idx = locate(index, flipped ? (a ^ p.site_mask) : a);
           }
           if (idx >= 0) {
-            v_add(acc, v_mul(h, to_v(load_x<CE>(p.x, idx), (V *)nullptr)));
+            const int64_t xi = xslot ? (int64_t)__ldg(xslot + idx) : idx;
+            v_add(acc, v_mul(h, to_v(load_x<CE>(p.x, xi), (V *)nullptr)));
           } else if (v_nonzero(h) && atomicAdd(p.status, 1ull) == 0) {
             p.status[1] = a;
           }
@@ -775,7 +782,7 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
       if (p.n_diag > 0) {
         double dre, dim;
         diagonal<CV>(T, p.n_diag, b, dre, dim);
-        const E xi = load_x<CE>(p.x, i);
+        const E xi = load_x<CE>(p.x, p.x_row_offset + i);
         if (CE) out = v_make(dre * v_re(xi) - dim * v_im(xi), dre * v_im(xi) + dim * v_re(xi), (E *)nullptr);
         else out = v_make(dre * v_re(xi), 0.0, (E *)nullptr);
       } else {

@@ -280,6 +280,17 @@ class Operator:
         nat.check(fn(self._ctx, elt, _ptr(x), _ptr(y)))
         return y
 
+    def lanczos(self, max_iters: int = 300, tol: float = 1e-10, seed: int = 42, complex_vectors: bool = False,
+                eigenvector: bool = True):
+        """Lowest eigenpair by Lanczos on the device (dmv_lanczos): -> (energy, vector or None, iterations, residual)."""
+        elt = nat.DMV_C128 if complex_vectors else nat.DMV_F64
+        n = self.basis.numberStates()
+        vec = np.zeros(n, dtype=np.complex128 if complex_vectors else np.float64) if eigenvector else None
+        e, it, res = C.c_double(), C.c_int(), C.c_double()
+        nat.check(nat.lib().dmv_lanczos(self._ctx, elt, max_iters, tol, seed, C.byref(e),
+                                        vec.ctypes.data if eigenvector else None, C.byref(it), C.byref(res)))
+        return float(e.value), vec, int(it.value), float(res.value)
+
     def plan(self) -> np.ndarray:
         counts = np.zeros(self.num_ranks, dtype=np.int64)
         nat.check(nat.lib().dmv_plan(self._ctx, counts.ctypes.data))

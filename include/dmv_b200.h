@@ -141,10 +141,10 @@ int dmv_accumulate(dmv_context *ctx, int elt, int64_t count, const uint64_t *bet
                    const double *coeffs, void *y);
 
 /* ---- replicated-x form of the distributed product (B200-first alternative to the record exchange of DMV:313-436,
- * chosen automatically by dmv_matvec -- option "exchange" = -1 / 2 -- when the operator passes the bit-parallel emit
- * test, the basis has no permutation symmetries and the whole basis fits on one device): every rank keeps the whole
- * sorted basis, x is all-gathered (E bytes per state instead of 8 + E bytes per off-diagonal term over NVLink) into
- * slots of dmv_get_info(ctx, "replicated_block") elements per rank, and each rank computes ITS rows without atomics.
+ * chosen automatically by dmv_matvec -- option "exchange" = -1 / 2 -- when the whole basis fits on one device): every
+ * rank keeps the whole sorted basis, x is all-gathered (E bytes per state instead of 8 + E bytes per off-diagonal term
+ * over NVLink) into slots of dmv_get_info(ctx, "replicated_block") elements per rank, and each rank computes ITS rows by
+ * the row traversal (k_gather, or the queued k_pull for bases with permutation symmetries): no records, no atomics on y.
  * The hash partition of x, y and the representatives seen by the caller (SE:129-156) is unchanged.
  *   dmv_replicated_setup:   local set-up (whole basis, slot table); no communication.
  *   dmv_replicated_product: y <- rows of this rank applied to a caller-assembled gathered x (device pointers); for
@@ -174,6 +174,14 @@ int dmv_hashed_to_block(dmv_context *ctx, int elt, int64_t chunk_count, const ui
 /* ---- communicator (NCCL over NVLink): 128-byte unique id made on rank 0, shared by the host */
 int dmv_comm_unique_id(void *id128);
 int dmv_comm_init(dmv_context *ctx, const void *id128);
+
+/* ---- Lanczos ground state on the device ("next" row f3; the reference gives its product to PRIMME as the matvec
+ * callback, src/Diagonalize.chpl:134-225).  Three-term recurrence with the vectors resident in HBM, dot products reduced
+ * over the ranks with NCCL; converged when |beta_k s_k| <= tol * max(1, |theta|).  Collective when num_ranks > 1.
+ * eigenvector (optional, host or device, dmv_number_states elements of type elt) is rebuilt in a second pass.
+ * The start vector is a deterministic function of `seed`. */
+int dmv_lanczos(dmv_context *ctx, int elt, int max_iters, double tol, uint64_t seed, double *eigenvalue,
+                void *eigenvector, int *iterations, double *residual);
 
 /* ---- per-stage timings of the last product, in milliseconds (the reference's timing tree,
  * DMV:1028-1052).  names: see dmv_timing_name(i); returns the number of stages. */
@@ -221,6 +229,8 @@ void ls_chpl_enumerate_representatives(const void *ls_hs_basis_ptr, uint64_t low
  * Compiles the symmetry group of `basis` into the device orbit program, verifies it against bit-by-bit
  * permutation and evaluates the compiled program on the host for `count` states: reps[k] = min_g g(s_k),
  * stab[k] = |{g : g(s_k) = s_k}|.  info[0..5] = {n_q, n_stages, n_t, n_left, n_right, has_flip}. */
+/* lowest eigenpair of a symmetric tridiagonal matrix: the host half of dmv_lanczos, exposed for the CPU tests */
+int dmv_debug_tridiagonal_lowest(int k, const double *diag, const double *offdiag, double *eigenvalue, double *vector);
 int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t count,
                             const uint64_t *states, uint64_t *reps, int32_t *stab);
 

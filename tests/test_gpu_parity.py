@@ -509,10 +509,12 @@ def test_gather_is_bit_reproducible_and_chunked_d2h(need_cuda):
 @pytest.mark.parametrize("num_ranks", [2, 3, 8])
 @pytest.mark.parametrize("name", ["heisenberg_chain_10", "heisenberg_chain_12", "heisenberg_kagome_16",
                                   "heisenberg_chain_16", "anisotropic_bonds", "wide_two_magnon",
-                                  "complex_hopping"])
+                                  "complex_hopping", "heisenberg_kagome_12_symm", "heisenberg_square_4x4",
+                                  "issue_01", "heisenberg_chain_24_symm", "three_site", "momentum_sector"])
 def test_replicated_x_product_matches_oracle(need_cuda, name, num_ranks, cplx):
-    """The replicated-x form of the distributed product (all-gather of x + rows without atomics) on P logical
-    ranks: same hash partition, same result as the oracle's P-rank product."""
+    """The replicated-x form of the distributed product (all-gather of x + row traversal: k_gather, or the queued
+    k_pull for bases with permutation symmetries / general operators) on P logical ranks: same hash partition,
+    same result as the oracle's P-rank product."""
     basis, matrix = GENERAL_MODELS[name]() if name in GENERAL_MODELS else _load(name)
     o_reps, _ = po.enumerate_states(basis)
     masks, blocks = po.partition_by_hash(o_reps, num_ranks)
@@ -527,15 +529,6 @@ def test_replicated_x_product_matches_oracle(need_cuda, name, num_ranks, cplx):
     # same answer as the record-exchange form on the same ranks
     y_push = hashed_to_block([t.cpu().numpy() for t in cl.matvec(xb)], masks)
     assert _close(y, y_push)
-    cl.close()
-
-
-def test_replicated_x_needs_an_applicable_operator(need_cuda):
-    basis, matrix = _load("heisenberg_kagome_12_symm")      # permutation symmetries: record exchange only
-    cl = EmulatedCluster(matrix, 2).build()
-    with pytest.raises(Exception, match="k_gather"):
-        cl.matvec_replicated([torch.zeros(op.basis.numberStates(), dtype=torch.float64, device="cuda")
-                              for op in cl.ops])
     cl.close()
 
 
@@ -570,6 +563,55 @@ def test_block_rotation_canonical_form(need_cuda, name, mode):
     assert np.array_equal(np.sort(betas), np.sort(ob))
     assert np.array_equal(op.basis.stateInfo(alphas)[0], want)
     op.close()
+
+
+def _dense_from_oracle(matrix, reps, cplx):
+    n = reps.shape[0]
+    H = np.zeros((n, n), dtype=np.complex128 if cplx else np.float64)
+    for j in range(n):
+        e = np.zeros(n, dtype=H.dtype)
+        e[j] = 1.0
+        H[:, j] = po.matvec_global(matrix, reps, e, 1)
+    return H
+
+
+@pytest.mark.parametrize("name,known", [("heisenberg_chain_4", -8.0), ("heisenberg_chain_6", -11.2111),
+                                        ("heisenberg_chain_8", -14.6044), ("heisenberg_chain_10", -18.0618),
+                                        ("heisenberg_square_4x4", None), ("heisenberg_kagome_12_symm", None),
+                                        ("complex_hopping", None), ("momentum_sector", None)])
+def test_lanczos_ground_state(need_cuda, name, known):
+    """dmv_lanczos (device-resident three-term recurrence on top of the product) against dense diagonalisation of the
+    oracle's matrix, and the Heisenberg-ring ground-state energies in sigma units (SURVEY.md section 8c pin 3)."""
+    basis, matrix = GENERAL_MODELS[name]() if name in GENERAL_MODELS else _load(name)
+    reps, _ = po.enumerate_states(basis)
+    cplx = name in ("complex_hopping", "momentum_sector")
+    H = _dense_from_oracle(matrix, reps, cplx)
+    assert np.allclose(H, H.conj().T, atol=1e-12)
+    w = np.linalg.eigvalsh(H)
+    op = Operator(matrix)
+    op.basis.build()
+    e0, vec, iters, res = op.lanczos(max_iters=400, tol=1e-12, complex_vectors=cplx)
+    assert abs(e0 - w[0]) <= 1e-9 * max(1.0, abs(w[0])), (e0, w[0], iters, res)
+    if known is not None:
+        assert abs(e0 - known) < 5e-4
+    assert iters <= reps.shape[0] and abs(np.linalg.norm(vec) - 1.0) < 1e-8
+    assert np.linalg.norm(H @ vec - e0 * vec) <= 1e-6 * max(1.0, abs(w[0])), res
+    op.close()
+
+
+def test_lanczos_sector_spectrum_at_size(need_cuda):
+    """The fully symmetric sector contains the ground state of the chain: the lowest eigenvalue of chain_24 (2.7 M
+    states, k_gather) equals that of chain_24_symm (28 968 states, orbit scans) -- SURVEY.md section 8c pin 3."""
+    energies = []
+    for name in ("heisenberg_chain_24", "heisenberg_chain_24_symm"):
+        basis, matrix = _load(name)
+        op = Operator(matrix)
+        op.basis.build()
+        e0, _, iters, res = op.lanczos(max_iters=300, tol=1e-11, eigenvector=False)
+        energies.append(e0)
+        op.close()
+    assert abs(energies[0] - energies[1]) <= 1e-8 * abs(energies[0]), energies
+    assert abs(energies[0] / 24 - (-1.7738)) < 0.02      # approaches 4 (1/4 - ln 2) = -1.7726 per site from below
 
 
 def test_bitparallel_matches_group_walk(need_cuda):

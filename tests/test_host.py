@@ -137,3 +137,27 @@ def test_group_compiler_matches_oracle(name):
           "orbit (n_q, n_stages, n_t) =", [int(v) for v in ext[:3]])
     if name == "heisenberg_square_6x6":      # D4 walked with three reflections (3 + 3 + 5 delta-swaps), no full network
         assert ext[9] == 1 and ext[10] == 8 and ext[11] <= 7 * 5
+
+
+def test_tridiagonal_lowest_eigenpair():
+    """Host half of dmv_lanczos (Sturm bisection + pivoted inverse iteration) against numpy, including nearly
+    decoupled blocks, tiny off-diagonals and clustered eigenvalues."""
+    rng = np.random.default_rng(4)
+    cases = []
+    for k in (1, 2, 3, 10, 57, 300):
+        cases.append((rng.normal(size=k), rng.normal(size=max(k - 1, 0))))
+    a, b = rng.normal(size=40), rng.normal(size=39)
+    b[17] = 1e-13                                   # nearly decoupled blocks
+    cases.append((a, b))
+    cases.append((np.full(30, 2.0), np.full(29, -1.0)))          # discrete Laplacian
+    cases.append((np.concatenate([np.full(10, -3.0), rng.normal(size=10)]), np.full(19, 1e-9)))   # clustered
+    for a, b in cases:
+        k = a.shape[0]
+        a = np.ascontiguousarray(a); b = np.ascontiguousarray(b if k > 1 else np.zeros(1))
+        theta, vec = C.c_double(), np.zeros(k)
+        nat.check(nat.lib().dmv_debug_tridiagonal_lowest(k, a.ctypes.data, b.ctypes.data, C.byref(theta), vec.ctypes.data))
+        T = np.diag(a) + (np.diag(b[:k - 1], 1) + np.diag(b[:k - 1], -1) if k > 1 else 0)
+        w = np.linalg.eigvalsh(T)
+        assert abs(theta.value - w[0]) <= 1e-12 * max(1.0, np.abs(w).max())
+        assert abs(np.linalg.norm(vec) - 1.0) < 1e-12
+        assert np.linalg.norm(T @ vec - theta.value * vec) <= 1e-8 * max(1.0, np.abs(w).max())

@@ -66,6 +66,17 @@ def main():
                       f"err_host={e1:.1e} err_dev={e2:.1e} exchange={'replicated-x' if dop.op.info('replicated') else ('peer-direct' if dop.op.info('peer_direct') else 'nccl')} "
                       f"{'OK' if int(flag) == 0 else 'FAIL'}", flush=True)
             failures += int(flag)
+        # Lanczos across the ranks (dot products reduced with NCCL) against the single-rank oracle matrix
+        if o_reps.shape[0] <= 13000:
+            e0, _, iters, res = dop.op.lanczos(max_iters=200, tol=1e-11, eigenvector=False)
+            e_all = torch.tensor([e0], device="cuda", dtype=torch.float64)
+            lst = [torch.zeros_like(e_all) for _ in range(world)]
+            dist.all_gather(lst, e_all)
+            same = all(abs(float(t) - e0) <= 1e-12 * abs(e0) for t in lst)
+            if rank == 0:
+                print(f"{name:28s} P={world} lanczos E0={e0:.10f} iters={iters} residual={res:.1e} ranks agree={same} "
+                      f"{'OK' if same else 'FAIL'}", flush=True)
+            failures += 0 if same else 1
         dop.op.close()
     dist.barrier()
     dist.destroy_process_group()
