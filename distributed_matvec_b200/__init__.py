@@ -6,11 +6,13 @@ src/DistributedMatrixVector.chpl + src/BatchedOperator.chpl); all compute is in 
 """
 from .config import BasisSpec, OperatorSpec, load_config_from_yaml  # noqa: F401
 from .operator import (BatchedOperator, Basis, ChapelKernels, Operator, local_matrix_vector, locale_idx_of)  # noqa: F401
-from .distributed import (DistributedOperator, EmulatedCluster, block_to_hashed, hashed_to_block,  # noqa: F401
-                          masks_of, matrix_vector_product)
+from .distributed import (DistributedOperator, EmulatedCluster, HostExchangedProduct,  # noqa: F401
+                          HostReplicatedProduct, block_to_hashed, hashed_to_block, masks_of,
+                          matrix_vector_product)
 
 __all__ = [
     "BasisSpec", "OperatorSpec", "load_config_from_yaml", "Operator", "Basis", "BatchedOperator", "ChapelKernels",
     "local_matrix_vector", "matrix_vector_product", "locale_idx_of", "DistributedOperator",
-    "EmulatedCluster", "block_to_hashed", "hashed_to_block", "masks_of",
+    "EmulatedCluster", "HostExchangedProduct", "HostReplicatedProduct", "block_to_hashed", "hashed_to_block",
+    "masks_of",
 ]

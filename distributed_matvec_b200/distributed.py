@@ -181,3 +181,33 @@ class HostExchangedProduct:
                                [c * width for c in self.send_counts])
         self.ops.accumulate_tensors(x, betas_in, coeffs_in, y)
         return y
+
+
+class HostReplicatedProduct:
+    """The replicated-x form of ``matrixVectorProduct`` with the all-gather owned by the HOST through torch.distributed
+    (any backend): every rank contributes its block of x to a gathered vector with one equally sized slot per rank
+    (slot size = the largest block, as dmv_replicated_setup reports it) and computes its own rows.  `rank_ops` is this
+    rank's Operator (methods replicated_setup / replicated_rows), or in the CPU tests a stand-in with the same
+    methods built on the oracle, so that the slot logic is covered without a GPU."""
+
+    def __init__(self, rank_ops):
+        import torch.distributed as dist
+        self.ops = rank_ops
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.block = int(self.ops.replicated_setup())
+        import torch
+        sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world)]
+        dist.all_gather(sizes, torch.tensor([self.block], dtype=torch.int64))
+        if any(int(b) != self.block for b in sizes):      # every rank derives it from the same global basis
+            raise RuntimeError("ranks disagree on the slot size of the gathered x")
+
+    def matvec(self, x, y):
+        import torch
+        import torch.distributed as dist
+        if x.shape[0] > self.block:
+            raise ValueError("block larger than its slot")
+        slot = torch.zeros(self.block, dtype=x.dtype, device=x.device)
+        slot[:x.shape[0]] = x
+        slots = [torch.empty_like(slot) for _ in range(self.world)]
+        dist.all_gather(slots, slot)
+        return self.ops.replicated_rows(torch.cat(slots), y)

@@ -291,6 +291,21 @@ class Operator:
                                         vec.ctypes.data if eigenvector else None, C.byref(it), C.byref(res)))
         return float(e.value), vec, int(it.value), float(res.value)
 
+    # -- replicated-x form of the distributed product (dmv_replicated_*), for hosts that own the all-gather -------
+    def replicated_setup(self) -> int:
+        """Build the whole basis and the slot table on this rank; returns the slot size (elements per rank)."""
+        nat.check(nat.lib().dmv_replicated_setup(self._ctx))
+        return self.info("replicated_block")
+
+    def replicated_block(self) -> int:
+        return self.info("replicated_block")
+
+    def replicated_rows(self, x_cat, y):
+        """y <- this rank's rows of H applied to the gathered x (torch CUDA tensors)."""
+        self.use_torch_stream()
+        nat.check(nat.lib().dmv_replicated_product(self._ctx, _elt_of(y), _ptr(x_cat), _ptr(y)))
+        return y
+
     def plan(self) -> np.ndarray:
         counts = np.zeros(self.num_ranks, dtype=np.int64)
         nat.check(nat.lib().dmv_plan(self._ctx, counts.ctypes.data))

@@ -84,6 +84,57 @@ def _worker(rank, world, port, name, cplx, queue):
         dist.destroy_process_group()
 
 
+class OracleReplicatedRank:
+    """Stand-in for one rank's `Operator` with the methods HostReplicatedProduct drives: the rows of this rank from the
+    gathered x, computed by the oracle on the whole basis."""
+
+    def __init__(self, matrix, reps, masks, rank, world):
+        from oracle import pyoracle as po
+        self.po, self.matrix, self.reps, self.masks, self.rank, self.world = po, matrix, reps, masks, rank, world
+        self.block = 0
+
+    def replicated_setup(self):
+        largest = max(int((self.masks == r).sum()) for r in range(self.world))
+        self.block = (largest + 1) // 2 * 2            # same rule as dmv_replicated_setup
+        return self.block
+
+    def replicated_rows(self, x_cat, y):
+        xc = x_cat.numpy()
+        assert xc.shape[0] == self.block * self.world
+        x = np.zeros(self.reps.shape[0], dtype=xc.dtype)
+        for r in range(self.world):                    # slot r holds rank r's block, zero padded
+            n_r = int((self.masks == r).sum())
+            x[self.masks == r] = xc[r * self.block:r * self.block + n_r]
+            assert not np.any(xc[r * self.block + n_r:(r + 1) * self.block])
+        y_all = self.po.matvec_global(self.matrix, self.reps, x, 1)
+        y.copy_(torch.from_numpy(np.ascontiguousarray(y_all[self.masks == self.rank])))
+        return y
+
+
+def _worker_replicated(rank, world, port, name, cplx, queue):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from distributed_matvec_b200 import load_config_from_yaml
+        from distributed_matvec_b200.distributed import HostReplicatedProduct, block_to_hashed
+        from oracle import pyoracle as po
+        basis, matrix = load_config_from_yaml(os.path.join(ROOT, "data", name + ".yaml"))
+        reps, _ = po.enumerate_states(basis)
+        masks, blocks = po.partition_by_hash(reps, world)
+        rng = np.random.default_rng(42)
+        x = rng.random(reps.shape[0]) - 0.5
+        if cplx:
+            x = x + 1j * (rng.random(reps.shape[0]) - 0.5)
+        y_ref = po.matvec_global(matrix, reps, x, world)
+        mine = torch.from_numpy(block_to_hashed(x, masks, world)[rank])
+        prod = HostReplicatedProduct(OracleReplicatedRank(matrix, reps, masks, rank, world))
+        y = prod.matvec(mine, torch.zeros_like(mine))
+        err = float(np.abs(y.numpy() - y_ref[masks == rank]).max() / np.abs(y_ref).max())
+        queue.put((rank, err < 1e-12 and prod.block >= mine.shape[0], err))
+    finally:
+        dist.destroy_process_group()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -98,6 +149,25 @@ def test_host_exchanged_product_gloo(name, cplx, world):
     queue = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, name, cplx, queue)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [queue.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, err in results:
+        assert ok, (rank, err)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name,cplx", [("heisenberg_chain_10", True), ("heisenberg_kagome_12_symm", False)])
+def test_host_replicated_product_gloo(name, cplx, world):
+    """The replicated-x form with the all-gather owned by the host: equal slots (largest block, zero padded), every rank
+    computes its own rows -- the N > 1 host logic on CPU (gloo)."""
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_replicated, args=(r, world, port, name, cplx, queue)) for r in range(world)]
     for p in procs:
         p.start()
     results = [queue.get(timeout=120) for _ in range(world)]
