@@ -386,6 +386,97 @@ def test_hermiticity_and_linearity_at_size(need_cuda):
     op.close()
 
 
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "matvec_golden.npz")
+
+
+@pytest.mark.parametrize("name", ["heisenberg_chain_4", "heisenberg_chain_6", "heisenberg_chain_8",
+                                  "heisenberg_chain_10", "heisenberg_chain_12", "heisenberg_chain_16",
+                                  "heisenberg_chain_24_symm", "heisenberg_kagome_12", "heisenberg_kagome_12_symm",
+                                  "heisenberg_kagome_16", "heisenberg_square_4x4"])
+def test_golden_vectors(need_cuda, name):
+    """The committed fixtures in the layout of the reference's data/matvec/*.h5 (/representatives, /x, /y): /x follows
+    the reference generator's RandomState stream, /y is the oracle's (tests/golden/make_golden.py).  Checked with the
+    reference's own criterion (test/TestMatrixVectorProduct.chpl:15-20: atol 1e-14, rtol 1e-12)."""
+    g = np.load(GOLDEN)
+    basis, matrix = _load(name)
+    op = Operator(matrix)
+    op.basis.build()
+    assert np.array_equal(op.basis.representatives(), g[name + "/representatives"])      # bit-exact
+    want = g[name + "/y"]
+    for mode in (-1, 0):
+        op.set_option("mode", mode)
+        y = op.matvec(g[name + "/x"])
+        assert np.all(np.abs(y - want) <= np.maximum(1e-14, 1e-12 * np.maximum(np.abs(y), np.abs(want))) + 1e-13)
+    op.close()
+
+
+def test_golden_digest_chain_20(need_cuda):
+    import hashlib
+    sys_path = os.path.dirname(GOLDEN)
+    import sys
+    sys.path.insert(0, sys_path)
+    import make_golden as mg
+    g = np.load(GOLDEN)
+    for name, reps, x in mg.replay():
+        if name == "heisenberg_chain_20":
+            break
+    assert np.array_equal(np.frombuffer(hashlib.sha256(x.tobytes()).digest(), dtype=np.uint8), g[name + "/x_sha256"])
+    basis, matrix = _load(name)
+    op = Operator(matrix)
+    op.basis.build()
+    y = op.matvec(x)
+    d = g[name + "/digest"]
+    assert abs(x.sum() - d[0]) < 1e-9 and abs(y.sum() - d[1]) <= 1e-9 * max(1.0, abs(d[1]))
+    assert abs(np.abs(y).max() - d[2]) <= 1e-12 * d[2] and abs(y[0] - d[3]) < 1e-12 and abs(y[-1] - d[4]) < 1e-12
+    op.close()
+
+
+def test_symmetric_properties_at_size(need_cuda):
+    """heisenberg_chain_32_symm at full size (4 707 969 states, |G| = 128; the oracle would need minutes): exact
+    dimension, Hermiticity in the symmetry-adapted basis, linearity, and the canonical form against the chain walk."""
+    basis, matrix = _load("heisenberg_chain_32_symm")
+    op = Operator(matrix)
+    op.basis.build()
+    n = op.basis.numberStates()
+    assert n == 4707969                                   # SURVEY.md section 8 table (Burnside)
+    reps = op.basis.representatives()
+    assert np.all(np.diff(reps.astype(np.int64)) > 0)     # ascending, unique
+    u = torch.from_numpy(_x(n, True, 1)).cuda()
+    v = torch.from_numpy(_x(n, True, 2)).cuda()
+    Hu, Hv = op.matvec(u), op.matvec(v)
+    lhs, rhs = torch.vdot(u, Hv), torch.vdot(Hu, v)
+    assert abs(lhs - rhs) <= 1e-10 * abs(lhs)
+    w = op.matvec(1.5 * u + 0.25j * v)
+    assert torch.allclose(w, 1.5 * Hu + 0.25j * Hv, rtol=1e-11, atol=1e-11)
+    op.set_option("canon", 0)
+    assert torch.allclose(op.matvec(u), Hu, rtol=1e-12, atol=1e-12)
+    op.set_option("canon", -1)
+    op.set_option("mode", 1)                              # queued row traversal: no atomics on y
+    assert torch.allclose(op.matvec(u), Hu, rtol=1e-12, atol=1e-12)
+    op.close()
+
+
+def test_rank_invariance_at_size(need_cuda):
+    """P-invariance (SURVEY.md section 8c pin 4) on heisenberg_chain_20 (184 756 states): one rank, 4 logical ranks with
+    the record exchange and 4 logical ranks with the replicated-x form give the same vector after un-hashing."""
+    basis, matrix = _load("heisenberg_chain_20")
+    one = Operator(matrix)
+    one.basis.build()
+    reps = one.basis.representatives()
+    x = _x(reps.shape[0], True, 11)
+    y_one = one.matvec(x)
+    one.close()
+    P = 4
+    masks = po.locale_idx_of(reps, P)
+    cl = EmulatedCluster(matrix, P).build()
+    assert sum(op.basis.numberStates() for op in cl.ops) == reps.shape[0]
+    xb = [torch.from_numpy(b).cuda() for b in block_to_hashed(x, masks, P)]
+    y_rec = hashed_to_block([t.cpu().numpy() for t in cl.matvec(xb)], masks)
+    y_rep = hashed_to_block([t.cpu().numpy() for t in cl.matvec_replicated(xb)], masks)
+    assert _close(y_rec, y_one) and _close(y_rep, y_one)
+    cl.close()
+
+
 def _custom(n, hw, terms, **basis_kw):
     from distributed_matvec_b200.config import basis_from_dict, operator_from_dict
     basis = basis_from_dict({"number_spins": n, "hamming_weight": hw, **basis_kw})

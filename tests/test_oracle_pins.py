@@ -3,6 +3,7 @@ cannot be built here and its golden HDF5 files are downloaded at test time (refe
 these are the substitute pins of SURVEY.md section 8(c): an independent dense Kronecker construction,
 exact dimensions, physics known answers, Hermiticity and P-invariance."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -183,3 +184,43 @@ def test_hermiticity_and_branches_of_compute_off_diag():
         assert offsets[-1] == betas.shape[0]
         assert np.array_equal(keys, po.locale_idx_of(betas, 4))
         assert np.all(po.state_index(reps, betas) >= 0)      # every produced state is a representative
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "matvec_golden.npz")
+
+
+def test_golden_inputs_follow_the_reference_generator_stream():
+    """tests/golden/matvec_golden.npz: /x replays the RandomState stream of the reference's input_for_matvec.py (seed 42,
+    rand(N, 1) - 0.5, files in the order of its main()), so it is bit-for-bit the /x of the reference's HDF5 files;
+    /y is the oracle's (the reference cannot run here: parity stays unpinned, see make_golden.py)."""
+    import hashlib
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN)))
+    import make_golden as mg
+    g = np.load(GOLDEN)
+    rs = np.random.RandomState(42)
+    for name in mg.ORDER:
+        n = mg.KNOWN_DIMENSIONS.get(name) or g[name + "/x"].shape[0]
+        x = rs.rand(n, 1)[:, 0] - 0.5
+        if name in mg.FULL:
+            assert np.array_equal(x, g[name + "/x"]), name
+            assert g[name + "/representatives"].shape[0] == n
+        if name in mg.DIGEST:
+            assert np.array_equal(np.frombuffer(hashlib.sha256(x.tobytes()).digest(), dtype=np.uint8), g[name + "/x_sha256"])
+    dims = {name: g[name + "/x"].shape[0] for name in mg.FULL}
+    assert dims == {"heisenberg_chain_4": 6, "heisenberg_chain_6": 20, "heisenberg_chain_8": 70, "heisenberg_chain_10": 126,
+                    "heisenberg_chain_12": 4096, "heisenberg_chain_16": 12870, "heisenberg_chain_24_symm": 28968,
+                    "heisenberg_kagome_12": 924, "heisenberg_kagome_12_symm": 472, "heisenberg_kagome_16": 12870,
+                    "heisenberg_square_4x4": 107}
+
+
+@pytest.mark.parametrize("name", ["heisenberg_chain_10", "heisenberg_chain_12", "heisenberg_kagome_12_symm",
+                                  "heisenberg_square_4x4", "heisenberg_kagome_16"])
+def test_oracle_reproduces_golden_vectors(name):
+    g = np.load(GOLDEN)
+    basis, matrix = load_config_from_yaml(os.path.join(DATA, name + ".yaml"))
+    reps, _ = po.enumerate_states(basis)
+    assert np.array_equal(reps, g[name + "/representatives"])
+    y = po.matvec_global(matrix, reps, g[name + "/x"], 1)
+    assert np.allclose(y, g[name + "/y"], rtol=1e-13, atol=1e-13)
+    for P in (2, 3):          # and the P-locale form of the oracle on the same inputs
+        assert np.allclose(po.matvec_global(matrix, reps, g[name + "/x"], P), g[name + "/y"], rtol=1e-12, atol=1e-12)
