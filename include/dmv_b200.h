@@ -72,10 +72,18 @@ int dmv_context_destroy(dmv_context *ctx);
  * non-blocking stream when use_own_stream != 0 (the initial state) */
 int dmv_set_stream(dmv_context *ctx, void *cuda_stream, int use_own_stream);
 int dmv_synchronize(dmv_context *ctx);
-/* options: "mode"  = -1 auto | 0 push: scatter with FP64 atomics, the reference's traversal (DMV:73-127)
- *                  | 1 pull: the same product traversed by rows (gather), only when num_ranks == 1;
- *          "index" = -1 auto | 0 directory + binary search | 2 combinadic rank (full fixed-Hamming bases).
- * dmv_get_info: "index_mode", "pull", "projection", "n_groups", "orbit_n_q", "orbit_n_t", ... (-1: unknown) */
+/* options: "mode"     = -1 auto (row traversal k_gather on one rank when the operator passes the bit-parallel emit test
+ *                        and the basis has no permutation symmetries, else push) | 0 push: scatter with FP64 atomics,
+ *                        the reference's traversal (DMV:73-127) | 1 rows (k_gather, or the queued k_pull); one rank only
+ *          "gather"   = -1 auto | 0 use the queued k_pull instead of k_gather when "mode" selects rows
+ *          "index"    = -1 auto (identity / Lin tables / directory) | 0 directory + binary search | 2 combinadic rank
+ *                        | 3 Lin tables (full fixed-Hamming bases)
+ *          "bitparallel" = 1 | 0 walk the flip-mask groups one by one
+ *          "canon"    = -1 auto (orbit minima through the canonical form of the translation subgroup) | 0 walk the chain
+ *          "exchange" = -1 auto (replicated x when the whole basis fits, else peer-direct records, else NCCL buckets)
+ *                        | 0 NCCL send/recv of record buckets | 1 peer-direct records over NVLink | 2 replicated x
+ * dmv_get_info: "index_mode", "pull", "gather", "projection", "n_groups", "orbit_n_q", "orbit_n_t", "canon_mode",
+ *               "peer_direct", "replicated", "replicated_block", "global_states", ... (-1: unknown) */
 int dmv_set_option(dmv_context *ctx, const char *name, int64_t value);
 int64_t dmv_get_info(const dmv_context *ctx, const char *name);
 
