@@ -76,6 +76,7 @@ _SIGNATURES = [
     ("dmv_replicated_product", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("dmv_comm_unique_id", C.c_int, [C.c_void_p]),
     ("dmv_comm_init", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("dmv_matvec_batch", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("dmv_lanczos", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_uint64, C.POINTER(C.c_double), C.c_void_p,
                               C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     ("dmv_last_timings", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),

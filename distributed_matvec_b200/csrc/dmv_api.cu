@@ -1957,6 +1957,44 @@ int dmv_replicated_product(dmv_context *ctx, int elt, const void *x_cat, void *y
   API_END
 }
 
+// ---- several vectors per call (the reference's numVectors > 1, "not yet implemented" there: DMV:1101-1102, and what
+// PRIMME's blockSize > 1 would use, src/Diagonalize.chpl:154-158).  x, y: num_vectors arrays of dmv_number_states
+// elements, one after the other (the [numVectors, N] layout of the reference's BlockVector).  On one rank with device
+// pointers and an operator k_gather applies to, four vectors share one walk over the terms and one index look-up per
+// term; every other case is the loop over single products.
+int dmv_matvec_batch(dmv_context *ctx, int elt, int num_vectors, const void *x, void *y) {
+  API_BEGIN
+  use_device(ctx);
+  require_states(ctx);
+  if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
+  if (num_vectors < 1) throw std::runtime_error("num_vectors must be positive");
+  if (x == y) throw std::runtime_error("x and y must not alias");
+  const size_t vec_bytes = (size_t)ctx->n_states * 8 * elt;
+  const char *xb = reinterpret_cast<const char *>(x);
+  char *yb = reinterpret_cast<char *>(y);
+  int k = 0;
+  if (ctx->num_ranks == 1 && use_pull(ctx) && use_gather(ctx) && is_device_pointer(x) && is_device_pointer(y)) {
+    for (; k + 4 <= num_vectors; k += 4) {
+      KernelParams p = base_params(ctx);
+      p.x = xb + (size_t)k * vec_bytes;
+      p.y = yb + (size_t)k * vec_bytes;
+      p.batch = 4;
+      p.batch_stride = ctx->n_states;
+      select_tables(ctx, p, true, ctx->complex_coefficients);
+      p.row_split = choose_row_split(ctx->n_states, (int)ctx->h_pull.groups.size());
+      p.uni_re = ctx->gather_uni[0]; p.uni_im = ctx->gather_uni[1];
+      launch_gather(p, ctx->proj == PROJ_INVERSION, ctx->complex_coefficients, elt == DMV_C128, ctx->gather_narrow,
+                    ctx->index_mode == INDEX_LIN, ctx->gather_uniform, ctx->stream);
+    }
+  }
+  for (; k < num_vectors; ++k) {
+    const int rc = ctx->num_ranks == 1 ? dmv_local_matvec(ctx, elt, xb + (size_t)k * vec_bytes, yb + (size_t)k * vec_bytes)
+                                       : dmv_matvec(ctx, elt, xb + (size_t)k * vec_bytes, yb + (size_t)k * vec_bytes);
+    if (rc) throw std::runtime_error(g_last_error);
+  }
+  API_END
+}
+
 // ---- Lanczos ground-state solver on the device ("next" row f3): the consumer of the product.  The reference hands its
 // matvec to PRIMME (src/Diagonalize.chpl:134-225); here the three-term recurrence, its dot products (NCCL all-reduce
 // across ranks) and the Ritz-vector accumulation all stay in HBM, only alpha_j / beta_j (two doubles) visit the host.

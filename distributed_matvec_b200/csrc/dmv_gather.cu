@@ -106,7 +106,7 @@ __device__ __forceinline__ uint32_t lin_index(const uint32_t *__restrict__ lin_a
   return r < n ? r : kNone;   // with spin inversion only the first half are representatives
 }
 
-template <bool INV, bool CV, bool CE, bool NARROW, bool LIN, bool UNI>
+template <bool INV, bool CV, bool CE, bool NARROW, bool LIN, bool UNI, int KB>
 __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
   using V = typename Val<CV>::type;            // coefficient type
   using E = typename Val<CE>::type;            // vector element type
@@ -164,7 +164,11 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
     const int64_t i = p.row_begin + tile * rows_per_tile + lane / S;
     const bool valid = i < p.row_end;
     const W b = valid ? (W)__ldg(row_states + i) : (W)0;
-    A acc = zero_of((A *)nullptr);
+    // KB vectors at once (x, y: KB arrays of p.batch_stride elements apart): one walk over the terms and one index
+    // look-up per term serve all of them
+    A acc[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) acc[k] = zero_of((A *)nullptr);
 
     for (int w = 0; w < p.n_bp; ++w) {
       const BpWord &Wd = s_bp[w];
@@ -206,12 +210,20 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
           if (i0 != kNone) i0 = __ldg(pos + i0);
           if (two && i1 != kNone) i1 = __ldg(pos + i1);
         }
-        E x0 = zero_of((E *)nullptr), x1 = zero_of((E *)nullptr);
-        if (i0 != kNone) x0 = ldx(xv, i0);
-        if (two && i1 != kNone) x1 = ldx(xv, i1);
+        E x0[KB], x1[KB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+          x0[k] = zero_of((E *)nullptr);
+          x1[k] = zero_of((E *)nullptr);
+          if (i0 != kNone) x0[k] = ldx(xv + (int64_t)k * p.batch_stride, i0);
+          if (two && i1 != kNone) x1[k] = ldx(xv + (int64_t)k * p.batch_stride, i1);
+        }
         if (INV) { c0 = scale(c0, s0); c1 = scale(c1, s1); }
-        fma_to(acc, c0, x0);
-        if (two) fma_to(acc, c1, x1);
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+          fma_to(acc[k], c0, x0[k]);
+          if (two) fma_to(acc[k], c1, x1[k]);
+        }
         if ((i0 == kNone) | (two & (i1 == kNone))) {   // DMV:115-118 (rare)
           if (i0 == kNone && nonzero(c0)) { ++bad; bad_state = (unsigned long long)k0; }
           if (two && i1 == kNone && nonzero(c1)) { ++bad; bad_state = (unsigned long long)k1; }
@@ -219,13 +231,15 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
       }
     }
     if (S > 1)
-      for (int m = 1; m < S; m <<= 1) add_to(acc, shfl_xor_v(acc, m));
+      for (int m = 1; m < S; m <<= 1) {
+#pragma unroll
+        for (int k = 0; k < KB; ++k) add_to(acc[k], shfl_xor_v(acc[k], m));
+      }
 
     if (valid && slice == 0) {
       // diagonal (DMV:36-53) and the single store of y[i]; without diagonal terms y is accumulated into
-      E out;
+      double dre = 0.0, dim = 0.0;
       if (p.n_diag > 0) {
-        double dre = 0.0, dim = 0.0;
         for (int c = 0; c < p.n_diag_classes; ++c) {
           const DiagClass &D = s_dclass[c];
           const W d0 = bp_gather<W>(D.p0, D.n0, b), d1 = bp_gather<W>(D.p1, D.n1, b);
@@ -241,16 +255,23 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
             dim += sg * d.v_im;
           }
         }
-        const E xi = ldx(xv, (uint32_t)(p.x_row_offset + i));
-        if constexpr (CE) out = make_double2(dre * xi.x - dim * xi.y, dre * xi.y + dim * xi.x);
-        else out = dre * xi;   // real vectors take the real part of the diagonal
-      } else {
-        out = reinterpret_cast<const E *>(p.y)[i];
       }
-      if constexpr (CE) { out.x += acc.x; out.y += acc.y; }
-      else if constexpr (CV) out += acc.x;
-      else out += acc;
-      reinterpret_cast<E *>(p.y)[i] = out;
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        E *yk = reinterpret_cast<E *>(p.y) + (int64_t)k * p.batch_stride;
+        E out;
+        if (p.n_diag > 0) {
+          const E xi = ldx(xv + (int64_t)k * p.batch_stride, (uint32_t)(p.x_row_offset + i));
+          if constexpr (CE) out = make_double2(dre * xi.x - dim * xi.y, dre * xi.y + dim * xi.x);
+          else out = dre * xi;   // real vectors take the real part of the diagonal
+        } else {
+          out = yk[i];
+        }
+        if constexpr (CE) { out.x += acc[k].x; out.y += acc[k].y; }
+        else if constexpr (CV) out += acc[k].x;
+        else out += acc[k];
+        yk[i] = out;
+      }
     }
   }
   if (bad) {
@@ -298,11 +319,11 @@ int sm_count() {
   return n;
 }
 
-template <bool INV, bool CV, bool CE, bool NARROW, bool LIN, bool UNI>
+template <bool INV, bool CV, bool CE, bool NARROW, bool LIN, bool UNI, int KB>
 void launch_t(const KernelParams &p, cudaStream_t stream) {
   using V = typename Val<CV>::type;
   const GatherLayout L = gather_layout(p, NARROW ? 4 : 8, sizeof(V), UNI);
-  auto kernel = k_gather<INV, CV, CE, NARROW, LIN, UNI>;
+  auto kernel = k_gather<INV, CV, CE, NARROW, LIN, UNI, KB>;
   if (L.total > 48 * 1024) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess)
       throw std::runtime_error("k_gather: operator tables do not fit in shared memory");
@@ -322,10 +343,16 @@ void launch_t(const KernelParams &p, cudaStream_t stream) {
   count_launch();
 }
 
+template <bool INV, bool CV, bool CE, bool NARROW, bool LIN, bool UNI>
+void launch_k(const KernelParams &p, cudaStream_t s) {
+  if (p.batch == 4) launch_t<INV, CV, CE, NARROW, LIN, UNI, 4>(p, s);
+  else if (p.batch <= 1) launch_t<INV, CV, CE, NARROW, LIN, UNI, 1>(p, s);
+  else throw std::runtime_error("k_gather: vectors come one or four at a time");
+}
 template <bool INV, bool CV, bool CE, bool NARROW>
 void launch_n(const KernelParams &p, bool lin, bool uni, cudaStream_t s) {
-  if (lin) { if (uni) launch_t<INV, CV, CE, NARROW, true, true>(p, s); else launch_t<INV, CV, CE, NARROW, true, false>(p, s); }
-  else { if (uni) launch_t<INV, CV, CE, NARROW, false, true>(p, s); else launch_t<INV, CV, CE, NARROW, false, false>(p, s); }
+  if (lin) { if (uni) launch_k<INV, CV, CE, NARROW, true, true>(p, s); else launch_k<INV, CV, CE, NARROW, true, false>(p, s); }
+  else { if (uni) launch_k<INV, CV, CE, NARROW, false, true>(p, s); else launch_k<INV, CV, CE, NARROW, false, false>(p, s); }
 }
 template <bool INV, bool CV, bool CE>
 void launch_w(const KernelParams &p, bool narrow, bool lin, bool uni, cudaStream_t s) {

@@ -93,6 +93,9 @@ struct KernelParams {
   const double *row_norms;     // norms of the rows (k_pull on bases with permutation symmetries); `norms` is then global
   const uint32_t *pos;
   int64_t x_row_offset;
+  // k_gather on several vectors at once: vector k of x / y starts batch_stride elements after vector k - 1
+  int32_t batch;               // 0 / 1: one vector; 4: four vectors per launch
+  int64_t batch_stride;
 };
 
 // launchers (dmv_kernels.cu)

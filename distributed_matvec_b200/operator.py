@@ -280,6 +280,22 @@ class Operator:
         nat.check(fn(self._ctx, elt, _ptr(x), _ptr(y)))
         return y
 
+    def matvec_batch(self, X, Y=None):
+        """Several vectors per call: X, Y of shape (num_vectors, number_states), C-contiguous (dmv_matvec_batch)."""
+        assert X.ndim == 2 and int(X.shape[1]) == self.basis.numberStates()
+        if _is_torch(X):
+            import torch
+            self.use_torch_stream()
+            X = X.contiguous()
+            Y = torch.zeros_like(X) if Y is None else Y
+        else:
+            X = np.ascontiguousarray(X)
+            Y = np.zeros_like(X) if Y is None else Y
+        nat.check(nat.lib().dmv_matvec_batch(self._ctx, _elt_of(X), int(X.shape[0]), _ptr(X), _ptr(Y)))
+        if not _is_torch(X):
+            self.synchronize()
+        return Y
+
     def lanczos(self, max_iters: int = 300, tol: float = 1e-10, seed: int = 42, complex_vectors: bool = False,
                 eigenvector: bool = True):
         """Lowest eigenpair by Lanczos on the device (dmv_lanczos): -> (energy, vector or None, iterations, residual)."""

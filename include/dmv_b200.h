@@ -183,6 +183,14 @@ int dmv_hashed_to_block(dmv_context *ctx, int elt, int64_t chunk_count, const ui
 int dmv_comm_unique_id(void *id128);
 int dmv_comm_init(dmv_context *ctx, const void *id128);
 
+/* ---- several vectors per call: numVectors > 1 of ls_chpl_matrix_vector_product, which the reference itself does not
+ * implement (DMV:1101-1102 halts; its eigensolver loops over columns, src/Diagonalize.chpl:154-158).  x, y hold
+ * num_vectors vectors of dmv_number_states elements one after the other (the [numVectors, N] layout of BlockVector).
+ * With device pointers on one rank, four vectors at a time share the term walk and the index look-ups (k_gather);
+ * otherwise this is the loop over dmv_local_matvec / dmv_matvec.  Semantics per vector as for a single product.
+ * (The ls_chpl_* entry keeps the reference's behaviour and halts for numVectors != 1.) */
+int dmv_matvec_batch(dmv_context *ctx, int elt, int num_vectors, const void *x, void *y);
+
 /* ---- Lanczos ground state on the device ("next" row f3; the reference gives its product to PRIMME as the matvec
  * callback, src/Diagonalize.chpl:134-225).  Three-term recurrence with the vectors resident in HBM, dot products reduced
  * over the ranks with NCCL; converged when |beta_k s_k| <= tol * max(1, |theta|).  Collective when num_ranks > 1.

@@ -386,6 +386,37 @@ def test_hermiticity_and_linearity_at_size(need_cuda):
     op.close()
 
 
+@pytest.mark.parametrize("name", ["heisenberg_chain_16", "heisenberg_chain_10", "heisenberg_kagome_16",
+                                  "anisotropic_bonds", "complex_hopping", "heisenberg_chain_24_symm", "no_diagonal"])
+def test_matvec_batch(need_cuda, name):
+    """numVectors > 1 (dmv_matvec_batch): every column equals the single-vector product -- bit for bit on the k_gather
+    path (same order of operations per column), within rounding elsewhere -- for 1 .. 9 columns, real and complex,
+    device and host pointers; operators without a diagonal accumulate into Y (DMV:1062-1069)."""
+    if name == "no_diagonal":
+        bonds = [[i, (i + 1) % 8] for i in range(8)]
+        basis, matrix = _custom(8, 4, [{"expression": "σ⁺₀ σ⁻₁", "sites": bonds}, {"expression": "σ⁻₀ σ⁺₁", "sites": bonds}])
+    else:
+        basis, matrix = GENERAL_MODELS[name]() if name in GENERAL_MODELS else _load(name)
+    op = Operator(matrix)
+    op.basis.build()
+    n = op.basis.numberStates()
+    gather = bool(op.info("gather"))
+    for cplx in (False, True):
+        for k in (1, 3, 4, 9):
+            X = np.stack([_x(n, cplx, 100 + j) for j in range(k)])
+            Y0 = np.stack([_x(n, cplx, 200 + j) for j in range(k)]) if name == "no_diagonal" else np.zeros_like(X)
+            singles = np.stack([op.matvec(torch.from_numpy(X[j]).cuda(), torch.from_numpy(Y0[j].copy()).cuda()).cpu().numpy()
+                                for j in range(k)])
+            Yd = op.matvec_batch(torch.from_numpy(X).cuda(), torch.from_numpy(Y0.copy()).cuda()).cpu().numpy()
+            if gather:
+                assert np.array_equal(Yd, singles), (name, cplx, k)
+            else:
+                assert _close(Yd, singles), (name, cplx, k)
+            Yh = op.matvec_batch(X, Y0.copy())
+            assert _close(Yh, singles), (name, cplx, k)
+    op.close()
+
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "matvec_golden.npz")
 
 

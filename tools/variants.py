@@ -65,6 +65,27 @@ def main():
                     print(f"  {'c128' if cplx else 'f64 '} mode={('gather' if op.info('gather') else 'pull') if mode else 'push'} index_mode={op.info('index_mode')}"
                           f"  median {ms:.4f} ms  min {min(times):.4f} ms  {n / ms / 1e6:.2f} Gstates/s "
                           f"{nnz / ms / 1e6:.1f} Gterms/s  alg {gbs:.0f} GB/s  diff_vs_first {err:.1e}", flush=True)
+        if op.info("gather") or True:
+            op.set_option("mode", -1); op.set_option("gather", -1); op.set_option("index", -1)
+            if op.info("gather"):
+                for cplx in (True, False):
+                    K = 8
+                    X = torch.from_numpy(np.stack([rng.random(n) - 0.5 + (1j * (rng.random(n) - 0.5) if cplx else 0) for _ in range(K)])).cuda()
+                    Y = torch.zeros_like(X)
+                    for label, fn in (("8 single products", lambda: [op.matvec(X[j], Y[j]) for j in range(K)]),
+                                      ("one batch of 8 (2 x 4 vectors)", lambda: op.matvec_batch(X, Y))):
+                        for _ in range(2):
+                            fn()
+                        torch.cuda.synchronize()
+                        times = []
+                        for k in range(6):
+                            flush.fill_(k)
+                            s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+                            s.record(); fn(); e.record(); torch.cuda.synchronize()
+                            times.append(s.elapsed_time(e))
+                        ms = float(np.median(times))
+                        print(f"  {'c128' if cplx else 'f64 '} {label}: median {ms:.4f} ms  = {ms / K:.4f} ms per vector  "
+                              f"{K * n / ms / 1e6:.2f} Gstates/s", flush=True)
         op.close()
 
 
