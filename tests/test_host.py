@@ -161,3 +161,60 @@ def test_tridiagonal_lowest_eigenpair():
         assert abs(theta.value - w[0]) <= 1e-12 * max(1.0, np.abs(w).max())
         assert abs(np.linalg.norm(vec) - 1.0) < 1e-12
         assert np.linalg.norm(T @ vec - theta.value * vec) <= 1e-8 * max(1.0, np.abs(w).max())
+
+
+def _torus_generators(k, R, reflections=True):
+    """Translations (and reflections) of an R x k torus numbered row by row, site = k y + x."""
+    n = k * R
+    gens = [[k * (i // k) + ((i % k + 1) % k) for i in range(n)]]
+    if R > 1:
+        gens.append([(i + k) % n for i in range(n)])
+    if reflections:
+        gens.append([k * (i // k) + (k - 1 - i % k) for i in range(n)])          # x -> -x
+        if R > 1:
+            gens.append([k * (R - 1 - i // k) + i % k for i in range(n)])        # y -> -y
+        if R == k and k > 1:
+            gens.append([k * (i % k) + i // k for i in range(n)])                # transpose
+    return [{"permutation": g, "sector": 0} for g in gens]
+
+
+@pytest.mark.parametrize("k,R,inversion,expect_mode", [
+    (5, 1, None, 2), (7, 1, 1, 2), (12, 1, 1, 2), (33, 1, 1, 2), (40, 1, None, 2), (64, 1, 1, 2),   # chains: zero runs
+    (2, 2, 1, 1), (3, 2, None, 1), (4, 3, 1, 1), (5, 5, 1, 1), (6, 4, None, 1), (4, 8, 1, 1),      # tori: pair LUT
+    (7, 3, 1, 1), (8, 8, 1, 1), (8, 2, None, 1),                                                  # tori: single-block LUT
+    (16, 2, 1, 0)])                                                                               # blocks too wide: walk
+def test_block_rotation_canonical_form_on_random_lattices(k, R, inversion, expect_mode):
+    """The canonical form of the translation subgroup (zero-run search, block LUT, pair LUT, coset chain through cheap
+    involutions) against the oracle's bit-by-bit group action, for chains and tori of many shapes -- evaluated on the
+    host by the library (the same functions the kernels run).  dmv_debug_compile_group additionally checks every probe
+    state against the chain walk and runs the 266-state self-check of the compiler."""
+    from distributed_matvec_b200.symmetry import build_group
+    from distributed_matvec_b200.config import basis_from_dict
+    n = k * R
+    basis = basis_from_dict({"number_spins": n, "hamming_weight": None, "spin_inversion": inversion,
+                             "symmetries": _torus_generators(k, R)})
+    g = basis.group
+    bd = nat.BasisDesc()
+    bd.number_sites, bd.hamming_weight, bd.spin_inversion, bd.has_permutations = n, -1, inversion or 0, 1
+    perms, flips, chars = (np.ascontiguousarray(g.perms), np.ascontiguousarray(g.flips), np.ascontiguousarray(g.characters))
+    bd.group_order, bd.perms, bd.flips, bd.characters = len(g), perms.ctypes.data, flips.ctypes.data, chars.ctypes.data
+    rng = np.random.default_rng(k * 100 + R)
+    hi = 2**n if n < 64 else 2**63
+    states = rng.integers(0, hi, size=1500, dtype=np.uint64)
+    if n == 64:
+        states |= rng.integers(0, 2, size=1500, dtype=np.uint64) << np.uint64(63)
+    states[:6] = [0, (2**n - 1) if n < 64 else 2**64 - 1, 1, 0x5555555555555555 & (2**n - 1 if n < 64 else 2**64 - 1),
+                  (1 << (n - 1)), 3]
+    states[6:300] &= rng.integers(0, hi, size=294, dtype=np.uint64)       # sparse words: long zero runs, many ties
+    reps = np.zeros_like(states)
+    stab = np.zeros(states.shape[0], dtype=np.int32)
+    info = np.zeros(6, dtype=np.int64)
+    nat.check(nat.lib().dmv_debug_compile_group(C.byref(bd), info.ctypes.data, states.shape[0], states.ctypes.data,
+                                                reps.ctypes.data, stab.ctypes.data))
+    o_reps, _, o_norms = po.state_info(basis, states)
+    assert np.array_equal(reps, o_reps)
+    ext = np.zeros(12, dtype=np.int64)
+    nat.check(nat.lib().dmv_debug_compile_group(C.byref(bd), ext.ctypes.data, -1, None, None, None))
+    assert ext[6] == expect_mode, (k, R, [int(v) for v in ext])
+    if expect_mode == 1:
+        assert (ext[7], ext[8]) == (k, R) and ext[9] == (1 if 2 * k <= 12 else 0)
