@@ -39,17 +39,24 @@ def main():
         for m in METRICS:
             if m in col:
                 print(f"| {m} | {row[col[m]]} | {units[col[m]]} |")
-        print("\nstall reasons (warp-cycles per issued instruction share, > 2 %):\n")
+        print("\nstall reasons (warps stalled per issued instruction, smsp__average_warps_issue_stalled_*_per_issue_active; > 0.2):\n")
         stalls = []
         for h, i in col.items():
-            if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct"):
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
                 try:
-                    stalls.append((float(row[i]), h.replace("smsp__warp_issue_stalled_", "").replace("_per_warp_active.pct", "")))
+                    stalls.append((float(row[i]), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
                 except ValueError:
                     pass
         for v, h in sorted(stalls, reverse=True):
-            if v > 2:
-                print(f"* {h}: {v:.1f} %")
+            if v > 0.2 and h != "selected":
+                print(f"* {h}: {v:.2f}")
+        extra = ["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+                 "lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                 "smsp__average_warp_latency_per_inst_issued.ratio"]
+        print()
+        for m in extra:
+            if m in col and row[col[m]] not in ("", "n/a"):
+                print(f"* {m}: {row[col[m]]}")
         print()
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
                          capture_output=True, text=True).stdout
