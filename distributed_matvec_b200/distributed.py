@@ -1,17 +1,22 @@
 """Hash-partitioned (multi-GPU) form of the product: ``matrixVectorProduct`` (DMV:1072-1093).
 
-Two ways to run P ranks:
+Ways to run P ranks:
 
 * ``DistributedOperator``: one process per GPU under torch.distributed (the bench / production shape).
-  The all-to-all of (beta, coeff) records is done by NCCL inside libdmv_b200 (``dmv_matvec``); torch is
-  only used to share the NCCL unique id and for barriers.
+  The exchange -- all-gather of x (replicated-x form) or the all-to-all of (beta, coeff) records -- is done inside
+  libdmv_b200 (``dmv_matvec``, NCCL / NVLink peer stores); torch is only used to share the NCCL unique id and for
+  barriers.
+* ``HostExchangedProduct`` / ``HostReplicatedProduct``: the same two forms with the collective owned by the host
+  through torch.distributed (any backend; covered on CPU with gloo).
 * ``EmulatedCluster``: P logical ranks (P contexts) on ONE GPU, the analogue of the reference's
   GASNet-smp oversubscription (reference env/setup-env.sh:5,13).  The exchange is replaced by handing
   each destination context the sender's outgoing bucket (same device, so the pointers are valid).
   Used by the single-GPU tests to cover the bucketing / accumulate path for P in {2, 3, 4, ...}.
 
 The block <-> hashed conversions of vectors (arrFromBlockToHashed / arrFromHashedToBlock,
-src/BlockToHashed.chpl:87, src/HashedToBlock.chpl:67) are host-side numpy helpers here ("next" row f2).
+src/BlockToHashed.chpl:87, src/HashedToBlock.chpl:67) run on the GPU through ``Operator.block_to_hashed`` /
+``Operator.hashed_to_block`` (dmv_block_to_hashed / dmv_hashed_to_block); the numpy helpers below state the same
+permutation for the tests.
 """
 from __future__ import annotations
 

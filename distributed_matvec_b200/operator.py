@@ -235,7 +235,7 @@ class Operator:
         return out
 
     def set_option(self, name: str, value: int):
-        """"mode": -1 auto / 0 push (scatter + atomics) / 1 pull (gather); "index": -1 auto / 0 directory / 2 rank"""
+        """Options of include/dmv_b200.h: "mode", "gather", "index", "bitparallel", "canon", "exchange"."""
         nat.check(nat.lib().dmv_set_option(self._ctx, name.encode(), int(value)))
         return self
 
