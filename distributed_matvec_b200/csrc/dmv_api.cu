@@ -289,6 +289,10 @@ struct dmv_context {
   DevBuf<uint64_t> d_canon_masks, d_cc_mask;
   DevBuf<uint32_t> d_canon_lut2;
   DevBuf<int32_t> d_cc_begin, d_cc_delta;
+  DevBuf<uint16_t> d_tor_lutm;
+  DevBuf<uint32_t> d_tor_luts;
+  DevBuf<uint64_t> d_tor_net_mask;
+  DevBuf<int32_t> d_tor_net_delta;
   int opt_canon = -1;    // -1 auto (block-rotation canonical form when the chain subgroup allows it), 0 walk the chain
   OrbitProgram orbit{};  // device view
   // operator
@@ -661,6 +665,15 @@ void upload_orbit(dmv_context *ctx) {
   P.cc_begin = ctx->d_cc_begin.ptr;
   P.cc_mask = ctx->d_cc_mask.ptr;
   P.cc_delta = ctx->d_cc_delta.ptr;
+  ctx->d_tor_lutm.upload(H.tor_lutm, ctx->stream);
+  ctx->d_tor_luts.upload(H.tor_luts, ctx->stream);
+  ctx->d_tor_net_mask.upload(H.tor_net_mask, ctx->stream);
+  ctx->d_tor_net_delta.upload(H.tor_net_delta, ctx->stream);
+  P.tor_lutm = ctx->d_tor_lutm.ptr;
+  P.tor_luts = ctx->d_tor_luts.ptr;
+  P.tor_net_mask = ctx->d_tor_net_mask.ptr;
+  P.tor_net_delta = ctx->d_tor_net_delta.ptr;
+  if (ctx->opt_canon >= 0) P.tor_mode = 0;   // 1: block-rotation form with the coset chain (round 1)
   if (ctx->opt_canon == 2) { P.canon_lut2 = nullptr; P.cc_n = 0; P.cc_stages = 0; }   // first version: single-block LUT, independent networks
   if (ctx->opt_canon == 0) P.canon_mode = 0;
   ctx->orbit = P;
@@ -1419,7 +1432,7 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
   } else if (key == "canon") {
-    ctx->opt_canon = (value == 0 || value == 2) ? (int)value : -1;
+    ctx->opt_canon = (value >= 0 && value <= 2) ? (int)value : -1;
     if (ctx->proj == PROJ_GROUP) { CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); upload_orbit(ctx); }
   } else if (key == "bitparallel") {
     ctx->opt_bitparallel = value != 0;
@@ -1447,6 +1460,7 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
   if (key == "bp_words") return (int64_t)ctx->h_push.bp.size();
   if (key == "bp_pairs") { int64_t n = 0; for (auto &w : ctx->h_push.bp) n += w.n0 + w.n1; return n; }
   if (key == "canon_mode") return ctx->orbit.canon_mode;
+  if (key == "torus_mode") return ctx->orbit.tor_mode;
   if (key == "canon_k") return ctx->host_orbit.canon_k;
   if (key == "orbit_n_q") return ctx->host_orbit.n_q;
   if (key == "orbit_n_t") return ctx->host_orbit.n_t;
@@ -2274,12 +2288,21 @@ int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t 
       info[10] = H.cc_begin.empty() ? 0 : (int64_t)H.cc_begin.size() - 1;
       info[11] = (int64_t)H.cc_mask.size();
     }
+    if (count < -1) {  // count = -2: info holds 16 entries
+      info[12] = H.tor_mode; info[13] = H.tor_rho_n; info[14] = H.tor_tau_n; info[15] = (int64_t)H.tor_lutm.size();
+    }
   }
   OrbitProgram P = H.view();
   for (int64_t k = 0; k < count; ++k) {
     const OrbitResult r = orbit_scan<true, false>(P, states[k]);
     if (P.canon_mode && orbit_min_canon(P, states[k]) != r.rep)
-      throw std::runtime_error("block-rotation canonical form disagrees with the chain walk");
+      throw std::runtime_error("canonical form disagrees with the chain walk");
+    if (P.tor_mode) {
+      OrbitProgram P1 = P;
+      P1.tor_mode = 0;
+      if (orbit_min_canon(P1, states[k]) != r.rep)
+        throw std::runtime_error("block-rotation canonical form disagrees with the chain walk");
+    }
     if (reps) reps[k] = r.rep;
     if (stab) stab[k] = r.stab;
   }

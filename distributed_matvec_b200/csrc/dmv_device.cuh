@@ -119,6 +119,19 @@ struct OrbitProgram {
   const int32_t *cc_begin;     // [cc_n + 1] stage ranges
   const uint64_t *cc_mask;     // delta-swap stages
   const int32_t *cc_delta;
+  // canonical form under the FULL space group of an R x k torus (sites numbered row by row, trivial characters):
+  //   G = {block rotations} x {1, rho} x {1, sigma} [x {1, tau}] [x {1, flip}]
+  // rho = reverse the bits inside every row, sigma = reverse the order of the rows, tau = transpose (R == k).
+  // Every image is "a row pair on top": tor_lutm[hi << k | lo] is the smallest top pair over the 2k (x2 with the flip)
+  // maps F = flip^f . rho^e . rot_a applied to both rows, tor_luts the set of (f, e, a) reaching it (bit (2f + e) k + a);
+  // only the few (row pair, F) whose top pair is the global minimum are expanded.  See orbit_min_torus().
+  int32_t tor_mode;            // 0: off; 1: rho and sigma (4 cosets of the block rotations); 2: and tau (8 cosets)
+  int32_t tor_rho_n, tor_tau_n;   // delta-swap stages of rho / tau inside tor_net_*: rho first, then tau
+  int32_t tor_div_r;           // floor(bit / R) = (bit * tor_div_r) >> 16 for bit < 32
+  const uint16_t *tor_lutm;    // [2^(2k)]
+  const uint32_t *tor_luts;    // [2^(2k)]  (stays in global memory: read about once per state)
+  const uint64_t *tor_net_mask;
+  const int32_t *tor_net_delta;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -461,6 +474,96 @@ __host__ __device__ __forceinline__ uint64_t min_rotation_pairs_flip(const uint3
   return best;
 }
 
+
+// reverse the low n bits of v
+__host__ __device__ __forceinline__ uint64_t reverse_bits_n(uint64_t v, int n) {
+#ifdef __CUDA_ARCH__
+  return __brevll(v) >> (64 - n);
+#else
+  v = ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
+  v = ((v >> 2) & 0x3333333333333333ull) | ((v & 0x3333333333333333ull) << 2);
+  v = ((v >> 4) & 0x0f0f0f0f0f0f0f0full) | ((v & 0x0f0f0f0f0f0f0f0full) << 4);
+  v = ((v >> 8) & 0x00ff00ff00ff00ffull) | ((v & 0x00ff00ff00ff00ffull) << 8);
+  v = ((v >> 16) & 0x0000ffff0000ffffull) | ((v & 0x0000ffff0000ffffull) << 16);
+  v = (v >> 32) | (v << 32);
+  return v >> (64 - n);
+#endif
+}
+
+// min_g g(w) over the full space group of an R x k torus (see OrbitProgram::tor_mode).  An image of w is fixed by
+//   t   : transpose first or not                       u = tau^t (w)
+//   s,y : which row comes on top and whether the rows below it descend (s = 0: y, y-1, ...) or ascend (s = 1)
+//   F   : the map applied to every row, F = flip^f . rho^e . rot_a
+// and images compare lexicographically from the top row down, so the minimum has the smallest top PAIR of rows: pass 1
+// looks the 2R (4R with tau) adjacent row pairs up in tor_lutm and keeps the set of pairs reaching the minimum, pass 2
+// expands only those (about 1.3 images per state instead of |G|).
+__host__ __device__ __forceinline__ uint64_t orbit_min_torus(const OrbitProgram &P, uint64_t w) {
+  const int k = P.canon_k, R = P.canon_r, n = P.n_sites;
+  const uint64_t mask = P.site_mask;
+  const uint32_t bm = (1u << k) - 1u;
+  uint64_t u1 = w;
+  const int nt = P.tor_mode == 2 ? 2 : 1;
+  if (nt == 2)
+    for (int st = P.tor_rho_n; st < P.tor_rho_n + P.tor_tau_n; ++st) u1 = butterfly(u1, P.tor_net_mask[st], P.tor_net_delta[st]);
+  uint32_t mstar = 0xffffffffu, cand = 0;   // cand bit (2 t + s) R + y
+  uint32_t bit = 1u;
+  for (int t = 0; t < nt; ++t) {
+    const uint64_t u = t ? u1 : w;
+    uint64_t wy = u;
+    uint64_t wd = rotl_n(u, k, n, mask);        // block y of wd = block y - 1 of u
+    uint64_t wu = rotl_n(u, n - k, n, mask);    // block y of wu = block y + 1 of u
+    uint32_t bit_u = bit << R;
+    for (int y = 0; y < R; ++y) {
+      const uint32_t hi = ((uint32_t)wy & bm) << k;
+      const uint32_t md = P.tor_lutm[hi | ((uint32_t)wd & bm)], mu = P.tor_lutm[hi | ((uint32_t)wu & bm)];
+      cand = md < mstar ? bit : (md == mstar ? (cand | bit) : cand);
+      mstar = md < mstar ? md : mstar;
+      cand = mu < mstar ? bit_u : (mu == mstar ? (cand | bit_u) : cand);
+      mstar = mu < mstar ? mu : mstar;
+      wy >>= k; wd >>= k; wu >>= k;
+      bit <<= 1; bit_u <<= 1;
+    }
+    bit <<= R;
+  }
+  uint64_t best = ~0ull;
+  while (cand) {
+#ifdef __CUDA_ARCH__
+    const int cb = __ffs((int)cand) - 1;
+#else
+    const int cb = __builtin_ffs((int)cand) - 1;
+#endif
+    cand &= cand - 1;
+    const int ts = (cb * P.tor_div_r) >> 16;   // (t, s) pair index = cb / R
+    const int y = cb - ts * R, s = ts & 1;
+    const uint64_t u = (ts >> 1) ? u1 : w;
+    const int yn = s ? (y + 1 == R ? 0 : y + 1) : (y == 0 ? R - 1 : y - 1);
+    const uint32_t idx = (((uint32_t)(u >> (k * y)) & bm) << k) | ((uint32_t)(u >> (k * yn)) & bm);
+#ifdef __CUDA_ARCH__
+    uint32_t S = __ldg(P.tor_luts + idx);
+#else
+    uint32_t S = P.tor_luts[idx];
+#endif
+    const int sh = (s ? y : R - 1 - y) * k;   // brings row y to the top (after the row order was reversed when s = 1)
+    while (S) {
+#ifdef __CUDA_ARCH__
+      const int sb = __ffs((int)S) - 1;
+#else
+      const int sb = __builtin_ffs((int)S) - 1;
+#endif
+      S &= S - 1;
+      const int fe = (sb * P.canon_div) >> 16, a = sb - fe * k, e = fe & 1;
+      uint64_t v = (fe >> 1) ? (u ^ mask) : u;
+      if (a) v = ((v >> a) & P.canon_masks[2 * a]) | ((v << (k - a)) & P.canon_masks[2 * a + 1]);
+      if (e != s)                                            // rho alone, or sigma = (rho sigma) . rho
+        for (int st = 0; st < P.tor_rho_n; ++st) v = butterfly(v, P.tor_net_mask[st], P.tor_net_delta[st]);
+      if (s) v = reverse_bits_n(v, n);                       // rho sigma: reverse the whole word
+      const uint64_t c = rotl_n(v, sh, n, mask);
+      best = c < best ? c : best;
+    }
+  }
+  return best;
+}
+
 __host__ __device__ __forceinline__ uint64_t translation_canon(const OrbitProgram &P, uint64_t w) {
   if (P.canon_mode == 2) return min_rotation_runs(w, P.n_sites, P.site_mask);
   if (P.canon_lut2)
@@ -470,6 +573,7 @@ __host__ __device__ __forceinline__ uint64_t translation_canon(const OrbitProgra
 
 // min_g g(s) through the canonical form of every coset representative (trivial characters)
 __host__ __device__ __forceinline__ uint64_t orbit_min_canon(const OrbitProgram &P, uint64_t s) {
+  if (P.tor_mode) return orbit_min_torus(P, s);
   if (P.canon_mode == 2 && P.n_sites <= 32) {   // chains of up to 32 sites: everything in 32-bit registers
     const uint32_t site = (uint32_t)P.site_mask;
     uint32_t best32 = 0xffffffffu;

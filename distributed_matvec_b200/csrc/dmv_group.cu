@@ -406,6 +406,73 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
     }
   }
 
+  // ---- full space group of an R x k torus: block rotations x {1, rho} x {1, sigma} [x {1, tau}]
+  // (rho: reverse the bits inside every row, sigma: reverse the order of the rows, tau: transpose).  Then the orbit
+  // minimum needs neither the coset chain nor one look-up per (coset, row pair): see orbit_min_torus().
+  if (H.canon_mode == 1 && !H.canon_lut2.empty() && H.canon_k >= 3 && H.canon_r >= 3 && 4 * H.canon_r <= 32) {
+    const int k = H.canon_k, R = H.canon_r;
+    Perm rho(n_sites), sigma(n_sites), tau(n_sites);
+    for (int y = 0; y < R; ++y)
+      for (int a = 0; a < k; ++a) {
+        rho[y * k + a] = y * k + (k - 1 - a);
+        sigma[y * k + a] = (R - 1 - y) * k + a;
+        tau[y * k + a] = (R == k) ? a * k + y : y * k + a;
+      }
+    const bool has_tau = R == k && perm_index.count(tau);
+    if (perm_index.count(rho) && perm_index.count(sigma)) {
+      std::map<Perm, int> coset_of;
+      for (size_t i = 0; i < best.transversal.size(); ++i)
+        for (auto &t : best.chain) coset_of[compose(t, best.transversal[i])] = (int)i;
+      std::vector<Perm> D{ident, rho, sigma, compose(rho, sigma)};
+      if (has_tau)
+        for (int i = 0; i < 4; ++i) D.push_back(compose(D[i], tau));
+      std::set<int> cosets;
+      bool ok = true;
+      for (auto &d : D) {
+        auto it = coset_of.find(d);
+        if (it == coset_of.end()) { ok = false; break; }
+        cosets.insert(it->second);
+      }
+      if (ok && cosets.size() == D.size() && D.size() == best.transversal.size()) {
+        H.tor_mode = has_tau ? 2 : 1;
+        auto add_involution = [&](const Perm &p) {
+          std::map<int, uint64_t> stages;
+          for (int i = 0; i < n_sites; ++i)
+            if (p[i] > i) stages[p[i] - i] |= 1ull << i;
+          for (auto &st : stages) { H.tor_net_mask.push_back(st.second); H.tor_net_delta.push_back(st.first); }
+          return (int32_t)stages.size();
+        };
+        H.tor_rho_n = add_involution(rho);
+        H.tor_tau_n = has_tau ? add_involution(tau) : 0;
+        H.tor_div_r = 65536 / R + 1;
+        for (int bit = 0; bit < 32; ++bit)
+          if (((bit * H.tor_div_r) >> 16) != bit / R) throw std::runtime_error("tor_div_r is not exact");
+        const uint32_t bm = (1u << k) - 1u;
+        auto rot = [&](uint32_t v, int a) { return a ? (((v >> a) | (v << (k - a))) & bm) : v; };
+        auto rev = [&](uint32_t v) { uint32_t r = 0; for (int b = 0; b < k; ++b) r |= ((v >> b) & 1u) << (k - 1 - b); return r; };
+        H.tor_lutm.resize((size_t)1 << (2 * k));
+        H.tor_luts.resize((size_t)1 << (2 * k));
+        for (uint32_t hi = 0; hi <= bm; ++hi)
+          for (uint32_t lo = 0; lo <= bm; ++lo) {
+            uint32_t best_v = ~0u, set = 0;
+            for (int f = 0; f < (any_flip ? 2 : 1); ++f)
+              for (int e = 0; e < 2; ++e)
+                for (int a = 0; a < k; ++a) {
+                  uint32_t h = rot(hi, a), l = rot(lo, a);
+                  if (e) { h = rev(h); l = rev(l); }
+                  if (f) { h ^= bm; l ^= bm; }
+                  const uint32_t v = (h << k) | l;
+                  const uint32_t bit = 1u << ((2 * f + e) * k + a);
+                  if (v < best_v) { best_v = v; set = bit; }
+                  else if (v == best_v) set |= bit;
+                }
+            H.tor_lutm[(hi << k) | lo] = (uint16_t)best_v;
+            H.tor_luts[(hi << k) | lo] = set;
+          }
+      }
+    }
+  }
+
   H.characters.resize((size_t)H.n_q * H.n_t * 2 * 2, 0.0);
   for (int q = 0; q < H.n_q; ++q)
     for (int j = 0; j < H.n_t; ++j) {
@@ -447,7 +514,13 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
     OrbitResult r = orbit_scan<true, false>(P, s);
     if (r.rep != expect || r.stab != stab) throw std::runtime_error("orbit program self-check failed");
     if (H.canon_mode && orbit_min_canon(P, s) != expect)
-      throw std::runtime_error("orbit program self-check failed (block-rotation canonical form)");
+      throw std::runtime_error("orbit program self-check failed (canonical form)");
+    if (H.tor_mode) {   // the block-rotation form underneath stays selectable (option "canon" = 1): check it as well
+      OrbitProgram P1 = P;
+      P1.tor_mode = 0;
+      if (orbit_min_canon(P1, s) != expect)
+        throw std::runtime_error("orbit program self-check failed (block-rotation canonical form)");
+    }
     // the element reported as minimising must really map s to rep
     const int e = r.arg >> 1;
     const Perm g = compose(best.chain[e % H.n_t], best.transversal[e / H.n_t]);
@@ -483,6 +556,11 @@ OrbitProgram HostOrbitProgram::view() const {
   P.cc_begin = cc_begin.data();
   P.cc_mask = cc_mask.data();
   P.cc_delta = cc_delta.data();
+  P.tor_mode = tor_mode; P.tor_rho_n = tor_rho_n; P.tor_tau_n = tor_tau_n; P.tor_div_r = tor_div_r;
+  P.tor_lutm = tor_lutm.data();
+  P.tor_luts = tor_luts.data();
+  P.tor_net_mask = tor_net_mask.data();
+  P.tor_net_delta = tor_net_delta.data();
   return P;
 }
 

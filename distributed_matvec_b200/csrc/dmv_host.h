@@ -30,6 +30,11 @@ struct HostOrbitProgram {
   int32_t canon_div = 0;
   std::vector<int32_t> cc_begin, cc_delta;   // coset chain of the canonical-form scan
   std::vector<uint64_t> cc_mask;
+  int32_t tor_mode = 0, tor_rho_n = 0, tor_tau_n = 0, tor_div_r = 0;   // full-space-group canonical form of a torus
+  std::vector<uint16_t> tor_lutm;
+  std::vector<uint32_t> tor_luts;
+  std::vector<uint64_t> tor_net_mask;
+  std::vector<int32_t> tor_net_delta;
   OrbitProgram view() const;       // pointers into the host vectors
 };
 

@@ -110,7 +110,14 @@ __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int pro
   // canonical-form scan: coset chain (masks, then begin / delta) and the pair LUT
   off = align_up(off, 8);
   L.canon = off;
-  if (proj == PROJ_GROUP && p.orbit.canon_mode != 0) {
+  if (proj == PROJ_GROUP && p.orbit.canon_mode != 0 && p.orbit.tor_mode != 0) {
+    // full-space-group canonical form: delta-swap stages of rho / tau and the 16-bit pair table
+    const size_t n_st = (size_t)(p.orbit.tor_rho_n + p.orbit.tor_tau_n);
+    off += 8 * n_st + 4 * n_st;
+    off = align_up(off, 4);
+    off += 2 * ((size_t)1 << (2 * p.orbit.canon_k));
+    off = align_up(off, 8);
+  } else if (proj == PROJ_GROUP && p.orbit.canon_mode != 0) {
     const size_t n_st = p.orbit.cc_n > 0 ? (size_t)p.orbit.cc_stages : 0;
     off += 8 * n_st + 4 * (n_st + (p.orbit.cc_n > 0 ? (size_t)p.orbit.cc_n + 1 : 0));
     off = align_up(off, 4);
@@ -197,7 +204,19 @@ __device__ __forceinline__ Tables<CV> stage_tables(const KernelParams &p, unsign
       T.orbit.step_shift = s32 + T.orbit.n_stages;
     }
   }
-  if (PROJ == PROJ_GROUP && T.orbit.canon_mode != 0) {
+  if (PROJ == PROJ_GROUP && T.orbit.canon_mode != 0 && T.orbit.tor_mode != 0) {
+    unsigned char *base = smem + L.canon;
+    const int n_st = T.orbit.tor_rho_n + T.orbit.tor_tau_n;
+    uint64_t *nm = reinterpret_cast<uint64_t *>(base);
+    int32_t *nd = reinterpret_cast<int32_t *>(base + 8 * (size_t)n_st);
+    uint16_t *lm = reinterpret_cast<uint16_t *>(smem + align_up((size_t)(base - smem) + 12 * (size_t)n_st, 4));
+    stage(nm, p.orbit.tor_net_mask, n_st);
+    stage(nd, p.orbit.tor_net_delta, n_st);
+    // the table is copied as 32-bit words (two entries each)
+    stage(reinterpret_cast<uint32_t *>(lm), reinterpret_cast<const uint32_t *>(p.orbit.tor_lutm),
+          1 << (2 * T.orbit.canon_k - 1));
+    T.orbit.tor_net_mask = nm; T.orbit.tor_net_delta = nd; T.orbit.tor_lutm = lm;
+  } else if (PROJ == PROJ_GROUP && T.orbit.canon_mode != 0) {
     unsigned char *base = smem + L.canon;
     if (T.orbit.cc_n > 0) {
       const int n_st = T.orbit.cc_stages;

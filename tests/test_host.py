@@ -181,6 +181,7 @@ def _torus_generators(k, R, reflections=True):
 @pytest.mark.parametrize("k,R,inversion,expect_mode", [
     (5, 1, None, 2), (7, 1, 1, 2), (12, 1, 1, 2), (33, 1, 1, 2), (40, 1, None, 2), (64, 1, 1, 2),   # chains: zero runs
     (2, 2, 1, 1), (3, 2, None, 1), (4, 3, 1, 1), (5, 5, 1, 1), (6, 4, None, 1), (4, 8, 1, 1),      # tori: pair LUT
+    (6, 6, 1, 1), (6, 6, None, 1), (3, 3, 1, 1), (4, 4, None, 1), (6, 8, 1, 1), (3, 8, None, 1), (5, 4, 1, 1),
     (7, 3, 1, 1), (8, 8, 1, 1), (8, 2, None, 1),                                                  # tori: single-block LUT
     (16, 2, 1, 0)])                                                                               # blocks too wide: walk
 def test_block_rotation_canonical_form_on_random_lattices(k, R, inversion, expect_mode):
@@ -206,6 +207,17 @@ def test_block_rotation_canonical_form_on_random_lattices(k, R, inversion, expec
     states[:6] = [0, (2**n - 1) if n < 64 else 2**64 - 1, 1, 0x5555555555555555 & (2**n - 1 if n < 64 else 2**64 - 1),
                   (1 << (n - 1)), 3]
     states[6:300] &= rng.integers(0, hi, size=294, dtype=np.uint64)       # sparse words: long zero runs, many ties
+    if R > 1:   # lattices with repeated rows / columns and transpose-symmetric patterns: tied top pairs
+        bm = (1 << k) - 1
+        for j in range(300, 600):
+            rows = rng.integers(0, bm + 1, size=2)
+            pattern = [int(rows[(y * int(rng.integers(1, 3))) % 2]) for y in range(R)]
+            states[j] = sum(r << (k * y) for y, r in enumerate(pattern)) & (hi - 1 if n < 64 else 2**64 - 1)
+        if R == k:
+            for j in range(600, 800):
+                m = rng.integers(0, 2, size=(k, k))
+                m = np.triu(m) | np.triu(m, 1).T        # symmetric bit matrix
+                states[j] = sum(int(m[y, a]) << (k * y + a) for y in range(R) for a in range(k))
     reps = np.zeros_like(states)
     stab = np.zeros(states.shape[0], dtype=np.int32)
     info = np.zeros(6, dtype=np.int64)
@@ -216,5 +228,12 @@ def test_block_rotation_canonical_form_on_random_lattices(k, R, inversion, expec
     ext = np.zeros(12, dtype=np.int64)
     nat.check(nat.lib().dmv_debug_compile_group(C.byref(bd), ext.ctypes.data, -1, None, None, None))
     assert ext[6] == expect_mode, (k, R, [int(v) for v in ext])
+    # full-space-group canonical form (orbit_min_torus): needs both reflections, 3 <= k <= 6, 3 <= R <= 8
+    ext = np.zeros(16, dtype=np.int64)
+    nat.check(nat.lib().dmv_debug_compile_group(C.byref(bd), ext.ctypes.data, -2, None, None, None))
+    want = 0
+    if expect_mode == 1 and 3 <= k <= 6 and 3 <= R <= 8:
+        want = 2 if R == k else 1
+    assert ext[12] == want, (k, R, [int(v) for v in ext])
     if expect_mode == 1:
         assert (ext[7], ext[8]) == (k, R) and ext[9] == (1 if 2 * k <= 12 else 0)
