@@ -311,6 +311,14 @@ struct dmv_context {
   int opt_gather = -1;      // row traversal kernel: -1 auto (k_gather when it applies), 0 always the queued k_pull
   // k_gather applicability (set at context creation from the row-traversal tables)
   bool gather_ok = false, gather_narrow = false, gather_uniform = false;
+  // k_rows applicability (bases with permutation symmetries, trivial characters, real bit-parallel operator) and its
+  // hash table over this context's representatives (see table_slot in dmv_device.cuh)
+  bool rows_ok = false;
+  int opt_rows = -1;        // -1 auto (k_rows when it applies), 0 the queued k_pull
+  DevBuf<unsigned char> d_table;
+  DevBuf<uint32_t> d_slot_of;
+  uint32_t table_slots = 0;
+  int table_elt = 0;        // element type the slots are laid out for (0: not built)
   double gather_uni[2] = {0.0, 0.0};
   int index_mode = INDEX_DIRECTORY;
   DevBuf<uint32_t> d_binom, d_lin_a, d_lin_b;
@@ -394,13 +402,16 @@ namespace {
 bool use_gather(const dmv_context *ctx) {   // the lean row-gather kernel applies and is not switched off
   return ctx->gather_ok && ctx->opt_gather != 0 && ctx->opt_bitparallel != 0 && ctx->proj != PROJ_GROUP;
 }
+bool use_rows(const dmv_context *ctx) {   // the pipelined row kernel for bases with permutation symmetries
+  return ctx->rows_ok && ctx->opt_rows != 0 && ctx->opt_bitparallel != 0 && ctx->orbit.trivial_characters;
+}
 bool use_pull(const dmv_context *ctx) {
   // auto: one rank, bit-parallel operator, no permutation symmetries -> k_gather (rows, no atomics, see
   // dmv_gather.cu); everything else -> push (k_generate).  "mode" = 1 forces the row traversal (k_gather
   // when it applies, else the queued k_pull), "mode" = 0 the scatter form.
   if (ctx->num_ranks != 1) return false;
   if (ctx->opt_mode == 1) return true;
-  return ctx->opt_mode == -1 && use_gather(ctx);
+  return ctx->opt_mode == -1 && (use_gather(ctx) || use_rows(ctx));
 }
 
 void use_device(const dmv_context *ctx) { CUDA_CHECK(cudaSetDevice(ctx->device)); }
@@ -625,6 +636,7 @@ void install_directory(dmv_context *ctx) {
   ctx->d_dir.alloc(2 * ctx->n_buckets + 2);
   launch_build_directory(ctx->d_reps.ptr, n, ctx->d_dir.ptr, ctx->n_buckets, shift, ctx->stream);
   ctx->planned = false;
+  ctx->table_elt = 0;
   select_index_mode(ctx);
 }
 
@@ -810,6 +822,39 @@ void do_plan(dmv_context *ctx) {
   ctx->planned = true;
 }
 
+// hash table of k_rows over ctx's representatives: keys once per basis and element type, values once per product
+void ensure_table(dmv_context *ctx, int elt) {
+  if (ctx->table_elt == elt) return;
+  const int64_t n = ctx->n_states;
+  if (2 * n + 16 >= 4294967295ll) throw std::runtime_error("k_rows: more than 2^31 states per table");
+  const uint32_t slots = (uint32_t)std::max<int64_t>(16, 2 * n);
+  const int slot_bytes = elt == DMV_C128 ? 32 : 16;
+  ctx->d_table.alloc((size_t)slots * slot_bytes);
+  ctx->d_slot_of.alloc((size_t)std::max<int64_t>(1, n));
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_table.ptr, 0xff, (size_t)slots * slot_bytes, ctx->stream));
+  launch_table_insert(ctx->d_reps.ptr, n, ctx->d_table.ptr, slots, slot_bytes, ctx->d_slot_of.ptr, ctx->stream);
+  ctx->table_slots = slots;
+  ctx->table_elt = elt;
+}
+
+// y[rows] <- rows of H through k_rows.  `basis` owns the table (this rank's context, or the twin holding the whole
+// basis in the replicated-x product), x_all is indexed like basis' states (through pos when given), p names the rows.
+void rows_product(dmv_context *basis, KernelParams &p, int elt, const void *x_all, const uint32_t *pos,
+                  cudaStream_t stream) {
+  cudaStream_t keep = basis->stream;
+  basis->stream = stream;
+  ensure_table(basis, elt);
+  basis->stream = keep;
+  launch_table_fill(basis->n_states, elt == DMV_C128, x_all, basis->d_norms.ptr, pos, basis->d_slot_of.ptr,
+                    basis->d_table.ptr, stream);
+  select_tables(basis, p, true, false);
+  p.uni_re = basis->gather_uni[0]; p.uni_im = basis->gather_uni[1];
+  p.table = basis->d_table.ptr;
+  p.table_slots = basis->table_slots;
+  p.row_split = 1;
+  launch_rows(p, elt == DMV_C128, stream);
+}
+
 void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev,
                  const void *x_host_pending = nullptr, int64_t row_begin = 0, int64_t row_end = 0) {
   if (use_pull(ctx)) {   // one rank owns the basis: traverse by rows (gather), see k_gather / k_pull
@@ -823,6 +868,10 @@ void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev,
       p.uni_re = ctx->gather_uni[0]; p.uni_im = ctx->gather_uni[1];
       launch_gather(p, ctx->proj == PROJ_INVERSION, ctx->complex_coefficients, elt == DMV_C128,
                     ctx->gather_narrow, ctx->index_mode == INDEX_LIN, ctx->gather_uniform, ctx->stream);
+      return;
+    }
+    if (use_rows(ctx)) {
+      rows_product(ctx, p, elt, x_dev, nullptr, ctx->stream);
       return;
     }
     select_tables(ctx, p, true, complex_values(ctx, elt));
@@ -1056,6 +1105,8 @@ void setup_replicated(dmv_context *ctx) {
     dmv_context *g = nullptr;
     if (dmv_context_create(&b, &o, ctx->device, 0, 1, &g) != 0) throw std::runtime_error(g_last_error);
     ctx->global = g;
+    g->opt_rows = ctx->opt_rows;
+    if (ctx->opt_canon != g->opt_canon && g->proj == PROJ_GROUP) { g->opt_canon = ctx->opt_canon; upload_orbit(g); }
     if (dmv_basis_build(g) != 0) throw std::runtime_error(g_last_error);
   }
   dmv_context *g = ctx->global;
@@ -1108,9 +1159,13 @@ void replicated_rows(dmv_context *ctx, int elt, const void *x_cat, void *y_dev) 
                   g->index_mode == INDEX_LIN, g->gather_uniform, ctx->stream);
     return;
   }
-  // bases with permutation symmetries / operators outside the bit-parallel test: the queued row traversal
-  if (p.index.mode == INDEX_RANK) p.index.mode = INDEX_DIRECTORY;   // the incremental rank needs row index == rank
   p.row_norms = ctx->d_norms.ptr;
+  if (use_rows(g)) {   // bases with permutation symmetries: hash table over the whole basis, filled from the gathered x
+    rows_product(g, p, elt, x_cat, ctx->d_pos.ptr, ctx->stream);
+    return;
+  }
+  // operators outside the bit-parallel test / non-trivial characters: the queued row traversal
+  if (p.index.mode == INDEX_RANK) p.index.mode = INDEX_DIRECTORY;   // the incremental rank needs row index == rank
   p.row_split = 1;
   select_tables(g, p, true, complex_values(g, elt));
   launch_pull(p, g->proj, complex_values(g, elt), elt == DMV_C128, ctx->stream);
@@ -1377,6 +1432,8 @@ int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op,
     upload_orbit(ctx.get());
   }
   ctx->complex_coefficients = cplx;
+  ctx->rows_ok = ctx->proj == PROJ_GROUP && !cplx && ctx->host_orbit.trivial_characters &&
+                 !ctx->h_pull.bp.empty() && !ctx->h_pull.any_generic;
   ctx->d_status.alloc(3);
   CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
   ctx->d_out_count.alloc(num_ranks);
@@ -1431,6 +1488,10 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
   } else if (key == "gather") {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
+  } else if (key == "rows") {
+    if (value < -1 || value > 0) throw std::runtime_error("rows: -1 auto, 0 off (queued k_pull / k_generate for symmetric bases)");
+    ctx->opt_rows = (int)value;
+    if (ctx->global) ctx->global->opt_rows = (int)value;
   } else if (key == "canon") {
     ctx->opt_canon = (value >= 0 && value <= 2) ? (int)value : -1;
     if (ctx->proj == PROJ_GROUP) { CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); upload_orbit(ctx); }
@@ -1448,7 +1509,8 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
   if (!ctx) return -1;
   if (key == "index_mode") return ctx->index_mode;
   if (key == "pull") return use_pull(ctx) ? 1 : 0;
-  if (key == "gather") return ((use_pull(ctx) && use_gather(ctx)) || ctx->replicated) ? 1 : 0;
+  if (key == "gather")
+    return ((use_pull(ctx) && use_gather(ctx)) || (ctx->replicated && ctx->global && use_gather(ctx->global))) ? 1 : 0;
   if (key == "gather_narrow") return ctx->gather_narrow ? 1 : 0;
   if (key == "gather_uniform") return ctx->gather_uniform ? 1 : 0;
   if (key == "peer_direct") return ctx->peer_direct ? 1 : 0;
@@ -1461,6 +1523,10 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
   if (key == "bp_pairs") { int64_t n = 0; for (auto &w : ctx->h_push.bp) n += w.n0 + w.n1; return n; }
   if (key == "canon_mode") return ctx->orbit.canon_mode;
   if (key == "torus_mode") return ctx->orbit.tor_mode;
+  if (key == "rows")
+    return ((use_pull(ctx) && !use_gather(ctx) && use_rows(ctx)) ||
+            (ctx->replicated && ctx->global && !use_gather(ctx->global) && use_rows(ctx->global))) ? 1 : 0;
+  if (key == "rows_ok") return ctx->rows_ok ? 1 : 0;
   if (key == "canon_k") return ctx->host_orbit.canon_k;
   if (key == "orbit_n_q") return ctx->host_orbit.n_q;
   if (key == "orbit_n_t") return ctx->host_orbit.n_t;

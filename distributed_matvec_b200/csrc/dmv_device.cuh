@@ -246,6 +246,21 @@ __device__ __forceinline__ int64_t locate(const StateIndex &ix, uint64_t key) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// State -> vector element in ONE dependent memory access: open-addressing hash table over the representatives with
+// the vector element stored in the slot (row traversal of bases with permutation symmetries, k_rows).  The sorted
+// array + directory needs  directory -> several probes -> norm -> x  dependent loads per term, and orbit minima
+// cluster at small values, which unbalances any directory over the top bits; here a term costs the 32-byte sector of
+// its slot (plus 0.5 on average for linear probing at load factor 1/2).  The values are refreshed once per product
+// (k_table_fill: x[i] * norm[i] at slot_of[i]).  180 GB of HBM pays for the 64 bytes per state.
+//   complex128: slot = { key, pad, re, im } (32 bytes);  float64: slot = { key, value } (16 bytes)
+// ---------------------------------------------------------------------------------------------
+constexpr uint64_t kEmptyKey = ~0ull;
+__host__ __device__ __forceinline__ uint32_t table_slot(uint64_t key, uint32_t n_slots) {
+  const uint64_t h = key * 0x9E3779B97F4A7C15ull;
+  return (uint32_t)(((h >> 32) * (uint64_t)n_slots) >> 32);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Bit permutations
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t butterfly(uint64_t s, uint64_t mask, int delta) {
@@ -557,6 +572,71 @@ __host__ __device__ __forceinline__ uint64_t orbit_min_torus(const OrbitProgram 
       if (e != s)                                            // rho alone, or sigma = (rho sigma) . rho
         for (int st = 0; st < P.tor_rho_n; ++st) v = butterfly(v, P.tor_net_mask[st], P.tor_net_delta[st]);
       if (s) v = reverse_bits_n(v, n);                       // rho sigma: reverse the whole word
+      const uint64_t c = rotl_n(v, sh, n, mask);
+      best = c < best ? c : best;
+    }
+  }
+  return best;
+}
+
+// The same for a K x K torus with the transposition in the group (tor_mode == 2), rows and columns in registers:
+// pass 1 is fully unrolled, 32-bit, with one shared-memory look-up per adjacent (row, row) / (column, column) pair.
+// Column a of the lattice (= row a of the transposed image) comes out of one masked multiply:
+//   t = (w >> a) & STRIDE has site (y, a) at bit K y; t * CMUL puts it at bit S + y (S = (K-1)^2; no two partial
+//   products meet, so there are no carries).
+template <int K>
+__device__ __forceinline__ uint64_t orbit_min_torus_sq(const OrbitProgram &P, uint64_t w) {
+  constexpr int R = K, n = K * K;
+  constexpr uint32_t BM = (1u << K) - 1u;
+  constexpr int S = (K - 1) * (K - 1);
+  uint32_t stride = 0, cmul = 0;
+#pragma unroll
+  for (int y = 0; y < K; ++y) { stride |= 1u << (K * y); cmul |= 1u << ((K - 1) * (K - 1 - y)); }
+  const uint64_t mask = P.site_mask;
+  uint32_t rows[2][K];
+#pragma unroll
+  for (int y = 0; y < K; ++y) rows[0][y] = (uint32_t)(w >> (K * y)) & BM;
+#pragma unroll
+  for (int a = 0; a < K; ++a) rows[1][a] = ((((uint32_t)(w >> a) & stride) * cmul) >> S) & BM;
+  uint32_t mstar = 0xffffffffu, cand = 0;   // cand bit (2 t + s) R + y
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+#pragma unroll
+    for (int y = 0; y < K; ++y) {
+      const uint32_t hi = rows[t][y] << K;
+      const uint32_t md = P.tor_lutm[hi | rows[t][(y + K - 1) % K]], mu = P.tor_lutm[hi | rows[t][(y + 1) % K]];
+      const uint32_t bit_d = 1u << ((2 * t) * R + y), bit_u = 1u << ((2 * t + 1) * R + y);
+      cand = md < mstar ? bit_d : (md == mstar ? (cand | bit_d) : cand);
+      mstar = md < mstar ? md : mstar;
+      cand = mu < mstar ? bit_u : (mu == mstar ? (cand | bit_u) : cand);
+      mstar = mu < mstar ? mu : mstar;
+    }
+  }
+  uint64_t u1 = 0;
+  if (cand >> (2 * R)) {   // a transposed image is among the candidates: assemble it
+#pragma unroll
+    for (int a = 0; a < K; ++a) u1 |= (uint64_t)rows[1][a] << (K * a);
+  }
+  uint64_t best = ~0ull;
+  while (cand) {
+    const int cb = __ffs((int)cand) - 1;
+    cand &= cand - 1;
+    const int ts = (cb * P.tor_div_r) >> 16;
+    const int y = cb - ts * R, s = ts & 1;
+    const uint64_t u = (ts >> 1) ? u1 : w;
+    const int yn = s ? (y + 1 == R ? 0 : y + 1) : (y == 0 ? R - 1 : y - 1);
+    const uint32_t idx = (((uint32_t)(u >> (K * y)) & BM) << K) | ((uint32_t)(u >> (K * yn)) & BM);
+    uint32_t Sset = __ldg(P.tor_luts + idx);
+    const int sh = (s ? y : R - 1 - y) * K;
+    while (Sset) {
+      const int sb = __ffs((int)Sset) - 1;
+      Sset &= Sset - 1;
+      const int fe = (sb * P.canon_div) >> 16, a = sb - fe * K, e = fe & 1;
+      uint64_t v = (fe >> 1) ? (u ^ mask) : u;
+      if (a) v = ((v >> a) & P.canon_masks[2 * a]) | ((v << (K - a)) & P.canon_masks[2 * a + 1]);
+      if (e != s)
+        for (int st = 0; st < P.tor_rho_n; ++st) v = butterfly(v, P.tor_net_mask[st], P.tor_net_delta[st]);
+      if (s) v = __brevll(v) >> (64 - n);
       const uint64_t c = rotl_n(v, sh, n, mask);
       best = c < best ? c : best;
     }

@@ -101,6 +101,10 @@ struct KernelParams {
   // k_gather on several vectors at once: vector k of x / y starts batch_stride elements after vector k - 1
   int32_t batch;               // 0 / 1: one vector; 4: four vectors per launch
   int64_t batch_stride;
+  // k_rows (row traversal of bases with permutation symmetries): hash table over the representatives with the scaled
+  // vector element in the slot (see table_slot in dmv_device.cuh)
+  const void *table;
+  uint32_t table_slots;
 };
 
 // launchers (dmv_kernels.cu)
@@ -112,6 +116,14 @@ void launch_pull(const KernelParams &p, Projection proj, bool complex_values, bo
 // row traversal without queue / atomics for bit-parallel operators on unprojected or inversion-only bases
 void launch_gather(const KernelParams &p, bool inversion, bool complex_values, bool complex_elements,
                    bool narrow, bool lin, bool uniform, cudaStream_t stream);
+// k_rows applies to real operators with a bit-parallel emit test on bases with trivial characters
+void launch_rows(const KernelParams &p, bool complex_elements, cudaStream_t stream);
+// hash table of k_rows: insert every state (slot_of[i] = its slot), then per product table[slot_of[i]] = x[src(i)] * norm[i]
+// with src(i) = pos ? pos[i] : i
+void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t n_slots, int slot_bytes,
+                         uint32_t *slot_of, cudaStream_t stream);
+void launch_table_fill(int64_t n, bool complex_elements, const void *x, const double *norms, const uint32_t *pos,
+                       const uint32_t *slot_of, void *table, cudaStream_t stream);
 void launch_accumulate(const KernelParams &p, Projection proj, bool complex_values, bool complex_elements,
                        int64_t count, const uint64_t *betas, const double *coeffs, cudaStream_t stream);
 // plugin kernels (BO:217-275): diagonal coefficients / CSR list of off-diagonal terms of caller-given states

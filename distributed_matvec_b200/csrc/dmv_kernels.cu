@@ -78,7 +78,8 @@ struct SmemLayout {
   size_t groups, gx, bp, lut, terms, diag, dclass, orbit64, orbit32, canon, binom, queues, total;
 };
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-__host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int proj, size_t val_bytes) {
+__host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int proj, size_t val_bytes,
+                                                  bool queues = true) {
   SmemLayout L;
   size_t off = 0;
   // bit-parallel mode keeps only the flip masks (compact) and the word descriptors; the full group
@@ -127,7 +128,7 @@ __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int pro
   if (p.index.mode == INDEX_RANK) off += 4 * (size_t)p.index.n_sites * p.index.stride;
   off = align_up(off, 16);
   // per warp: ring of (beta, value) + (pull mode) source lane and a row accumulator
-  L.queues = off; off += (size_t)kWarps * (kQueue * (8 + val_bytes) + kQueue + 32 * val_bytes);
+  L.queues = off; off += queues ? (size_t)kWarps * (kQueue * (8 + val_bytes) + kQueue + 32 * val_bytes) : 0;
   L.total = off;
   return L;
 }
@@ -813,6 +814,155 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// k_rows: the row traversal for bases with permutation symmetries, real operators with a bit-parallel emit test and
+// trivial characters (every symmetric model input of the reference) -- the product kernel of one rank and of the
+// replicated-x form on several ranks.
+//   y[b] = D(b) x[b] + 1/n_b sum_t h_t(b) (n x)[rep(b ^ x_t)]
+// One lane owns one row and walks ITS emitting groups: no warp queue, no shared-memory atomics, y written once.  Per term:
+// orbit minimum in registers (canonical form, dmv_device.cuh), then ONE dependent memory access -- the slot of the
+// representative in a hash table that carries the scaled vector element (table_slot) -- and that access is software
+// pipelined: the slot of term j is requested right after its orbit minimum and consumed after the orbit minimum of
+// term j + 2, so its latency hides behind ~10^3 integer instructions of the same lane.
+// -------------------------------------------------------------------------------------------------
+template <bool CE>
+__device__ __forceinline__ void slot_load(const unsigned char *__restrict__ table, uint32_t s, uint64_t &key,
+                                          typename ValT<CE>::type &val) {
+  if constexpr (CE) {
+    const unsigned char *q = table + (size_t)s * 32;
+    key = __ldg(reinterpret_cast<const uint64_t *>(q));
+    val = __ldg(reinterpret_cast<const double2 *>(q + 16));
+  } else {
+    const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(table + (size_t)s * 16));
+    key = t.x;
+    val = __longlong_as_double((long long)t.y);
+  }
+}
+__device__ __forceinline__ void axpy(double &acc, double c, double v) { acc = fma(c, v, acc); }
+__device__ __forceinline__ void axpy(double2 &acc, double c, double2 v) { acc.x = fma(c, v.x, acc.x); acc.y = fma(c, v.y, acc.y); }
+
+template <bool CE, int TK>
+__global__ void __launch_bounds__(kThreads, 3) k_rows(const KernelParams p) {
+  using E = typename ValT<CE>::type;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(p, PROJ_GROUP, sizeof(double), false);
+  const Tables<false> T = stage_tables<PROJ_GROUP, false>(p, smem, L);   // p.groups / p.lut: row-traversal tables
+  __syncthreads();
+  const OrbitProgram &orbit = T.orbit;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const bool any_s_out = p.any_s_out != 0;
+  const unsigned char *__restrict__ table = reinterpret_cast<const unsigned char *>(p.table);
+  const uint32_t n_slots = p.table_slots;
+  const uint64_t *__restrict__ row_states = p.row_states ? p.row_states : p.index.reps;
+  const double *__restrict__ row_norms = p.row_norms ? p.row_norms : p.norms;
+  unsigned long long bad = 0, bad_state = 0;
+
+  const int64_t n_rows = p.row_end - p.row_begin;
+  const int64_t n_tiles = (n_rows + 31) / 32;
+  const int64_t warps_total = (int64_t)gridDim.x * kWarps;
+  for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += warps_total) {
+    const int64_t i = p.row_begin + tile * 32 + lane;
+    const bool valid = i < p.row_end;
+    const uint64_t b = valid ? __ldg(row_states + i) : 0ull;
+    E acc = v_make(0.0, 0.0, (E *)nullptr);
+    // two requests in flight per lane: (wanted key, coefficient, slot, loaded key, loaded value)
+    bool live0 = false, live1 = false;
+    uint64_t want0 = 0, want1 = 0, got0 = 0, got1 = 0;
+    double c0 = 0.0, c1 = 0.0;
+    uint32_t s0 = 0, s1 = 0;
+    E v0 = v_make(0.0, 0.0, (E *)nullptr), v1 = v0;
+    int w = 0;
+    RowTerms rt = row_terms<false>(T, 0, 0, min(64, p.n_groups), b);
+    if (!valid) rt.mask = 0;
+    for (;;) {
+      while (valid && rt.mask == 0 && 64 * (w + 1) < p.n_groups) {
+        ++w;
+        rt = row_terms<false>(T, w, 64 * w, min(64 * w + 64, p.n_groups), b);
+      }
+      const bool has = rt.mask != 0;
+      if (!has && !live0 && !live1) break;
+      if (live1) {   // consume the older request
+        if (got1 != want1) {   // linear probing (load factor 1/2: rare) or a state outside the basis (DMV:115-118)
+          for (;;) {
+            if (got1 == kEmptyKey) {
+              if (c1 != 0.0) { ++bad; bad_state = want1; }
+              v1 = v_make(0.0, 0.0, (E *)nullptr);
+              break;
+            }
+            s1 = s1 + 1 == n_slots ? 0 : s1 + 1;
+            slot_load<CE>(table, s1, got1, v1);
+            if (got1 == want1) break;
+          }
+        }
+        axpy(acc, c1, v1);
+      }
+      live1 = live0; want1 = want0; got1 = got0; c1 = c0; s1 = s0; v1 = v0;
+      live0 = has;
+      if (has) {
+        uint64_t flip;
+        c0 = pop_term<false>(T, rt, 64 * w, b, any_s_out, flip);
+        const uint64_t raw = b ^ flip;
+        if constexpr (TK > 0) want0 = orbit_min_torus_sq<TK>(orbit, raw);
+        else want0 = orbit_representative(orbit, raw);
+        s0 = table_slot(want0, n_slots);
+        slot_load<CE>(table, s0, got0, v0);
+      }
+    }
+    if (valid) {
+      const double inv_nb = 1.0 / __ldg(row_norms + i);
+      E out;
+      if (p.n_diag > 0) {
+        double dre, dim;
+        diagonal<false>(T, p.n_diag, b, dre, dim);
+        const E xi = load_x<CE>(p.x, p.x_row_offset + i);
+        out = v_scale(xi, dre);   // real operator: the diagonal is real
+      } else {
+        out = reinterpret_cast<const E *>(p.y)[i];
+      }
+      axpy(out, inv_nb, acc);
+      reinterpret_cast<E *>(p.y)[i] = out;
+    }
+  }
+  if (bad) {
+    if (atomicAdd(p.status, bad) == 0) p.status[1] = bad_state;
+  }
+}
+
+// hash table set-up: claim a slot per state (keys pre-set to kEmptyKey), remember it in slot_of
+__global__ void k_table_insert(const uint64_t *__restrict__ reps, int64_t n, unsigned char *table, uint32_t n_slots,
+                               int slot_bytes, uint32_t *slot_of) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = reps[i];
+  uint32_t s = table_slot(key, n_slots);
+  for (;;) {
+    unsigned long long *q = reinterpret_cast<unsigned long long *>(table + (size_t)s * slot_bytes);
+    if (atomicCAS(q, (unsigned long long)kEmptyKey, (unsigned long long)key) == (unsigned long long)kEmptyKey) break;
+    s = s + 1 == n_slots ? 0 : s + 1;
+  }
+  slot_of[i] = s;
+}
+
+// per product: table[slot_of[i]] = x[src(i)] * norm[i]   (src(i) = pos ? pos[i] : i)
+template <bool CE>
+__global__ void k_table_fill(int64_t n, const void *__restrict__ x, const double *__restrict__ norms,
+                             const uint32_t *__restrict__ pos, const uint32_t *__restrict__ slot_of,
+                             unsigned char *table) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t src = pos ? (int64_t)__ldg(pos + i) : i;
+    const double nrm = __ldg(norms + i);
+    const uint32_t s = __ldg(slot_of + i);
+    if constexpr (CE) {
+      const double2 v = __ldg(reinterpret_cast<const double2 *>(x) + src);
+      *reinterpret_cast<double2 *>(table + (size_t)s * 32 + 16) = make_double2(v.x * nrm, v.y * nrm);
+    } else {
+      *reinterpret_cast<double *>(table + (size_t)s * 16 + 8) = __ldg(reinterpret_cast<const double *>(x) + src) * nrm;
+    }
+  }
+}
+
 // localProcess for records that arrived from other ranks: already projected and hashed by the sender.
 // Two records per thread with their searches advanced in lock step (see locate2).
 template <int PROJ, bool CV, bool CE>
@@ -1124,6 +1274,58 @@ void launch_accumulate_p(const KernelParams &p, bool cv, bool ce, int64_t count,
 }
 
 }  // namespace
+
+namespace {
+template <bool CE, int TK>
+void launch_rows_t(const KernelParams &p, cudaStream_t stream) {
+  const SmemLayout L = smem_layout(p, PROJ_GROUP, sizeof(double), false);
+  auto kernel = k_rows<CE, TK>;
+  if (L.total > 48 * 1024)
+    DMV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  int per_sm = 0;
+  DMV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, L.total));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t tiles = (p.row_end - p.row_begin + 31) / 32;
+  const int blocks = grid_for(tiles, kWarps, sm_count() * per_sm);
+  kernel<<<blocks, kThreads, L.total, stream>>>(p);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+template <bool CE>
+void launch_rows_e(const KernelParams &p, cudaStream_t stream) {
+  const OrbitProgram &o = p.orbit;
+  const int k = (o.canon_mode != 0 && o.tor_mode == 2 && o.canon_k == o.canon_r) ? o.canon_k : 0;
+  if (k == 6) launch_rows_t<CE, 6>(p, stream);
+  else if (k == 4) launch_rows_t<CE, 4>(p, stream);
+  else launch_rows_t<CE, 0>(p, stream);
+}
+}  // namespace
+
+void launch_rows(const KernelParams &p, bool complex_elements, cudaStream_t stream) {
+  if (p.row_end <= p.row_begin) return;
+  if (complex_elements) launch_rows_e<true>(p, stream);
+  else launch_rows_e<false>(p, stream);
+}
+
+void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t n_slots, int slot_bytes,
+                         uint32_t *slot_of, cudaStream_t stream) {
+  if (n <= 0) return;
+  k_table_insert<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reps, n, reinterpret_cast<unsigned char *>(table),
+                                                                 n_slots, slot_bytes, slot_of);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
+void launch_table_fill(int64_t n, bool complex_elements, const void *x, const double *norms, const uint32_t *pos,
+                       const uint32_t *slot_of, void *table, cudaStream_t stream) {
+  if (n <= 0) return;
+  const int blocks = grid_for(n, 256, sm_count() * 16);
+  unsigned char *t = reinterpret_cast<unsigned char *>(table);
+  if (complex_elements) k_table_fill<true><<<blocks, 256, 0, stream>>>(n, x, norms, pos, slot_of, t);
+  else k_table_fill<false><<<blocks, 256, 0, stream>>>(n, x, norms, pos, slot_of, t);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
 
 void launch_generate(const KernelParams &p, Projection proj, bool cv, bool ce, bool count_only,
                      cudaStream_t stream) {

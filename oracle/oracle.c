@@ -255,6 +255,142 @@ int64_t oracle_enumerate_states(uint64_t lower, uint64_t upper, int fixed_hammin
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * The same third-party kernels with the group applied as Benes networks (oracle/networks.py): what a tuned CPU
+ * library does, used ONLY by the timed CPU arm (bench.py cpu_baseline / --impl reference) and by the parallel
+ * enumeration that prepares its input.  The bit-by-bit versions above stay the checker.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n; int64_t G; int64_t n_stages;
+  const int32_t *delta; const uint64_t *masks; const uint8_t *flips; const c128 *chars;
+} oracle_networks;
+
+static inline uint64_t network_apply(const oracle_networks *g, int64_t e, uint64_t s) {
+  const uint64_t *m = g->masks + e * g->n_stages;
+  for (int64_t st = 0; st < g->n_stages; ++st) {
+    const int d = g->delta[st];
+    const uint64_t t = ((s >> d) ^ s) & m[st];
+    s ^= t ^ (t << d);
+  }
+  if (g->flips[e]) s ^= (g->n == 64) ? ~UINT64_C(0) : ((UINT64_C(1) << g->n) - 1);
+  return s;
+}
+
+void oracle_state_info_networks(int n, int64_t G, int64_t n_stages, const int32_t *delta, const uint64_t *masks,
+                                const uint8_t *flips, const c128 *chars, int64_t batch, const uint64_t *alphas,
+                                uint64_t *betas, c128 *characters, double *norms) {
+  const oracle_networks g = {n, G, n_stages, delta, masks, flips, chars};
+  for (int64_t k = 0; k < batch; ++k) {
+    const uint64_t alpha = alphas[k];
+    uint64_t best = alpha;
+    c128 chi = {1.0, 0.0};
+    int have = 0;
+    double stab = 0.0;
+    for (int64_t e = 0; e < G; ++e) {
+      const uint64_t y = network_apply(&g, e, alpha);
+      if (!have || y < best) { best = y; chi = chars[e]; have = 1; }
+      if (y == alpha) stab += chars[e].re;
+    }
+    betas[k] = best;
+    characters[k].re = chi.re;
+    characters[k].im = -chi.im;
+    double nn = stab / (double)G;
+    if (nn < 0.0 && nn > -1e-12) nn = 0.0;
+    norms[k] = (nn > 1e-12) ? sqrt(nn) : 0.0;
+  }
+}
+
+/* combinadic rank / unrank of fixed-Hamming-weight states (ls_hs_fixed_hamming_state_to_index / index_to_state,
+ * reference src/FFI.chpl:165-166; used by determineEnumerationRanges, src/StatesEnumeration.chpl:80-116) */
+static uint64_t g_binom[65][65];
+static void binom_init(void) {
+  if (g_binom[0][0] == 1) return;
+  for (int i = 0; i <= 64; ++i) {
+    g_binom[i][0] = 1;
+    for (int j = 1; j <= i; ++j) {
+      const uint64_t a = g_binom[i - 1][j - 1], b = (j <= i - 1) ? g_binom[i - 1][j] : 0;
+      g_binom[i][j] = (a > UINT64_MAX - b) ? UINT64_MAX : a + b;
+    }
+  }
+}
+static uint64_t fixed_hamming_rank(uint64_t s) {
+  uint64_t r = 0;
+  int k = 0;
+  while (s) { const int pos = __builtin_ctzll(s); ++k; r += g_binom[pos][k]; s &= s - 1; }
+  return r;
+}
+static uint64_t fixed_hamming_unrank(uint64_t r, int weight) {
+  uint64_t s = 0;
+  for (int k = weight; k >= 1; --k) {
+    int pos = k - 1;
+    while (pos + 1 <= 63 && g_binom[pos + 1][k] <= r) ++pos;
+    r -= g_binom[pos][k];
+    s |= UINT64_C(1) << pos;
+  }
+  return s;
+}
+
+/* enumerateStates on one locale with the candidate range cut into chunks handled by OpenMP threads
+ * (reference src/StatesEnumeration.chpl:94-116 determineEnumerationRanges, :158-224 per-chunk filter).
+ * Result identical to oracle_enumerate_states; out == NULL counts.  masks == NULL: bit-by-bit group. */
+int64_t oracle_enumerate_states_parallel(uint64_t lower, uint64_t upper, int fixed_hamming, int n, int64_t G,
+                                         const int32_t *perms, const uint8_t *flips, const c128 *chars,
+                                         int64_t n_stages, const int32_t *delta, const uint64_t *masks,
+                                         uint64_t *out, double *out_norms) {
+  if (lower > upper) return 0;
+  binom_init();
+  const int weight = __builtin_popcountll(lower);
+  const uint64_t first = fixed_hamming ? fixed_hamming_rank(lower) : lower;
+  const uint64_t last = fixed_hamming ? fixed_hamming_rank(upper) : upper;
+  const uint64_t total = last - first + 1;
+  int64_t n_chunks = 4096;
+  if ((uint64_t)n_chunks > total) n_chunks = (int64_t)total;
+  int64_t *counts = (int64_t *)calloc((size_t)n_chunks + 1, sizeof(int64_t));
+  const oracle_group gb = {n, G, perms, flips, chars};
+  const oracle_networks gn = {n, G, n_stages, delta, masks, flips, chars};
+  for (int pass = 0; pass < (out ? 2 : 1); ++pass) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t c = 0; c < n_chunks; ++c) {
+      const uint64_t lo = first + (uint64_t)(((__uint128_t)total * (uint64_t)c) / (uint64_t)n_chunks);
+      const uint64_t hi = first + (uint64_t)(((__uint128_t)total * (uint64_t)(c + 1)) / (uint64_t)n_chunks);
+      if (hi <= lo) continue;
+      uint64_t v = fixed_hamming ? fixed_hamming_unrank(lo, weight) : lo;
+      int64_t cnt = 0;
+      const int64_t base = pass ? counts[c] : 0;
+      for (uint64_t idx = lo; idx < hi; ++idx) {
+        int keep = 1;
+        double norm = 1.0;
+        if (G > 0) {
+          double stab = 0.0;
+          for (int64_t e = 0; e < G; ++e) {
+            const uint64_t y = masks ? network_apply(&gn, e, v) : group_apply(&gb, e, v);
+            if (y < v) { keep = 0; break; }
+            if (y == v) stab += chars[e].re;
+          }
+          if (keep) {
+            const double nn = stab / (double)G;
+            norm = (nn > 1e-12) ? sqrt(nn) : 0.0;
+            if (!(norm > 0.0)) keep = 0;
+          }
+        }
+        if (keep) {
+          if (pass) { out[base + cnt] = v; if (out_norms) out_norms[base + cnt] = norm; }
+          ++cnt;
+        }
+        if (idx + 1 < hi) v = fixed_hamming ? next_state_fixed_hamming(v) : v + 1;
+      }
+      if (!pass) counts[c + 1] = cnt;
+    }
+    if (!pass) {
+      counts[0] = 0;
+      for (int64_t c = 0; c < n_chunks; ++c) counts[c + 1] += counts[c];
+    }
+  }
+  const int64_t result = counts[n_chunks];
+  free(counts);
+  return result;
+}
+
+/* ---------------------------------------------------------------------------------------------
  * ls_hs_state_index(basis, batch, spins, 1, indices, 1)
  *   declared src/FFI.chpl:173-175; called src/DistributedMatrixVector.chpl:102.
  *   Position in the ascending `representatives` installed by uncheckedSetRepresentatives
@@ -284,6 +420,9 @@ typedef struct {
   /* basis */
   int n; int spin_inversion; int has_permutations; int state_index_is_identity;
   int64_t G; const int32_t *perms; const uint8_t *flips; const c128 *chars;
+  /* optional: the same group as Benes networks (oracle/networks.py).  Only the TIMED arm sets them; the checker
+   * leaves net_masks NULL and permutes bit by bit. */
+  int64_t n_stages; const int32_t *net_delta; const uint64_t *net_masks;   /* [G][n_stages] */
 } oracle_model;
 
 typedef struct {
@@ -348,8 +487,12 @@ static int64_t bo_compute_off_diag(batched_operator *bo, const oracle_model *M, 
                                                  M->off_s, count, alphas, bo->spins2, bo->coeffs2,
                                                  bo->offsets, xs, elt);
   memcpy(bo->spins2 + total, alphas, (size_t)count * sizeof(uint64_t));              /* BO:181 */
-  oracle_state_info(M->n, M->G, M->perms, M->flips, M->chars, total + count, bo->spins2,
-                    bo->spins1, bo->coeffs1, bo->norms);                              /* BO:188-194 */
+  if (M->net_masks != NULL)   /* timed arm: the group as Benes networks */
+    oracle_state_info_networks(M->n, M->G, M->n_stages, M->net_delta, M->net_masks, M->flips, M->chars,
+                               total + count, bo->spins2, bo->spins1, bo->coeffs1, bo->norms);
+  else
+    oracle_state_info(M->n, M->G, M->perms, M->flips, M->chars, total + count, bo->spins2,
+                      bo->spins1, bo->coeffs1, bo->norms);                            /* BO:188-194 */
   for (int64_t i = 0; i < count; ++i) {                                               /* BO:198-202 */
     for (int64_t k = bo->offsets[i]; k < bo->offsets[i + 1]; ++k) {
       /* cs[k] *= tempCoeffs[k] * norms[k] / norms[totalCount + i] */
@@ -438,16 +581,39 @@ static int64_t local_process(const oracle_model *M, int num_locales, int64_t N,
  * Chunk sizing follows DMV:871-883,905-907 with num_producer_tasks.
  * Returns 0, or -(1) on an invalid index (DMV:115-118).  OpenMP parallelises over chunks (the
  * reference's producer tasks, DMV:957-1011). */
+static int64_t matvec_impl(const oracle_model *M, int P, const int64_t *sizes, const uint64_t *const *reps,
+                           const double *const *xs, double *const *ys, int elt, int64_t remote_buffer_size,
+                           int num_producer_tasks, int64_t row_lo, int64_t row_hi);
+
 int64_t oracle_matvec(const oracle_model *M, int P, const int64_t *sizes, const uint64_t *const *reps,
                       const double *const *xs, double *const *ys, int elt, int64_t remote_buffer_size,
                       int num_producer_tasks) {
+  return matvec_impl(M, P, sizes, reps, xs, ys, elt, remote_buffer_size, num_producer_tasks, 0, -1);
+}
+
+/* The same product restricted to the SOURCE rows [row_lo, row_hi) of one locale: the bounded sample the CPU arm of
+ * bench.py times (the contributions of those rows to y; chunk sizing as for the whole block). */
+int64_t oracle_matvec_rows(const oracle_model *M, int64_t N, const uint64_t *reps, const double *x, double *y,
+                           int elt, int64_t remote_buffer_size, int num_producer_tasks, int64_t row_lo,
+                           int64_t row_hi) {
+  const uint64_t *rp[1] = {reps};
+  const double *xp[1] = {x};
+  double *yp[1] = {y};
+  return matvec_impl(M, 1, &N, rp, xp, yp, elt, remote_buffer_size, num_producer_tasks, row_lo, row_hi);
+}
+
+static int64_t matvec_impl(const oracle_model *M, int P, const int64_t *sizes, const uint64_t *const *reps,
+                           const double *const *xs, double *const *ys, int elt, int64_t remote_buffer_size,
+                           int num_producer_tasks, int64_t row_lo, int64_t row_hi) {
+  const int slab = row_hi >= 0;   /* only with P == 1 */
   if (M->T_diag > 0) {
     for (int p = 0; p < P; ++p) {
       const int64_t N = sizes[p];
       const int64_t nchunks = 64;
+      const int64_t r0 = slab ? row_lo : 0, r1 = slab ? row_hi : N;
 #pragma omp parallel for schedule(dynamic, 1)
       for (int64_t c = 0; c < nchunks; ++c) {
-        const int64_t lo = N * c / nchunks, hi = N * (c + 1) / nchunks;
+        const int64_t lo = r0 + (r1 - r0) * c / nchunks, hi = r0 + (r1 - r0) * (c + 1) / nchunks;
         if (hi > lo)
           oracle_apply_diag_x1(M->T_diag, M->diag_v, M->diag_m, M->diag_r, M->diag_s, hi - lo,
                                reps[p] + lo, ys[p] + elt * lo, xs[p] + elt * lo, elt);
@@ -459,8 +625,9 @@ int64_t oracle_matvec(const oracle_model *M, int P, const int64_t *sizes, const 
   const int64_t T = M->max_off_diag > 0 ? M->max_off_diag : 1;
   if (remote_buffer_size < T) remote_buffer_size = T;                          /* DMV:871 */
   for (int p = 0; p < P; ++p) {
-    const int64_t N = sizes[p];
-    if (N == 0) continue;
+    const int64_t N = slab ? row_hi - row_lo : sizes[p];          /* source rows handled here */
+    const int64_t row0 = slab ? row_lo : 0;
+    if (N <= 0) continue;
     int64_t num_chunks = (N * T + remote_buffer_size - 1) / remote_buffer_size; /* DMV:879-883 */
     if (num_chunks < 10 * num_producer_tasks) num_chunks = 10 * num_producer_tasks;
     if (num_chunks > N) num_chunks = N;
@@ -475,7 +642,7 @@ int64_t oracle_matvec(const oracle_model *M, int P, const int64_t *sizes, const 
 #pragma omp for schedule(dynamic, 1)
       for (int64_t c = 0; c < num_chunks; ++c) {
         /* chunks(0 ..# N, numChunks): DMV:905 */
-        const int64_t lo = N * c / num_chunks, hi = N * (c + 1) / num_chunks;
+        const int64_t lo = row0 + N * c / num_chunks, hi = row0 + N * (c + 1) / num_chunks;
         if (hi <= lo) continue;
         uint64_t *betas; c128 *coeffs; uint8_t *keys;
         const int64_t n = bo_compute_off_diag(&bo, M, P, hi - lo, reps[p] + lo, xs[p] + elt * lo,
@@ -512,6 +679,58 @@ int64_t oracle_compute_off_diag(const oracle_model *M, int num_locales, int64_t 
   memcpy(offsets, bo.offsets, (size_t)(count + 1) * sizeof(int64_t));
   bo_free(&bo);
   return n;
+}
+
+/* y[i] for a SAMPLE of rows of one block, column by column -- the at-size check of bench.py and tests/:
+ *   y[i] = D(a_i) x[i] + sum_k conj(c_k) x[index(b_k)],   (b_k, c_k) = computeOffDiag(a_i, xs = 1)
+ * i.e. row i of H from column i of H: valid for HERMITIAN operators (every model input of the reference).  It costs
+ * |rows| * (T + 1) orbit scans instead of a whole product, so it also runs for bases of 10^7..10^8 states.
+ * reps: the whole ascending basis, x its vector.  Returns 0, or -1 when a generated state is missing. */
+int64_t oracle_expected_rows(const oracle_model *M, int64_t N, const uint64_t *reps, const double *x, int elt,
+                             int64_t count, const int64_t *rows, double *y_out) {
+  int64_t failed = 0;
+#pragma omp parallel
+  {
+    batched_operator bo;
+    bo_init(&bo, 1, M->T_off);
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t q = 0; q < count; ++q) {
+      const int64_t i = rows[q];
+      const uint64_t alpha = reps[i];
+      c128 acc = {0.0, 0.0};
+      if (M->T_diag > 0) {
+        double d[2] = {0.0, 0.0};
+        oracle_apply_diag_x1(M->T_diag, M->diag_v, M->diag_m, M->diag_r, M->diag_s, 1, &alpha, d, x + elt * i, elt);
+        acc.re = d[0];
+        if (elt == 2) acc.im = d[1];
+      }
+      uint64_t *betas; c128 *coeffs; uint8_t *keys;
+      const int64_t n = bo_compute_off_diag(&bo, M, 1, 1, &alpha, NULL, 1, &betas, &coeffs, &keys);
+      for (int64_t k = 0; k < n; ++k) {
+        const c128 c = coeffs[k];
+        if (c.re == 0.0 && c.im == 0.0) continue;
+        int64_t j;
+        oracle_state_index(N, reps, 1, &betas[k], &j);
+        if (j < 0) {
+#pragma omp atomic write
+          failed = 1;
+          continue;
+        }
+        const c128 cc = {c.re, -c.im};
+        if (elt == 1) {
+          acc.re += cc.re * x[j];
+        } else {
+          const c128 xj = {x[2 * j], x[2 * j + 1]};
+          const c128 t = c_mul(cc, xj);
+          acc.re += t.re; acc.im += t.im;
+        }
+      }
+      y_out[elt * q] = acc.re;
+      if (elt == 2) y_out[2 * q + 1] = acc.im;
+    }
+    bo_free(&bo);
+  }
+  return failed ? -1 : 0;
 }
 
 int oracle_num_threads(void) {

@@ -33,6 +33,7 @@ class OracleModel(C.Structure):
         ("n", C.c_int), ("spin_inversion", C.c_int), ("has_permutations", C.c_int),
         ("state_index_is_identity", C.c_int),
         ("G", C.c_int64), ("perms", C.c_void_p), ("flips", C.c_void_p), ("chars", C.c_void_p),
+        ("n_stages", C.c_int64), ("net_delta", C.c_void_p), ("net_masks", C.c_void_p),
     ]
 
 
@@ -71,6 +72,19 @@ def lib():
         L.oracle_compute_off_diag.restype = C.c_int64
         L.oracle_compute_off_diag.argtypes = [C.POINTER(OracleModel), C.c_int, C.c_int64, u64_p,
                                               C.c_void_p, C.c_int, u64_p, c128_p, u8_p, i64_p]
+        L.oracle_state_info_networks.restype = None
+        L.oracle_state_info_networks.argtypes = [C.c_int, C.c_int64, C.c_int64, i32_p, u64_p, u8_p, c128_p, C.c_int64,
+                                                 u64_p, u64_p, c128_p, f64_p]
+        L.oracle_enumerate_states_parallel.restype = C.c_int64
+        L.oracle_enumerate_states_parallel.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int64,
+                                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_matvec_rows.restype = C.c_int64
+        L.oracle_matvec_rows.argtypes = [C.POINTER(OracleModel), C.c_int64, u64_p, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_int64, C.c_int, C.c_int64, C.c_int64]
+        L.oracle_expected_rows.restype = C.c_int64
+        L.oracle_expected_rows.argtypes = [C.POINTER(OracleModel), C.c_int64, u64_p, C.c_void_p, C.c_int, C.c_int64,
+                                           i64_p, C.c_void_p]
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_num_threads.argtypes = [C.c_int]
         _lib = L
@@ -84,7 +98,9 @@ def _ptr(a: np.ndarray | None):
 class Model:
     """Keeps the numpy arrays alive next to the C struct."""
 
-    def __init__(self, op):
+    def __init__(self, op, networks: bool = False):
+        """networks = True: also hand the group over as Benes networks (oracle/networks.py) -- the TIMED CPU arm;
+        the checker keeps the bit-by-bit group."""
         b = op.basis
         off, diag = op.off_diag, op.diag
         self._keep = [np.ascontiguousarray(a) for a in
@@ -106,6 +122,12 @@ class Model:
             m.G, m.perms, m.flips, m.chars = len(g), _ptr(self.perms), _ptr(self.flips), _ptr(self.chars)
         else:
             m.G, m.perms, m.flips, m.chars = 0, None, None, None
+        m.n_stages, m.net_delta, m.net_masks = 0, None, None
+        if networks and b.has_permutation_symmetries():
+            from . import networks as nw
+            self.net_masks = np.ascontiguousarray(nw.group_networks(b.group))
+            self.net_delta = np.array(nw.DELTAS, dtype=np.int32)
+            m.n_stages, m.net_delta, m.net_masks = len(nw.DELTAS), _ptr(self.net_delta), _ptr(self.net_masks)
         self.c = m
         self.op = op
 
@@ -163,6 +185,51 @@ def enumerate_states(basis):
     out = np.zeros(count, dtype=np.uint64)
     norms = np.zeros(count, dtype=np.float64)
     L.oracle_enumerate_states(lo, hi, fixed, basis.number_sites, *args, _ptr(out), _ptr(norms))
+    return out, norms
+
+
+def state_info_networks(basis, alphas: np.ndarray):
+    """state_info with the group applied as Benes networks (what the timed CPU arm runs)."""
+    from . import networks as nw
+    g = basis.group
+    alphas = np.ascontiguousarray(alphas, dtype=np.uint64)
+    n = alphas.shape[0]
+    betas = np.zeros(n, dtype=np.uint64)
+    chars = np.zeros(n, dtype=np.complex128)
+    norms = np.zeros(n, dtype=np.float64)
+    lib().oracle_state_info_networks(basis.number_sites, len(g), len(nw.DELTAS), np.array(nw.DELTAS, dtype=np.int32),
+                                     np.ascontiguousarray(nw.group_networks(g)), np.ascontiguousarray(g.flips),
+                                     np.ascontiguousarray(g.characters), n, alphas, betas, chars, norms)
+    return betas, chars, norms
+
+
+def enumerate_states_parallel(basis, networks: bool = True):
+    """``enumerateStates`` for one locale with OpenMP over candidate chunks (same result as enumerate_states);
+    networks = True applies the group as Benes networks.  Prepares the input of the CPU arm of bench.py."""
+    lo, hi = basis.min_state_estimate(), basis.max_state_estimate()
+    fixed = int(basis.is_hamming_weight_fixed())
+    keep = []
+    if basis.requires_projection():
+        g = basis.group
+        perms, flips, chars = (np.ascontiguousarray(g.perms), np.ascontiguousarray(g.flips),
+                               np.ascontiguousarray(g.characters))
+        keep += [perms, flips, chars]
+        args = [len(g), _ptr(perms), _ptr(flips), _ptr(chars)]
+        if networks:
+            from . import networks as nw
+            masks = np.ascontiguousarray(nw.group_networks(g))
+            delta = np.array(nw.DELTAS, dtype=np.int32)
+            keep += [masks, delta]
+            args += [len(nw.DELTAS), _ptr(delta), _ptr(masks)]
+        else:
+            args += [0, None, None]
+    else:
+        args = [0, None, None, None, 0, None, None]
+    L = lib()
+    count = L.oracle_enumerate_states_parallel(lo, hi, fixed, basis.number_sites, *args, None, None)
+    out = np.zeros(count, dtype=np.uint64)
+    norms = np.zeros(count, dtype=np.float64)
+    L.oracle_enumerate_states_parallel(lo, hi, fixed, basis.number_sites, *args, _ptr(out), _ptr(norms))
     return out, norms
 
 
@@ -263,6 +330,32 @@ def matvec_blocks(op, reps_blocks, x_blocks, remote_buffer_size: int = 150000, n
     if st != 0:
         raise RuntimeError("invalid index: a generated state is not in the basis (DMV:115-118)")
     return ys
+
+
+def matvec_rows(model: "Model", representatives: np.ndarray, x: np.ndarray, y: np.ndarray, row_lo: int, row_hi: int,
+                remote_buffer_size: int = 150000, num_tasks: int = 1):
+    """Contributions of the source rows [row_lo, row_hi) of a one-locale product to y (accumulated in place): the
+    bounded sample the CPU arm of bench.py times."""
+    elt = 2 if np.iscomplexobj(x) else 1
+    st = lib().oracle_matvec_rows(C.byref(model.c), representatives.shape[0], representatives, _ptr(x), _ptr(y), elt,
+                                  remote_buffer_size, num_tasks, row_lo, row_hi)
+    if st != 0:
+        raise RuntimeError("invalid index: a generated state is not in the basis (DMV:115-118)")
+
+
+def expected_rows(op, representatives: np.ndarray, x: np.ndarray, rows: np.ndarray, model: "Model | None" = None):
+    """y[rows] of y = H x for a HERMITIAN operator, computed column by column with computeOffDiag on the sampled rows
+    only (oracle_expected_rows): the at-size parity check for bases too large for a whole CPU product."""
+    model = model or Model(op)
+    reps = np.ascontiguousarray(representatives, dtype=np.uint64)
+    elt = 2 if np.iscomplexobj(x) else 1
+    x = np.ascontiguousarray(x, dtype=np.complex128 if elt == 2 else np.float64)
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    out = np.zeros(rows.shape[0], dtype=x.dtype)
+    st = lib().oracle_expected_rows(C.byref(model.c), reps.shape[0], reps, _ptr(x), elt, rows.shape[0], rows, _ptr(out))
+    if st != 0:
+        raise RuntimeError("invalid index: a generated state is not in the basis (DMV:115-118)")
+    return out
 
 
 def matvec_global(op, representatives: np.ndarray, x: np.ndarray, num_locales: int = 1, **kw) -> np.ndarray:

@@ -37,14 +37,17 @@ def main():
             xd = torch.from_numpy(x).cuda()
             yd = torch.zeros_like(xd)
             ref = None
+            sym = bool(op.info("rows_ok"))
             for mode, gather in ((0, -1), (1, -1), (1, 0)):
                 for index in (0, -1):
                     op.set_option("mode", mode)
                     op.set_option("gather", gather)
+                    if sym:   # symmetric bases: (1, -1) = pipelined k_rows, (1, 0) = queued k_pull
+                        op.set_option("rows", gather)
                     op.set_option("index", index)
                     if index == -1 and op.info("index_mode") == 0:
                         continue
-                    if mode == 1 and gather == -1 and not op.info("gather"):
+                    if mode == 1 and gather == -1 and not (op.info("gather") or op.info("rows")):
                         continue
                     for _ in range(3):
                         op.matvec(xd, yd)
@@ -62,7 +65,7 @@ def main():
                     E = 16 if cplx else 8
                     ms = float(np.median(times))
                     gbs = (n * (8 + 2 * E) + nnz * (8 + 2 * E)) / (ms * 1e-3) / 1e9
-                    print(f"  {'c128' if cplx else 'f64 '} mode={('gather' if op.info('gather') else 'pull') if mode else 'push'} index_mode={op.info('index_mode')}"
+                    print(f"  {'c128' if cplx else 'f64 '} mode={('gather' if op.info('gather') else ('rows' if op.info('rows') else 'pull')) if mode else 'push'} index_mode={op.info('index_mode')}"
                           f"  median {ms:.4f} ms  min {min(times):.4f} ms  {n / ms / 1e6:.2f} Gstates/s "
                           f"{nnz / ms / 1e6:.1f} Gterms/s  alg {gbs:.0f} GB/s  diff_vs_first {err:.1e}", flush=True)
         if op.info("gather") or True:
