@@ -80,11 +80,18 @@ def recipe_x(n: int, cplx: bool) -> np.ndarray:
     return x
 
 
-def host_threads() -> int:
+def _affinity_threads() -> int:
     try:
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+_HOST_THREADS = _affinity_threads()   # read before libgomp binds the main thread to one place (OMP_PROC_BIND)
+
+
+def host_threads() -> int:
+    return _HOST_THREADS
 
 
 def host_description() -> dict:

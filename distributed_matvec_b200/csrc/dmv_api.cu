@@ -637,6 +637,14 @@ void install_directory(dmv_context *ctx) {
   launch_build_directory(ctx->d_reps.ptr, n, ctx->d_dir.ptr, ctx->n_buckets, shift, ctx->stream);
   ctx->planned = false;
   ctx->table_elt = 0;
+  // a new block also invalidates the exchange set-up: the replicated-x twin / slot table and the record plan
+  ctx->exchange_decided = false;
+  ctx->replicated = false;
+  ctx->repl_block = 0;
+  if (ctx->global) { delete ctx->global; ctx->global = nullptr; }
+  ctx->d_pos.release();
+  ctx->d_xcat.release();
+  std::fill(ctx->recv_counts.begin(), ctx->recv_counts.end(), -1);
   select_index_mode(ctx);
 }
 
@@ -1527,6 +1535,7 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
     return ((use_pull(ctx) && !use_gather(ctx) && use_rows(ctx)) ||
             (ctx->replicated && ctx->global && !use_gather(ctx->global) && use_rows(ctx->global))) ? 1 : 0;
   if (key == "rows_ok") return ctx->rows_ok ? 1 : 0;
+  if (key == "complex_coefficients") return ctx->complex_coefficients ? 1 : 0;
   if (key == "canon_k") return ctx->host_orbit.canon_k;
   if (key == "orbit_n_q") return ctx->host_orbit.n_q;
   if (key == "orbit_n_t") return ctx->host_orbit.n_t;
@@ -2116,6 +2125,13 @@ int dmv_lanczos(dmv_context *ctx, int elt, int max_iters, double tol, uint64_t s
   };
   std::vector<double> alphas, betas, ritz;
   double theta = 0.0, res = 0.0;
+  // every rank must take the same stopping decision: the Krylov space is exhausted at the GLOBAL dimension
+  int64_t n_global = n;
+  if (P > 1) {
+    const double mine = (double)n;
+    CUDA_CHECK(cudaMemcpyAsync(scal, &mine, sizeof(double), cudaMemcpyHostToDevice, st));
+    n_global = (int64_t)std::llround(reduce(1)[0]);
+  }
   {
     double *v = ctx->lz_v[0].ptr, *u = ctx->lz_v[1].ptr, *w = ctx->lz_v[2].ptr;
     start_vector(v);
@@ -2134,7 +2150,7 @@ int dmv_lanczos(dmv_context *ctx, int elt, int max_iters, double tol, uint64_t s
       theta = tridiagonal_lowest(alphas, betas, ritz);
       res = std::fabs(beta * ritz.back());
       const bool done = res <= tol * std::max(1.0, std::fabs(theta)) || beta <= 1e-14 * std::max(1.0, std::fabs(alpha)) ||
-                        (int64_t)alphas.size() >= n * (P > 1 ? (int64_t)P : 1);
+                        (int64_t)alphas.size() >= n_global;
       if (done || j + 1 == max_iters) break;
       betas.push_back(beta);
       launch_scale((int64_t)words, 1.0 / beta, w, w, false, st);

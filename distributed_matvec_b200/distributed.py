@@ -168,6 +168,8 @@ class HostExchangedProduct:
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         send = torch.from_numpy(np.asarray(self.ops.plan(), dtype=np.int64).copy())
         send[self.rank] = 0
+        if dist.get_backend() == "nccl":      # NCCL moves device tensors only
+            send = send.cuda(getattr(self.ops, "device", None))
         gathered = [torch.zeros_like(send) for _ in range(self.world)]
         dist.all_gather(gathered, send)
         self.send_counts = send.tolist()
@@ -201,8 +203,9 @@ class HostReplicatedProduct:
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.block = int(self.ops.replicated_setup())
         import torch
-        sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world)]
-        dist.all_gather(sizes, torch.tensor([self.block], dtype=torch.int64))
+        dev = torch.device("cuda", getattr(self.ops, "device", 0)) if dist.get_backend() == "nccl" else torch.device("cpu")
+        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.world)]
+        dist.all_gather(sizes, torch.tensor([self.block], dtype=torch.int64, device=dev))
         if any(int(b) != self.block for b in sizes):      # every rank derives it from the same global basis
             raise RuntimeError("ranks disagree on the slot size of the gathered x")
 

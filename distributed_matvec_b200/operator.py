@@ -342,9 +342,9 @@ class Operator:
 
     # -- tensor views for hosts that own the exchange (HostExchangedProduct) ----------------------
     def record_width(self, x) -> int:
-        """doubles per coefficient of the records generated for vectors like x"""
-        return 2 if (_elt_of(x) == nat.DMV_C128 or not self.spec.is_real() or
-                     not self.spec.basis.group.all_characters_trivial) else 1
+        """doubles per coefficient of the records generated for vectors like x: 2 for complex vectors or when a
+        coefficient / character has a non-zero imaginary part (the library's own rule, dmv_get_info), else 1"""
+        return 2 if (_elt_of(x) == nat.DMV_C128 or self.info("complex_coefficients") == 1) else 1
 
     def outgoing_tensors(self, width: int):
         """(betas int64, coeffs float64) torch views of all outgoing buckets, concatenated by destination."""

@@ -29,7 +29,13 @@ class OracleRank:
         return np.bincount(keys, minlength=self.num_ranks).astype(np.int64)
 
     def record_width(self, x):
-        return 2
+        # the library's rule (Operator.record_width / complex_values in csrc/dmv_api.cu): two doubles per coefficient for
+        # complex vectors or when a coefficient / character has an imaginary part; real -1 characters stay width 1
+        b = self.matrix.basis
+        cplx = bool(np.any(self.matrix.off_diag.v.imag != 0) or np.any(self.matrix.diag.v.imag != 0))
+        if b.has_permutation_symmetries():
+            cplx |= bool(np.any(b.group.characters.imag != 0))
+        return 2 if (x.is_complex() or cplx) else 1
 
     def generate(self, x, y):
         po, mine = self.po, self.blocks[self.rank]
@@ -45,8 +51,8 @@ class OracleRank:
 
     def outgoing_tensors(self, width):
         b, c = self._out
-        return (torch.from_numpy(b.view(np.int64).copy()),
-                torch.from_numpy(np.ascontiguousarray(c).view(np.float64).copy()))
+        flat = np.ascontiguousarray(c).view(np.float64).copy() if width == 2 else np.ascontiguousarray(c.real)
+        return torch.from_numpy(b.view(np.int64).copy()), torch.from_numpy(flat)
 
     def _accumulate(self, betas, coeffs, y):
         idx = self.po.state_index(self.blocks[self.rank], betas)
@@ -55,7 +61,9 @@ class OracleRank:
         np.add.at(yn, idx, coeffs if np.iscomplexobj(yn) else coeffs.real)
 
     def accumulate_tensors(self, x, betas, coeffs, y):
-        self._accumulate(betas.numpy().view(np.uint64), coeffs.numpy().view(np.complex128), y)
+        c = coeffs.numpy()
+        c = c.view(np.complex128) if self.record_width(x) == 2 else c.astype(np.complex128)
+        self._accumulate(betas.numpy().view(np.uint64), c, y)
 
 
 def _worker(rank, world, port, name, cplx, queue):

@@ -38,9 +38,22 @@ def _x(n, cplx, seed=42):
     return x
 
 
-def _close(a, b, rtol=1e-12):
-    scale = max(np.abs(b).max(), 1e-300)
-    return np.abs(a - b).max() <= 1e-14 + rtol * scale * 50
+def _close(a, b, rtol=1e-12, atol=1e-14):
+    """The reference's per-element criterion |a - b| <= max(atol, rtol max(|a|, |b|)) (test/TestMatrixVectorProduct.chpl:
+    15-20), with the absolute floor in units of the largest element: on symmetric bases the orbit-norm ratios of BO:200
+    scale individual terms by up to sqrt(|G|), and so the rounding of a sum that cancels."""
+    a, b = np.asarray(a), np.asarray(b)
+    floor = atol * max(1.0, float(np.abs(b).max(initial=0.0)))
+    return bool(np.all(np.abs(a - b) <= np.maximum(floor, rtol * np.maximum(np.abs(a), np.abs(b)))))
+
+
+def _recipe_x(n, cplx):
+    """x of the reference's generator (input_for_matvec.py:8,31): RandomState(42), rand(N) - 0.5, global sorted order."""
+    rs = np.random.RandomState(42)
+    x = rs.rand(n) - 0.5
+    if cplx:
+        x = x + 1j * (rs.rand(n) - 0.5)
+    return x
 
 
 @pytest.fixture(scope="module")
@@ -121,7 +134,7 @@ def test_state_info_matches_oracle(need_cuda, name):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
-@pytest.mark.parametrize("mode", ["auto", "push", "pull", "pull_queued"])
+@pytest.mark.parametrize("mode", ["auto", "push", "pull", "pull_queued"])  # pull = k_gather / k_rows where they apply
 @pytest.mark.parametrize("name", SMALL + MEDIUM)
 def test_local_matvec_matches_oracle(need_cuda, name, cplx, mode):
     """test/TestMatrixVectorProduct.chpl on one locale: host vectors through the C ABI.
@@ -132,6 +145,7 @@ def test_local_matvec_matches_oracle(need_cuda, name, cplx, mode):
     op.set_option("mode", {"auto": -1, "push": 0, "pull": 1, "pull_queued": 1}[mode])
     if mode == "pull_queued":
         op.set_option("gather", 0)
+        op.set_option("rows", 0)
     op.basis.build()
     reps = op.basis.representatives()
     x = _x(reps.shape[0], cplx)
@@ -146,11 +160,16 @@ def test_local_matvec_matches_oracle(need_cuda, name, cplx, mode):
         torch.cuda.synchronize()
         assert _close(yd.cpu().numpy(), y_ref)
     gather_applies = not basis.has_permutation_symmetries()    # two-body operators: bit-parallel emit test
+    # k_rows: permutation symmetries with trivial characters, real two-body operator
+    rows_applies = basis.has_permutation_symmetries() and basis.group.all_characters_trivial
+    assert op.info("rows_ok") == (1 if rows_applies else 0)
     if mode == "auto":
-        assert op.info("pull") == op.info("gather") == (1 if gather_applies else 0)
+        assert op.info("pull") == (1 if (gather_applies or rows_applies) else 0)
+        assert op.info("gather") == (1 if gather_applies else 0) and op.info("rows") == (1 if rows_applies else 0)
     else:
         assert op.info("pull") == (0 if mode == "push" else 1)
         assert op.info("gather") == (1 if (mode == "pull" and gather_applies) else 0)
+        assert op.info("rows") == (1 if (mode == "pull" and rows_applies) else 0)
     op.close()
 
 
@@ -482,9 +501,110 @@ def test_symmetric_properties_at_size(need_cuda):
     op.set_option("canon", 0)
     assert torch.allclose(op.matvec(u), Hu, rtol=1e-12, atol=1e-12)
     op.set_option("canon", -1)
-    op.set_option("mode", 1)                              # queued row traversal: no atomics on y
-    assert torch.allclose(op.matvec(u), Hu, rtol=1e-12, atol=1e-12)
+    for mode, rows in ((0, -1), (1, 0)):                  # scatter with atomics; queued row traversal (k_pull)
+        op.set_option("mode", mode)
+        op.set_option("rows", rows)
+        assert torch.allclose(op.matvec(u), Hu, rtol=1e-12, atol=1e-12)
     op.close()
+
+
+def test_chain_24_full_vector_at_size(need_cuda):
+    """BASELINE configs[1] at full size (2 704 156 states), every element against the oracle's product, x by the
+    reference's recipe, f64 (the reference's element type) and c128, row and scatter traversals."""
+    basis, matrix = _load("heisenberg_chain_24")
+    op = Operator(matrix)
+    op.basis.build()
+    reps = op.basis.representatives()
+    assert reps.shape[0] == 2704156
+    po.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    for cplx in (False, True):
+        x = _recipe_x(reps.shape[0], cplx)
+        y_ref = po.matvec_blocks(matrix, [reps], [x], num_tasks=po.num_threads())[0]
+        for mode in (-1, 0):
+            op.set_option("mode", mode)
+            y = op.matvec(torch.from_numpy(x).cuda()).cpu().numpy()
+            assert _close(y, y_ref), (cplx, mode, np.abs(y - y_ref).max())
+    op.close()
+
+
+@pytest.mark.parametrize("name,states", [("heisenberg_chain_32_symm", 4707969), ("heisenberg_square_6x6", 15804956),
+                                         ("heisenberg_chain_36_symm", 63068876)])
+def test_symmetric_products_at_size_sampled_rows(need_cuda, name, states):
+    """The symmetric BASELINE configs at full size: 4096 sampled rows of y against the oracle, which recomputes them
+    column by column (oracle_expected_rows: computeOffDiag on the sampled sources with the bit-by-bit group), for the
+    three forms of the product: rows (k_rows), scatter with atomics (k_generate) and the replicated-x form on two
+    logical ranks (every rank holds the whole basis; hash partition of x and y)."""
+    basis, matrix = _load(name)
+    po.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    op = Operator(matrix)
+    op.basis.build()
+    reps = op.basis.representatives()
+    assert reps.shape[0] == states
+    x = _recipe_x(states, True)
+    rows = np.sort(np.random.default_rng(5).choice(states, size=4096, replace=False))
+    expect = po.expected_rows(matrix, reps, x, rows)
+    xd = torch.from_numpy(x).cuda()
+    for mode, rows_opt in ((-1, -1), (0, -1), (1, 0)):
+        if name == "heisenberg_chain_36_symm" and mode == 1:
+            continue                                  # the queued kernel adds nothing new at this size
+        op.set_option("mode", mode)
+        op.set_option("rows", rows_opt)
+        y = op.matvec(xd)
+        torch.cuda.synchronize()
+        got = y[torch.from_numpy(rows).cuda()].cpu().numpy()
+        assert _close(got, expect), (name, mode, np.abs(got - expect).max())
+        del y
+    assert op.info("rows_ok") == 1
+    op.close()
+    del xd
+    if name == "heisenberg_chain_36_symm":
+        return                                        # two more whole bases of 63 M states: covered by the two above
+    P = 2
+    masks = po.locale_idx_of(reps, P)
+    cl = EmulatedCluster(matrix, P).build()
+    xb = [torch.from_numpy(np.ascontiguousarray(x[masks == r])).cuda() for r in range(P)]
+    yb = cl.matvec_replicated(xb)
+    y = np.zeros(states, dtype=np.complex128)
+    for r in range(P):
+        y[masks == r] = yb[r].cpu().numpy()
+    assert _close(y[rows], expect), np.abs(y[rows] - expect).max()
+    cl.close()
+
+
+def test_host_exchange_views_with_real_records(need_cuda):
+    """HostExchangedProduct's tensor views on a basis with a real -1 character (spin_inversion = -1): float64 vectors
+    give one double per record, and the views handed to the host exchange must have that layout (Operator.record_width
+    asks the library).  The host all-to-all is played in-process between two logical ranks on one GPU."""
+    basis, matrix = _load("heisenberg_chain_10")
+    o_reps, _ = po.enumerate_states(basis)
+    P = 2
+    masks, blocks = po.partition_by_hash(o_reps, P)
+    for cplx in (False, True):
+        x = _x(o_reps.shape[0], cplx, seed=8)
+        y_ref = po.matvec_global(matrix, o_reps, x, P)
+        cl = EmulatedCluster(matrix, P).build()
+        xb = [torch.from_numpy(np.ascontiguousarray(x[masks == r])).cuda() for r in range(P)]
+        ys = [torch.zeros_like(t) for t in xb]
+        counts = [op.plan() for op in cl.ops]
+        outs = []
+        for r, op in enumerate(cl.ops):
+            width = op.record_width(xb[r])
+            assert width == (2 if cplx else 1)
+            op.generate(xb[r], ys[r])
+            op.synchronize()
+            betas, coeffs = op.outgoing_tensors(width)
+            total = int(sum(counts[r][q] for q in range(P) if q != r))
+            assert betas.numel() == total and coeffs.numel() == total * width
+            outs.append((betas.clone(), coeffs.clone(), width))
+        for r, (betas, coeffs, width) in enumerate(outs):      # two ranks: everything rank r emits goes to the other one
+            dst = 1 - r
+            cl.ops[dst].accumulate_tensors(xb[dst], betas, coeffs, ys[dst])
+            cl.ops[dst].synchronize()
+        y = np.zeros_like(y_ref)
+        for r in range(P):
+            y[masks == r] = ys[r].cpu().numpy()
+        assert _close(y, y_ref), np.abs(y - y_ref).max()
+        cl.close()
 
 
 def test_rank_invariance_at_size(need_cuda):

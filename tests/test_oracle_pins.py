@@ -13,7 +13,8 @@ from distributed_matvec_b200.config import basis_from_dict, load_config_from_yam
 from oracle import dense_pin as dp
 from oracle import pyoracle as po
 
-DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = os.path.join(ROOT, "data")
 
 
 def _load(name):
@@ -224,3 +225,114 @@ def test_oracle_reproduces_golden_vectors(name):
     assert np.allclose(y, g[name + "/y"], rtol=1e-13, atol=1e-13)
     for P in (2, 3):          # and the P-locale form of the oracle on the same inputs
         assert np.allclose(po.matvec_global(matrix, reps, g[name + "/x"], P), g[name + "/y"], rtol=1e-12, atol=1e-12)
+
+
+# ---- round 2: the oracle's own reading of the model inputs, the timed CPU arm's kernels, the sampled-row check ------
+PIN_MODELS = ["heisenberg_chain_10", "heisenberg_kagome_16", "issue_01", "heisenberg_square_4x4",
+              "heisenberg_chain_24_symm", "heisenberg_kagome_12_symm", "heisenberg_chain_12", "heisenberg_chain_16"]
+
+
+@pytest.mark.parametrize("name", PIN_MODELS)
+def test_oracle_model_reader_agrees_with_the_product_reader(name):
+    """oracle/model.py (what `bench.py --impl reference` reads the inputs with) and the product's host layer are two
+    independent readings of data/*.yaml: same basis, same group order, same product."""
+    from distributed_matvec_b200 import load_config_from_yaml
+    from oracle import model as om
+    path = os.path.join(DATA, name + ".yaml")
+    b1, m1 = load_config_from_yaml(path)
+    b2, m2 = om.load_model(path)
+    r1, n1 = po.enumerate_states(b1)
+    r2, n2 = po.enumerate_states(b2)
+    assert np.array_equal(r1, r2) and np.allclose(n1, n2, rtol=0, atol=1e-15)
+    assert m1.number_off_diag_terms() == m2.number_off_diag_terms()
+    if b1.requires_projection():
+        assert len(b1.group) == len(b2.group)
+    rng = np.random.default_rng(3)
+    x = rng.random(r1.shape[0]) - 0.5 + 1j * (rng.random(r1.shape[0]) - 0.5)
+    y1, y2 = po.matvec_global(m1, r1, x, 2), po.matvec_global(m2, r2, x, 3)
+    assert np.abs(y1 - y2).max() <= 1e-13 * max(1.0, np.abs(y1).max())
+
+
+def test_benes_networks_equal_bit_by_bit_permutation():
+    from oracle import networks as nw
+    rng = np.random.default_rng(0)
+    for n in (5, 24, 33, 36, 64):
+        for _ in range(10):
+            p = rng.permutation(n)
+            masks = nw.benes(p)
+            for s in rng.integers(0, 2**min(n, 63), size=10):
+                s = int(s)
+                want = sum(((s >> int(p[i])) & 1) << i for i in range(n))
+                assert nw.apply_network(masks, s) == want
+
+
+@pytest.mark.parametrize("name", ["heisenberg_square_4x4", "heisenberg_chain_24_symm", "heisenberg_kagome_12_symm",
+                                  "issue_01", "heisenberg_chain_10", "heisenberg_chain_16"])
+def test_timed_cpu_arm_kernels_equal_the_checker(name):
+    """What the CPU arm of bench.py times (group elements as Benes networks, OpenMP enumeration, row slabs) gives the
+    checker's results: state_info, the basis, and slabs that add up to the whole product."""
+    from oracle import model as om
+    basis, matrix = om.load_model(os.path.join(DATA, name + ".yaml"))
+    reps, norms = po.enumerate_states(basis)
+    for networks in (True, False):
+        r2, n2 = po.enumerate_states_parallel(basis, networks=networks)
+        assert np.array_equal(reps, r2) and np.allclose(norms, n2, rtol=0, atol=1e-15)
+    rng = np.random.default_rng(1)
+    if basis.has_permutation_symmetries():
+        st = rng.integers(0, 2**basis.number_sites, size=400, dtype=np.uint64)
+        for u, v in zip(po.state_info(basis, st), po.state_info_networks(basis, st)):
+            assert np.array_equal(u, v)
+    n = reps.shape[0]
+    model = po.Model(matrix, networks=True)
+    for cplx in (False, True):
+        x = rng.random(n) - 0.5
+        if cplx:
+            x = x + 1j * (rng.random(n) - 0.5)
+        y = po.matvec_global(matrix, reps, x, 1)
+        parts = np.zeros_like(y)
+        cuts = [0, n // 3, n // 3 + 1, n]
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            part = np.zeros_like(y)
+            po.matvec_rows(model, reps, x, part, lo, hi, num_tasks=2)
+            parts += part
+        assert np.abs(parts - y).max() <= 1e-13 * max(1.0, np.abs(y).max())
+
+
+@pytest.mark.parametrize("name", PIN_MODELS)
+def test_sampled_rows_equal_the_whole_product(name):
+    """oracle_expected_rows (row i of H from column i: the at-size check of bench.py and of the GPU tests) against the
+    oracle's whole product, real and complex vectors, including a sector with complex characters (issue_01)."""
+    basis, matrix, _ = _load(name)
+    reps, _ = po.enumerate_states(basis)
+    n = reps.shape[0]
+    rng = np.random.default_rng(2)
+    for cplx in (False, True):
+        x = rng.random(n) - 0.5
+        if cplx:
+            x = x + 1j * (rng.random(n) - 0.5)
+        y = po.matvec_global(matrix, reps, x, 1)
+        rows = np.sort(rng.choice(n, size=min(n, 300), replace=False))
+        e = po.expected_rows(matrix, reps, x, rows)
+        assert np.abs(e - y[rows]).max() <= 1e-13 * max(1.0, np.abs(y).max())
+
+
+def test_reference_arm_runs_without_the_product():
+    """`bench.py --impl reference` must not import or map anything of the product (the driver lists the shared objects
+    the process loaded): run it in a subprocess that prints its modules and memory maps afterwards."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, runpy\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'heisenberg_chain_24_symm', '--steps', '2', '--warmup', '1']\n"
+        "runpy.run_path('bench.py', run_name='__main__')\n"
+        "mods = [m for m in sys.modules if m.startswith('distributed_matvec_b200')]\n"
+        "maps = [l for l in open('/proc/self/maps') if 'libdmv_b200' in l]\n"
+        "print('PRODUCT_MODULES', mods)\nprint('PRODUCT_MAPS', len(maps))\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "PRODUCT_MODULES []" in out.stdout and "PRODUCT_MAPS 0" in out.stdout
+    import json
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert line["impl"] == "reference" and line["config"]["workload"] == "heisenberg_chain_24_symm"
+    assert line["config"]["basis_states"] == 28968 and line["cpu_baseline"]["kind"] == "port"
+    assert set(line["config"]) == {"workload", "basis_states", "off_diag_terms", "x", "l2"}
