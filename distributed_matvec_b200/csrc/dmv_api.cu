@@ -693,7 +693,7 @@ void upload_orbit(dmv_context *ctx) {
   P.tor_luts = ctx->d_tor_luts.ptr;
   P.tor_net_mask = ctx->d_tor_net_mask.ptr;
   P.tor_net_delta = ctx->d_tor_net_delta.ptr;
-  if (ctx->opt_canon >= 0) P.tor_mode = 0;   // 1: block-rotation form with the coset chain (round 1)
+  if (ctx->opt_canon >= 0) { P.tor_mode = 0; P.chain_dihedral = 0; }   // 1: round-1 forms (coset chain / four run searches)
   if (ctx->opt_canon == 2) { P.canon_lut2 = nullptr; P.cc_n = 0; P.cc_stages = 0; }   // first version: single-block LUT, independent networks
   if (ctx->opt_canon == 0) P.canon_mode = 0;
   ctx->orbit = P;
@@ -2371,7 +2371,7 @@ int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t 
       info[11] = (int64_t)H.cc_mask.size();
     }
     if (count < -1) {  // count = -2: info holds 16 entries
-      info[12] = H.tor_mode; info[13] = H.tor_rho_n; info[14] = H.tor_tau_n; info[15] = (int64_t)H.tor_lutm.size();
+      info[12] = H.tor_mode; info[13] = H.tor_rho_n; info[14] = H.tor_tau_n; info[15] = H.chain_dihedral;
     }
   }
   OrbitProgram P = H.view();
@@ -2379,9 +2379,10 @@ int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t 
     const OrbitResult r = orbit_scan<true, false>(P, states[k]);
     if (P.canon_mode && orbit_min_canon(P, states[k]) != r.rep)
       throw std::runtime_error("canonical form disagrees with the chain walk");
-    if (P.tor_mode) {
+    if (P.tor_mode || P.chain_dihedral) {
       OrbitProgram P1 = P;
       P1.tor_mode = 0;
+      P1.chain_dihedral = 0;
       if (orbit_min_canon(P1, states[k]) != r.rep)
         throw std::runtime_error("block-rotation canonical form disagrees with the chain walk");
     }

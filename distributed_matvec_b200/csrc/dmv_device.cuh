@@ -106,6 +106,7 @@ struct OrbitProgram {
   //      values); only the few (block, amount) pairs reaching it are expanded
   //   2: R = 1: the minimum rotation starts with the longest cyclic run of zeros; runs are found by iterated AND
   int32_t canon_mode, canon_k, canon_r;
+  int32_t chain_dihedral;      // mode 2: G = rotations [x mirror] [x flip] exactly: one pass over the runs (min_rotation_dihedral); 1 | 2 (with mirror)
   const uint16_t *canon_lut;   // [2^k]: (set of amounts reaching the minimum) << 8 | minimum rotation of the block value
   const uint64_t *canon_masks; // [2 k]: masks of rotating every block right by a: (low part, wrapped part)
   //   mode 1 with 2 k <= 12: the LUT runs over PAIRS of adjacent blocks (top two blocks of a candidate), which leaves
@@ -381,6 +382,87 @@ __host__ __device__ __forceinline__ uint32_t min_rotation_runs32(uint32_t w, int
   return best;
 }
 
+// reverse the low n bits of v
+__host__ __device__ __forceinline__ uint64_t reverse_bits_n(uint64_t v, int n) {
+#ifdef __CUDA_ARCH__
+  return __brevll(v) >> (64 - n);
+#else
+  v = ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
+  v = ((v >> 2) & 0x3333333333333333ull) | ((v & 0x3333333333333333ull) << 2);
+  v = ((v >> 4) & 0x0f0f0f0f0f0f0f0full) | ((v & 0x0f0f0f0f0f0f0f0full) << 4);
+  v = ((v >> 8) & 0x00ff00ff00ff00ffull) | ((v & 0x00ff00ff00ff00ffull) << 8);
+  v = ((v >> 16) & 0x0000ffff0000ffffull) | ((v & 0x0000ffff0000ffffull) << 16);
+  v = (v >> 32) | (v << 32);
+  return v >> (64 - n);
+#endif
+}
+
+// min over the rotations of w, of its mirror image (reflect != 0: the group holds i -> n-1-i) and of the spin-flipped
+// images (flip != 0), from ONE pass over the runs of w: a minimal image starts with a longest cyclic run of zeros of w
+// or -- flipped -- of ones of w, the mirror image has the same runs, and only the kind with the longer longest run can
+// win.  Replaces four independent run searches (w, ~w, mirror, ~mirror) and the reflection network.
+template <typename W>
+__host__ __device__ __forceinline__ W min_rotation_dihedral(W w, int n, W mask, int reflect, int flip) {
+  constexpr int BITS = 8 * (int)sizeof(W);
+  if (w == 0) return 0;
+  if (w == mask) return flip ? (W)0 : mask;
+  const W z = (W)(~w & mask);
+  W r0 = z, r1 = w, a0 = z, a1 = w;       // r: top ends of the runs of length >= L; a: the mask rotated L times
+  int L0 = 1, L1 = 1;
+  bool more0 = true, more1 = flip != 0;
+  while (more0 | more1) {
+    if (more0) {
+      a0 = (W)(((a0 << 1) | (a0 >> (n - 1))) & mask);
+      const W t = r0 & a0;
+      if (t) { r0 = t; ++L0; } else more0 = false;
+    }
+    if (more1) {
+      a1 = (W)(((a1 << 1) | (a1 >> (n - 1))) & mask);
+      const W t = r1 & a1;
+      if (t) { r1 = t; ++L1; } else more1 = false;
+    }
+  }
+  W best = (W)~(W)0;
+  for (int kind = 0; kind < (flip ? 2 : 1); ++kind) {
+    if (flip && (kind == 0 ? L0 < L1 : L1 < L0)) continue;
+    const W src = kind ? (W)(w ^ mask) : w;           // zeros of src = the runs found
+    const int L = kind ? L1 : L0;
+    W r = kind ? r1 : r0;
+    W mir = 0;
+    if (reflect) {                                    // mirror image: bit i <-> bit n-1-i
+      uint64_t t = (uint64_t)src;
+#ifdef __CUDA_ARCH__
+      t = __brevll(t) >> (64 - n);
+#else
+      t = reverse_bits_n(t, n);
+#endif
+      mir = (W)t;
+    }
+    while (r) {
+      int p;
+      if (BITS == 64) p = top_bit((uint64_t)r);
+      else {
+#ifdef __CUDA_ARCH__
+        p = 31 - __clz((int)(uint32_t)r);
+#else
+        p = 31 - __builtin_clz((uint32_t)r);
+#endif
+      }
+      r = (W)(r & ~((W)1 << p));
+      int sh = n - 1 - p;                             // the run ends at bit p: bring p to the top
+      W c = sh ? (W)(((src << sh) | (src >> (n - sh))) & mask) : src;
+      best = c < best ? c : best;
+      if (reflect) {                                  // in the mirror image the same run ends at bit n - 2 - p + L
+        sh = p - L + 1;
+        if (sh < 0) sh += n;
+        c = sh ? (W)(((mir << sh) | (mir >> (n - sh))) & mask) : mir;
+        best = c < best ? c : best;
+      }
+    }
+  }
+  return best;
+}
+
 // minimum over { rotate inside every k-bit block by a, rotate the R blocks by b }
 __host__ __device__ __forceinline__ uint64_t min_rotation_blocks(const uint16_t *lut, const uint64_t *masks, int k,
                                                                  int R, int n, uint64_t mask, uint64_t w) {
@@ -489,21 +571,6 @@ __host__ __device__ __forceinline__ uint64_t min_rotation_pairs_flip(const uint3
   return best;
 }
 
-
-// reverse the low n bits of v
-__host__ __device__ __forceinline__ uint64_t reverse_bits_n(uint64_t v, int n) {
-#ifdef __CUDA_ARCH__
-  return __brevll(v) >> (64 - n);
-#else
-  v = ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
-  v = ((v >> 2) & 0x3333333333333333ull) | ((v & 0x3333333333333333ull) << 2);
-  v = ((v >> 4) & 0x0f0f0f0f0f0f0f0full) | ((v & 0x0f0f0f0f0f0f0f0full) << 4);
-  v = ((v >> 8) & 0x00ff00ff00ff00ffull) | ((v & 0x00ff00ff00ff00ffull) << 8);
-  v = ((v >> 16) & 0x0000ffff0000ffffull) | ((v & 0x0000ffff0000ffffull) << 16);
-  v = (v >> 32) | (v << 32);
-  return v >> (64 - n);
-#endif
-}
 
 // min_g g(w) over the full space group of an R x k torus (see OrbitProgram::tor_mode).  An image of w is fixed by
 //   t   : transpose first or not                       u = tau^t (w)
@@ -654,6 +721,11 @@ __host__ __device__ __forceinline__ uint64_t translation_canon(const OrbitProgra
 // min_g g(s) through the canonical form of every coset representative (trivial characters)
 __host__ __device__ __forceinline__ uint64_t orbit_min_canon(const OrbitProgram &P, uint64_t s) {
   if (P.tor_mode) return orbit_min_torus(P, s);
+  if (P.canon_mode == 2 && P.chain_dihedral) {
+    if (P.n_sites <= 32)
+      return (uint64_t)min_rotation_dihedral<uint32_t>((uint32_t)s, P.n_sites, (uint32_t)P.site_mask, P.chain_dihedral == 2, P.has_flip);
+    return min_rotation_dihedral<uint64_t>(s, P.n_sites, P.site_mask, P.chain_dihedral == 2, P.has_flip);
+  }
   if (P.canon_mode == 2 && P.n_sites <= 32) {   // chains of up to 32 sites: everything in 32-bit registers
     const uint32_t site = (uint32_t)P.site_mask;
     uint32_t best32 = 0xffffffffu;

@@ -267,6 +267,14 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
     }
   }
 
+  // chains: rotations alone, or rotations x mirror (i -> n-1-i): the whole permutation group in one pass over the runs
+  if (H.canon_mode == 2) {
+    Perm mirror(n_sites);
+    for (int i = 0; i < n_sites; ++i) mirror[i] = n_sites - 1 - i;
+    if (best.transversal.size() == 1) H.chain_dihedral = 1;
+    else if (best.transversal.size() == 2 && perm_index.count(mirror)) H.chain_dihedral = 2;
+  }
+
   // prefer the identity as the first coset representative (cheaper network: all-zero masks)
   H.n_q = (int)best.transversal.size();
   H.n_t = (int)best.chain.size();
@@ -515,9 +523,10 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
     if (r.rep != expect || r.stab != stab) throw std::runtime_error("orbit program self-check failed");
     if (H.canon_mode && orbit_min_canon(P, s) != expect)
       throw std::runtime_error("orbit program self-check failed (canonical form)");
-    if (H.tor_mode) {   // the block-rotation form underneath stays selectable (option "canon" = 1): check it as well
+    if (H.tor_mode || H.chain_dihedral) {   // the forms underneath stay selectable (option "canon" = 1): check them as well
       OrbitProgram P1 = P;
       P1.tor_mode = 0;
+      P1.chain_dihedral = 0;
       if (orbit_min_canon(P1, s) != expect)
         throw std::runtime_error("orbit program self-check failed (block-rotation canonical form)");
     }
@@ -547,6 +556,7 @@ OrbitProgram HostOrbitProgram::view() const {
   P.step_pack32 = step_pack32.empty() ? nullptr : reinterpret_cast<const uint4 *>(step_pack32.data());
   P.step_pack64 = step_pack64.data();
   P.canon_mode = canon_mode; P.canon_k = canon_k; P.canon_r = canon_r;
+  P.chain_dihedral = chain_dihedral;
   P.canon_lut = canon_lut.data();
   P.canon_masks = canon_masks.data();
   P.canon_lut2 = canon_lut2.empty() ? nullptr : canon_lut2.data();

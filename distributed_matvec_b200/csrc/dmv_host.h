@@ -24,6 +24,7 @@ struct HostOrbitProgram {
   std::vector<uint64_t> step_pack64;  // 3 words per step (empty unless simple)
   int32_t simple = 0;
   int32_t canon_mode = 0, canon_k = 0, canon_r = 0;   // block-rotation canonical form of the chain subgroup
+  int32_t chain_dihedral = 0;
   std::vector<uint16_t> canon_lut;
   std::vector<uint64_t> canon_masks;
   std::vector<uint32_t> canon_lut2;      // pair LUT (empty: single-block LUT)

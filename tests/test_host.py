@@ -235,5 +235,6 @@ def test_block_rotation_canonical_form_on_random_lattices(k, R, inversion, expec
     if expect_mode == 1 and 3 <= k <= 6 and 3 <= R <= 8:
         want = 2 if R == k else 1
     assert ext[12] == want, (k, R, [int(v) for v in ext])
+    assert ext[15] == (2 if expect_mode == 2 else 0)      # chains with the mirror: one pass over the runs
     if expect_mode == 1:
         assert (ext[7], ext[8]) == (k, R) and ext[9] == (1 if 2 * k <= 12 else 0)
