@@ -381,6 +381,16 @@ struct dmv_context {
   int64_t repl_block = 0;        // slot size per rank in the gathered x (the largest block)
   DevBuf<double> d_xcat;
   bool replicated = false, exchange_decided = false, timeline_replicated = false;
+  // peer-direct all-gather of x (launch_push_block): the peers' gathered vectors (two buffers, alternating by epoch) and
+  // flag words mapped with CUDA IPC
+  bool peer_gather = false;
+  int opt_peer_gather = -1;                 // -1 auto, 0 NCCL all-gather
+  std::vector<void *> peer_xcat, peer_flagmem;
+  DevBuf<unsigned> d_flags, d_push_done;    // [num_ranks] epochs raised by the peers; CTA counter of k_push_block
+  DevBuf<void *> d_peer_slot[2];            // [num_ranks] slot `rank` of every rank's buffer b
+  DevBuf<unsigned *> d_peer_flags;          // [num_ranks]
+  int peer_slot_elt = 0;                    // element width the slot pointers were computed for
+  unsigned gather_epoch = 0;
   // Lanczos work space (dmv_lanczos)
   DevBuf<double> lz_v[4];
   DevBuf<double> lz_scal;
@@ -389,6 +399,8 @@ struct dmv_context {
     delete global;
     for (void *q : peer_betas) if (q) cudaIpcCloseMemHandle(q);
     for (void *q : peer_coeffs) if (q) cudaIpcCloseMemHandle(q);
+    for (void *q : peer_xcat) if (q) cudaIpcCloseMemHandle(q);
+    for (void *q : peer_flagmem) if (q) cudaIpcCloseMemHandle(q);
     if (comm) nccl().CommDestroy(comm);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
     for (auto &e : ev_chunk) if (e) cudaEventDestroy(e);
@@ -534,13 +546,15 @@ void require_states(const dmv_context *ctx) {
 }
 
 void check_status(dmv_context *ctx) {
-  unsigned long long st[3];
+  unsigned long long st[4];
   CUDA_CHECK(cudaMemcpyAsync(st, ctx->d_status.ptr, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  if (st[0] != 0 || st[2] != 0) {
-    CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  if (st[0] != 0 || st[2] != 0 || st[3] != 0) {
+    CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 4 * sizeof(unsigned long long), ctx->stream));
     char buf[256];
-    if (st[2] != 0)
+    if (st[3] != 0)
+      snprintf(buf, sizeof(buf), "peer-direct all-gather of x: a rank did not raise its flag within the time limit");
+    else if (st[2] != 0)
       snprintf(buf, sizeof(buf), "outgoing bucket overflow (%llu records): plan is stale", st[2]);
     else  // message of the reference: DMV:116-118
       snprintf(buf, sizeof(buf), "invalid index: -1 for state %llu (%llu such records): the operator does "
@@ -611,12 +625,12 @@ void select_index_mode(dmv_context *ctx) {
   }
   ctx->rank_total = total;
   // the block must be exactly the first `expect` fixed-weight states: index(reps[i]) == i for all i
-  CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 4 * sizeof(unsigned long long), ctx->stream));
   launch_verify_rank(ix, ctx->d_status.ptr, ctx->stream);
   unsigned long long bad = 0;
   CUDA_CHECK(cudaMemcpyAsync(&bad, ctx->d_status.ptr, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 4 * sizeof(unsigned long long), ctx->stream));
   if (bad == 0) ctx->index_mode = ix.mode;
 }
 
@@ -643,6 +657,10 @@ void install_directory(dmv_context *ctx) {
   ctx->repl_block = 0;
   if (ctx->global) { delete ctx->global; ctx->global = nullptr; }
   ctx->d_pos.release();
+  for (auto &q : ctx->peer_xcat) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+  for (auto &q : ctx->peer_flagmem) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+  ctx->peer_gather = false;
+  ctx->peer_slot_elt = 0;
   ctx->d_xcat.release();
   std::fill(ctx->recv_counts.begin(), ctx->recv_counts.end(), -1);
   select_index_mode(ctx);
@@ -1142,8 +1160,8 @@ void setup_replicated(dmv_context *ctx) {
   d_base.upload(base, ctx->stream);
   launch_owner_positions(g->d_reps.ptr, nullptr, n, P, chunk, true, d_counts.ptr, d_base.ptr, block, ctx->d_pos.ptr, ctx->stream);
   ctx->repl_block = block;
-  ctx->d_xcat.alloc((size_t)block * P * 2);
-  CUDA_CHECK(cudaMemsetAsync(ctx->d_xcat.ptr, 0, (size_t)block * P * 2 * sizeof(double), ctx->stream));
+  ctx->d_xcat.alloc((size_t)block * P * 2 * 2);   // two buffers of P slots (alternating products), 16 bytes per element
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_xcat.ptr, 0, (size_t)block * P * 2 * 2 * sizeof(double), ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -1179,6 +1197,84 @@ void replicated_rows(dmv_context *ctx, int elt, const void *x_cat, void *y_dev) 
   launch_pull(p, g->proj, complex_values(g, elt), elt == DMV_C128, ctx->stream);
 }
 
+// Collective: map every rank's gathered-x buffers and flag words into every other rank (CUDA IPC over NVLink) so that
+// the all-gather of x becomes one kernel of peer stores + flags (launch_push_block).  Falls back to the NCCL all-gather
+// when any rank cannot map.
+void setup_peer_gather(dmv_context *ctx) {
+  NcclApi &N = nccl();
+  const int P = ctx->num_ranks;
+  ctx->peer_gather = false;
+  ctx->d_flags.alloc(P);
+  ctx->d_push_done.alloc(1);
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_flags.ptr, 0, sizeof(unsigned) * P, ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_push_done.ptr, 0, sizeof(unsigned), ctx->stream));
+  ctx->gather_epoch = 0;
+  struct Handles { cudaIpcMemHandle_t xcat, flags; int ok; int pad[15]; };
+  static_assert(sizeof(Handles) % 8 == 0, "handle block");
+  Handles mine{};
+  mine.ok = (ctx->opt_peer_gather != 0 && cudaIpcGetMemHandle(&mine.xcat, ctx->d_xcat.ptr) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine.flags, ctx->d_flags.ptr) == cudaSuccess) ? 1 : 0;
+  cudaGetLastError();
+  DevBuf<char> d_mine, d_handles;
+  d_mine.alloc(sizeof(Handles));
+  d_handles.alloc(sizeof(Handles) * P);
+  CUDA_CHECK(cudaMemcpyAsync(d_mine.ptr, &mine, sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_CHECK(N.AllGather(d_mine.ptr, d_handles.ptr, sizeof(Handles), ncclChar, ctx->comm, ctx->stream));
+  std::vector<Handles> handles(P);
+  CUDA_CHECK(cudaMemcpyAsync(handles.data(), d_handles.ptr, sizeof(Handles) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  int ok = 1;
+  for (int q = 0; q < P; ++q) ok &= handles[q].ok;
+  for (auto &q : ctx->peer_xcat) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+  for (auto &q : ctx->peer_flagmem) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+  ctx->peer_xcat.assign(P, nullptr);
+  ctx->peer_flagmem.assign(P, nullptr);
+  if (ok) {
+    for (int q = 0; q < P && ok; ++q) {
+      if (q == ctx->rank) continue;
+      if (cudaIpcOpenMemHandle(&ctx->peer_xcat[q], handles[q].xcat, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&ctx->peer_flagmem[q], handles[q].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        ok = 0;
+        cudaGetLastError();
+      }
+    }
+  }
+  int agree = ok;   // everybody must agree; the all-reduce is also the barrier after which flags may be raised
+  ctx->d_barrier.alloc(1);
+  CUDA_CHECK(cudaMemcpyAsync(ctx->d_barrier.ptr, &agree, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_CHECK(N.AllReduce(ctx->d_barrier.ptr, ctx->d_barrier.ptr, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(&agree, ctx->d_barrier.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (!agree) {
+    for (auto &q : ctx->peer_xcat) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    for (auto &q : ctx->peer_flagmem) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    return;
+  }
+  std::vector<unsigned *> flags(P);
+  for (int q = 0; q < P; ++q)
+    flags[q] = q == ctx->rank ? ctx->d_flags.ptr : reinterpret_cast<unsigned *>(ctx->peer_flagmem[q]);
+  ctx->d_peer_flags.upload(flags, ctx->stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->peer_slot_elt = 0;
+  ctx->peer_gather = true;
+}
+
+// slot `rank` of buffer b of every rank's gathered vector, for elements of `elt` doubles
+void upload_peer_slots(dmv_context *ctx, int elt) {
+  const int P = ctx->num_ranks;
+  const size_t buffer_doubles = (size_t)ctx->repl_block * P * 2;   // buffers are sized for 16-byte elements
+  for (int b = 0; b < 2; ++b) {
+    std::vector<void *> slots(P);
+    for (int q = 0; q < P; ++q) {
+      double *base = q == ctx->rank ? ctx->d_xcat.ptr : reinterpret_cast<double *>(ctx->peer_xcat[q]);
+      slots[q] = base + b * buffer_doubles + (size_t)ctx->rank * ctx->repl_block * elt;
+    }
+    ctx->d_peer_slot[b].upload(slots, ctx->stream);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->peer_slot_elt = elt;
+}
+
 // Collective: which exchange the distributed product uses.  exchange = -1 (auto) prefers the replicated-x product
 // when k_gather applies and the whole basis fits, else the record exchange (peer-direct / NCCL, see setup_exchange).
 void decide_exchange(dmv_context *ctx) {
@@ -1199,6 +1295,7 @@ void decide_exchange(dmv_context *ctx) {
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   ctx->replicated = agree != 0;
   ctx->exchange_decided = true;
+  if (ctx->replicated) setup_peer_gather(ctx);
   if (!ctx->replicated) {
     delete ctx->global; ctx->global = nullptr;
     ctx->d_pos.release(); ctx->d_xcat.release();
@@ -1442,8 +1539,8 @@ int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op,
   ctx->complex_coefficients = cplx;
   ctx->rows_ok = ctx->proj == PROJ_GROUP && !cplx && ctx->host_orbit.trivial_characters &&
                  !ctx->h_pull.bp.empty() && !ctx->h_pull.any_generic;
-  ctx->d_status.alloc(3);
-  CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  ctx->d_status.alloc(4);
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_status.ptr, 0, 4 * sizeof(unsigned long long), ctx->stream));
   ctx->d_out_count.alloc(num_ranks);
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   *out = ctx.release();
@@ -1496,6 +1593,10 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
   } else if (key == "gather") {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
+  } else if (key == "peer_gather") {
+    if (value < -1 || value > 0) throw std::runtime_error("peer_gather: -1 auto, 0 NCCL all-gather of x");
+    ctx->opt_peer_gather = (int)value;
+    ctx->exchange_decided = false;
   } else if (key == "rows") {
     if (value < -1 || value > 0) throw std::runtime_error("rows: -1 auto, 0 off (queued k_pull / k_generate for symmetric bases)");
     ctx->opt_rows = (int)value;
@@ -1535,6 +1636,7 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
     return ((use_pull(ctx) && !use_gather(ctx) && use_rows(ctx)) ||
             (ctx->replicated && ctx->global && !use_gather(ctx->global) && use_rows(ctx->global))) ? 1 : 0;
   if (key == "rows_ok") return ctx->rows_ok ? 1 : 0;
+  if (key == "peer_gather") return (ctx->replicated && ctx->peer_gather) ? 1 : 0;
   if (key == "complex_coefficients") return ctx->complex_coefficients ? 1 : 0;
   if (key == "canon_k") return ctx->host_orbit.canon_k;
   if (key == "orbit_n_q") return ctx->host_orbit.n_q;
@@ -1823,9 +1925,7 @@ int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
     // ---- replicated-x product: all-gather x into equal slots, then this rank's rows by the row traversal
     if (x == y) throw std::runtime_error("x and y must not alias");
     const size_t esz = (size_t)8 * elt, bytes = (size_t)ctx->n_states * esz;
-    char *slot = reinterpret_cast<char *>(ctx->d_xcat.ptr) + (size_t)ctx->rank * ctx->repl_block * esz;
     CUDA_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CUDA_CHECK(cudaMemcpyAsync(slot, x, bytes, cudaMemcpyDefault, ctx->stream));   // host or device x
     void *y_dev = y;
     const bool y_host = !is_device_pointer(y);
     if (y_host) {
@@ -1833,10 +1933,35 @@ int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
       y_dev = ctx->d_y.ptr;
       if (ctx->h_diag_kept == 0) CUDA_CHECK(cudaMemcpyAsync(y_dev, y, bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
-    CUDA_CHECK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    NCCL_CHECK(N.AllGather(slot, ctx->d_xcat.ptr, (size_t)ctx->repl_block * elt, ncclDouble, ctx->comm, ctx->stream));
+    const double *x_cat = ctx->d_xcat.ptr;
+    if (ctx->peer_gather) {
+      // ---- peer-direct: my block goes straight into slot `rank` of every rank's buffer (epoch parity picks the buffer:
+      // a rank raises its flag for epoch e + 1 only after it has consumed buffer e)
+      const void *x_dev = x;
+      if (!is_device_pointer(x)) {
+        ctx->d_x.alloc((size_t)ctx->n_states * elt);
+        CUDA_CHECK(cudaMemcpyAsync(ctx->d_x.ptr, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        x_dev = ctx->d_x.ptr;
+      }
+      CUDA_CHECK(cudaEventRecord(ctx->ev[1], ctx->stream));
+      if (ctx->peer_slot_elt != elt) upload_peer_slots(ctx, elt);
+      const unsigned epoch = ++ctx->gather_epoch;
+      const int b = (int)(epoch & 1u);
+      const int64_t n_doubles = ctx->n_states * elt;
+      const bool wide = (n_doubles % 2 == 0) && (reinterpret_cast<uintptr_t>(x_dev) % 16 == 0) &&
+                        ((size_t)ctx->repl_block * elt) % 2 == 0;
+      launch_push_block(x_dev, n_doubles, P, ctx->d_peer_slot[b].ptr, ctx->d_push_done.ptr, ctx->d_peer_flags.ptr,
+                        ctx->rank, epoch, wide, ctx->stream);
+      launch_wait_flags(ctx->d_flags.ptr, P, epoch, ctx->d_status.ptr, ctx->stream);
+      x_cat = ctx->d_xcat.ptr + (size_t)b * ctx->repl_block * P * 2;
+    } else {
+      char *slot = reinterpret_cast<char *>(ctx->d_xcat.ptr) + (size_t)ctx->rank * ctx->repl_block * esz;
+      CUDA_CHECK(cudaMemcpyAsync(slot, x, bytes, cudaMemcpyDefault, ctx->stream));   // host or device x
+      CUDA_CHECK(cudaEventRecord(ctx->ev[1], ctx->stream));
+      NCCL_CHECK(N.AllGather(slot, ctx->d_xcat.ptr, (size_t)ctx->repl_block * elt, ncclDouble, ctx->comm, ctx->stream));
+    }
     CUDA_CHECK(cudaEventRecord(ctx->ev[6], ctx->stream));
-    replicated_rows(ctx, elt, ctx->d_xcat.ptr, y_dev);
+    replicated_rows(ctx, elt, x_cat, y_dev);
     CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
     CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
     CUDA_CHECK(cudaEventRecord(ctx->ev[4], ctx->stream));

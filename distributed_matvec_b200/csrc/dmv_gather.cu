@@ -408,6 +408,81 @@ void launch_owner_positions(const uint64_t *states, const uint8_t *masks, int64_
   count_launch();
 }
 
+// -------------------------------------------------------------------------------------------------
+// Peer-direct all-gather of x for the replicated-x product: every rank stores its block straight into slot `rank` of
+// the gathered vector of EVERY rank (its own included) over NVLink -- one kernel, 8- or 16-byte coalesced stores to the
+// CUDA-IPC-mapped buffers of the peers -- and then raises its flag in every peer with a system-scope release store; the
+// consumer waits for all flags of the epoch with acquire loads (k_wait_flags).  Replaces the reference's
+// PUT + `isEmpty` flag handshake (DMV:361-410) for the one exchange this form of the product has, and the NCCL
+// all-gather whose latency dominated small blocks.
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_push_block(const T *__restrict__ x, int64_t n_words, int num_ranks,
+                                                    T *const *__restrict__ peer_slot, unsigned *done,
+                                                    unsigned *const *__restrict__ peer_flags, int rank, unsigned epoch) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+    const T v = x[i];
+    for (int q = 0; q < num_ranks; ++q) peer_slot[q][i] = v;
+  }
+  __threadfence_system();            // my stores are visible system-wide before this CTA is counted
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {     // last CTA: every block of the grid has fenced its stores
+      __threadfence();
+      *done = 0;
+      for (int q = 0; q < num_ranks; ++q) {
+        unsigned *f = peer_flags[q] + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+      }
+    }
+  }
+}
+
+// wait until every rank has raised flag[q] to `epoch`; gives up after ~4 s (a dead peer must not hang the box)
+__global__ void k_wait_flags(const unsigned *flags, int num_ranks, unsigned epoch, unsigned long long *status) {
+  const int q = threadIdx.x;
+  if (q < num_ranks) {
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + q) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      if (clock64() - t0 > 8000000000ll) { atomicAdd(status + 3, 1ull); break; }
+      __nanosleep(200);
+    }
+  }
+}
+
+void launch_push_block(const void *x, int64_t n_doubles, int num_ranks, void *const *peer_slot, unsigned *done,
+                       unsigned *const *peer_flags, int rank, unsigned epoch, bool wide, cudaStream_t stream) {
+  // wide: 16-byte words (x and every slot 16-byte aligned, even number of doubles)
+  const int64_t words = wide ? n_doubles / 2 : n_doubles;
+  int64_t blocks = (words + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  if (blocks < 1) blocks = 1;
+  if (wide)
+    k_push_block<double2><<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const double2 *>(x), words, num_ranks,
+                                                               reinterpret_cast<double2 *const *>(peer_slot), done,
+                                                               peer_flags, rank, epoch);
+  else
+    k_push_block<double><<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const double *>(x), words, num_ranks,
+                                                             reinterpret_cast<double *const *>(peer_slot), done,
+                                                             peer_flags, rank, epoch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_push_block launch: ") + cudaGetErrorString(e));
+  count_launch();
+}
+
+void launch_wait_flags(const unsigned *flags, int num_ranks, unsigned epoch, unsigned long long *status,
+                       cudaStream_t stream) {
+  k_wait_flags<<<1, 32, 0, stream>>>(flags, num_ranks, epoch, status);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_wait_flags launch: ") + cudaGetErrorString(e));
+  count_launch();
+}
+
 // p.groups / p.lut / p.bp must point at the ROW-traversal tables (see k_pull); complex_values says whether the
 // LUT is the interleaved complex one.
 void launch_gather(const KernelParams &p, bool inversion, bool complex_values, bool complex_elements,

@@ -157,6 +157,12 @@ void launch_owner_positions(const uint64_t *states, const uint8_t *masks, int64_
                             int64_t block, uint32_t *pos, cudaStream_t stream);
 // out[pos[i]] = in[i] (gather == false) or out[i] = in[pos[i]]; elt = 8-byte words per element (1 or 2)
 void launch_permute(int64_t n, int elt, const uint32_t *pos, const void *in, void *out, bool gather, cudaStream_t stream);
+// peer-direct all-gather of x (replicated-x product): my block into slot `rank` of every rank's gathered vector over
+// NVLink, then my flag in every peer; the consumer waits for all flags of the epoch
+void launch_push_block(const void *x, int64_t n_doubles, int num_ranks, void *const *peer_slot, unsigned *done,
+                       unsigned *const *peer_flags, int rank, unsigned epoch, bool wide, cudaStream_t stream);
+void launch_wait_flags(const unsigned *flags, int num_ranks, unsigned epoch, unsigned long long *status,
+                       cudaStream_t stream);
 // Lanczos vector kernels (dmv_solver.cu); n = elements, words = 8-byte words
 void launch_dot(int64_t n, bool complex_elements, const double *a, const double *b, double *out2, cudaStream_t s);
 void launch_lanczos_update(int64_t n, bool complex_elements, double *w, const double *v, const double *u,
