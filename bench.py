@@ -354,8 +354,10 @@ class Workload:
         return "records: NCCL send/recv buckets"
 
     def kernel_name(self) -> str:
-        if self.op.info("gather") and (self.world == 1 or self.op.info("replicated")):
+        if self.op.info("gather"):
             return "k_gather"
+        if self.op.info("rows"):
+            return "k_rows"
         if self.world > 1 and self.op.info("replicated"):
             return "k_pull"
         return "k_pull" if self.op.info("pull") else "k_generate"

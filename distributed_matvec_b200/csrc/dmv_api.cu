@@ -290,6 +290,7 @@ struct dmv_context {
   DevBuf<uint32_t> d_canon_lut2;
   DevBuf<int32_t> d_cc_begin, d_cc_delta;
   DevBuf<uint16_t> d_tor_lutm;
+  DevBuf<uint8_t> d_tor_frow;
   DevBuf<uint32_t> d_tor_luts;
   DevBuf<uint64_t> d_tor_net_mask;
   DevBuf<int32_t> d_tor_net_delta;
@@ -315,6 +316,7 @@ struct dmv_context {
   // hash table over this context's representatives (see table_slot in dmv_device.cuh)
   bool rows_ok = false;
   int opt_rows = -1;        // -1 auto (k_rows when it applies), 0 the queued k_pull
+  int opt_gather_walk = 0;  // k_gather: 0 group-major warp-uniform walk, 1 per-lane walk (round 1)
   DevBuf<unsigned char> d_table;
   DevBuf<uint32_t> d_slot_of;
   uint32_t table_slots = 0;
@@ -470,6 +472,7 @@ KernelParams base_params(dmv_context *ctx) {
   p.status = ctx->d_status.ptr;
   p.row_begin = 0;
   p.row_end = ctx->n_states;
+  p.gather_walk = ctx->opt_gather_walk;
   return p;
 }
 
@@ -709,6 +712,8 @@ void upload_orbit(dmv_context *ctx) {
   ctx->d_tor_net_delta.upload(H.tor_net_delta, ctx->stream);
   P.tor_lutm = ctx->d_tor_lutm.ptr;
   P.tor_luts = ctx->d_tor_luts.ptr;
+  ctx->d_tor_frow.upload(H.tor_frow, ctx->stream);
+  P.tor_frow = ctx->d_tor_frow.ptr;
   P.tor_net_mask = ctx->d_tor_net_mask.ptr;
   P.tor_net_delta = ctx->d_tor_net_delta.ptr;
   if (ctx->opt_canon >= 0) { P.tor_mode = 0; P.chain_dihedral = 0; }   // 1: round-1 forms (coset chain / four run searches)
@@ -852,9 +857,9 @@ void do_plan(dmv_context *ctx) {
 void ensure_table(dmv_context *ctx, int elt) {
   if (ctx->table_elt == elt) return;
   const int64_t n = ctx->n_states;
-  if (2 * n + 16 >= 4294967295ll) throw std::runtime_error("k_rows: more than 2^31 states per table");
-  const uint32_t slots = (uint32_t)std::max<int64_t>(16, 2 * n);
-  const int slot_bytes = elt == DMV_C128 ? 32 : 16;
+  if (2 * n + 16 >= 2147483647ll) throw std::runtime_error("k_rows: more than 2^30 states per table");
+  const uint32_t slots = (uint32_t)std::max<int64_t>(16, 2 * n);   // buckets of two slots: 0.5 states per bucket
+  const int slot_bytes = elt == DMV_C128 ? 64 : 32;
   ctx->d_table.alloc((size_t)slots * slot_bytes);
   ctx->d_slot_of.alloc((size_t)std::max<int64_t>(1, n));
   CUDA_CHECK(cudaMemsetAsync(ctx->d_table.ptr, 0xff, (size_t)slots * slot_bytes, ctx->stream));
@@ -1132,6 +1137,7 @@ void setup_replicated(dmv_context *ctx) {
     if (dmv_context_create(&b, &o, ctx->device, 0, 1, &g) != 0) throw std::runtime_error(g_last_error);
     ctx->global = g;
     g->opt_rows = ctx->opt_rows;
+    g->opt_gather_walk = ctx->opt_gather_walk;
     if (ctx->opt_canon != g->opt_canon && g->proj == PROJ_GROUP) { g->opt_canon = ctx->opt_canon; upload_orbit(g); }
     if (dmv_basis_build(g) != 0) throw std::runtime_error(g_last_error);
   }
@@ -1593,6 +1599,9 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
   } else if (key == "gather") {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
+  } else if (key == "gather_walk") {
+    ctx->opt_gather_walk = value != 0;
+    if (ctx->global) ctx->global->opt_gather_walk = ctx->opt_gather_walk;
   } else if (key == "peer_gather") {
     if (value < -1 || value > 0) throw std::runtime_error("peer_gather: -1 auto, 0 NCCL all-gather of x");
     ctx->opt_peer_gather = (int)value;
@@ -2504,6 +2513,10 @@ int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t 
     const OrbitResult r = orbit_scan<true, false>(P, states[k]);
     if (P.canon_mode && orbit_min_canon(P, states[k]) != r.rep)
       throw std::runtime_error("canonical form disagrees with the chain walk");
+    if (P.tor_mode == 2 && P.canon_k == P.canon_r && (P.canon_k == 4 || P.canon_k == 6)) {
+      const uint64_t got = P.canon_k == 6 ? orbit_min_torus_sq<6>(P, states[k]) : orbit_min_torus_sq<4>(P, states[k]);
+      if (got != r.rep) throw std::runtime_error("square-torus canonical form disagrees with the chain walk");
+    }
     if (P.tor_mode || P.chain_dihedral) {
       OrbitProgram P1 = P;
       P1.tor_mode = 0;

@@ -131,6 +131,7 @@ struct OrbitProgram {
   int32_t tor_div_r;           // floor(bit / R) = (bit * tor_div_r) >> 16 for bit < 32
   const uint16_t *tor_lutm;    // [2^(2k)]
   const uint32_t *tor_luts;    // [2^(2k)]  (stays in global memory: read about once per state)
+  const uint8_t *tor_frow;     // [4 k][2^k]: image of one row under F = flip^f rho^e rot_a, F = (2 f + e) k + a
   const uint64_t *tor_net_mask;
   const int32_t *tor_net_delta;
 };
@@ -251,14 +252,18 @@ __device__ __forceinline__ int64_t locate(const StateIndex &ix, uint64_t key) {
 // the vector element stored in the slot (row traversal of bases with permutation symmetries, k_rows).  The sorted
 // array + directory needs  directory -> several probes -> norm -> x  dependent loads per term, and orbit minima
 // cluster at small values, which unbalances any directory over the top bits; here a term costs the 32-byte sector of
-// its slot (plus 0.5 on average for linear probing at load factor 1/2).  The values are refreshed once per product
-// (k_table_fill: x[i] * norm[i] at slot_of[i]).  180 GB of HBM pays for the 64 bytes per state.
-//   complex128: slot = { key, pad, re, im } (32 bytes);  float64: slot = { key, value } (16 bytes)
+// its bucket.  The values are refreshed once per product
+// (k_table_fill: x[i] * norm[i] at slot_of[i]).  180 GB of HBM pays for the 128 bytes per state.
+// Buckets of two slots, two buckets per state (0.5 keys per bucket): a look-up requests the whole bucket at once
+// (both keys, both values: independent loads) and finds its key there in 98 % of the cases; otherwise it moves on to the
+// next bucket (a state goes to the first bucket from its home with a free slot, slot 0 first).
+//   complex128: bucket = { key0, key1, re0, im0, re1, im1, pad, pad } (64 bytes)
+//   float64:    bucket = { key0, key1, value0, value1 }               (32 bytes)
 // ---------------------------------------------------------------------------------------------
 constexpr uint64_t kEmptyKey = ~0ull;
-__host__ __device__ __forceinline__ uint32_t table_slot(uint64_t key, uint32_t n_slots) {
+__host__ __device__ __forceinline__ uint32_t table_slot(uint64_t key, uint32_t n_buckets) {
   const uint64_t h = key * 0x9E3779B97F4A7C15ull;
-  return (uint32_t)(((h >> 32) * (uint64_t)n_slots) >> 32);
+  return (uint32_t)(((h >> 32) * (uint64_t)n_buckets) >> 32);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -651,64 +656,92 @@ __host__ __device__ __forceinline__ uint64_t orbit_min_torus(const OrbitProgram 
 // Column a of the lattice (= row a of the transposed image) comes out of one masked multiply:
 //   t = (w >> a) & STRIDE has site (y, a) at bit K y; t * CMUL puts it at bit S + y (S = (K-1)^2; no two partial
 //   products meet, so there are no carries).
+// Pass 2 builds the image of a candidate row by row from tor_frow[F][row] (F = flip^f rho^e rot_a on one row): its top
+// two rows are the minimal pair already, the other K - 2 are byte look-ups on a 32-bit word -- no 64-bit networks.
+// Candidate bit layout here: (t, s = 0, y) -> t K + y, (t, s = 1, y) -> 16 + t K + y.
 template <int K>
-__device__ __forceinline__ uint64_t orbit_min_torus_sq(const OrbitProgram &P, uint64_t w) {
-  constexpr int R = K, n = K * K;
+__host__ __device__ __forceinline__ uint64_t orbit_min_torus_sq(const OrbitProgram &P, uint64_t w) {
+  constexpr int n = K * K;
   constexpr uint32_t BM = (1u << K) - 1u;
   constexpr int S = (K - 1) * (K - 1);
+  constexpr int LOW = K * (K - 2);            // bits of the rows below the top pair
   uint32_t stride = 0, cmul = 0;
 #pragma unroll
   for (int y = 0; y < K; ++y) { stride |= 1u << (K * y); cmul |= 1u << ((K - 1) * (K - 1 - y)); }
-  const uint64_t mask = P.site_mask;
   uint32_t rows[2][K];
 #pragma unroll
   for (int y = 0; y < K; ++y) rows[0][y] = (uint32_t)(w >> (K * y)) & BM;
 #pragma unroll
   for (int a = 0; a < K; ++a) rows[1][a] = ((((uint32_t)(w >> a) & stride) * cmul) >> S) & BM;
-  uint32_t mstar = 0xffffffffu, cand = 0;   // cand bit (2 t + s) R + y
+  uint32_t md[2][K], mu[2][K];
+  uint32_t mstar = 0xffffffffu;
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
 #pragma unroll
     for (int y = 0; y < K; ++y) {
       const uint32_t hi = rows[t][y] << K;
-      const uint32_t md = P.tor_lutm[hi | rows[t][(y + K - 1) % K]], mu = P.tor_lutm[hi | rows[t][(y + 1) % K]];
-      const uint32_t bit_d = 1u << ((2 * t) * R + y), bit_u = 1u << ((2 * t + 1) * R + y);
-      cand = md < mstar ? bit_d : (md == mstar ? (cand | bit_d) : cand);
-      mstar = md < mstar ? md : mstar;
-      cand = mu < mstar ? bit_u : (mu == mstar ? (cand | bit_u) : cand);
-      mstar = mu < mstar ? mu : mstar;
+      md[t][y] = P.tor_lutm[hi | rows[t][(y + K - 1) % K]];
+      mu[t][y] = P.tor_lutm[hi | rows[t][(y + 1) % K]];
+      mstar = md[t][y] < mstar ? md[t][y] : mstar;
+      mstar = mu[t][y] < mstar ? mu[t][y] : mstar;
+    }
+  }
+  uint32_t cand = 0;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+#pragma unroll
+    for (int y = 0; y < K; ++y) {
+      if (md[t][y] == mstar) cand |= 1u << (t * K + y);
+      if (mu[t][y] == mstar) cand |= 1u << (16 + t * K + y);
     }
   }
   uint64_t u1 = 0;
-  if (cand >> (2 * R)) {   // a transposed image is among the candidates: assemble it
+  if (cand & (((1u << K) - 1u) * 0x00010001u << K)) {   // a transposed image is among the candidates: assemble it
 #pragma unroll
     for (int a = 0; a < K; ++a) u1 |= (uint64_t)rows[1][a] << (K * a);
   }
-  uint64_t best = ~0ull;
+  uint32_t best = 0xffffffffu;   // rows below the top pair of the best image (the top pair is mstar for every candidate)
   while (cand) {
+#ifdef __CUDA_ARCH__
     const int cb = __ffs((int)cand) - 1;
+#else
+    const int cb = __builtin_ffs((int)cand) - 1;
+#endif
     cand &= cand - 1;
-    const int ts = (cb * P.tor_div_r) >> 16;
-    const int y = cb - ts * R, s = ts & 1;
-    const uint64_t u = (ts >> 1) ? u1 : w;
-    const int yn = s ? (y + 1 == R ? 0 : y + 1) : (y == 0 ? R - 1 : y - 1);
+    const int s = cb >> 4, ty = cb & 15;
+    const int t = ty >= K ? 1 : 0, y = ty - t * K;
+    const uint64_t u = t ? u1 : w;
+    const int yn = s ? (y + 1 == K ? 0 : y + 1) : (y == 0 ? K - 1 : y - 1);
     const uint32_t idx = (((uint32_t)(u >> (K * y)) & BM) << K) | ((uint32_t)(u >> (K * yn)) & BM);
+#ifdef __CUDA_ARCH__
     uint32_t Sset = __ldg(P.tor_luts + idx);
-    const int sh = (s ? y : R - 1 - y) * K;
+#else
+    uint32_t Sset = P.tor_luts[idx];
+#endif
+    // the K - 2 rows below the top pair, in image order (most significant first), as one LOW-bit word `below`:
+    //   s = 0: rows y-2, y-3, ...: rotate row y to the top, they are the low LOW bits, already in image order
+    //   s = 1: rows y+2, y+3, ...: rotate row y to block 0, they are blocks 2 .. K-1 in REVERSE image order
+    const int sh = s ? (K - y == K ? 0 : (K - y) * K) : (K - 1 - y) * K;   // left rotation by whole rows
+    const uint64_t ur = sh ? (((u << sh) | (u >> (n - sh))) & P.site_mask) : u;
+    const uint32_t below = s ? (uint32_t)(ur >> (2 * K)) : (uint32_t)ur & ((1u << LOW) - 1u);
     while (Sset) {
+#ifdef __CUDA_ARCH__
       const int sb = __ffs((int)Sset) - 1;
+#else
+      const int sb = __builtin_ffs((int)Sset) - 1;
+#endif
       Sset &= Sset - 1;
-      const int fe = (sb * P.canon_div) >> 16, a = sb - fe * K, e = fe & 1;
-      uint64_t v = (fe >> 1) ? (u ^ mask) : u;
-      if (a) v = ((v >> a) & P.canon_masks[2 * a]) | ((v << (K - a)) & P.canon_masks[2 * a + 1]);
-      if (e != s)
-        for (int st = 0; st < P.tor_rho_n; ++st) v = butterfly(v, P.tor_net_mask[st], P.tor_net_delta[st]);
-      if (s) v = __brevll(v) >> (64 - n);
-      const uint64_t c = rotl_n(v, sh, n, mask);
-      best = c < best ? c : best;
+      const uint8_t *fr = P.tor_frow + (sb << K);
+      uint32_t img = 0;
+#pragma unroll
+      for (int q = 0; q < K - 2; ++q) {
+        const uint32_t r = (below >> (K * q)) & BM;
+        img |= (uint32_t)fr[r] << (s ? K * (K - 3 - q) : K * q);
+      }
+      best = img < best ? img : best;
     }
   }
-  return best;
+  return ((uint64_t)mstar << LOW) | best;
 }
 
 __host__ __device__ __forceinline__ uint64_t translation_canon(const OrbitProgram &P, uint64_t w) {

@@ -178,13 +178,9 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
       mask &= slice_mask;
       if (!valid) mask = 0;
       const int g_base = 64 * w;
-      while (mask) {
-        // two terms per trip: both index look-ups, then both gathers, are in flight together
-        const int g0 = ffs_w(mask) - 1;
-        mask &= mask - 1;
-        const bool two = mask != 0;
-        const int g1 = two ? ffs_w(mask) - 1 : g0;
-        mask &= mask - 1;   // no-op when mask is already empty
+      // one pair of terms (groups g0, g1 of this word; `two`: g1 is a second term; on0 / on1: this lane emits them):
+      // both index look-ups, then both gathers, are in flight together
+      auto pair = [&](int g0, int g1, bool on0, bool on1) {
         W k0 = b ^ s_gx[g_base + g0], k1 = b ^ s_gx[g_base + g1];
         double s0 = 1.0, s1 = 1.0;
         if (INV) {   // reference src/BatchedOperator.chpl:145-152
@@ -192,13 +188,13 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
           if (f0 < k0) { k0 = f0; s0 = p.inversion_character; }
           if (f1 < k1) { k1 = f1; s1 = p.inversion_character; }
         }
-        uint32_t i0, i1;
+        uint32_t i0 = kNone, i1 = kNone;
         if (LIN) {
-          i0 = lin_index<W>(lin_a, lin_b, lin_bits, lo_mask, weight, n_states, k0);
-          i1 = lin_index<W>(lin_a, lin_b, lin_bits, lo_mask, weight, n_states, k1);
+          if (on0) i0 = lin_index<W>(lin_a, lin_b, lin_bits, lo_mask, weight, n_states, k0);
+          if (on1) i1 = lin_index<W>(lin_a, lin_b, lin_bits, lo_mask, weight, n_states, k1);
         } else {
-          i0 = (uint32_t)locate(p.index, (uint64_t)k0);   // -1 -> kNone
-          i1 = (uint32_t)locate(p.index, (uint64_t)k1);
+          if (on0) i0 = (uint32_t)locate(p.index, (uint64_t)k0);   // -1 -> kNone
+          if (on1) i1 = (uint32_t)locate(p.index, (uint64_t)k1);
         }
         V c0, c1;
         if (UNI) { c0 = uni; c1 = uni; }
@@ -208,7 +204,7 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
         }
         if (pos) {
           if (i0 != kNone) i0 = __ldg(pos + i0);
-          if (two && i1 != kNone) i1 = __ldg(pos + i1);
+          if (i1 != kNone) i1 = __ldg(pos + i1);
         }
         E x0[KB], x1[KB];
 #pragma unroll
@@ -216,17 +212,46 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
           x0[k] = zero_of((E *)nullptr);
           x1[k] = zero_of((E *)nullptr);
           if (i0 != kNone) x0[k] = ldx(xv + (int64_t)k * p.batch_stride, i0);
-          if (two && i1 != kNone) x1[k] = ldx(xv + (int64_t)k * p.batch_stride, i1);
+          if (i1 != kNone) x1[k] = ldx(xv + (int64_t)k * p.batch_stride, i1);
         }
         if (INV) { c0 = scale(c0, s0); c1 = scale(c1, s1); }
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
-          fma_to(acc[k], c0, x0[k]);
-          if (two) fma_to(acc[k], c1, x1[k]);
+          if (on0) fma_to(acc[k], c0, x0[k]);
+          if (on1) fma_to(acc[k], c1, x1[k]);
         }
-        if ((i0 == kNone) | (two & (i1 == kNone))) {   // DMV:115-118 (rare)
-          if (i0 == kNone && nonzero(c0)) { ++bad; bad_state = (unsigned long long)k0; }
-          if (two && i1 == kNone && nonzero(c1)) { ++bad; bad_state = (unsigned long long)k1; }
+        if ((on0 & (i0 == kNone)) | (on1 & (i1 == kNone))) {   // DMV:115-118 (rare)
+          if (on0 && i0 == kNone && nonzero(c0)) { ++bad; bad_state = (unsigned long long)k0; }
+          if (on1 && i1 == kNone && nonzero(c1)) { ++bad; bad_state = (unsigned long long)k1; }
+        }
+      };
+      if (S == 1 && p.gather_walk == 0) {
+        // GROUP-MAJOR walk, warp-uniform: all 32 lanes handle the same group at the same time.  For a fixed flip mask
+        // consecutive rows map to (nearly) consecutive indices, so the 32 gathers of a group fall into a few 128-byte
+        // lines instead of 32 (the per-lane walk has every lane on a different group at any instant).
+        W any;
+        if constexpr (sizeof(W) == 4) any = __reduce_or_sync(0xffffffffu, mask);
+        else {
+          const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)mask);
+          const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)((uint64_t)mask >> 32));
+          any = (W)(((uint64_t)hi << 32) | lo);
+        }
+        while (any) {
+          const int g0 = ffs_w(any) - 1;
+          any &= any - 1;
+          const bool two = any != 0;
+          const int g1 = two ? ffs_w(any) - 1 : g0;
+          any &= any - 1;   // no-op when already empty
+          pair(g0, g1, (mask >> g0) & 1, two && ((mask >> g1) & 1));
+        }
+      } else {
+        while (mask) {   // lanes of one row share it: every lane walks its own slice of the groups
+          const int g0 = ffs_w(mask) - 1;
+          mask &= mask - 1;
+          const bool two = mask != 0;
+          const int g1 = two ? ffs_w(mask) - 1 : g0;
+          mask &= mask - 1;   // no-op when mask is already empty
+          pair(g0, g1, true, two);
         }
       }
     }

@@ -458,6 +458,16 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
         const uint32_t bm = (1u << k) - 1u;
         auto rot = [&](uint32_t v, int a) { return a ? (((v >> a) | (v << (k - a))) & bm) : v; };
         auto rev = [&](uint32_t v) { uint32_t r = 0; for (int b = 0; b < k; ++b) r |= ((v >> b) & 1u) << (k - 1 - b); return r; };
+        H.tor_frow.assign((((size_t)4 * k << k) + 15) / 16 * 16, 0);   // padded: staged with 16-byte bulk copies
+        for (int f = 0; f < 2; ++f)
+          for (int e = 0; e < 2; ++e)
+            for (int a = 0; a < k; ++a)
+              for (uint32_t r = 0; r <= bm; ++r) {
+                uint32_t v = rot(r, a);
+                if (e) v = rev(v);
+                if (f) v ^= bm;
+                H.tor_frow[((size_t)((2 * f + e) * k + a) << k) + r] = (uint8_t)v;
+              }
         H.tor_lutm.resize((size_t)1 << (2 * k));
         H.tor_luts.resize((size_t)1 << (2 * k));
         for (uint32_t hi = 0; hi <= bm; ++hi)
@@ -523,6 +533,10 @@ HostOrbitProgram compile_orbit_program(int n_sites, int64_t group_order, const i
     if (r.rep != expect || r.stab != stab) throw std::runtime_error("orbit program self-check failed");
     if (H.canon_mode && orbit_min_canon(P, s) != expect)
       throw std::runtime_error("orbit program self-check failed (canonical form)");
+    if (H.tor_mode == 2 && H.canon_k == H.canon_r && (H.canon_k == 4 || H.canon_k == 6)) {
+      const uint64_t got = H.canon_k == 6 ? orbit_min_torus_sq<6>(P, s) : orbit_min_torus_sq<4>(P, s);
+      if (got != expect) throw std::runtime_error("orbit program self-check failed (square-torus form)");
+    }
     if (H.tor_mode || H.chain_dihedral) {   // the forms underneath stay selectable (option "canon" = 1): check them as well
       OrbitProgram P1 = P;
       P1.tor_mode = 0;
@@ -569,6 +583,7 @@ OrbitProgram HostOrbitProgram::view() const {
   P.tor_mode = tor_mode; P.tor_rho_n = tor_rho_n; P.tor_tau_n = tor_tau_n; P.tor_div_r = tor_div_r;
   P.tor_lutm = tor_lutm.data();
   P.tor_luts = tor_luts.data();
+  P.tor_frow = tor_frow.data();
   P.tor_net_mask = tor_net_mask.data();
   P.tor_net_delta = tor_net_delta.data();
   return P;

@@ -34,6 +34,7 @@ struct HostOrbitProgram {
   int32_t tor_mode = 0, tor_rho_n = 0, tor_tau_n = 0, tor_div_r = 0;   // full-space-group canonical form of a torus
   std::vector<uint16_t> tor_lutm;
   std::vector<uint32_t> tor_luts;
+  std::vector<uint8_t> tor_frow;
   std::vector<uint64_t> tor_net_mask;
   std::vector<int32_t> tor_net_delta;
   OrbitProgram view() const;       // pointers into the host vectors
@@ -100,6 +101,7 @@ struct KernelParams {
   const uint32_t *pos;
   int64_t x_row_offset;
   // k_gather on several vectors at once: vector k of x / y starts batch_stride elements after vector k - 1
+  int32_t gather_walk;         // k_gather: 0 group-major warp-uniform walk (coalesced gathers), 1 every lane walks its own bits
   int32_t batch;               // 0 / 1: one vector; 4: four vectors per launch
   int64_t batch_stride;
   // k_rows (row traversal of bases with permutation symmetries): hash table over the representatives with the scaled

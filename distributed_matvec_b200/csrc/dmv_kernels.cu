@@ -115,8 +115,10 @@ __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int pro
     // full-space-group canonical form: delta-swap stages of rho / tau and the 16-bit pair table
     const size_t n_st = (size_t)(p.orbit.tor_rho_n + p.orbit.tor_tau_n);
     off += 8 * n_st + 4 * n_st;
-    off = align_up(off, 4);
-    off += 2 * ((size_t)1 << (2 * p.orbit.canon_k));
+    off = align_up(off, 16);                                    // bulk copies need 16-byte aligned destinations
+    off += 2 * ((size_t)1 << (2 * p.orbit.canon_k));            // tor_lutm
+    off += align_up((size_t)4 * p.orbit.canon_k << p.orbit.canon_k, 16);   // tor_frow
+    off += 16;                                                  // mbarrier of the bulk copies
     off = align_up(off, 8);
   } else if (proj == PROJ_GROUP && p.orbit.canon_mode != 0) {
     const size_t n_st = p.orbit.cc_n > 0 ? (size_t)p.orbit.cc_stages : 0;
@@ -136,6 +138,30 @@ __host__ __device__ inline SmemLayout smem_layout(const KernelParams &p, int pro
 template <typename T>
 __device__ __forceinline__ void stage(T *dst, const T *src, int count) {
   for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+}
+
+// Two global -> shared bulk copies through the TMA engine (cp.async.bulk; sizes multiples of 16, 16-byte aligned), issued
+// by one thread and awaited by the whole CTA on an mbarrier.  The source buffers are over-allocated to the padded size.
+__device__ __forceinline__ void bulk_stage2(void *dst0, const void *src0, uint32_t bytes0, void *dst1, const void *src1,
+                                            uint32_t bytes1, uint64_t *mbar) {
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes0 + bytes1) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(dst0)), "l"(src0), "r"(bytes0), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(dst1)), "l"(src1), "r"(bytes1), "r"(bar) : "memory");
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar) : "memory");
+  }
 }
 
 // Everything a CTA keeps in shared memory, set up once per CTA.
@@ -210,13 +236,17 @@ __device__ __forceinline__ Tables<CV> stage_tables(const KernelParams &p, unsign
     const int n_st = T.orbit.tor_rho_n + T.orbit.tor_tau_n;
     uint64_t *nm = reinterpret_cast<uint64_t *>(base);
     int32_t *nd = reinterpret_cast<int32_t *>(base + 8 * (size_t)n_st);
-    uint16_t *lm = reinterpret_cast<uint16_t *>(smem + align_up((size_t)(base - smem) + 12 * (size_t)n_st, 4));
+    uint16_t *lm = reinterpret_cast<uint16_t *>(smem + align_up((size_t)(base - smem) + 12 * (size_t)n_st, 16));
     stage(nm, p.orbit.tor_net_mask, n_st);
     stage(nd, p.orbit.tor_net_delta, n_st);
-    // the table is copied as 32-bit words (two entries each)
-    stage(reinterpret_cast<uint32_t *>(lm), reinterpret_cast<const uint32_t *>(p.orbit.tor_lutm),
-          1 << (2 * T.orbit.canon_k - 1));
-    T.orbit.tor_net_mask = nm; T.orbit.tor_net_delta = nd; T.orbit.tor_lutm = lm;
+    // the pair table (8 KB for k = 6) and the row table arrive as two TMA bulk copies (cp.async.bulk, one elected
+    // thread, completion on an mbarrier) instead of a strided loop of every thread
+    const uint32_t lut_bytes = 2u << (2 * T.orbit.canon_k);
+    const uint32_t frow_bytes = (uint32_t)align_up((size_t)4 * T.orbit.canon_k << T.orbit.canon_k, 16);
+    uint8_t *fr = reinterpret_cast<uint8_t *>(lm) + lut_bytes;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(fr + frow_bytes);
+    bulk_stage2(lm, p.orbit.tor_lutm, lut_bytes, fr, p.orbit.tor_frow, frow_bytes, mbar);
+    T.orbit.tor_net_mask = nm; T.orbit.tor_net_delta = nd; T.orbit.tor_lutm = lm; T.orbit.tor_frow = fr;
   } else if (PROJ == PROJ_GROUP && T.orbit.canon_mode != 0) {
     unsigned char *base = smem + L.canon;
     if (T.orbit.cc_n > 0) {
@@ -825,24 +855,30 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
 // pipelined: the slot of term j is requested right after its orbit minimum and consumed after the orbit minimum of
 // term j + 2, so its latency hides behind ~10^3 integer instructions of the same lane.
 // -------------------------------------------------------------------------------------------------
+// one bucket = two slots (layout: table_slot in dmv_device.cuh); all loads of a bucket are independent
 template <bool CE>
-__device__ __forceinline__ void slot_load(const unsigned char *__restrict__ table, uint32_t s, uint64_t &key,
-                                          typename ValT<CE>::type &val) {
+__device__ __forceinline__ void bucket_load(const unsigned char *__restrict__ table, uint32_t b, ulonglong2 &keys,
+                                            typename ValT<CE>::type &v0, typename ValT<CE>::type &v1) {
   if constexpr (CE) {
-    const unsigned char *q = table + (size_t)s * 32;
-    key = __ldg(reinterpret_cast<const uint64_t *>(q));
-    val = __ldg(reinterpret_cast<const double2 *>(q + 16));
+    const unsigned char *q = table + (size_t)b * 64;
+    keys = __ldg(reinterpret_cast<const ulonglong2 *>(q));
+    v0 = __ldg(reinterpret_cast<const double2 *>(q + 16));
+    v1 = __ldg(reinterpret_cast<const double2 *>(q + 32));
   } else {
-    const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(table + (size_t)s * 16));
-    key = t.x;
-    val = __longlong_as_double((long long)t.y);
+    const unsigned char *q = table + (size_t)b * 32;
+    keys = __ldg(reinterpret_cast<const ulonglong2 *>(q));
+    const double2 vv = __ldg(reinterpret_cast<const double2 *>(q + 16));
+    v0 = vv.x;
+    v1 = vv.y;
   }
 }
 __device__ __forceinline__ void axpy(double &acc, double c, double v) { acc = fma(c, v, acc); }
 __device__ __forceinline__ void axpy(double2 &acc, double c, double2 v) { acc.x = fma(c, v.x, acc.x); acc.y = fma(c, v.y, acc.y); }
 
+// two CTAs per SM: the pipeline state must stay in registers (a spilled request waits for its load at once), and the
+// latency is hidden inside the lane, not by occupancy
 template <bool CE, int TK>
-__global__ void __launch_bounds__(kThreads, 3) k_rows(const KernelParams p) {
+__global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
   using E = typename ValT<CE>::type;
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(p, PROJ_GROUP, sizeof(double), false);
@@ -853,10 +889,11 @@ __global__ void __launch_bounds__(kThreads, 3) k_rows(const KernelParams p) {
   const unsigned warp = threadIdx.x >> 5;
   const bool any_s_out = p.any_s_out != 0;
   const unsigned char *__restrict__ table = reinterpret_cast<const unsigned char *>(p.table);
-  const uint32_t n_slots = p.table_slots;
+  const uint32_t n_buckets = p.table_slots;
   const uint64_t *__restrict__ row_states = p.row_states ? p.row_states : p.index.reps;
   const double *__restrict__ row_norms = p.row_norms ? p.row_norms : p.norms;
   unsigned long long bad = 0, bad_state = 0;
+  const E zero = v_make(0.0, 0.0, (E *)nullptr);
 
   const int64_t n_rows = p.row_end - p.row_begin;
   const int64_t n_tiles = (n_rows + 31) / 32;
@@ -865,13 +902,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_rows(const KernelParams p) {
     const int64_t i = p.row_begin + tile * 32 + lane;
     const bool valid = i < p.row_end;
     const uint64_t b = valid ? __ldg(row_states + i) : 0ull;
-    E acc = v_make(0.0, 0.0, (E *)nullptr);
-    // two requests in flight per lane: (wanted key, coefficient, slot, loaded key, loaded value)
+    E acc = zero;
+    // two requests in flight per lane: wanted key, coefficient, bucket, and what the bucket held
     bool live0 = false, live1 = false;
-    uint64_t want0 = 0, want1 = 0, got0 = 0, got1 = 0;
+    uint64_t want0 = 0, want1 = 0;
     double c0 = 0.0, c1 = 0.0;
-    uint32_t s0 = 0, s1 = 0;
-    E v0 = v_make(0.0, 0.0, (E *)nullptr), v1 = v0;
+    uint32_t b0 = 0, b1 = 0;
+    ulonglong2 k0 = make_ulonglong2(0, 0), k1 = k0;
+    E v00 = zero, v01 = zero, v10 = zero, v11 = zero;
     int w = 0;
     RowTerms rt = row_terms<false>(T, 0, 0, min(64, p.n_groups), b);
     if (!valid) rt.mask = 0;
@@ -882,31 +920,38 @@ __global__ void __launch_bounds__(kThreads, 3) k_rows(const KernelParams p) {
       }
       const bool has = rt.mask != 0;
       if (!has && !live0 && !live1) break;
-      if (live1) {   // consume the older request
-        if (got1 != want1) {   // linear probing (load factor 1/2: rare) or a state outside the basis (DMV:115-118)
-          for (;;) {
-            if (got1 == kEmptyKey) {
-              if (c1 != 0.0) { ++bad; bad_state = want1; }
-              v1 = v_make(0.0, 0.0, (E *)nullptr);
-              break;
-            }
-            s1 = s1 + 1 == n_slots ? 0 : s1 + 1;
-            slot_load<CE>(table, s1, got1, v1);
-            if (got1 == want1) break;
-          }
+      // ---- consume the older request
+      bool retry = false;
+      if (live1) {
+        const bool hit0 = k1.x == want1, hit1 = k1.y == want1;
+        if (hit0 | hit1) {
+          axpy(acc, c1, hit0 ? v10 : v11);
+        } else if (k1.x == kEmptyKey || k1.y == kEmptyKey) {   // a free slot in the bucket: the state is not in the basis
+          if (c1 != 0.0) { ++bad; bad_state = want1; }         // DMV:115-118
+        } else {
+          retry = true;                                        // both slots taken by other states: next bucket
         }
-        axpy(acc, c1, v1);
       }
-      live1 = live0; want1 = want0; got1 = got0; c1 = c0; s1 = s0; v1 = v0;
-      live0 = has;
-      if (has) {
+      const uint64_t want_r = want1;
+      const double c_r = c1;
+      const uint32_t b_r = b1 + 1 == n_buckets ? 0 : b1 + 1;
+      live1 = live0; want1 = want0; c1 = c0; b1 = b0; k1 = k0; v10 = v00; v11 = v01;
+      // ---- issue a new request: the continuation of a missed one, else the next term of the row
+      if (retry) {
+        want0 = want_r; c0 = c_r; b0 = b_r;
+        bucket_load<CE>(table, b0, k0, v00, v01);
+        live0 = true;
+      } else if (has) {
         uint64_t flip;
         c0 = pop_term<false>(T, rt, 64 * w, b, any_s_out, flip);
         const uint64_t raw = b ^ flip;
         if constexpr (TK > 0) want0 = orbit_min_torus_sq<TK>(orbit, raw);
         else want0 = orbit_representative(orbit, raw);
-        s0 = table_slot(want0, n_slots);
-        slot_load<CE>(table, s0, got0, v0);
+        b0 = table_slot(want0, n_buckets);
+        bucket_load<CE>(table, b0, k0, v00, v01);
+        live0 = true;
+      } else {
+        live0 = false;
       }
     }
     if (valid) {
@@ -929,22 +974,29 @@ __global__ void __launch_bounds__(kThreads, 3) k_rows(const KernelParams p) {
   }
 }
 
-// hash table set-up: claim a slot per state (keys pre-set to kEmptyKey), remember it in slot_of
-__global__ void k_table_insert(const uint64_t *__restrict__ reps, int64_t n, unsigned char *table, uint32_t n_slots,
-                               int slot_bytes, uint32_t *slot_of) {
+// hash table set-up: claim a slot per state (keys pre-set to kEmptyKey; slot 0 of a bucket before slot 1, then the
+// next bucket), remember it in slot_of (= 2 bucket + slot)
+__global__ void k_table_insert(const uint64_t *__restrict__ reps, int64_t n, unsigned char *table, uint32_t n_buckets,
+                               int bucket_bytes, uint32_t *slot_of) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t key = reps[i];
-  uint32_t s = table_slot(key, n_slots);
+  uint32_t b = table_slot(key, n_buckets);
   for (;;) {
-    unsigned long long *q = reinterpret_cast<unsigned long long *>(table + (size_t)s * slot_bytes);
-    if (atomicCAS(q, (unsigned long long)kEmptyKey, (unsigned long long)key) == (unsigned long long)kEmptyKey) break;
-    s = s + 1 == n_slots ? 0 : s + 1;
+    unsigned long long *q = reinterpret_cast<unsigned long long *>(table + (size_t)b * bucket_bytes);
+    if (atomicCAS(q, (unsigned long long)kEmptyKey, (unsigned long long)key) == (unsigned long long)kEmptyKey) {
+      slot_of[i] = 2 * b;
+      return;
+    }
+    if (atomicCAS(q + 1, (unsigned long long)kEmptyKey, (unsigned long long)key) == (unsigned long long)kEmptyKey) {
+      slot_of[i] = 2 * b + 1;
+      return;
+    }
+    b = b + 1 == n_buckets ? 0 : b + 1;
   }
-  slot_of[i] = s;
 }
 
-// per product: table[slot_of[i]] = x[src(i)] * norm[i]   (src(i) = pos ? pos[i] : i)
+// per product: value of slot_of[i] = x[src(i)] * norm[i]   (src(i) = pos ? pos[i] : i)
 template <bool CE>
 __global__ void k_table_fill(int64_t n, const void *__restrict__ x, const double *__restrict__ norms,
                              const uint32_t *__restrict__ pos, const uint32_t *__restrict__ slot_of,
@@ -956,9 +1008,10 @@ __global__ void k_table_fill(int64_t n, const void *__restrict__ x, const double
     const uint32_t s = __ldg(slot_of + i);
     if constexpr (CE) {
       const double2 v = __ldg(reinterpret_cast<const double2 *>(x) + src);
-      *reinterpret_cast<double2 *>(table + (size_t)s * 32 + 16) = make_double2(v.x * nrm, v.y * nrm);
+      *reinterpret_cast<double2 *>(table + (size_t)(s >> 1) * 64 + 16 + 16 * (s & 1)) = make_double2(v.x * nrm, v.y * nrm);
     } else {
-      *reinterpret_cast<double *>(table + (size_t)s * 16 + 8) = __ldg(reinterpret_cast<const double *>(x) + src) * nrm;
+      *reinterpret_cast<double *>(table + (size_t)(s >> 1) * 32 + 16 + 8 * (s & 1)) =
+          __ldg(reinterpret_cast<const double *>(x) + src) * nrm;
     }
   }
 }
@@ -1307,11 +1360,11 @@ void launch_rows(const KernelParams &p, bool complex_elements, cudaStream_t stre
   else launch_rows_e<false>(p, stream);
 }
 
-void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t n_slots, int slot_bytes,
+void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t n_buckets, int bucket_bytes,
                          uint32_t *slot_of, cudaStream_t stream) {
   if (n <= 0) return;
   k_table_insert<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reps, n, reinterpret_cast<unsigned char *>(table),
-                                                                 n_slots, slot_bytes, slot_of);
+                                                                 n_buckets, bucket_bytes, slot_of);
   DMV_CUDA_CHECK(cudaGetLastError());
   g_launches++;
 }

@@ -24,6 +24,8 @@ def main():
         t0.record(); op.basis.build(); t1.record(); torch.cuda.synchronize()
         n = op.basis.numberStates()
         op.use_torch_stream()
+        if os.environ.get("DMV_GATHER_WALK"):
+            op.set_option("gather_walk", int(os.environ["DMV_GATHER_WALK"]))
         op.set_option("mode", 0)
         nnz = int(op.plan().sum())
         print(f"== {name}: N={n} nnz={nnz} build {t0.elapsed_time(t1):.1f} ms "
