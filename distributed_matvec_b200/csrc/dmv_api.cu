@@ -393,6 +393,34 @@ struct dmv_context {
   DevBuf<unsigned *> d_peer_flags;          // [num_ranks]
   int peer_slot_elt = 0;                    // element width the slot pointers were computed for
   unsigned gather_epoch = 0;
+  // record exchange in overlapped ROUNDS (peer-direct records; reference DMV:638-661, 818-852, 957-1011): the rows are cut
+  // into R rounds; round r's records land in the owners' buffers while round r + 1 is being generated, and the owner
+  // accumulates round r on a second stream as soon as every sender has raised its flag for it
+  struct Rounds {
+    bool ready = false, tried = false;
+    int R = 0, grid = 0, row_split = 1;
+    std::vector<int64_t> row_begin;           // [R + 1]
+    DevBuf<int64_t> d_warp_offsets;           // [R][warps][P]: first slot of every warp inside MY region of (round, dest)
+    DevBuf<int64_t> d_capacity;               // [R][P]
+    std::vector<int64_t> in_slice;            // [R + 1]: rounds inside my incoming buffer (records)
+    std::vector<int64_t> my_off;              // [R][P]: my region of round r inside rank q's incoming buffer
+    int64_t in_total = 0;
+    std::vector<int64_t> peer_total;          // [P]: in_total of every rank (start of its second buffer)
+    DevBuf<uint64_t> d_in_betas;              // two buffers (alternating products) of in_total records
+    DevBuf<double> d_in_coeffs;               // two doubles per record
+    std::vector<void *> peer_betas, peer_coeffs, peer_flags;
+    DevBuf<unsigned> d_flags;                 // [P] raised by the senders: product * R + round + 1
+    DevBuf<unsigned *> d_peer_flags;
+    DevBuf<uint64_t *> d_bptr;                // [2][R][P]
+    DevBuf<double *> d_cptr;
+    int ptr_width = 0;
+    unsigned seq = 0;
+    cudaStream_t acc_stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
+    int64_t terms = 0;
+  } rounds;
+  int opt_rounds = -1;                        // -1 auto, 0 / 1 off (generate everything, fence, accumulate), R > 1
+
   // Lanczos work space (dmv_lanczos)
   DevBuf<double> lz_v[4];
   DevBuf<double> lz_scal;
@@ -402,6 +430,12 @@ struct dmv_context {
     for (void *q : peer_betas) if (q) cudaIpcCloseMemHandle(q);
     for (void *q : peer_coeffs) if (q) cudaIpcCloseMemHandle(q);
     for (void *q : peer_xcat) if (q) cudaIpcCloseMemHandle(q);
+    for (void *q : rounds.peer_betas) if (q) cudaIpcCloseMemHandle(q);
+    for (void *q : rounds.peer_coeffs) if (q) cudaIpcCloseMemHandle(q);
+    for (void *q : rounds.peer_flags) if (q) cudaIpcCloseMemHandle(q);
+    if (rounds.acc_stream) cudaStreamDestroy(rounds.acc_stream);
+    if (rounds.ev_begin) cudaEventDestroy(rounds.ev_begin);
+    if (rounds.ev_done) cudaEventDestroy(rounds.ev_done);
     for (void *q : peer_flagmem) if (q) cudaIpcCloseMemHandle(q);
     if (comm) nccl().CommDestroy(comm);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
@@ -665,6 +699,10 @@ void install_directory(dmv_context *ctx) {
   ctx->peer_gather = false;
   ctx->peer_slot_elt = 0;
   ctx->d_xcat.release();
+  for (auto *v : {&ctx->rounds.peer_betas, &ctx->rounds.peer_coeffs, &ctx->rounds.peer_flags})
+    for (auto &q : *v) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+  ctx->rounds.ready = false;
+  ctx->rounds.tried = false;
   std::fill(ctx->recv_counts.begin(), ctx->recv_counts.end(), -1);
   select_index_mode(ctx);
 }
@@ -1203,6 +1241,212 @@ void replicated_rows(dmv_context *ctx, int elt, const void *x_cat, void *y_dev) 
   launch_pull(p, g->proj, complex_values(g, elt), elt == DMV_C128, ctx->stream);
 }
 
+// Collective set-up of the overlapped record exchange: per-round counting passes, exchange of the counts, incoming
+// buffers laid out round-major, CUDA IPC mapping of buffers and flags.  Leaves rounds.ready false when it does not apply
+// (one round, IPC impossible): the caller then uses the one-shot exchange.
+void setup_rounds(dmv_context *ctx) {
+  dmv_context::Rounds &Q = ctx->rounds;
+  NcclApi &N = nccl();
+  const int P = ctx->num_ranks;
+  Q.tried = true;
+  Q.ready = false;
+  int R = ctx->opt_rounds;
+  if (R < 0) R = ctx->n_states >= (1 << 18) ? 4 : 1;
+  // every rank must use the same number of rounds
+  ctx->d_barrier.alloc(1);
+  CUDA_CHECK(cudaMemcpyAsync(ctx->d_barrier.ptr, &R, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_CHECK(N.AllReduce(ctx->d_barrier.ptr, ctx->d_barrier.ptr, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(&R, ctx->d_barrier.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (R <= 1 || P > 32 || ctx->opt_exchange == 0) return;
+  Q.R = R;
+  Q.row_split = 1;
+  Q.row_begin.assign(R + 1, 0);
+  for (int r = 0; r <= R; ++r) Q.row_begin[r] = std::min<int64_t>(ctx->n_states, (ctx->n_states * r / R + 31) / 32 * 32);
+  Q.row_begin[R] = ctx->n_states;
+  Q.grid = planned_grid((ctx->n_states + R - 1) / R, 1);
+  const size_t n_warps = (size_t)Q.grid * kWarpsPerCta;
+  // ---- counting pass per round: exact share of every warp for every destination
+  std::vector<int64_t> offsets((size_t)R * n_warps * P, 0), counts((size_t)R * P, 0);
+  ctx->d_warp_counts.alloc(n_warps * P);
+  ctx->d_out_count.alloc(P);
+  std::vector<unsigned long long> wc(n_warps * P);
+  Q.terms = 0;
+  for (int r = 0; r < R; ++r) {
+    CUDA_CHECK(cudaMemsetAsync(ctx->d_warp_counts.ptr, 0, sizeof(unsigned long long) * n_warps * P, ctx->stream));
+    KernelParams p = base_params(ctx);
+    p.grid_blocks = Q.grid;
+    p.row_split = 1;
+    p.row_begin = Q.row_begin[r];
+    p.row_end = Q.row_begin[r + 1];
+    p.warp_counts = ctx->d_warp_counts.ptr;
+    select_tables(ctx, p, false, ctx->complex_coefficients);
+    launch_generate(p, ctx->proj, ctx->complex_coefficients, false, /*count_only=*/true, ctx->stream);
+    CUDA_CHECK(cudaMemcpyAsync(wc.data(), ctx->d_warp_counts.ptr, sizeof(unsigned long long) * wc.size(),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int d = 0; d < P; ++d)
+      for (size_t w = 0; w < n_warps; ++w) {
+        offsets[((size_t)r * n_warps + w) * P + d] = counts[(size_t)r * P + d];
+        counts[(size_t)r * P + d] += (int64_t)wc[w * P + d];
+      }
+    for (int d = 0; d < P; ++d) Q.terms += counts[(size_t)r * P + d];
+  }
+  Q.d_warp_offsets.upload(offsets, ctx->stream);
+  if (!ctx->planned) ctx->number_terms = Q.terms;
+  std::vector<int64_t> capacity((size_t)R * P);
+  for (int r = 0; r < R; ++r)
+    for (int d = 0; d < P; ++d) capacity[(size_t)r * P + d] = d == ctx->rank ? 0 : counts[(size_t)r * P + d];
+  Q.d_capacity.upload(capacity, ctx->stream);
+  // ---- everybody's counts: all[s][r][d]
+  DevBuf<int64_t> d_send, d_all;
+  d_send.upload(counts, ctx->stream);
+  d_all.alloc((size_t)P * R * P);
+  NCCL_CHECK(N.AllGather(d_send.ptr, d_all.ptr, (size_t)R * P, ncclInt64, ctx->comm, ctx->stream));
+  std::vector<int64_t> all((size_t)P * R * P);
+  CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.ptr, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  auto cnt = [&](int s, int r, int d) { return all[((size_t)s * R + r) * P + d]; };
+  // incoming buffer of rank q, round-major: [round 0: sources 0 .. P-1 (without q)] [round 1: ...] ...
+  auto region = [&](int q, int r, int src) {   // first record of (round r, source src) inside q's buffer
+    int64_t off = 0;
+    for (int rr = 0; rr < r; ++rr)
+      for (int s = 0; s < P; ++s) if (s != q) off += cnt(s, rr, q);
+    for (int s = 0; s < src; ++s) if (s != q) off += cnt(s, r, q);
+    return off;
+  };
+  Q.in_slice.assign(R + 1, 0);
+  for (int r = 0; r <= R; ++r) Q.in_slice[r] = region(ctx->rank, r, 0);
+  Q.in_total = Q.in_slice[R];
+  Q.peer_total.assign(P, 0);
+  for (int q = 0; q < P; ++q) Q.peer_total[q] = region(q, R, 0);
+  Q.my_off.assign((size_t)R * P, 0);
+  for (int r = 0; r < R; ++r)
+    for (int q = 0; q < P; ++q) if (q != ctx->rank) Q.my_off[(size_t)r * P + q] = region(q, r, ctx->rank);
+  Q.d_in_betas.alloc((size_t)std::max<int64_t>(1, 2 * Q.in_total));
+  Q.d_in_coeffs.alloc((size_t)std::max<int64_t>(1, 4 * Q.in_total));
+  Q.d_flags.alloc(P);
+  CUDA_CHECK(cudaMemsetAsync(Q.d_flags.ptr, 0, sizeof(unsigned) * P, ctx->stream));
+  Q.seq = 0;
+  // ---- map the peers' buffers and flags
+  for (auto *v : {&Q.peer_betas, &Q.peer_coeffs, &Q.peer_flags})
+    for (auto &q : *v) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+  struct Handles { cudaIpcMemHandle_t betas, coeffs, flags; int ok; int pad[15]; };
+  static_assert(sizeof(Handles) % 8 == 0, "handle block");
+  Handles mine{};
+  mine.ok = (cudaIpcGetMemHandle(&mine.betas, Q.d_in_betas.ptr) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine.coeffs, Q.d_in_coeffs.ptr) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine.flags, Q.d_flags.ptr) == cudaSuccess) ? 1 : 0;
+  cudaGetLastError();
+  DevBuf<char> d_mine, d_handles;
+  d_mine.alloc(sizeof(Handles));
+  d_handles.alloc(sizeof(Handles) * P);
+  CUDA_CHECK(cudaMemcpyAsync(d_mine.ptr, &mine, sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_CHECK(N.AllGather(d_mine.ptr, d_handles.ptr, sizeof(Handles), ncclChar, ctx->comm, ctx->stream));
+  std::vector<Handles> handles(P);
+  CUDA_CHECK(cudaMemcpyAsync(handles.data(), d_handles.ptr, sizeof(Handles) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  int ok = 1;
+  for (int q = 0; q < P; ++q) ok &= handles[q].ok;
+  Q.peer_betas.assign(P, nullptr); Q.peer_coeffs.assign(P, nullptr); Q.peer_flags.assign(P, nullptr);
+  for (int q = 0; q < P && ok; ++q) {
+    if (q == ctx->rank) continue;
+    if (cudaIpcOpenMemHandle(&Q.peer_betas[q], handles[q].betas, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&Q.peer_coeffs[q], handles[q].coeffs, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&Q.peer_flags[q], handles[q].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      ok = 0;
+      cudaGetLastError();
+    }
+  }
+  int agree = ok;
+  CUDA_CHECK(cudaMemcpyAsync(ctx->d_barrier.ptr, &agree, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_CHECK(N.AllReduce(ctx->d_barrier.ptr, ctx->d_barrier.ptr, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(&agree, ctx->d_barrier.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (!agree) {
+    for (auto *v : {&Q.peer_betas, &Q.peer_coeffs, &Q.peer_flags})
+      for (auto &q : *v) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    return;
+  }
+  std::vector<unsigned *> flags(P);
+  for (int q = 0; q < P; ++q) flags[q] = q == ctx->rank ? Q.d_flags.ptr : reinterpret_cast<unsigned *>(Q.peer_flags[q]);
+  Q.d_peer_flags.upload(flags, ctx->stream);
+  if (!Q.acc_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&Q.acc_stream, cudaStreamNonBlocking));
+  if (!Q.ev_begin) CUDA_CHECK(cudaEventCreateWithFlags(&Q.ev_begin, cudaEventDisableTiming));
+  if (!Q.ev_done) CUDA_CHECK(cudaEventCreateWithFlags(&Q.ev_done, cudaEventDisableTiming));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  Q.ptr_width = 0;
+  Q.ready = true;
+}
+
+// where my records of (buffer, round, destination) go: [2][R][P] pointers into the peers' incoming buffers
+void upload_round_pointers(dmv_context *ctx, int width) {
+  dmv_context::Rounds &Q = ctx->rounds;
+  const int P = ctx->num_ranks, R = Q.R;
+  std::vector<uint64_t *> bp((size_t)2 * R * P, nullptr);
+  std::vector<double *> cp((size_t)2 * R * P, nullptr);
+  for (int b = 0; b < 2; ++b)
+    for (int r = 0; r < R; ++r)
+      for (int q = 0; q < P; ++q) {
+        if (q == ctx->rank) continue;
+        const int64_t first = (int64_t)b * Q.peer_total[q] + Q.my_off[(size_t)r * P + q];
+        bp[((size_t)b * R + r) * P + q] = reinterpret_cast<uint64_t *>(Q.peer_betas[q]) + first;
+        cp[((size_t)b * R + r) * P + q] = reinterpret_cast<double *>(Q.peer_coeffs[q]) + first * width;
+      }
+  Q.d_bptr.upload(bp, ctx->stream);
+  Q.d_cptr.upload(cp, ctx->stream);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  Q.ptr_width = width;
+}
+
+// One product through the overlapped rounds (x, y device pointers).  Main stream: generate round 0, raise flags,
+// generate round 1, ...; second stream: wait for every sender's flag of round r, accumulate its slice.  Returns with the
+// main stream waiting for the last accumulate.
+void rounds_product(dmv_context *ctx, int elt, const void *x_dev, void *y_dev) {
+  dmv_context::Rounds &Q = ctx->rounds;
+  const int P = ctx->num_ranks, R = Q.R;
+  const bool cv = complex_values(ctx, elt);
+  const int width = cv ? 2 : 1;
+  if (Q.ptr_width != width) upload_round_pointers(ctx, width);
+  ctx->record_width = width;
+  zero_y_if_diag(ctx, elt, y_dev);
+  CUDA_CHECK(cudaEventRecord(Q.ev_begin, ctx->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(Q.acc_stream, Q.ev_begin, 0));
+  const int b = (int)(Q.seq & 1u);
+  const size_t n_warps = (size_t)Q.grid * kWarpsPerCta;
+  for (int r = 0; r < R; ++r) {
+    KernelParams p = base_params(ctx);
+    p.x = x_dev;
+    p.y = y_dev;
+    p.grid_blocks = Q.grid;
+    p.row_split = 1;
+    p.row_begin = Q.row_begin[r];
+    p.row_end = Q.row_begin[r + 1];
+    p.warp_offsets = Q.d_warp_offsets.ptr + (size_t)r * n_warps * P;
+    p.out_capacity = Q.d_capacity.ptr + (size_t)r * P;
+    p.out_betas_ptr = Q.d_bptr.ptr + ((size_t)b * R + r) * P;
+    p.out_coeffs_ptr = Q.d_cptr.ptr + ((size_t)b * R + r) * P;
+    select_tables(ctx, p, false, cv);
+    launch_generate(p, ctx->proj, cv, elt == DMV_C128, false, ctx->stream);
+    const unsigned value = Q.seq * (unsigned)R + (unsigned)r + 1u;
+    launch_raise_flags(Q.d_peer_flags.ptr, P, ctx->rank, value, ctx->stream);
+    // owner side, second stream: every sender has delivered round r -> search + accumulate its slice
+    launch_wait_flags(Q.d_flags.ptr, P, value, ctx->d_status.ptr, Q.acc_stream);
+    const int64_t first = (int64_t)b * Q.in_total + Q.in_slice[r], count = Q.in_slice[r + 1] - Q.in_slice[r];
+    if (count > 0) {
+      KernelParams pa = base_params(ctx);
+      pa.y = y_dev;
+      launch_accumulate(pa, ctx->proj, cv, elt == DMV_C128, count, Q.d_in_betas.ptr + first,
+                        Q.d_in_coeffs.ptr + first * width, Q.acc_stream);
+    }
+  }
+  ++Q.seq;
+  CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));   // end of generation
+  CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  CUDA_CHECK(cudaEventRecord(Q.ev_done, Q.acc_stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, Q.ev_done, 0));   // what is left of the accumulate is the exposed part
+}
+
 // Collective: map every rank's gathered-x buffers and flag words into every other rank (CUDA IPC over NVLink) so that
 // the all-gather of x becomes one kernel of peer stores + flags (launch_push_block).  Falls back to the NCCL all-gather
 // when any rank cannot map.
@@ -1596,9 +1840,16 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
     ctx->planned = false;
     ctx->exchange_decided = false;
     ctx->replicated = false;
+    ctx->rounds.tried = false;
+    ctx->rounds.ready = false;
   } else if (key == "gather") {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
+  } else if (key == "rounds") {
+    if (value < -1 || value > 64) throw std::runtime_error("rounds: -1 auto, 0 / 1 one-shot exchange, R <= 64 overlapped rounds");
+    ctx->opt_rounds = (int)value;
+    ctx->rounds.tried = false;
+    ctx->rounds.ready = false;
   } else if (key == "gather_walk") {
     ctx->opt_gather_walk = value != 0;
     if (ctx->global) ctx->global->opt_gather_walk = ctx->opt_gather_walk;
@@ -1645,6 +1896,7 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
     return ((use_pull(ctx) && !use_gather(ctx) && use_rows(ctx)) ||
             (ctx->replicated && ctx->global && !use_gather(ctx->global) && use_rows(ctx->global))) ? 1 : 0;
   if (key == "rows_ok") return ctx->rows_ok ? 1 : 0;
+  if (key == "rounds") return ctx->rounds.ready ? ctx->rounds.R : 0;
   if (key == "peer_gather") return (ctx->replicated && ctx->peer_gather) ? 1 : 0;
   if (key == "complex_coefficients") return ctx->complex_coefficients ? 1 : 0;
   if (key == "canon_k") return ctx->host_orbit.canon_k;
@@ -1984,6 +2236,21 @@ int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
     return 0;
   }
   ctx->timeline_replicated = false;
+  if (!ctx->rounds.tried) setup_rounds(ctx);
+  if (ctx->rounds.ready) {
+    // ---- record exchange in overlapped rounds (peer-direct NVLink stores + per-round flags)
+    VecStage v = stage_vectors(ctx, elt, x, y);
+    if (v.x_host_pending) {   // (single-rank pipelining of the upload does not apply here)
+      CUDA_CHECK(cudaMemcpyAsync(ctx->d_x.ptr, v.x_host_pending, v.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rounds_product(ctx, elt, v.x_dev, v.y_dev);
+    finish_vectors(ctx, v);
+    if (v.y_host || !is_device_pointer(x)) {
+      check_status(ctx);
+      collect_timings(ctx);
+    }
+    return 0;
+  }
   if (!ctx->planned) do_plan(ctx);
   if (ctx->recv_counts[0] < 0) setup_exchange(ctx);
   auto barrier = [&]() {

@@ -178,57 +178,64 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
       mask &= slice_mask;
       if (!valid) mask = 0;
       const int g_base = 64 * w;
-      // one pair of terms (groups g0, g1 of this word; `two`: g1 is a second term; on0 / on1: this lane emits them):
-      // both index look-ups, then both gathers, are in flight together
-      auto pair = [&](int g0, int g1, bool on0, bool on1) {
-        W k0 = b ^ s_gx[g_base + g0], k1 = b ^ s_gx[g_base + g1];
-        double s0 = 1.0, s1 = 1.0;
-        if (INV) {   // reference src/BatchedOperator.chpl:145-152
-          const W f0 = k0 ^ site, f1 = k1 ^ site;
-          if (f0 < k0) { k0 = f0; s0 = p.inversion_character; }
-          if (f1 < k1) { k1 = f1; s1 = p.inversion_character; }
-        }
-        uint32_t i0 = kNone, i1 = kNone;
-        if (LIN) {
-          if (on0) i0 = lin_index<W>(lin_a, lin_b, lin_bits, lo_mask, weight, n_states, k0);
-          if (on1) i1 = lin_index<W>(lin_a, lin_b, lin_bits, lo_mask, weight, n_states, k1);
-        } else {
-          if (on0) i0 = (uint32_t)locate(p.index, (uint64_t)k0);   // -1 -> kNone
-          if (on1) i1 = (uint32_t)locate(p.index, (uint64_t)k1);
-        }
-        V c0, c1;
-        if (UNI) { c0 = uni; c1 = uni; }
-        else {
-          c0 = s_lut[4 * (g_base + g0) + ((unsigned)((a0 >> g0) & 1) | ((unsigned)((a1 >> g0) & 1) << 1))];
-          c1 = s_lut[4 * (g_base + g1) + ((unsigned)((a0 >> g1) & 1) | ((unsigned)((a1 >> g1) & 1) << 1))];
-        }
-        if (pos) {
-          if (i0 != kNone) i0 = __ldg(pos + i0);
-          if (i1 != kNone) i1 = __ldg(pos + i1);
-        }
-        E x0[KB], x1[KB];
+      // NB terms per trip (groups g[j] of this word; on[j]: this lane emits them): all index look-ups, then all
+      // gathers, are in flight together
+      auto batch = [&](auto nb, const int *g, const bool *on) {
+        constexpr int NB = decltype(nb)::value;
+        W key[NB];
+        double sg[NB];
+        uint32_t idx[NB];
+        V c[NB];
 #pragma unroll
-        for (int k = 0; k < KB; ++k) {
-          x0[k] = zero_of((E *)nullptr);
-          x1[k] = zero_of((E *)nullptr);
-          if (i0 != kNone) x0[k] = ldx(xv + (int64_t)k * p.batch_stride, i0);
-          if (i1 != kNone) x1[k] = ldx(xv + (int64_t)k * p.batch_stride, i1);
+        for (int j = 0; j < NB; ++j) {
+          key[j] = b ^ s_gx[g_base + g[j]];
+          sg[j] = 1.0;
+          if (INV) {   // reference src/BatchedOperator.chpl:145-152
+            const W f = key[j] ^ site;
+            if (f < key[j]) { key[j] = f; sg[j] = p.inversion_character; }
+          }
         }
-        if (INV) { c0 = scale(c0, s0); c1 = scale(c1, s1); }
 #pragma unroll
-        for (int k = 0; k < KB; ++k) {
-          if (on0) fma_to(acc[k], c0, x0[k]);
-          if (on1) fma_to(acc[k], c1, x1[k]);
+        for (int j = 0; j < NB; ++j) {
+          idx[j] = kNone;
+          if (on[j]) {
+            if (LIN) idx[j] = lin_index<W>(lin_a, lin_b, lin_bits, lo_mask, weight, n_states, key[j]);
+            else idx[j] = (uint32_t)locate(p.index, (uint64_t)key[j]);   // -1 -> kNone
+          }
         }
-        if ((on0 & (i0 == kNone)) | (on1 & (i1 == kNone))) {   // DMV:115-118 (rare)
-          if (on0 && i0 == kNone && nonzero(c0)) { ++bad; bad_state = (unsigned long long)k0; }
-          if (on1 && i1 == kNone && nonzero(c1)) { ++bad; bad_state = (unsigned long long)k1; }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          if (UNI) c[j] = uni;
+          else c[j] = s_lut[4 * (g_base + g[j]) + ((unsigned)((a0 >> g[j]) & 1) | ((unsigned)((a1 >> g[j]) & 1) << 1))];
+          if (pos && idx[j] != kNone) idx[j] = __ldg(pos + idx[j]);
+        }
+        E xs[NB][KB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+#pragma unroll
+          for (int k = 0; k < KB; ++k) {
+            xs[j][k] = zero_of((E *)nullptr);
+            if (idx[j] != kNone) xs[j][k] = ldx(xv + (int64_t)k * p.batch_stride, idx[j]);
+          }
+        bool miss = false;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          if (INV) c[j] = scale(c[j], sg[j]);
+#pragma unroll
+          for (int k = 0; k < KB; ++k)
+            if (on[j]) fma_to(acc[k], c[j], xs[j][k]);
+          miss |= on[j] & (idx[j] == kNone);
+        }
+        if (miss) {   // DMV:115-118 (rare)
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+            if (on[j] && idx[j] == kNone && nonzero(c[j])) { ++bad; bad_state = (unsigned long long)key[j]; }
         }
       };
       if (S == 1 && p.gather_walk == 0) {
-        // GROUP-MAJOR walk, warp-uniform: all 32 lanes handle the same group at the same time.  For a fixed flip mask
-        // consecutive rows map to (nearly) consecutive indices, so the 32 gathers of a group fall into a few 128-byte
-        // lines instead of 32 (the per-lane walk has every lane on a different group at any instant).
+        // GROUP-MAJOR walk, warp-uniform, four groups per trip: all 32 lanes handle the same group at the same time.
+        // For a fixed flip mask consecutive rows map to (nearly) consecutive indices, so the 32 gathers of a group fall
+        // into a few 128-byte lines instead of 32 (the per-lane walk has every lane on a different group at any instant).
         W any;
         if constexpr (sizeof(W) == 4) any = __reduce_or_sync(0xffffffffu, mask);
         else {
@@ -237,21 +244,28 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
           any = (W)(((uint64_t)hi << 32) | lo);
         }
         while (any) {
-          const int g0 = ffs_w(any) - 1;
-          any &= any - 1;
-          const bool two = any != 0;
-          const int g1 = two ? ffs_w(any) - 1 : g0;
-          any &= any - 1;   // no-op when already empty
-          pair(g0, g1, (mask >> g0) & 1, two && ((mask >> g1) & 1));
+          int g[4];
+          bool on[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool more = any != 0;
+            g[j] = more ? ffs_w(any) - 1 : g[0];
+            any &= any - 1;   // no-op when already empty
+            on[j] = more && ((mask >> g[j]) & 1);
+          }
+          batch(std::integral_constant<int, 4>{}, g, on);
         }
       } else {
-        while (mask) {   // lanes of one row share it: every lane walks its own slice of the groups
-          const int g0 = ffs_w(mask) - 1;
+        while (mask) {   // every lane walks its own bits (S > 1: its own slice of the groups), two per trip
+          int g[2];
+          bool on[2];
+          g[0] = ffs_w(mask) - 1;
           mask &= mask - 1;
-          const bool two = mask != 0;
-          const int g1 = two ? ffs_w(mask) - 1 : g0;
+          on[0] = true;
+          on[1] = mask != 0;
+          g[1] = on[1] ? ffs_w(mask) - 1 : g[0];
           mask &= mask - 1;   // no-op when mask is already empty
-          pair(g0, g1, true, two);
+          batch(std::integral_constant<int, 2>{}, g, on);
         }
       }
     }
@@ -478,6 +492,22 @@ __global__ void k_wait_flags(const unsigned *flags, int num_ranks, unsigned epoc
       __nanosleep(200);
     }
   }
+}
+
+// raise my flag in every rank to `value` (after everything this stream has stored into the peers before)
+__global__ void k_raise_flags(unsigned *const *__restrict__ peer_flags, int num_ranks, int rank, unsigned value) {
+  const int q = threadIdx.x;
+  if (q < num_ranks) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[q] + rank), "r"(value) : "memory");
+  }
+}
+
+void launch_raise_flags(unsigned *const *peer_flags, int num_ranks, int rank, unsigned value, cudaStream_t stream) {
+  k_raise_flags<<<1, 32, 0, stream>>>(peer_flags, num_ranks, rank, value);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_raise_flags launch: ") + cudaGetErrorString(e));
+  count_launch();
 }
 
 void launch_push_block(const void *x, int64_t n_doubles, int num_ranks, void *const *peer_slot, unsigned *done,

@@ -163,6 +163,7 @@ void launch_permute(int64_t n, int elt, const uint32_t *pos, const void *in, voi
 // NVLink, then my flag in every peer; the consumer waits for all flags of the epoch
 void launch_push_block(const void *x, int64_t n_doubles, int num_ranks, void *const *peer_slot, unsigned *done,
                        unsigned *const *peer_flags, int rank, unsigned epoch, bool wide, cudaStream_t stream);
+void launch_raise_flags(unsigned *const *peer_flags, int num_ranks, int rank, unsigned value, cudaStream_t stream);
 void launch_wait_flags(const unsigned *flags, int num_ranks, unsigned epoch, unsigned long long *status,
                        cudaStream_t stream);
 // Lanczos vector kernels (dmv_solver.cu); n = elements, words = 8-byte words

@@ -853,7 +853,8 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
 // orbit minimum in registers (canonical form, dmv_device.cuh), then ONE dependent memory access -- the slot of the
 // representative in a hash table that carries the scaled vector element (table_slot) -- and that access is software
 // pipelined: the slot of term j is requested right after its orbit minimum and consumed after the orbit minimum of
-// term j + 2, so its latency hides behind ~10^3 integer instructions of the same lane.
+// term j + 4 (prefetch into L2 first, registers only for the last step), so its latency -- DRAM plus address translation
+// over a table of gigabytes -- hides behind ~10^3 integer instructions of the same lane.
 // -------------------------------------------------------------------------------------------------
 // one bucket = two slots (layout: table_slot in dmv_device.cuh); all loads of a bucket are independent
 template <bool CE>
@@ -903,13 +904,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
     const bool valid = i < p.row_end;
     const uint64_t b = valid ? __ldg(row_states + i) : 0ull;
     E acc = zero;
-    // two requests in flight per lane: wanted key, coefficient, bucket, and what the bucket held
-    bool live0 = false, live1 = false;
-    uint64_t want0 = 0, want1 = 0;
-    double c0 = 0.0, c1 = 0.0;
-    uint32_t b0 = 0, b1 = 0;
-    ulonglong2 k0 = make_ulonglong2(0, 0), k1 = k0;
-    E v00 = zero, v01 = zero, v10 = zero, v11 = zero;
+    // Four requests in flight per lane.  A request is (wanted key, coefficient, bucket).  Its bucket is first only
+    // PREFETCHED into L2 (no registers held; address translation and the DRAM access happen now), three terms later
+    // it is loaded into registers (an L2 hit by then) and one term after that it is consumed.
+    bool liveA = false, liveB = false, liveC = false, liveL = false;   // A newest .. C oldest prefetched; L loaded
+    uint64_t wantA = 0, wantB = 0, wantC = 0, wantL = 0;
+    double cA = 0.0, cB = 0.0, cC = 0.0, cL = 0.0;
+    uint32_t bA = 0, bB = 0, bC = 0, bL = 0;
+    ulonglong2 keysL = make_ulonglong2(0, 0);
+    E v0L = zero, v1L = zero;
     int w = 0;
     RowTerms rt = row_terms<false>(T, 0, 0, min(64, p.n_groups), b);
     if (!valid) rt.mask = 0;
@@ -919,39 +922,43 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
         rt = row_terms<false>(T, w, 64 * w, min(64 * w + 64, p.n_groups), b);
       }
       const bool has = rt.mask != 0;
-      if (!has && !live0 && !live1) break;
-      // ---- consume the older request
+      if (!has && !liveA && !liveB && !liveC && !liveL) break;
+      // ---- consume the loaded request
       bool retry = false;
-      if (live1) {
-        const bool hit0 = k1.x == want1, hit1 = k1.y == want1;
+      if (liveL) {
+        const bool hit0 = keysL.x == wantL, hit1 = keysL.y == wantL;
         if (hit0 | hit1) {
-          axpy(acc, c1, hit0 ? v10 : v11);
-        } else if (k1.x == kEmptyKey || k1.y == kEmptyKey) {   // a free slot in the bucket: the state is not in the basis
-          if (c1 != 0.0) { ++bad; bad_state = want1; }         // DMV:115-118
+          axpy(acc, cL, hit0 ? v0L : v1L);
+        } else if (keysL.x == kEmptyKey || keysL.y == kEmptyKey) {   // a free slot in the bucket: not a basis state
+          if (cL != 0.0) { ++bad; bad_state = wantL; }               // DMV:115-118
         } else {
-          retry = true;                                        // both slots taken by other states: next bucket
+          retry = true;                                              // both slots hold other states: next bucket
         }
       }
-      const uint64_t want_r = want1;
-      const double c_r = c1;
-      const uint32_t b_r = b1 + 1 == n_buckets ? 0 : b1 + 1;
-      live1 = live0; want1 = want0; c1 = c0; b1 = b0; k1 = k0; v10 = v00; v11 = v01;
-      // ---- issue a new request: the continuation of a missed one, else the next term of the row
+      const uint64_t want_r = wantL;
+      const double c_r = cL;
+      const uint32_t b_r = bL + 1 == n_buckets ? 0 : bL + 1;
+      // ---- the oldest prefetched request is loaded into registers
+      liveL = liveC; wantL = wantC; cL = cC; bL = bC;
+      if (liveL) bucket_load<CE>(table, bL, keysL, v0L, v1L);
+      liveC = liveB; wantC = wantB; cC = cB; bC = bB;
+      liveB = liveA; wantB = wantA; cB = cA; bB = bA;
+      // ---- a new request: the continuation of a missed one, else the next term of the row
+      liveA = retry | has;
       if (retry) {
-        want0 = want_r; c0 = c_r; b0 = b_r;
-        bucket_load<CE>(table, b0, k0, v00, v01);
-        live0 = true;
+        wantA = want_r; cA = c_r; bA = b_r;
       } else if (has) {
         uint64_t flip;
-        c0 = pop_term<false>(T, rt, 64 * w, b, any_s_out, flip);
+        cA = pop_term<false>(T, rt, 64 * w, b, any_s_out, flip);
         const uint64_t raw = b ^ flip;
-        if constexpr (TK > 0) want0 = orbit_min_torus_sq<TK>(orbit, raw);
-        else want0 = orbit_representative(orbit, raw);
-        b0 = table_slot(want0, n_buckets);
-        bucket_load<CE>(table, b0, k0, v00, v01);
-        live0 = true;
-      } else {
-        live0 = false;
+        if constexpr (TK > 0) wantA = orbit_min_torus_sq<TK>(orbit, raw);
+        else wantA = orbit_representative(orbit, raw);
+        bA = table_slot(wantA, n_buckets);
+      }
+      if (liveA) {
+        const unsigned char *q = table + (size_t)bA * (CE ? 64 : 32);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        if (CE) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 32));
       }
     }
     if (valid) {
