@@ -6,6 +6,7 @@ src/DistributedMatrixVector.chpl + src/BatchedOperator.chpl); all compute is in 
 """
 from .config import BasisSpec, OperatorSpec, load_config_from_yaml  # noqa: F401
 from .operator import (BatchedOperator, Basis, ChapelKernels, Operator, local_matrix_vector, locale_idx_of)  # noqa: F401
+from .eigensolver import lobpcg  # noqa: F401
 from .distributed import (DistributedOperator, EmulatedCluster, HostExchangedProduct,  # noqa: F401
                           HostReplicatedProduct, block_to_hashed, hashed_to_block, masks_of,
                           matrix_vector_product)
@@ -14,5 +15,5 @@ __all__ = [
     "BasisSpec", "OperatorSpec", "load_config_from_yaml", "Operator", "Basis", "BatchedOperator", "ChapelKernels",
     "local_matrix_vector", "matrix_vector_product", "locale_idx_of", "DistributedOperator",
     "EmulatedCluster", "HostExchangedProduct", "HostReplicatedProduct", "block_to_hashed", "hashed_to_block",
-    "masks_of",
+    "masks_of", "lobpcg",
 ]

@@ -84,6 +84,8 @@ _SIGNATURES = [
     ("dmv_number_terms", C.c_int64, [C.c_void_p]),
     ("dmv_bind_operator", C.c_int, [C.c_void_p, C.c_void_p]),
     ("ls_chpl_matrix_vector_product", None, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    ("ls_chpl_primme_matvec", None, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]),
     ("dmv_apply_diag", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     ("dmv_apply_off_diag", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("ls_chpl_operator_apply_diag", None, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(ExternalArray), C.c_int64]),

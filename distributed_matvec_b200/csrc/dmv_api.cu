@@ -909,13 +909,14 @@ void ensure_table(dmv_context *ctx, int elt) {
 // y[rows] <- rows of H through k_rows.  `basis` owns the table (this rank's context, or the twin holding the whole
 // basis in the replicated-x product), x_all is indexed like basis' states (through pos when given), p names the rows.
 void rows_product(dmv_context *basis, KernelParams &p, int elt, const void *x_all, const uint32_t *pos,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, bool fill = true) {
   cudaStream_t keep = basis->stream;
   basis->stream = stream;
   ensure_table(basis, elt);
   basis->stream = keep;
-  launch_table_fill(basis->n_states, elt == DMV_C128, x_all, basis->d_norms.ptr, pos, basis->d_slot_of.ptr,
-                    basis->d_table.ptr, stream);
+  if (fill)   // (a product cut into row chunks refreshes the values once, with its first chunk)
+    launch_table_fill(basis->n_states, elt == DMV_C128, x_all, basis->d_norms.ptr, pos, basis->d_slot_of.ptr,
+                      basis->d_table.ptr, stream);
   select_tables(basis, p, true, false);
   p.uni_re = basis->gather_uni[0]; p.uni_im = basis->gather_uni[1];
   p.table = basis->d_table.ptr;
@@ -940,7 +941,7 @@ void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev,
       return;
     }
     if (use_rows(ctx)) {
-      rows_product(ctx, p, elt, x_dev, nullptr, ctx->stream);
+      rows_product(ctx, p, elt, x_dev, nullptr, ctx->stream, /*fill=*/row_begin == 0);
       return;
     }
     select_tables(ctx, p, true, complex_values(ctx, elt));
@@ -2114,7 +2115,7 @@ int dmv_local_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
   if (x == y) throw std::runtime_error("x and y must not alias");
   VecStage v = stage_vectors(ctx, elt, x, y);
   const bool host_result = v.y_host;
-  if (use_pull(ctx) && use_gather(ctx) && v.y_host && ctx->n_states >= (1 << 16)) {
+  if (use_pull(ctx) && (use_gather(ctx) || use_rows(ctx)) && v.y_host && ctx->n_states >= (1 << 16)) {
     // row traversal into a host y: every row chunk is final as soon as its launch ends, so its D2H copy
     // (copy stream) overlaps the gather of the next chunk
     const int chunks = dmv_context::kCopyChunks;
@@ -2819,6 +2820,36 @@ void ls_chpl_matrix_vector_product(const void *ls_hs_operator_ptr, int num_vecto
     abort();
   }
   if (dmv_local_matvec(ctx, DMV_F64, x, y) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
+}
+
+// reference: src/Diagonalize.chpl:134-162 -- the matrix-vector callback PRIMME drives (`primme.matrixMatvec`):
+// blockSize columns of real(64), leading dimensions ldx / ldy >= nLocal, column k through localMatrixVector.  The
+// reference reads the operator from primme->matrix; here the primme_params pointer itself is the handle, bound to a
+// context with dmv_bind_operator (no dependence on PRIMME's struct layout).  Contiguous columns go through
+// dmv_matvec_batch (four columns share one term walk in k_gather); collective when the context has several ranks.
+void ls_chpl_primme_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *block_size, void *primme, int *ierr) {
+  dmv_context *ctx = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_bind_mutex);
+    auto it = g_bindings.find(primme);
+    if (it != g_bindings.end()) ctx = it->second;
+  }
+  if (!ctx) { fprintf(stderr, "ls_chpl_primme_matvec: primme_params is not bound to a dmv context\n"); abort(); }
+  const int64_t n = ctx->n_states;
+  if (*ldx < n || *ldy < n) { fprintf(stderr, "ls_chpl_primme_matvec: leading dimension below nLocal\n"); abort(); }   // :143-144
+  int rc = 0;
+  if (*ldx == n && *ldy == n) {
+    rc = dmv_matvec_batch(ctx, DMV_F64, *block_size, x, y);
+  } else {
+    for (int k = 0; k < *block_size && rc == 0; ++k) {
+      const double *xk = reinterpret_cast<const double *>(x) + *ldx * k;
+      double *yk = reinterpret_cast<double *>(y) + *ldy * k;
+      rc = ctx->num_ranks == 1 ? dmv_local_matvec(ctx, DMV_F64, xk, yk) : dmv_matvec(ctx, DMV_F64, xk, yk);
+    }
+  }
+  if (rc == 0 && is_device_pointer(y)) rc = dmv_synchronize(ctx);
+  if (rc != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }   // the reference halts
+  *ierr = 0;                                                              // :160
 }
 
 }  // extern "C"

@@ -456,6 +456,19 @@ class ChapelKernels:
         nat.lib().ls_chpl_enumerate_representatives(self._handle, lower, upper, C.byref(out))
         return _take(out, C.c_uint64, np.uint64)
 
+    def primme_matvec(self, X: np.ndarray, ldy: int | None = None) -> np.ndarray:
+        """ls_chpl_primme_matvec (src/Diagonalize.chpl:134-162): X is column-major [ldx, blockSize] as PRIMME hands it
+        over, i.e. a C-contiguous array of shape (blockSize, ldx) here; returns Y of shape (blockSize, ldy)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        block, ldx = X.shape
+        ldy = ldx if ldy is None else ldy
+        Y = np.zeros((block, ldy), dtype=np.float64)
+        ierr = C.c_int(-1)
+        nat.lib().ls_chpl_primme_matvec(X.ctypes.data, C.byref(C.c_int64(ldx)), Y.ctypes.data, C.byref(C.c_int64(ldy)),
+                                        C.byref(C.c_int(block)), self._handle, C.byref(ierr))
+        assert ierr.value == 0
+        return Y
+
     def matrix_vector_product(self, x: np.ndarray) -> np.ndarray:
         """ls_chpl_matrix_vector_product (DMV:1095-1110): real(64), one vector."""
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -212,6 +212,13 @@ int64_t dmv_number_terms(const dmv_context *ctx);
 int dmv_bind_operator(const void *ls_hs_operator_ptr, dmv_context *ctx);
 void ls_chpl_matrix_vector_product(const void *ls_hs_operator_ptr, int num_vectors, double *x, double *y);
 
+/* PRIMME's matrix-vector callback (reference src/Diagonalize.chpl:134-162: `primme.matrixMatvec = ls_chpl_primme_matvec`):
+ * y[:, k] = H x[:, k] for k < *block_size, real(64) columns with leading dimensions *ldx, *ldy >= dmv_number_states.
+ * The reference finds the operator through primme->matrix; here the primme_params pointer is the handle and must have
+ * been bound with dmv_bind_operator(primme, ctx).  Host or device columns; collective when the context has several
+ * ranks; sets *ierr = 0 and halts on failure like the reference. */
+void ls_chpl_primme_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *block_size, void *primme, int *ierr);
+
 /* The other three entries of `ls_chpl_kernels` (src/FFI.chpl:233-239).  Outputs are returned the way Chapel's
  * convertToExternalArray does (BO:232,265-272): allocated by the callee, released by the caller through `freer`.
  * Layout of chpl_external_array (Chapel runtime, chpl-external-array.h): {void *elts; uint64_t num_elts; void *freer}.

@@ -289,6 +289,29 @@ def test_chapel_plugin_kernels_match_oracle(need_cuda, name):
     op.close()
 
 
+@pytest.mark.parametrize("name", ["heisenberg_chain_16", "heisenberg_kagome_12_symm", "heisenberg_chain_10"])
+def test_primme_matvec_callback(need_cuda, name):
+    """ls_chpl_primme_matvec (src/Diagonalize.chpl:134-162): blockSize columns with leading dimensions >= nLocal,
+    contiguous (batched on the GPU) and padded (column by column), against the oracle's product per column."""
+    basis, matrix = _load(name)
+    op = Operator(matrix)
+    op.basis.build()
+    reps = op.basis.representatives()
+    n = reps.shape[0]
+    ck = ChapelKernels(op)
+    rng = np.random.default_rng(12)
+    for block, pad in ((1, 0), (5, 0), (3, 7)):
+        X = np.zeros((block, n + pad))
+        X[:, :n] = rng.random((block, n)) - 0.5
+        Y = ck.primme_matvec(X, ldy=n + pad)
+        for k in range(block):
+            y_ref = po.matvec_global(matrix, reps, np.ascontiguousarray(X[k, :n]), 1)
+            assert _close(Y[k, :n], y_ref), (block, pad, k)
+            assert not np.any(Y[k, n:])
+    ck.close()
+    op.close()
+
+
 def test_chapel_plugin_kernels_refuse_projected_bases(need_cuda):
     """BO:224-227, 245-248: bases that require projection are not supported by the apply kernels."""
     basis, matrix = _load("heisenberg_chain_10")
@@ -838,6 +861,27 @@ def test_lanczos_ground_state(need_cuda, name, known):
         assert abs(e0 - known) < 5e-4
     assert iters <= reps.shape[0] and abs(np.linalg.norm(vec) - 1.0) < 1e-8
     assert np.linalg.norm(H @ vec - e0 * vec) <= 1e-6 * max(1.0, abs(w[0])), res
+    op.close()
+
+
+@pytest.mark.parametrize("name,cplx", [("heisenberg_chain_10", False), ("heisenberg_kagome_12_symm", False),
+                                       ("heisenberg_square_4x4", True), ("heisenberg_chain_12", False)])
+def test_block_eigensolver_lobpcg(need_cuda, name, cplx):
+    """The block eigensolver on dmv_matvec_batch (what PRIMME with blockSize > 1 is to the reference,
+    src/Diagonalize.chpl:134-225): three lowest eigenvalues against dense diagonalisation of the oracle's matrix."""
+    from distributed_matvec_b200 import lobpcg
+    basis, matrix = _load(name)
+    op = Operator(matrix)
+    op.basis.build()
+    reps = op.basis.representatives()
+    H = _dense_from_oracle(matrix, reps, cplx)
+    want = np.linalg.eigvalsh((H + H.conj().T) / 2)[:3]
+    lam, X, iters, res = lobpcg(op, k=3, max_iters=400, tol=1e-9, complex_vectors=cplx)
+    assert np.allclose(lam, want, rtol=0, atol=1e-8 * max(1.0, np.abs(want).max())), (lam, want, iters, res)
+    # the vectors are eigenvectors: H x = lambda x through the single-vector product
+    for j in range(3):
+        y = op.matvec(X[j].contiguous())
+        assert torch.linalg.norm(y - lam[j] * X[j]) <= 1e-6 * max(1.0, abs(lam[j]))
     op.close()
 
 

@@ -15,7 +15,7 @@ def main():
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     cur_file, cur_line, cur_src = None, None, ""
-    inst = defaultdict(int); samples = defaultdict(int); text = {}
+    inst = defaultdict(int); samples = defaultdict(int); tinst = defaultdict(int); text = {}
     header = None
     for r in rows:
         if not r:
@@ -26,6 +26,7 @@ def main():
         if r[0] == "Line No":
             header = r
             i_inst = header.index("Instructions Executed"); i_samp = header.index("# Samples")
+            i_tinst = header.index("Thread Instructions Executed")
             continue
         if header is None or len(r) < len(header):
             continue
@@ -33,14 +34,15 @@ def main():
             cur_line = (cur_file, int(r[0])); text[cur_line] = r[1].strip()
             continue
         try:
-            inst[cur_line] += int(r[i_inst]); samples[cur_line] += int(r[i_samp])
+            inst[cur_line] += int(r[i_inst]); samples[cur_line] += int(r[i_samp]); tinst[cur_line] += int(r[i_tinst])
         except ValueError:
             pass
     tot_i = sum(inst.values()) or 1; tot_s = sum(samples.values()) or 1
     print(f"total warp instructions {tot_i}, stall samples {tot_s}")
-    print("| file:line | inst % | samples % | source |\n|---|---|---|---|")
+    print("| file:line | inst % | samples % | avg threads | source |\n|---|---|---|---|---|")
     for k in sorted(inst, key=lambda k: -(inst[k] / tot_i + samples[k] / tot_s))[:top]:
-        print(f"| {k[0]}:{k[1]} | {100 * inst[k] / tot_i:.2f} | {100 * samples[k] / tot_s:.2f} | `{text.get(k, '')[:110]}` |")
+        print(f"| {k[0]}:{k[1]} | {100 * inst[k] / tot_i:.2f} | {100 * samples[k] / tot_s:.2f} | "
+              f"{tinst[k] / max(inst[k], 1):.1f} | `{text.get(k, '')[:110]}` |")
 
 
 if __name__ == "__main__":
