@@ -853,8 +853,8 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
 // orbit minimum in registers (canonical form, dmv_device.cuh), then ONE dependent memory access -- the slot of the
 // representative in a hash table that carries the scaled vector element (table_slot) -- and that access is software
 // pipelined: the slot of term j is requested right after its orbit minimum and consumed after the orbit minimum of
-// term j + 4 (prefetch into L2 first, registers only for the last step), so its latency -- DRAM plus address translation
-// over a table of gigabytes -- hides behind ~10^3 integer instructions of the same lane.
+// term j + 3 (cp.async into a per-lane shared-memory slot: nothing is held in registers meanwhile), so its latency -- DRAM
+// plus address translation over a table of gigabytes -- hides behind ~10^3 integer instructions of the same lane.
 // -------------------------------------------------------------------------------------------------
 // one bucket = two slots (layout: table_slot in dmv_device.cuh); all loads of a bucket are independent
 template <bool CE>
@@ -876,8 +876,40 @@ __device__ __forceinline__ void bucket_load(const unsigned char *__restrict__ ta
 __device__ __forceinline__ void axpy(double &acc, double c, double v) { acc = fma(c, v, acc); }
 __device__ __forceinline__ void axpy(double2 &acc, double c, double2 v) { acc.x = fma(c, v.x, acc.x); acc.y = fma(c, v.y, acc.y); }
 
-// two CTAs per SM: the pipeline state must stay in registers (a spilled request waits for its load at once), and the
-// latency is hidden inside the lane, not by occupancy
+// Software pipeline of k_rows: kDepth requests in flight per lane.  A request's bucket travels global -> shared with
+// cp.async.cg (16-byte chunks, L2 only: no L1 pollution, no registers held while in flight), one commit group per loop
+// trip; cp.async.wait_group kDepth - 1 then guarantees the bucket requested kDepth - 1 trips ago has landed.  Per-thread
+// slots are interleaved over the CTA ([stage][chunk][thread] x 16 bytes): conflict-free 16-byte shared loads.
+constexpr int kDepth = 4;
+template <bool CE> constexpr int bucket_chunks() { return CE ? 3 : 2; }   // keys | v0 | v1  or  keys | (v0, v1)
+template <bool CE> constexpr size_t rows_pipe_bytes() { return (size_t)kDepth * bucket_chunks<CE>() * kThreads * 16; }
+
+template <bool CE>
+__device__ __forceinline__ void bucket_request(uint32_t pipe, int stage, const unsigned char *__restrict__ table, uint32_t b) {
+  constexpr int CH = bucket_chunks<CE>();
+  const unsigned char *src = table + (size_t)b * (CE ? 64 : 32);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const uint32_t dst = pipe + (uint32_t)(((stage * CH + c) * kThreads + threadIdx.x) * 16);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * c) : "memory");
+  }
+}
+template <bool CE>
+__device__ __forceinline__ void bucket_read(const unsigned char *pipe_ptr, int stage, ulonglong2 &keys,
+                                            typename ValT<CE>::type &v0, typename ValT<CE>::type &v1) {
+  constexpr int CH = bucket_chunks<CE>();
+  const unsigned char *q = pipe_ptr + (size_t)((stage * CH) * kThreads + threadIdx.x) * 16;
+  keys = *reinterpret_cast<const ulonglong2 *>(q);
+  if constexpr (CE) {
+    v0 = *reinterpret_cast<const double2 *>(q + (size_t)kThreads * 16);
+    v1 = *reinterpret_cast<const double2 *>(q + (size_t)2 * kThreads * 16);
+  } else {
+    const double2 vv = *reinterpret_cast<const double2 *>(q + (size_t)kThreads * 16);
+    v0 = vv.x;
+    v1 = vv.y;
+  }
+}
+
 template <bool CE, int TK>
 __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
   using E = typename ValT<CE>::type;
@@ -895,6 +927,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
   const double *__restrict__ row_norms = p.row_norms ? p.row_norms : p.norms;
   unsigned long long bad = 0, bad_state = 0;
   const E zero = v_make(0.0, 0.0, (E *)nullptr);
+  const unsigned char *pipe_ptr = smem + align_up(L.total, 16);
+  const uint32_t pipe = (uint32_t)__cvta_generic_to_shared(pipe_ptr);
 
   const int64_t n_rows = p.row_end - p.row_begin;
   const int64_t n_tiles = (n_rows + 31) / 32;
@@ -904,15 +938,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
     const bool valid = i < p.row_end;
     const uint64_t b = valid ? __ldg(row_states + i) : 0ull;
     E acc = zero;
-    // Four requests in flight per lane.  A request is (wanted key, coefficient, bucket).  Its bucket is first only
-    // PREFETCHED into L2 (no registers held; address translation and the DRAM access happen now), three terms later
-    // it is loaded into registers (an L2 hit by then) and one term after that it is consumed.
-    bool liveA = false, liveB = false, liveC = false, liveL = false;   // A newest .. C oldest prefetched; L loaded
-    uint64_t wantA = 0, wantB = 0, wantC = 0, wantL = 0;
-    double cA = 0.0, cB = 0.0, cC = 0.0, cL = 0.0;
-    uint32_t bA = 0, bB = 0, bC = 0, bL = 0;
-    ulonglong2 keysL = make_ulonglong2(0, 0);
-    E v0L = zero, v1L = zero;
+    // requests in flight, newest first: A (this trip), B, C, D (consumed this trip); a request = (key, coefficient, bucket)
+    bool liveA = false, liveB = false, liveC = false, liveD = false;
+    uint64_t wantA = 0, wantB = 0, wantC = 0, wantD = 0;
+    double cA = 0.0, cB = 0.0, cC = 0.0, cD = 0.0;
+    uint32_t bA = 0, bB = 0, bC = 0, bD = 0;
+    int stage = 0;   // slot of the request issued this trip; the one consumed this trip sits in (stage + 1) % kDepth
     int w = 0;
     RowTerms rt = row_terms<false>(T, 0, 0, min(64, p.n_groups), b);
     if (!valid) rt.mask = 0;
@@ -922,25 +953,26 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
         rt = row_terms<false>(T, w, 64 * w, min(64 * w + 64, p.n_groups), b);
       }
       const bool has = rt.mask != 0;
-      if (!has && !liveA && !liveB && !liveC && !liveL) break;
-      // ---- consume the loaded request
+      if (!has && !liveA && !liveB && !liveC && !liveD) break;
+      // ---- consume the oldest request (issued kDepth - 1 trips ago)
       bool retry = false;
-      if (liveL) {
-        const bool hit0 = keysL.x == wantL, hit1 = keysL.y == wantL;
+      if (liveD) {
+        ulonglong2 keys;
+        E v0, v1;
+        bucket_read<CE>(pipe_ptr, (stage + 1) & (kDepth - 1), keys, v0, v1);
+        const bool hit0 = keys.x == wantD, hit1 = keys.y == wantD;
         if (hit0 | hit1) {
-          axpy(acc, cL, hit0 ? v0L : v1L);
-        } else if (keysL.x == kEmptyKey || keysL.y == kEmptyKey) {   // a free slot in the bucket: not a basis state
-          if (cL != 0.0) { ++bad; bad_state = wantL; }               // DMV:115-118
+          axpy(acc, cD, hit0 ? v0 : v1);
+        } else if (keys.x == kEmptyKey || keys.y == kEmptyKey) {   // a free slot in the bucket: not a basis state
+          if (cD != 0.0) { ++bad; bad_state = wantD; }             // DMV:115-118
         } else {
-          retry = true;                                              // both slots hold other states: next bucket
+          retry = true;                                            // both slots hold other states: next bucket
         }
       }
-      const uint64_t want_r = wantL;
-      const double c_r = cL;
-      const uint32_t b_r = bL + 1 == n_buckets ? 0 : bL + 1;
-      // ---- the oldest prefetched request is loaded into registers
-      liveL = liveC; wantL = wantC; cL = cC; bL = bC;
-      if (liveL) bucket_load<CE>(table, bL, keysL, v0L, v1L);
+      const uint64_t want_r = wantD;
+      const double c_r = cD;
+      const uint32_t b_r = bD + 1 == n_buckets ? 0 : bD + 1;
+      liveD = liveC; wantD = wantC; cD = cC; bD = bC;
       liveC = liveB; wantC = wantB; cC = cB; bC = bB;
       liveB = liveA; wantB = wantA; cB = cA; bB = bA;
       // ---- a new request: the continuation of a missed one, else the next term of the row
@@ -955,12 +987,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
         else wantA = orbit_representative(orbit, raw);
         bA = table_slot(wantA, n_buckets);
       }
-      if (liveA) {
-        const unsigned char *q = table + (size_t)bA * (CE ? 64 : 32);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-        if (CE) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 32));
-      }
+      stage = (stage + 1) & (kDepth - 1);
+      if (liveA) bucket_request<CE>(pipe, stage, table, bA);
+      asm volatile("cp.async.commit_group;" ::: "memory");            // one group per trip, empty or not
+      // at most the kDepth - 1 newest groups stay pending: the request that is D now (issued kDepth - 1 trips ago, read
+      // at the top of the next trip) has landed
+      asm volatile("cp.async.wait_group %0;" ::"n"(kDepth - 1) : "memory");
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (valid) {
       const double inv_nb = 1.0 / __ldg(row_norms + i);
       E out;
@@ -1339,15 +1373,16 @@ namespace {
 template <bool CE, int TK>
 void launch_rows_t(const KernelParams &p, cudaStream_t stream) {
   const SmemLayout L = smem_layout(p, PROJ_GROUP, sizeof(double), false);
+  const size_t smem_bytes = align_up(L.total, 16) + rows_pipe_bytes<CE>();
   auto kernel = k_rows<CE, TK>;
-  if (L.total > 48 * 1024)
-    DMV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  if (smem_bytes > 48 * 1024)
+    DMV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   int per_sm = 0;
-  DMV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, L.total));
+  DMV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem_bytes));
   if (per_sm < 1) per_sm = 1;
   const int64_t tiles = (p.row_end - p.row_begin + 31) / 32;
   const int blocks = grid_for(tiles, kWarps, sm_count() * per_sm);
-  kernel<<<blocks, kThreads, L.total, stream>>>(p);
+  kernel<<<blocks, kThreads, smem_bytes, stream>>>(p);
   DMV_CUDA_CHECK(cudaGetLastError());
   g_launches++;
 }
