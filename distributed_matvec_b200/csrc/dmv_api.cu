@@ -167,27 +167,37 @@ HostTables build_tables(const std::map<uint64_t, std::vector<OffTerm>> &by_x) {
     items.push_back(it);
   }
   if (bp_ok) {
-    // order the groups so that few distinct shifts (group index - bit position) occur
-    std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
-      if (a.p1 - a.p0 != b.p1 - b.p0) return a.p1 - a.p0 < b.p1 - b.p0;
-      return a.p0 < b.p0;
-    });
+    // Two orders of the groups are tried.  (1) by the LOWEST site they act on: the groups acting only on high sites get
+    // the high bits of the emit mask -- the 32 consecutive rows of a warp share their high bits, so k_gather, walking the
+    // mask from the top, keeps its lanes in step (chains: two shifts per operand).  (2) by the distance between the two
+    // sites, then position: few distinct shifts "group index - bit position" on two-dimensional lattices, where (1)
+    // needs more than kBpPairs of them.
     const int n_words = (int)((items.size() + 63) / 64);
-    std::vector<BpWord> words((size_t)n_words);
-    for (auto &w : words) memset(&w, 0, sizeof(w));
-    for (size_t g = 0; g < items.size() && bp_ok; ++g) {
-      BpWord &W = words[g / 64];
-      const int gl = (int)(g % 64);
-      auto add = [&](int pos, BpPair *pairs, int32_t &n) {
-        const int d = gl - pos;
-        const uint32_t sl = d >= 0 ? (uint32_t)d : 0u, sr = d >= 0 ? 0u : (uint32_t)(-d);
-        for (int k = 0; k < n; ++k)
-          if (pairs[k].l == sl && pairs[k].r == sr) { pairs[k].m |= 1ull << gl; return; }
-        if (n == kBpPairs) { bp_ok = false; return; }
-        pairs[n].l = sl; pairs[n].r = sr; pairs[n].m = 1ull << gl; ++n;
-      };
-      add(items[g].p0, W.p0, W.n0);
-      add(items[g].p1, W.p1, W.n1);
+    std::vector<BpWord> words;
+    for (int order = 0; order < 2; ++order) {
+      std::stable_sort(items.begin(), items.end(), [order](const Item &a, const Item &b) {
+        if (order == 0) return a.p0 != b.p0 ? a.p0 < b.p0 : a.p1 < b.p1;
+        if (a.p1 - a.p0 != b.p1 - b.p0) return a.p1 - a.p0 < b.p1 - b.p0;
+        return a.p0 < b.p0;
+      });
+      bp_ok = true;
+      words.assign((size_t)n_words, BpWord{});
+      for (auto &w : words) memset(&w, 0, sizeof(w));
+      for (size_t g = 0; g < items.size() && bp_ok; ++g) {
+        BpWord &W = words[g / 64];
+        const int gl = (int)(g % 64);
+        auto add = [&](int pos, BpPair *pairs, int32_t &n) {
+          const int d = gl - pos;
+          const uint32_t sl = d >= 0 ? (uint32_t)d : 0u, sr = d >= 0 ? 0u : (uint32_t)(-d);
+          for (int k = 0; k < n; ++k)
+            if (pairs[k].l == sl && pairs[k].r == sr) { pairs[k].m |= 1ull << gl; return; }
+          if (n == kBpPairs) { bp_ok = false; return; }
+          pairs[n].l = sl; pairs[n].r = sr; pairs[n].m = 1ull << gl; ++n;
+        };
+        add(items[g].p0, W.p0, W.n0);
+        add(items[g].p1, W.p1, W.n1);
+      }
+      if (bp_ok) break;
     }
     if (bp_ok) {
       for (size_t g = 0; g < items.size(); ++g) {
@@ -316,7 +326,8 @@ struct dmv_context {
   // hash table over this context's representatives (see table_slot in dmv_device.cuh)
   bool rows_ok = false;
   int opt_rows = -1;        // -1 auto (k_rows when it applies), 0 the queued k_pull
-  int opt_gather_walk = 0;  // k_gather: 0 group-major warp-uniform walk, 1 per-lane walk (round 1)
+  int opt_gather_walk = 0;  // k_gather: 0 per-lane walk from the top bit (default), 1 group-major warp-uniform walk
+                            // (measured slower), 2 per-lane walk from the bottom bit (round 1)
   DevBuf<unsigned char> d_table;
   DevBuf<uint32_t> d_slot_of;
   uint32_t table_slots = 0;
@@ -1852,7 +1863,7 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
     ctx->rounds.tried = false;
     ctx->rounds.ready = false;
   } else if (key == "gather_walk") {
-    ctx->opt_gather_walk = value != 0;
+    ctx->opt_gather_walk = (value >= 0 && value <= 2) ? (int)value : 0;
     if (ctx->global) ctx->global->opt_gather_walk = ctx->opt_gather_walk;
   } else if (key == "peer_gather") {
     if (value < -1 || value > 0) throw std::runtime_error("peer_gather: -1 auto, 0 NCCL all-gather of x");

@@ -37,6 +37,8 @@ __device__ __forceinline__ int popc_w(uint32_t v) { return __popc(v); }
 __device__ __forceinline__ int popc_w(uint64_t v) { return __popcll(v); }
 __device__ __forceinline__ int ffs_w(uint32_t v) { return __ffs((int)v); }
 __device__ __forceinline__ int ffs_w(uint64_t v) { return __ffsll((long long)v); }
+__device__ __forceinline__ int top_w(uint32_t v) { return 31 - __clz((int)v); }
+__device__ __forceinline__ int top_w(uint64_t v) { return 63 - __clzll((long long)v); }
 
 // acc += c * s * x for the four (coefficient, element) type combinations
 __device__ __forceinline__ void fma_to(double &acc, double c, double x) { acc = fma(c, x, acc); }
@@ -232,10 +234,13 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
             if (on[j] && idx[j] == kNone && nonzero(c[j])) { ++bad; bad_state = (unsigned long long)key[j]; }
         }
       };
-      if (S == 1 && p.gather_walk == 0) {
-        // GROUP-MAJOR walk, warp-uniform, four groups per trip: all 32 lanes handle the same group at the same time.
-        // For a fixed flip mask consecutive rows map to (nearly) consecutive indices, so the 32 gathers of a group fall
-        // into a few 128-byte lines instead of 32 (the per-lane walk has every lane on a different group at any instant).
+      if (S == 1 && p.gather_walk == 1) {
+        // GROUP-MAJOR walk (option "gather_walk" = 1), warp-uniform, four groups per trip: all 32 lanes handle the same
+        // group at the same time.  For a fixed flip mask consecutive rows map to (nearly) consecutive indices, so the 32
+        // gathers of a group fall into a few 128-byte lines instead of 32.  Measured (profiles/r02_gather_walks.md): the
+        // L1 wavefront share drops from 81 % to 45 % as intended, but every lane now walks all emitting groups of the
+        // warp (24 instead of its own ~12.5): 35 % more instructions, and the kernel ends up SLOWER (0.150 vs 0.131 ms
+        // on chain_24 c128).  Kept for reference; the per-lane walk below is the default.
         W any;
         if constexpr (sizeof(W) == 4) any = __reduce_or_sync(0xffffffffu, mask);
         else {
@@ -256,15 +261,20 @@ __global__ void __launch_bounds__(kThreads) k_gather(const KernelParams p) {
           batch(std::integral_constant<int, 4>{}, g, on);
         }
       } else {
-        while (mask) {   // every lane walks its own bits (S > 1: its own slice of the groups), two per trip
+        // every lane walks its own bits (S > 1: its own slice of the groups), two per trip -- from the TOP: the 32
+        // consecutive rows of a warp share their high bits, hence the emit bits of the groups acting there, so the lanes
+        // walk those groups in step and their gathers fall into the same few lines; only the groups touching the low,
+        // varying bits come out of step, and those move the index by little ("gather_walk" = 2: from the bottom, round 1)
+        const bool from_top = p.gather_walk != 2;
+        while (mask) {
           int g[2];
           bool on[2];
-          g[0] = ffs_w(mask) - 1;
-          mask &= mask - 1;
+          g[0] = from_top ? top_w(mask) : ffs_w(mask) - 1;
+          mask &= ~((W)1 << g[0]);
           on[0] = true;
           on[1] = mask != 0;
-          g[1] = on[1] ? ffs_w(mask) - 1 : g[0];
-          mask &= mask - 1;   // no-op when mask is already empty
+          g[1] = on[1] ? (from_top ? top_w(mask) : ffs_w(mask) - 1) : g[0];
+          if (on[1]) mask &= ~((W)1 << g[1]);
           batch(std::integral_constant<int, 2>{}, g, on);
         }
       }

@@ -101,7 +101,7 @@ struct KernelParams {
   const uint32_t *pos;
   int64_t x_row_offset;
   // k_gather on several vectors at once: vector k of x / y starts batch_stride elements after vector k - 1
-  int32_t gather_walk;         // k_gather: 0 group-major warp-uniform walk (coalesced gathers), 1 every lane walks its own bits
+  int32_t gather_walk;         // k_gather: 0 per-lane walk from the top bit (default), 1 group-major, 2 per-lane from the bottom
   int32_t batch;               // 0 / 1: one vector; 4: four vectors per launch
   int64_t batch_stride;
   // k_rows (row traversal of bases with permutation symmetries): hash table over the representatives with the scaled

@@ -853,63 +853,41 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
 // orbit minimum in registers (canonical form, dmv_device.cuh), then ONE dependent memory access -- the slot of the
 // representative in a hash table that carries the scaled vector element (table_slot) -- and that access is software
 // pipelined: the slot of term j is requested right after its orbit minimum and consumed after the orbit minimum of
-// term j + 3 (cp.async into a per-lane shared-memory slot: nothing is held in registers meanwhile), so its latency -- DRAM
-// plus address translation over a table of gigabytes -- hides behind ~10^3 integer instructions of the same lane.
+// term j + 2, so its latency hides behind ~10^3 integer instructions of the same lane.  (Deeper pipelines were measured
+// and are slower -- four requests per lane through prefetch.global.L2 or through cp.async into shared memory: 58 / 46 ms
+// against 29 ms on the 6x6 square; the look-ups are bound by the rate of random 64-byte requests the memory system takes,
+// not by their latency: profiles/r02_rows_pipelines.md.)
 // -------------------------------------------------------------------------------------------------
 // one bucket = two slots (layout: table_slot in dmv_device.cuh); all loads of a bucket are independent
+// 256-bit loads (sm_100: LDG.E.256), not allocated in L1: a bucket is touched once per product, and 50 GB of them
+// streaming through L1 would evict the small tables the orbit minimum reads from global memory
+__device__ __forceinline__ void load256(const unsigned char *q, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(q));
+}
 template <bool CE>
 __device__ __forceinline__ void bucket_load(const unsigned char *__restrict__ table, uint32_t b, ulonglong2 &keys,
                                             typename ValT<CE>::type &v0, typename ValT<CE>::type &v1) {
+  uint64_t w0, w1, w2, w3;
   if constexpr (CE) {
     const unsigned char *q = table + (size_t)b * 64;
-    keys = __ldg(reinterpret_cast<const ulonglong2 *>(q));
-    v0 = __ldg(reinterpret_cast<const double2 *>(q + 16));
-    v1 = __ldg(reinterpret_cast<const double2 *>(q + 32));
+    load256(q, w0, w1, w2, w3);
+    keys = make_ulonglong2(w0, w1);
+    v0 = make_double2(__longlong_as_double((long long)w2), __longlong_as_double((long long)w3));
+    uint64_t u0, u1, u2, u3;
+    load256(q + 32, u0, u1, u2, u3);
+    v1 = make_double2(__longlong_as_double((long long)u0), __longlong_as_double((long long)u1));
   } else {
-    const unsigned char *q = table + (size_t)b * 32;
-    keys = __ldg(reinterpret_cast<const ulonglong2 *>(q));
-    const double2 vv = __ldg(reinterpret_cast<const double2 *>(q + 16));
-    v0 = vv.x;
-    v1 = vv.y;
+    load256(table + (size_t)b * 32, w0, w1, w2, w3);
+    keys = make_ulonglong2(w0, w1);
+    v0 = __longlong_as_double((long long)w2);
+    v1 = __longlong_as_double((long long)w3);
   }
 }
 __device__ __forceinline__ void axpy(double &acc, double c, double v) { acc = fma(c, v, acc); }
 __device__ __forceinline__ void axpy(double2 &acc, double c, double2 v) { acc.x = fma(c, v.x, acc.x); acc.y = fma(c, v.y, acc.y); }
 
-// Software pipeline of k_rows: kDepth requests in flight per lane.  A request's bucket travels global -> shared with
-// cp.async.cg (16-byte chunks, L2 only: no L1 pollution, no registers held while in flight), one commit group per loop
-// trip; cp.async.wait_group kDepth - 1 then guarantees the bucket requested kDepth - 1 trips ago has landed.  Per-thread
-// slots are interleaved over the CTA ([stage][chunk][thread] x 16 bytes): conflict-free 16-byte shared loads.
-constexpr int kDepth = 4;
-template <bool CE> constexpr int bucket_chunks() { return CE ? 3 : 2; }   // keys | v0 | v1  or  keys | (v0, v1)
-template <bool CE> constexpr size_t rows_pipe_bytes() { return (size_t)kDepth * bucket_chunks<CE>() * kThreads * 16; }
-
-template <bool CE>
-__device__ __forceinline__ void bucket_request(uint32_t pipe, int stage, const unsigned char *__restrict__ table, uint32_t b) {
-  constexpr int CH = bucket_chunks<CE>();
-  const unsigned char *src = table + (size_t)b * (CE ? 64 : 32);
-#pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    const uint32_t dst = pipe + (uint32_t)(((stage * CH + c) * kThreads + threadIdx.x) * 16);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * c) : "memory");
-  }
-}
-template <bool CE>
-__device__ __forceinline__ void bucket_read(const unsigned char *pipe_ptr, int stage, ulonglong2 &keys,
-                                            typename ValT<CE>::type &v0, typename ValT<CE>::type &v1) {
-  constexpr int CH = bucket_chunks<CE>();
-  const unsigned char *q = pipe_ptr + (size_t)((stage * CH) * kThreads + threadIdx.x) * 16;
-  keys = *reinterpret_cast<const ulonglong2 *>(q);
-  if constexpr (CE) {
-    v0 = *reinterpret_cast<const double2 *>(q + (size_t)kThreads * 16);
-    v1 = *reinterpret_cast<const double2 *>(q + (size_t)2 * kThreads * 16);
-  } else {
-    const double2 vv = *reinterpret_cast<const double2 *>(q + (size_t)kThreads * 16);
-    v0 = vv.x;
-    v1 = vv.y;
-  }
-}
-
+// two CTAs per SM: the pipeline state must stay in registers (a spilled request waits for its load at once), and the
+// latency is hidden inside the lane, not by occupancy
 template <bool CE, int TK>
 __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
   using E = typename ValT<CE>::type;
@@ -927,8 +905,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
   const double *__restrict__ row_norms = p.row_norms ? p.row_norms : p.norms;
   unsigned long long bad = 0, bad_state = 0;
   const E zero = v_make(0.0, 0.0, (E *)nullptr);
-  const unsigned char *pipe_ptr = smem + align_up(L.total, 16);
-  const uint32_t pipe = (uint32_t)__cvta_generic_to_shared(pipe_ptr);
 
   const int64_t n_rows = p.row_end - p.row_begin;
   const int64_t n_tiles = (n_rows + 31) / 32;
@@ -938,12 +914,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
     const bool valid = i < p.row_end;
     const uint64_t b = valid ? __ldg(row_states + i) : 0ull;
     E acc = zero;
-    // requests in flight, newest first: A (this trip), B, C, D (consumed this trip); a request = (key, coefficient, bucket)
-    bool liveA = false, liveB = false, liveC = false, liveD = false;
-    uint64_t wantA = 0, wantB = 0, wantC = 0, wantD = 0;
-    double cA = 0.0, cB = 0.0, cC = 0.0, cD = 0.0;
-    uint32_t bA = 0, bB = 0, bC = 0, bD = 0;
-    int stage = 0;   // slot of the request issued this trip; the one consumed this trip sits in (stage + 1) % kDepth
+    // two requests in flight per lane: wanted key, coefficient, bucket, and what the bucket held
+    bool live0 = false, live1 = false;
+    uint64_t want0 = 0, want1 = 0;
+    double c0 = 0.0, c1 = 0.0;
+    uint32_t b0 = 0, b1 = 0;
+    ulonglong2 k0 = make_ulonglong2(0, 0), k1 = k0;
+    E v00 = zero, v01 = zero, v10 = zero, v11 = zero;
     int w = 0;
     RowTerms rt = row_terms<false>(T, 0, 0, min(64, p.n_groups), b);
     if (!valid) rt.mask = 0;
@@ -953,48 +930,41 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
         rt = row_terms<false>(T, w, 64 * w, min(64 * w + 64, p.n_groups), b);
       }
       const bool has = rt.mask != 0;
-      if (!has && !liveA && !liveB && !liveC && !liveD) break;
-      // ---- consume the oldest request (issued kDepth - 1 trips ago)
+      if (!has && !live0 && !live1) break;
+      // ---- consume the older request
       bool retry = false;
-      if (liveD) {
-        ulonglong2 keys;
-        E v0, v1;
-        bucket_read<CE>(pipe_ptr, (stage + 1) & (kDepth - 1), keys, v0, v1);
-        const bool hit0 = keys.x == wantD, hit1 = keys.y == wantD;
+      if (live1) {
+        const bool hit0 = k1.x == want1, hit1 = k1.y == want1;
         if (hit0 | hit1) {
-          axpy(acc, cD, hit0 ? v0 : v1);
-        } else if (keys.x == kEmptyKey || keys.y == kEmptyKey) {   // a free slot in the bucket: not a basis state
-          if (cD != 0.0) { ++bad; bad_state = wantD; }             // DMV:115-118
+          axpy(acc, c1, hit0 ? v10 : v11);
+        } else if (k1.x == kEmptyKey || k1.y == kEmptyKey) {   // a free slot in the bucket: the state is not in the basis
+          if (c1 != 0.0) { ++bad; bad_state = want1; }         // DMV:115-118
         } else {
-          retry = true;                                            // both slots hold other states: next bucket
+          retry = true;                                        // both slots taken by other states: next bucket
         }
       }
-      const uint64_t want_r = wantD;
-      const double c_r = cD;
-      const uint32_t b_r = bD + 1 == n_buckets ? 0 : bD + 1;
-      liveD = liveC; wantD = wantC; cD = cC; bD = bC;
-      liveC = liveB; wantC = wantB; cC = cB; bC = bB;
-      liveB = liveA; wantB = wantA; cB = cA; bB = bA;
-      // ---- a new request: the continuation of a missed one, else the next term of the row
-      liveA = retry | has;
+      const uint64_t want_r = want1;
+      const double c_r = c1;
+      const uint32_t b_r = b1 + 1 == n_buckets ? 0 : b1 + 1;
+      live1 = live0; want1 = want0; c1 = c0; b1 = b0; k1 = k0; v10 = v00; v11 = v01;
+      // ---- issue a new request: the continuation of a missed one, else the next term of the row
       if (retry) {
-        wantA = want_r; cA = c_r; bA = b_r;
+        want0 = want_r; c0 = c_r; b0 = b_r;
+        bucket_load<CE>(table, b0, k0, v00, v01);
+        live0 = true;
       } else if (has) {
         uint64_t flip;
-        cA = pop_term<false>(T, rt, 64 * w, b, any_s_out, flip);
+        c0 = pop_term<false>(T, rt, 64 * w, b, any_s_out, flip);
         const uint64_t raw = b ^ flip;
-        if constexpr (TK > 0) wantA = orbit_min_torus_sq<TK>(orbit, raw);
-        else wantA = orbit_representative(orbit, raw);
-        bA = table_slot(wantA, n_buckets);
+        if constexpr (TK > 0) want0 = orbit_min_torus_sq<TK>(orbit, raw);
+        else want0 = orbit_representative(orbit, raw);
+        b0 = table_slot(want0, n_buckets);
+        bucket_load<CE>(table, b0, k0, v00, v01);
+        live0 = true;
+      } else {
+        live0 = false;
       }
-      stage = (stage + 1) & (kDepth - 1);
-      if (liveA) bucket_request<CE>(pipe, stage, table, bA);
-      asm volatile("cp.async.commit_group;" ::: "memory");            // one group per trip, empty or not
-      // at most the kDepth - 1 newest groups stay pending: the request that is D now (issued kDepth - 1 trips ago, read
-      // at the top of the next trip) has landed
-      asm volatile("cp.async.wait_group %0;" ::"n"(kDepth - 1) : "memory");
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (valid) {
       const double inv_nb = 1.0 / __ldg(row_norms + i);
       E out;
@@ -1373,7 +1343,7 @@ namespace {
 template <bool CE, int TK>
 void launch_rows_t(const KernelParams &p, cudaStream_t stream) {
   const SmemLayout L = smem_layout(p, PROJ_GROUP, sizeof(double), false);
-  const size_t smem_bytes = align_up(L.total, 16) + rows_pipe_bytes<CE>();
+  const size_t smem_bytes = L.total;
   auto kernel = k_rows<CE, TK>;
   if (smem_bytes > 48 * 1024)
     DMV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));

@@ -72,18 +72,29 @@ int dmv_context_destroy(dmv_context *ctx);
  * non-blocking stream when use_own_stream != 0 (the initial state) */
 int dmv_set_stream(dmv_context *ctx, void *cuda_stream, int use_own_stream);
 int dmv_synchronize(dmv_context *ctx);
-/* options: "mode"     = -1 auto (row traversal k_gather on one rank when the operator passes the bit-parallel emit test
- *                        and the basis has no permutation symmetries, else push) | 0 push: scatter with FP64 atomics,
- *                        the reference's traversal (DMV:73-127) | 1 rows (k_gather, or the queued k_pull); one rank only
+/* options: "mode"     = -1 auto (row traversal on one rank when a row kernel applies -- k_gather: bit-parallel operator on a
+ *                        basis without permutation symmetries; k_rows: real bit-parallel operator on a basis with
+ *                        permutation symmetries and trivial characters -- else push) | 0 push: scatter with FP64
+ *                        atomics, the reference's traversal (DMV:73-127) | 1 rows (k_gather / k_rows, else the queued
+ *                        k_pull); one rank only
  *          "gather"   = -1 auto | 0 use the queued k_pull instead of k_gather when "mode" selects rows
+ *          "rows"     = -1 auto | 0 use the queued k_pull instead of k_rows
+ *          "gather_walk" = 0 every lane walks its emitting groups from the top bit | 1 group-major warp-uniform walk
+ *                        (measured slower) | 2 from the bottom bit (round 1)
  *          "index"    = -1 auto (identity / Lin tables / directory) | 0 directory + binary search | 2 combinadic rank
  *                        | 3 Lin tables (full fixed-Hamming bases)
  *          "bitparallel" = 1 | 0 walk the flip-mask groups one by one
- *          "canon"    = -1 auto (orbit minima through the canonical form of the translation subgroup) | 0 walk the chain
+ *          "canon"    = -1 auto (orbit minima through canonical forms: full space group of a torus, rotations x mirror x
+ *                        flip of a chain) | 1 the round-1 forms (block rotations + coset chain; four run searches)
+ *                        | 2 single-block LUT + independent networks | 0 walk the chain of group elements
  *          "exchange" = -1 auto (replicated x when the whole basis fits, else peer-direct records, else NCCL buckets)
  *                        | 0 NCCL send/recv of record buckets | 1 peer-direct records over NVLink | 2 replicated x
- * dmv_get_info: "index_mode", "pull", "gather", "projection", "n_groups", "orbit_n_q", "orbit_n_t", "canon_mode",
- *               "peer_direct", "replicated", "replicated_block", "global_states", ... (-1: unknown) */
+ *          "peer_gather" = -1 auto (replicated x: all-gather of x as peer-direct NVLink stores + flags) | 0 ncclAllGather
+ *          "rounds"   = -1 auto (peer-direct records in 4 overlapped rounds for blocks of >= 2^18 states) | 0, 1 one shot
+ *                        (generate everything, fence, accumulate) | R <= 64 rounds
+ * dmv_get_info: "index_mode", "pull", "gather", "rows", "rows_ok", "projection", "n_groups", "orbit_n_q", "orbit_n_t",
+ *               "canon_mode", "torus_mode", "peer_direct", "replicated", "replicated_block", "peer_gather", "rounds",
+ *               "global_states", "complex_coefficients", ... (-1: unknown) */
 int dmv_set_option(dmv_context *ctx, const char *name, int64_t value);
 int64_t dmv_get_info(const dmv_context *ctx, const char *name);
 
@@ -154,6 +165,9 @@ int dmv_accumulate(dmv_context *ctx, int elt, int64_t count, const uint64_t *bet
  * over NVLink) into slots of dmv_get_info(ctx, "replicated_block") elements per rank, and each rank computes ITS rows by
  * the row traversal (k_gather, or the queued k_pull for bases with permutation symmetries): no records, no atomics on y.
  * The hash partition of x, y and the representatives seen by the caller (SE:129-156) is unchanged.
+ * Inside dmv_matvec the all-gather of x is one kernel of peer-direct NVLink stores into the CUDA-IPC-mapped gathered
+ * vectors of all ranks plus release / acquire flags (option "peer_gather"; ncclAllGather when IPC mapping is impossible).
+ * Bases with permutation symmetries run k_rows on a hash table over the whole basis, refilled from the gathered x.
  *   dmv_replicated_setup:   local set-up (whole basis, slot table); no communication.
  *   dmv_replicated_product: y <- rows of this rank applied to a caller-assembled gathered x (device pointers); for
  *                           hosts that own the all-gather themselves (several logical ranks on one GPU, tests). */
