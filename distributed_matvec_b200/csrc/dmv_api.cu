@@ -906,13 +906,19 @@ void do_plan(dmv_context *ctx) {
 void ensure_table(dmv_context *ctx, int elt) {
   if (ctx->table_elt == elt) return;
   const int64_t n = ctx->n_states;
-  if (2 * n + 16 >= 2147483647ll) throw std::runtime_error("k_rows: more than 2^30 states per table");
-  const uint32_t slots = (uint32_t)std::max<int64_t>(16, 2 * n);   // buckets of two slots: 0.5 states per bucket
-  const int slot_bytes = elt == DMV_C128 ? 64 : 32;
+  // complex128: one-slot buckets, 8 per state (1.07 probes per look-up) while the table stays below a quarter of the
+  // free memory, else 4 or 2 per state; float64: two-slot buckets, 2 per state
+  size_t free_b = 0, total_b = 0;
+  CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  int64_t per_state = elt == DMV_C128 ? 8 : 2;
+  while (per_state > 2 && (double)per_state * n * 32.0 > 0.25 * (double)free_b) per_state /= 2;
+  if (per_state * n + 16 >= 2147483647ll) throw std::runtime_error("k_rows: table of more than 2^31 buckets");
+  const uint32_t slots = (uint32_t)std::max<int64_t>(16, per_state * n);
+  const int slot_bytes = 32;
   ctx->d_table.alloc((size_t)slots * slot_bytes);
   ctx->d_slot_of.alloc((size_t)std::max<int64_t>(1, n));
   CUDA_CHECK(cudaMemsetAsync(ctx->d_table.ptr, 0xff, (size_t)slots * slot_bytes, ctx->stream));
-  launch_table_insert(ctx->d_reps.ptr, n, ctx->d_table.ptr, slots, slot_bytes, ctx->d_slot_of.ptr, ctx->stream);
+  launch_table_insert(ctx->d_reps.ptr, n, ctx->d_table.ptr, slots, elt == DMV_C128 ? 1 : 2, ctx->d_slot_of.ptr, ctx->stream);
   ctx->table_slots = slots;
   ctx->table_elt = elt;
 }

@@ -253,12 +253,13 @@ __device__ __forceinline__ int64_t locate(const StateIndex &ix, uint64_t key) {
 // array + directory needs  directory -> several probes -> norm -> x  dependent loads per term, and orbit minima
 // cluster at small values, which unbalances any directory over the top bits; here a term costs the 32-byte sector of
 // its bucket.  The values are refreshed once per product
-// (k_table_fill: x[i] * norm[i] at slot_of[i]).  180 GB of HBM pays for the 128 bytes per state.
-// Buckets of two slots, two buckets per state (0.5 keys per bucket): a look-up requests the whole bucket at once
-// (both keys, both values: independent loads) and finds its key there in 98 % of the cases; otherwise it moves on to the
-// next bucket (a state goes to the first bucket from its home with a free slot, slot 0 first).
-//   complex128: bucket = { key0, key1, re0, im0, re1, im1, pad, pad } (64 bytes)
-//   float64:    bucket = { key0, key1, value0, value1 }               (32 bytes)
+// (k_table_fill: x[i] * norm[i] at slot_of[i]).  180 GB of HBM pays for the 64 .. 256 bytes per state.
+// A bucket is ONE 32-byte sector, fetched with one 256-bit load: HBM3e serves about 30 G random sectors per second
+// whatever their size up to 64 bytes (tools/random_access.cu, profiles/r02_random_access.md), so the look-up costs
+// what its sectors cost.  A state goes to the first bucket from its home with a free slot; a look-up that finds its
+// bucket taken by other states moves on to the next one (7 % of the look-ups for complex128, 2 % for float64).
+//   complex128: bucket = one slot  { key, spare, re, im },            8 buckets per state
+//   float64:    bucket = two slots { key0, key1, value0, value1 },    2 buckets per state
 // ---------------------------------------------------------------------------------------------
 constexpr uint64_t kEmptyKey = ~0ull;
 __host__ __device__ __forceinline__ uint32_t table_slot(uint64_t key, uint32_t n_buckets) {

@@ -123,7 +123,7 @@ void launch_gather(const KernelParams &p, bool inversion, bool complex_values, b
 void launch_rows(const KernelParams &p, bool complex_elements, cudaStream_t stream);
 // hash table of k_rows: insert every state (slot_of[i] = its slot), then per product table[slot_of[i]] = x[src(i)] * norm[i]
 // with src(i) = pos ? pos[i] : i
-void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t n_slots, int slot_bytes,
+void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t n_buckets, int slots_per_bucket,
                          uint32_t *slot_of, cudaStream_t stream);
 void launch_table_fill(int64_t n, bool complex_elements, const void *x, const double *norms, const uint32_t *pos,
                        const uint32_t *slot_of, void *table, cudaStream_t stream);

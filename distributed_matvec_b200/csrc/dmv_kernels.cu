@@ -868,16 +868,12 @@ template <bool CE>
 __device__ __forceinline__ void bucket_load(const unsigned char *__restrict__ table, uint32_t b, ulonglong2 &keys,
                                             typename ValT<CE>::type &v0, typename ValT<CE>::type &v1) {
   uint64_t w0, w1, w2, w3;
-  if constexpr (CE) {
-    const unsigned char *q = table + (size_t)b * 64;
-    load256(q, w0, w1, w2, w3);
-    keys = make_ulonglong2(w0, w1);
+  load256(table + (size_t)b * 32, w0, w1, w2, w3);   // one bucket = one 32-byte sector = one request
+  if constexpr (CE) {   // { key, spare, re, im }
+    keys = make_ulonglong2(w0, w1);                  // (one slot: the second word is spare)
     v0 = make_double2(__longlong_as_double((long long)w2), __longlong_as_double((long long)w3));
-    uint64_t u0, u1, u2, u3;
-    load256(q + 32, u0, u1, u2, u3);
-    v1 = make_double2(__longlong_as_double((long long)u0), __longlong_as_double((long long)u1));
-  } else {
-    load256(table + (size_t)b * 32, w0, w1, w2, w3);
+    v1 = v0;
+  } else {              // { key0, key1, value0, value1 }
     keys = make_ulonglong2(w0, w1);
     v0 = __longlong_as_double((long long)w2);
     v1 = __longlong_as_double((long long)w3);
@@ -934,10 +930,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
       // ---- consume the older request
       bool retry = false;
       if (live1) {
-        const bool hit0 = k1.x == want1, hit1 = k1.y == want1;
+        const bool hit0 = k1.x == want1, hit1 = !CE && k1.y == want1;
         if (hit0 | hit1) {
           axpy(acc, c1, hit0 ? v10 : v11);
-        } else if (k1.x == kEmptyKey || k1.y == kEmptyKey) {   // a free slot in the bucket: the state is not in the basis
+        } else if (k1.x == kEmptyKey || (!CE && k1.y == kEmptyKey)) {   // a free slot in the bucket: not a basis state
           if (c1 != 0.0) { ++bad; bad_state = want1; }         // DMV:115-118
         } else {
           retry = true;                                        // both slots taken by other states: next bucket
@@ -985,21 +981,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
   }
 }
 
-// hash table set-up: claim a slot per state (keys pre-set to kEmptyKey; slot 0 of a bucket before slot 1, then the
-// next bucket), remember it in slot_of (= 2 bucket + slot)
+// hash table set-up: claim a slot per state (keys pre-set to kEmptyKey; slot 0 of a bucket, then slot 1 when the bucket
+// has two, then the next bucket), remember it in slot_of (= 2 bucket + slot)
 __global__ void k_table_insert(const uint64_t *__restrict__ reps, int64_t n, unsigned char *table, uint32_t n_buckets,
-                               int bucket_bytes, uint32_t *slot_of) {
+                               int slots_per_bucket, uint32_t *slot_of) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t key = reps[i];
   uint32_t b = table_slot(key, n_buckets);
   for (;;) {
-    unsigned long long *q = reinterpret_cast<unsigned long long *>(table + (size_t)b * bucket_bytes);
+    unsigned long long *q = reinterpret_cast<unsigned long long *>(table + (size_t)b * 32);
     if (atomicCAS(q, (unsigned long long)kEmptyKey, (unsigned long long)key) == (unsigned long long)kEmptyKey) {
       slot_of[i] = 2 * b;
       return;
     }
-    if (atomicCAS(q + 1, (unsigned long long)kEmptyKey, (unsigned long long)key) == (unsigned long long)kEmptyKey) {
+    if (slots_per_bucket == 2 &&
+        atomicCAS(q + 1, (unsigned long long)kEmptyKey, (unsigned long long)key) == (unsigned long long)kEmptyKey) {
       slot_of[i] = 2 * b + 1;
       return;
     }
@@ -1019,7 +1016,7 @@ __global__ void k_table_fill(int64_t n, const void *__restrict__ x, const double
     const uint32_t s = __ldg(slot_of + i);
     if constexpr (CE) {
       const double2 v = __ldg(reinterpret_cast<const double2 *>(x) + src);
-      *reinterpret_cast<double2 *>(table + (size_t)(s >> 1) * 64 + 16 + 16 * (s & 1)) = make_double2(v.x * nrm, v.y * nrm);
+      *reinterpret_cast<double2 *>(table + (size_t)(s >> 1) * 32 + 16) = make_double2(v.x * nrm, v.y * nrm);
     } else {
       *reinterpret_cast<double *>(table + (size_t)(s >> 1) * 32 + 16 + 8 * (s & 1)) =
           __ldg(reinterpret_cast<const double *>(x) + src) * nrm;
@@ -1372,11 +1369,11 @@ void launch_rows(const KernelParams &p, bool complex_elements, cudaStream_t stre
   else launch_rows_e<false>(p, stream);
 }
 
-void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t n_buckets, int bucket_bytes,
+void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t n_buckets, int slots_per_bucket,
                          uint32_t *slot_of, cudaStream_t stream) {
   if (n <= 0) return;
   k_table_insert<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reps, n, reinterpret_cast<unsigned char *>(table),
-                                                                 n_buckets, bucket_bytes, slot_of);
+                                                                 n_buckets, slots_per_bucket, slot_of);
   DMV_CUDA_CHECK(cudaGetLastError());
   g_launches++;
 }
