@@ -933,7 +933,7 @@ void rows_product(dmv_context *basis, KernelParams &p, int elt, const void *x_al
   basis->stream = keep;
   if (fill)   // (a product cut into row chunks refreshes the values once, with its first chunk)
     launch_table_fill(basis->n_states, elt == DMV_C128, x_all, basis->d_norms.ptr, pos, basis->d_slot_of.ptr,
-                      basis->d_table.ptr, stream);
+                      basis->d_reps.ptr, basis->d_table.ptr, stream);
   select_tables(basis, p, true, false);
   p.uni_re = basis->gather_uni[0]; p.uni_im = basis->gather_uni[1];
   p.table = basis->d_table.ptr;

@@ -126,7 +126,7 @@ void launch_rows(const KernelParams &p, bool complex_elements, cudaStream_t stre
 void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t n_buckets, int slots_per_bucket,
                          uint32_t *slot_of, cudaStream_t stream);
 void launch_table_fill(int64_t n, bool complex_elements, const void *x, const double *norms, const uint32_t *pos,
-                       const uint32_t *slot_of, void *table, cudaStream_t stream);
+                       const uint32_t *slot_of, const uint64_t *reps, void *table, cudaStream_t stream);
 void launch_accumulate(const KernelParams &p, Projection proj, bool complex_values, bool complex_elements,
                        int64_t count, const uint64_t *betas, const double *coeffs, cudaStream_t stream);
 // plugin kernels (BO:217-275): diagonal coefficients / CSR list of off-diagonal terms of caller-given states

@@ -1004,11 +1004,12 @@ __global__ void k_table_insert(const uint64_t *__restrict__ reps, int64_t n, uns
   }
 }
 
-// per product: value of slot_of[i] = x[src(i)] * norm[i]   (src(i) = pos ? pos[i] : i)
+// per product: value of slot_of[i] = x[src(i)] * norm[i]   (src(i) = pos ? pos[i] : i).  complex128 rewrites the WHOLE
+// 32-byte bucket {key, spare, re, im} with one 256-bit store: a full-sector write needs no read-modify-write in DRAM
 template <bool CE>
 __global__ void k_table_fill(int64_t n, const void *__restrict__ x, const double *__restrict__ norms,
                              const uint32_t *__restrict__ pos, const uint32_t *__restrict__ slot_of,
-                             unsigned char *table) {
+                             const uint64_t *__restrict__ reps, unsigned char *table) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int64_t src = pos ? (int64_t)__ldg(pos + i) : i;
@@ -1016,7 +1017,10 @@ __global__ void k_table_fill(int64_t n, const void *__restrict__ x, const double
     const uint32_t s = __ldg(slot_of + i);
     if constexpr (CE) {
       const double2 v = __ldg(reinterpret_cast<const double2 *>(x) + src);
-      *reinterpret_cast<double2 *>(table + (size_t)(s >> 1) * 32 + 16) = make_double2(v.x * nrm, v.y * nrm);
+      const uint64_t key = __ldg(reps + i);
+      const uint64_t re = (uint64_t)__double_as_longlong(v.x * nrm), im = (uint64_t)__double_as_longlong(v.y * nrm);
+      asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(table + (size_t)(s >> 1) * 32), "l"(key), "l"(0ull),
+                   "l"(re), "l"(im) : "memory");
     } else {
       *reinterpret_cast<double *>(table + (size_t)(s >> 1) * 32 + 16 + 8 * (s & 1)) =
           __ldg(reinterpret_cast<const double *>(x) + src) * nrm;
@@ -1379,12 +1383,12 @@ void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t 
 }
 
 void launch_table_fill(int64_t n, bool complex_elements, const void *x, const double *norms, const uint32_t *pos,
-                       const uint32_t *slot_of, void *table, cudaStream_t stream) {
+                       const uint32_t *slot_of, const uint64_t *reps, void *table, cudaStream_t stream) {
   if (n <= 0) return;
   const int blocks = grid_for(n, 256, sm_count() * 16);
   unsigned char *t = reinterpret_cast<unsigned char *>(table);
-  if (complex_elements) k_table_fill<true><<<blocks, 256, 0, stream>>>(n, x, norms, pos, slot_of, t);
-  else k_table_fill<false><<<blocks, 256, 0, stream>>>(n, x, norms, pos, slot_of, t);
+  if (complex_elements) k_table_fill<true><<<blocks, 256, 0, stream>>>(n, x, norms, pos, slot_of, reps, t);
+  else k_table_fill<false><<<blocks, 256, 0, stream>>>(n, x, norms, pos, slot_of, reps, t);
   DMV_CUDA_CHECK(cudaGetLastError());
   g_launches++;
 }
