@@ -329,6 +329,10 @@ struct dmv_context {
   int opt_gather_walk = 0;  // k_gather: 0 per-lane walk from the top bit (default), 1 group-major warp-uniform walk
                             // (measured slower), 2 per-lane walk from the bottom bit (round 1)
   DevBuf<unsigned char> d_table;
+  DevBuf<unsigned char> d_mph_blocks, d_dense;   // dense index: perfect-hash blocks, dense table of (key, value) slots
+  PerfectHash mph{};
+  bool dense_index = false;
+  int opt_rows_index = -1;   // -1 auto (dense index through the perfect hash), 0 open-addressing table only
   DevBuf<uint32_t> d_slot_of;
   uint32_t table_slots = 0;
   int table_elt = 0;        // element type the slots are laid out for (0: not built)
@@ -906,19 +910,86 @@ void do_plan(dmv_context *ctx) {
 void ensure_table(dmv_context *ctx, int elt) {
   if (ctx->table_elt == elt) return;
   const int64_t n = ctx->n_states;
+  cudaStream_t st = ctx->stream;
+  const bool ce = elt == DMV_C128;
+  // ---- dense index: two perfect-hash levels of 4 bits per state; what they cannot place goes to the table below
+  const uint64_t *left_keys = ctx->d_reps.ptr;
+  int64_t n_left = n;
+  DevBuf<uint64_t> d_left[2];
+  ctx->dense_index = ctx->opt_rows_index != 0 && n >= 1;
+  ctx->mph = PerfectHash{};
+  if (ctx->dense_index) {
+    if (n >= 2147483647ll) throw std::runtime_error("k_rows: more than 2^31 states");
+    std::vector<unsigned long long> bits;      // seen & ~collide of both levels, 3 words per block
+    uint32_t nb[2] = {0, 0};
+    DevBuf<unsigned long long> d_count;
+    d_count.alloc(1);
+    for (int level = 0; level < 2 && n_left > 0; ++level) {
+      nb[level] = (uint32_t)std::max<int64_t>(1, (4 * n_left + kMphBits - 1) / kMphBits);
+      const size_t words = (size_t)nb[level] * 3;
+      DevBuf<unsigned long long> d_seen, d_coll;
+      d_seen.alloc(words); d_coll.alloc(words);
+      CUDA_CHECK(cudaMemsetAsync(d_seen.ptr, 0, words * 8, st));
+      CUDA_CHECK(cudaMemsetAsync(d_coll.ptr, 0, words * 8, st));
+      CUDA_CHECK(cudaMemsetAsync(d_count.ptr, 0, 8, st));
+      launch_mph_mark(left_keys, n_left, level, nb[level], d_seen.ptr, d_coll.ptr, st);
+      d_left[level].alloc((size_t)std::max<int64_t>(1, n_left));
+      launch_mph_compact(left_keys, n_left, level, nb[level], d_coll.ptr, d_left[level].ptr, d_count.ptr, st);
+      std::vector<unsigned long long> seen(words), coll(words);
+      unsigned long long cnt = 0;
+      CUDA_CHECK(cudaMemcpyAsync(seen.data(), d_seen.ptr, words * 8, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaMemcpyAsync(coll.data(), d_coll.ptr, words * 8, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaMemcpyAsync(&cnt, d_count.ptr, 8, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      for (size_t w = 0; w < words; ++w) bits.push_back(seen[w] & ~coll[w]);
+      left_keys = d_left[level].ptr;
+      n_left = (int64_t)cnt;
+    }
+    // blocks { w0, w1, w2, prefix }: prefix = number of set bits before the block, over both levels
+    const size_t n_blocks = (size_t)nb[0] + nb[1];
+    std::vector<unsigned long long> blocks(n_blocks * 4);
+    unsigned long long prefix = 0;
+    for (size_t b = 0; b < n_blocks; ++b) {
+      blocks[4 * b + 3] = prefix;
+      for (int k = 0; k < 3; ++k) {
+        blocks[4 * b + k] = bits[3 * b + k];
+        prefix += (unsigned long long)__builtin_popcountll(bits[3 * b + k]);
+      }
+    }
+    if ((int64_t)prefix + n_left != n) throw std::runtime_error("k_rows: perfect hash lost states");
+    ctx->d_mph_blocks.alloc(blocks.size() * 8);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->d_mph_blocks.ptr, blocks.data(), blocks.size() * 8, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    ctx->mph.blocks = ctx->d_mph_blocks.ptr;
+    ctx->mph.n_blocks0 = nb[0];
+    ctx->mph.n_blocks1 = nb[1];
+    ctx->mph.n_dense = (uint32_t)prefix;
+    const size_t dense_bytes = (size_t)std::max<unsigned long long>(1, prefix) * (ce ? 32 : 16);
+    ctx->d_dense.alloc(dense_bytes);
+    CUDA_CHECK(cudaMemsetAsync(ctx->d_dense.ptr, 0xff, dense_bytes, st));
+  }
+  // ---- open-addressing table over the states that are left (all of them without the dense index)
   // complex128: one-slot buckets, 8 per state (1.07 probes per look-up) while the table stays below a quarter of the
   // free memory, else 4 or 2 per state; float64: two-slot buckets, 2 per state
   size_t free_b = 0, total_b = 0;
   CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-  int64_t per_state = elt == DMV_C128 ? 8 : 2;
-  while (per_state > 2 && (double)per_state * n * 32.0 > 0.25 * (double)free_b) per_state /= 2;
-  if (per_state * n + 16 >= 2147483647ll) throw std::runtime_error("k_rows: table of more than 2^31 buckets");
-  const uint32_t slots = (uint32_t)std::max<int64_t>(16, per_state * n);
-  const int slot_bytes = 32;
-  ctx->d_table.alloc((size_t)slots * slot_bytes);
+  int64_t per_state = ce ? 8 : 2;
+  while (per_state > 2 && (double)per_state * n_left * 32.0 > 0.25 * (double)free_b) per_state /= 2;
+  if (per_state * n_left + 16 >= 2147483647ll) throw std::runtime_error("k_rows: table of more than 2^31 buckets");
+  const uint32_t slots = (uint32_t)std::max<int64_t>(16, per_state * n_left);
+  ctx->d_table.alloc((size_t)slots * 32);
   ctx->d_slot_of.alloc((size_t)std::max<int64_t>(1, n));
-  CUDA_CHECK(cudaMemsetAsync(ctx->d_table.ptr, 0xff, (size_t)slots * slot_bytes, ctx->stream));
-  launch_table_insert(ctx->d_reps.ptr, n, ctx->d_table.ptr, slots, elt == DMV_C128 ? 1 : 2, ctx->d_slot_of.ptr, ctx->stream);
+  CUDA_CHECK(cudaMemsetAsync(ctx->d_table.ptr, 0xff, (size_t)slots * 32, st));
+  if (ctx->dense_index) {
+    DevBuf<uint32_t> d_tmp;
+    d_tmp.alloc((size_t)std::max<int64_t>(1, n_left));
+    launch_table_insert(left_keys, n_left, ctx->d_table.ptr, slots, ce ? 1 : 2, d_tmp.ptr, st);
+    launch_mph_slots(ctx->d_reps.ptr, n, ctx->mph, ctx->d_table.ptr, slots, ce ? 1 : 2, ctx->d_slot_of.ptr,
+                     ctx->d_status.ptr, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  } else {
+    launch_table_insert(ctx->d_reps.ptr, n, ctx->d_table.ptr, slots, ce ? 1 : 2, ctx->d_slot_of.ptr, st);
+  }
   ctx->table_slots = slots;
   ctx->table_elt = elt;
 }
@@ -933,11 +1004,13 @@ void rows_product(dmv_context *basis, KernelParams &p, int elt, const void *x_al
   basis->stream = keep;
   if (fill)   // (a product cut into row chunks refreshes the values once, with its first chunk)
     launch_table_fill(basis->n_states, elt == DMV_C128, x_all, basis->d_norms.ptr, pos, basis->d_slot_of.ptr,
-                      basis->d_reps.ptr, basis->d_table.ptr, stream);
+                      basis->d_reps.ptr, basis->d_table.ptr, basis->dense_index ? basis->d_dense.ptr : nullptr, stream);
   select_tables(basis, p, true, false);
   p.uni_re = basis->gather_uni[0]; p.uni_im = basis->gather_uni[1];
   p.table = basis->d_table.ptr;
   p.table_slots = basis->table_slots;
+  p.mph = basis->mph;
+  p.dense = basis->dense_index ? basis->d_dense.ptr : nullptr;
   p.row_split = 1;
   launch_rows(p, elt == DMV_C128, stream);
 }
@@ -1194,6 +1267,7 @@ void setup_replicated(dmv_context *ctx) {
     ctx->global = g;
     g->opt_rows = ctx->opt_rows;
     g->opt_gather_walk = ctx->opt_gather_walk;
+    g->opt_rows_index = ctx->opt_rows_index;
     if (ctx->opt_canon != g->opt_canon && g->proj == PROJ_GROUP) { g->opt_canon = ctx->opt_canon; upload_orbit(g); }
     if (dmv_basis_build(g) != 0) throw std::runtime_error(g_last_error);
   }
@@ -1863,6 +1937,11 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
   } else if (key == "gather") {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
+  } else if (key == "rows_index") {
+    if (value < -1 || value > 1) throw std::runtime_error("rows_index: -1 auto / 1 dense index (perfect hash), 0 open-addressing table");
+    ctx->opt_rows_index = (int)value;
+    ctx->table_elt = 0;
+    if (ctx->global) { ctx->global->opt_rows_index = (int)value; ctx->global->table_elt = 0; }
   } else if (key == "rounds") {
     if (value < -1 || value > 64) throw std::runtime_error("rounds: -1 auto, 0 / 1 one-shot exchange, R <= 64 overlapped rounds");
     ctx->opt_rounds = (int)value;
@@ -1914,6 +1993,7 @@ int64_t dmv_get_info(const dmv_context *ctx, const char *name) {
     return ((use_pull(ctx) && !use_gather(ctx) && use_rows(ctx)) ||
             (ctx->replicated && ctx->global && !use_gather(ctx->global) && use_rows(ctx->global))) ? 1 : 0;
   if (key == "rows_ok") return ctx->rows_ok ? 1 : 0;
+  if (key == "rows_dense") return ctx->dense_index ? (int64_t)ctx->mph.n_dense : (ctx->global && ctx->global->dense_index ? (int64_t)ctx->global->mph.n_dense : 0);
   if (key == "rounds") return ctx->rounds.ready ? ctx->rounds.R : 0;
   if (key == "peer_gather") return (ctx->replicated && ctx->peer_gather) ? 1 : 0;
   if (key == "complex_coefficients") return ctx->complex_coefficients ? 1 : 0;

@@ -268,6 +268,49 @@ __host__ __device__ __forceinline__ uint32_t table_slot(uint64_t key, uint32_t n
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dense index for k_rows: a two-level perfect hash over the representatives.  The open-addressing table above is bound by
+// the rate at which HBM serves RANDOM sectors, and that rate falls from ~70 G/s to ~30 G/s as the table grows from 2 x L2
+// to gigabytes (profiles/r02_random_access.md); a perfect hash needs no empty slots, so the table of (key, value) slots
+// shrinks from 256 N to 32 N bytes.  Level l is an array of 32-byte blocks { w0, w1, w2, prefix }: 192 bits of which bit
+// p is set iff exactly ONE state hashes to p at this level (then it owns the slot prefix + popcount of the set bits
+// before p in the block); states that collide at level 0 try level 1, the few per cent left over live in the
+// open-addressing table.  Both blocks of a look-up are requested together (two 256-bit loads that hit L2: 5 bits per
+// state), the slot one pipeline step later.
+// ---------------------------------------------------------------------------------------------
+struct PerfectHash {
+  const unsigned char *blocks;   // [n_blocks0 + n_blocks1][32]
+  uint32_t n_blocks0, n_blocks1; // blocks of level 0 / level 1
+  uint32_t n_dense;              // states placed by the two levels = slots of the dense table
+};
+constexpr uint32_t kMphBits = 192;
+constexpr uint32_t kMphMissing = 0xffffffffu;
+// (block, bit) of a state at a level
+__host__ __device__ __forceinline__ void mph_position(uint64_t key, int level, uint32_t n_blocks, uint32_t &block, uint32_t &bit) {
+  uint64_t h = key * (level == 0 ? 0x9E3779B97F4A7C15ull : 0xC2B2AE3D27D4EB4Full);
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  block = (uint32_t)(((h >> 32) * (uint64_t)n_blocks) >> 32);
+  bit = (uint32_t)(((h & 0xffffffffull) * (uint64_t)kMphBits) >> 32);
+}
+// slot owned at position `bit` of a block, or kMphMissing when the bit is not set
+__host__ __device__ __forceinline__ uint32_t mph_rank(uint64_t w0, uint64_t w1, uint64_t w2, uint64_t prefix, uint32_t bit) {
+  const uint32_t word = bit >> 6, b = bit & 63u;
+  const uint64_t w = word == 0 ? w0 : (word == 1 ? w1 : w2);
+  if (!((w >> b) & 1ull)) return kMphMissing;
+  const uint64_t below = w & ((1ull << b) - 1ull);
+#ifdef __CUDA_ARCH__
+  uint32_t r = (uint32_t)prefix + (uint32_t)__popcll(below);
+  if (word > 0) r += (uint32_t)__popcll(w0);
+  if (word > 1) r += (uint32_t)__popcll(w1);
+#else
+  uint32_t r = (uint32_t)prefix + (uint32_t)__builtin_popcountll(below);
+  if (word > 0) r += (uint32_t)__builtin_popcountll(w0);
+  if (word > 1) r += (uint32_t)__builtin_popcountll(w1);
+#endif
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Bit permutations
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t butterfly(uint64_t s, uint64_t mask, int delta) {

@@ -108,6 +108,10 @@ struct KernelParams {
   // vector element in the slot (see table_slot in dmv_device.cuh)
   const void *table;
   uint32_t table_slots;
+  // ... or, with a dense index: perfect hash -> slot of `dense` (32 bytes: {key, spare, re, im} / 16 bytes: {key, value});
+  // `table` then only holds the few per cent of the states the two levels could not place
+  PerfectHash mph;
+  const void *dense;
 };
 
 // launchers (dmv_kernels.cu)
@@ -126,7 +130,16 @@ void launch_rows(const KernelParams &p, bool complex_elements, cudaStream_t stre
 void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t n_buckets, int slots_per_bucket,
                          uint32_t *slot_of, cudaStream_t stream);
 void launch_table_fill(int64_t n, bool complex_elements, const void *x, const double *norms, const uint32_t *pos,
-                       const uint32_t *slot_of, const uint64_t *reps, void *table, cudaStream_t stream);
+                       const uint32_t *slot_of, const uint64_t *reps, void *table, void *dense, cudaStream_t stream);
+// perfect-hash set-up (k_rows dense index): mark the positions of `n` states at a level in seen / collide bit arrays
+// (192 bits per block, 3 words each), and compact the states whose position collided into `next`
+void launch_mph_mark(const uint64_t *keys, int64_t n, int level, uint32_t n_blocks, unsigned long long *seen,
+                     unsigned long long *collide, cudaStream_t stream);
+void launch_mph_compact(const uint64_t *keys, int64_t n, int level, uint32_t n_blocks, const unsigned long long *collide,
+                        uint64_t *next, unsigned long long *next_count, cudaStream_t stream);
+// slot of every state: dense slot through the perfect hash, or 0x80000000 | (slot in the open-addressing table)
+void launch_mph_slots(const uint64_t *keys, int64_t n, PerfectHash mph, const void *table, uint32_t n_buckets,
+                      int slots_per_bucket, uint32_t *slot_of, unsigned long long *status, cudaStream_t stream);
 void launch_accumulate(const KernelParams &p, Projection proj, bool complex_values, bool complex_elements,
                        int64_t count, const uint64_t *betas, const double *coeffs, cudaStream_t stream);
 // plugin kernels (BO:217-275): diagonal coefficients / CSR list of off-diagonal terms of caller-given states

@@ -864,6 +864,10 @@ __global__ void __launch_bounds__(kThreads) k_pull(const KernelParams p) {
 __device__ __forceinline__ void load256(const unsigned char *q, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(q));
 }
+// the same through L1 (perfect-hash blocks: a few bits per state, read by every look-up)
+__device__ __forceinline__ void load256_cached(const unsigned char *q, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+  asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(q));
+}
 template <bool CE>
 __device__ __forceinline__ void bucket_load(const unsigned char *__restrict__ table, uint32_t b, ulonglong2 &keys,
                                             typename ValT<CE>::type &v0, typename ValT<CE>::type &v1) {
@@ -884,7 +888,7 @@ __device__ __forceinline__ void axpy(double2 &acc, double c, double2 v) { acc.x 
 
 // two CTAs per SM: the pipeline state must stay in registers (a spilled request waits for its load at once), and the
 // latency is hidden inside the lane, not by occupancy
-template <bool CE, int TK>
+template <bool CE, int TK, bool MPH>
 __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
   using E = typename ValT<CE>::type;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -901,6 +905,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
   const double *__restrict__ row_norms = p.row_norms ? p.row_norms : p.norms;
   unsigned long long bad = 0, bad_state = 0;
   const E zero = v_make(0.0, 0.0, (E *)nullptr);
+  const PerfectHash H = p.mph;
+  const unsigned char *__restrict__ dense = reinterpret_cast<const unsigned char *>(p.dense);
 
   const int64_t n_rows = p.row_end - p.row_begin;
   const int64_t n_tiles = (n_rows + 31) / 32;
@@ -910,6 +916,86 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
     const bool valid = i < p.row_end;
     const uint64_t b = valid ? __ldg(row_states + i) : 0ull;
     E acc = zero;
+    int w = 0;
+    RowTerms rt = row_terms<false>(T, 0, 0, min(64, p.n_groups), b);
+    if (!valid) rt.mask = 0;
+    if constexpr (MPH) {
+      // ---- dense index: request 0 holds the two perfect-hash blocks of its state (L2 hits), request 1 the slot of
+      // the dense table (or, for the few states the two levels could not place, a bucket of the open-addressing table)
+      bool live0 = false, live1 = false, in_table1 = false;
+      uint64_t want0 = 0, want1 = 0;
+      double c0 = 0.0, c1 = 0.0;
+      uint32_t bits0 = 0, b1 = 0;
+      uint64_t A0 = 0, A1 = 0, A2 = 0, A3 = 0, B0 = 0, B1 = 0, B2 = 0, B3 = 0;
+      ulonglong2 k1 = make_ulonglong2(0, 0);
+      E v10 = zero, v11 = zero;
+      for (;;) {
+        while (valid && rt.mask == 0 && 64 * (w + 1) < p.n_groups) {
+          ++w;
+          rt = row_terms<false>(T, w, 64 * w, min(64 * w + 64, p.n_groups), b);
+        }
+        const bool has = rt.mask != 0;
+        if (!has && !live0 && !live1) break;
+        // ---- consume request 1
+        bool retry = false;
+        if (live1) {
+          if (!in_table1) {
+            if (k1.x == want1) axpy(acc, c1, v10);
+            else if (c1 != 0.0) { ++bad; bad_state = want1; }   // the slot belongs to another state: not in the basis
+          } else {
+            const bool hit0 = k1.x == want1, hit1 = !CE && k1.y == want1;
+            if (hit0 | hit1) axpy(acc, c1, hit0 ? v10 : v11);
+            else if (k1.x == kEmptyKey || (!CE && k1.y == kEmptyKey)) { if (c1 != 0.0) { ++bad; bad_state = want1; } }
+            else retry = true;
+          }
+        }
+        if (retry) {   // next bucket of the open-addressing table; request 0 and the row wait one trip
+          b1 = b1 + 1 == n_buckets ? 0 : b1 + 1;
+          bucket_load<CE>(table, b1, k1, v10, v11);
+          continue;
+        }
+        // ---- request 0 -> request 1: resolve the slot, ask for it
+        live1 = live0;
+        if (live0) {
+          want1 = want0; c1 = c0;
+          uint32_t slot = mph_rank(A0, A1, A2, A3, bits0 & 0xffu);
+          if (slot == kMphMissing && H.n_blocks1 != 0) slot = mph_rank(B0, B1, B2, B3, bits0 >> 8);
+          in_table1 = slot == kMphMissing;
+          if (!in_table1) {
+            if constexpr (CE) {
+              uint64_t u0, u1, u2, u3;
+              load256(dense + (size_t)slot * 32, u0, u1, u2, u3);
+              k1 = make_ulonglong2(u0, u1);
+              v10 = make_double2(__longlong_as_double((long long)u2), __longlong_as_double((long long)u3));
+            } else {
+              const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(dense + (size_t)slot * 16));
+              k1 = make_ulonglong2(t.x, 0);
+              v10 = __longlong_as_double((long long)t.y);
+            }
+          } else {
+            b1 = table_slot(want1, n_buckets);
+            bucket_load<CE>(table, b1, k1, v10, v11);
+          }
+        }
+        // ---- a new request 0: the next term of the row
+        live0 = has;
+        if (has) {
+          uint64_t flip;
+          c0 = pop_term<false>(T, rt, 64 * w, b, any_s_out, flip);
+          const uint64_t raw = b ^ flip;
+          if constexpr (TK > 0) want0 = orbit_min_torus_sq<TK>(orbit, raw);
+          else want0 = orbit_representative(orbit, raw);
+          uint32_t blk, bit, blk1 = 0, bit1 = 0;
+          mph_position(want0, 0, H.n_blocks0, blk, bit);
+          load256_cached(H.blocks + (size_t)blk * 32, A0, A1, A2, A3);
+          if (H.n_blocks1 != 0) {
+            mph_position(want0, 1, H.n_blocks1, blk1, bit1);
+            load256_cached(H.blocks + ((size_t)H.n_blocks0 + blk1) * 32, B0, B1, B2, B3);
+          }
+          bits0 = bit | (bit1 << 8);
+        }
+      }
+    } else {
     // two requests in flight per lane: wanted key, coefficient, bucket, and what the bucket held
     bool live0 = false, live1 = false;
     uint64_t want0 = 0, want1 = 0;
@@ -917,9 +1003,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
     uint32_t b0 = 0, b1 = 0;
     ulonglong2 k0 = make_ulonglong2(0, 0), k1 = k0;
     E v00 = zero, v01 = zero, v10 = zero, v11 = zero;
-    int w = 0;
-    RowTerms rt = row_terms<false>(T, 0, 0, min(64, p.n_groups), b);
-    if (!valid) rt.mask = 0;
     for (;;) {
       while (valid && rt.mask == 0 && 64 * (w + 1) < p.n_groups) {
         ++w;
@@ -960,6 +1043,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
       } else {
         live0 = false;
       }
+    }
     }
     if (valid) {
       const double inv_nb = 1.0 / __ldg(row_norms + i);
@@ -1005,27 +1089,78 @@ __global__ void k_table_insert(const uint64_t *__restrict__ reps, int64_t n, uns
 }
 
 // per product: value of slot_of[i] = x[src(i)] * norm[i]   (src(i) = pos ? pos[i] : i).  complex128 rewrites the WHOLE
-// 32-byte bucket {key, spare, re, im} with one 256-bit store: a full-sector write needs no read-modify-write in DRAM
+// 32-byte slot {key, spare, re, im} with one 256-bit store: a full-sector write needs no read-modify-write in DRAM.
+// slot_of[i] < 2^31: slot of the dense table (perfect hash); else 0x80000000 | slot of the open-addressing table.
 template <bool CE>
 __global__ void k_table_fill(int64_t n, const void *__restrict__ x, const double *__restrict__ norms,
                              const uint32_t *__restrict__ pos, const uint32_t *__restrict__ slot_of,
-                             const uint64_t *__restrict__ reps, unsigned char *table) {
+                             const uint64_t *__restrict__ reps, unsigned char *table, unsigned char *dense) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int64_t src = pos ? (int64_t)__ldg(pos + i) : i;
     const double nrm = __ldg(norms + i);
-    const uint32_t s = __ldg(slot_of + i);
+    uint32_t s = __ldg(slot_of + i);
+    const bool in_table = dense == nullptr || (s & 0x80000000u);
+    s &= 0x7fffffffu;
+    const uint64_t key = __ldg(reps + i);
     if constexpr (CE) {
       const double2 v = __ldg(reinterpret_cast<const double2 *>(x) + src);
-      const uint64_t key = __ldg(reps + i);
       const uint64_t re = (uint64_t)__double_as_longlong(v.x * nrm), im = (uint64_t)__double_as_longlong(v.y * nrm);
-      asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(table + (size_t)(s >> 1) * 32), "l"(key), "l"(0ull),
-                   "l"(re), "l"(im) : "memory");
+      unsigned char *q = in_table ? table + (size_t)(s >> 1) * 32 : dense + (size_t)s * 32;
+      asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(q), "l"(key), "l"(0ull), "l"(re), "l"(im) : "memory");
     } else {
-      *reinterpret_cast<double *>(table + (size_t)(s >> 1) * 32 + 16 + 8 * (s & 1)) =
-          __ldg(reinterpret_cast<const double *>(x) + src) * nrm;
+      const double v = __ldg(reinterpret_cast<const double *>(x) + src) * nrm;
+      if (in_table) *reinterpret_cast<double *>(table + (size_t)(s >> 1) * 32 + 16 + 8 * (s & 1)) = v;
+      else *reinterpret_cast<ulonglong2 *>(dense + (size_t)s * 16) = make_ulonglong2(key, (uint64_t)__double_as_longlong(v));
     }
   }
+}
+
+// ---- perfect-hash set-up (see PerfectHash in dmv_device.cuh) ----
+__global__ void k_mph_mark(const uint64_t *__restrict__ keys, int64_t n, int level, uint32_t n_blocks,
+                           unsigned long long *seen, unsigned long long *collide) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t block, bit;
+  mph_position(keys[i], level, n_blocks, block, bit);
+  const size_t w = (size_t)block * 3 + (bit >> 6);
+  const unsigned long long m = 1ull << (bit & 63u);
+  if (atomicOr(seen + w, m) & m) atomicOr(collide + w, m);
+}
+__global__ void k_mph_compact(const uint64_t *__restrict__ keys, int64_t n, int level, uint32_t n_blocks,
+                              const unsigned long long *__restrict__ collide, uint64_t *next,
+                              unsigned long long *next_count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t block, bit;
+  mph_position(keys[i], level, n_blocks, block, bit);
+  if ((collide[(size_t)block * 3 + (bit >> 6)] >> (bit & 63u)) & 1ull) next[atomicAdd(next_count, 1ull)] = keys[i];
+}
+__device__ __forceinline__ uint32_t mph_lookup(const PerfectHash &H, uint64_t key) {
+  uint32_t block, bit;
+  mph_position(key, 0, H.n_blocks0, block, bit);
+  const unsigned long long *q = reinterpret_cast<const unsigned long long *>(H.blocks) + (size_t)block * 4;
+  uint32_t r = mph_rank(q[0], q[1], q[2], q[3], bit);
+  if (r != kMphMissing || H.n_blocks1 == 0) return r;
+  mph_position(key, 1, H.n_blocks1, block, bit);
+  q = reinterpret_cast<const unsigned long long *>(H.blocks) + ((size_t)H.n_blocks0 + block) * 4;
+  return mph_rank(q[0], q[1], q[2], q[3], bit);
+}
+__global__ void k_mph_slots(const uint64_t *__restrict__ keys, int64_t n, PerfectHash H, const unsigned char *table,
+                            uint32_t n_buckets, int slots_per_bucket, uint32_t *slot_of, unsigned long long *status) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = keys[i];
+  const uint32_t r = mph_lookup(H, key);
+  if (r != kMphMissing) { slot_of[i] = r; return; }
+  uint32_t b = table_slot(key, n_buckets);
+  for (uint32_t tries = 0; tries <= n_buckets; ++tries) {   // the state was inserted before: the probe sequence finds it
+    const unsigned long long *q = reinterpret_cast<const unsigned long long *>(table + (size_t)b * 32);
+    if (q[0] == key) { slot_of[i] = 0x80000000u | (2 * b); return; }
+    if (slots_per_bucket == 2 && q[1] == key) { slot_of[i] = 0x80000000u | (2 * b + 1); return; }
+    b = b + 1 == n_buckets ? 0 : b + 1;
+  }
+  atomicAdd(status + 2, 1ull);
 }
 
 // localProcess for records that arrived from other ranks: already projected and hashed by the sender.
@@ -1341,11 +1476,11 @@ void launch_accumulate_p(const KernelParams &p, bool cv, bool ce, int64_t count,
 }  // namespace
 
 namespace {
-template <bool CE, int TK>
+template <bool CE, int TK, bool MPH>
 void launch_rows_t(const KernelParams &p, cudaStream_t stream) {
   const SmemLayout L = smem_layout(p, PROJ_GROUP, sizeof(double), false);
   const size_t smem_bytes = L.total;
-  auto kernel = k_rows<CE, TK>;
+  auto kernel = k_rows<CE, TK, MPH>;
   if (smem_bytes > 48 * 1024)
     DMV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   int per_sm = 0;
@@ -1361,9 +1496,15 @@ template <bool CE>
 void launch_rows_e(const KernelParams &p, cudaStream_t stream) {
   const OrbitProgram &o = p.orbit;
   const int k = (o.canon_mode != 0 && o.tor_mode == 2 && o.canon_k == o.canon_r) ? o.canon_k : 0;
-  if (k == 6) launch_rows_t<CE, 6>(p, stream);
-  else if (k == 4) launch_rows_t<CE, 4>(p, stream);
-  else launch_rows_t<CE, 0>(p, stream);
+  if (p.dense != nullptr) {   // dense index (perfect hash)
+    if (k == 6) launch_rows_t<CE, 6, true>(p, stream);
+    else if (k == 4) launch_rows_t<CE, 4, true>(p, stream);
+    else launch_rows_t<CE, 0, true>(p, stream);
+    return;
+  }
+  if (k == 6) launch_rows_t<CE, 6, false>(p, stream);
+  else if (k == 4) launch_rows_t<CE, 4, false>(p, stream);
+  else launch_rows_t<CE, 0, false>(p, stream);
 }
 }  // namespace
 
@@ -1383,12 +1524,35 @@ void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t 
 }
 
 void launch_table_fill(int64_t n, bool complex_elements, const void *x, const double *norms, const uint32_t *pos,
-                       const uint32_t *slot_of, const uint64_t *reps, void *table, cudaStream_t stream) {
+                       const uint32_t *slot_of, const uint64_t *reps, void *table, void *dense, cudaStream_t stream) {
   if (n <= 0) return;
   const int blocks = grid_for(n, 256, sm_count() * 16);
-  unsigned char *t = reinterpret_cast<unsigned char *>(table);
-  if (complex_elements) k_table_fill<true><<<blocks, 256, 0, stream>>>(n, x, norms, pos, slot_of, reps, t);
-  else k_table_fill<false><<<blocks, 256, 0, stream>>>(n, x, norms, pos, slot_of, reps, t);
+  unsigned char *t = reinterpret_cast<unsigned char *>(table), *d = reinterpret_cast<unsigned char *>(dense);
+  if (complex_elements) k_table_fill<true><<<blocks, 256, 0, stream>>>(n, x, norms, pos, slot_of, reps, t, d);
+  else k_table_fill<false><<<blocks, 256, 0, stream>>>(n, x, norms, pos, slot_of, reps, t, d);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
+void launch_mph_mark(const uint64_t *keys, int64_t n, int level, uint32_t n_blocks, unsigned long long *seen,
+                     unsigned long long *collide, cudaStream_t stream) {
+  if (n <= 0) return;
+  k_mph_mark<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keys, n, level, n_blocks, seen, collide);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+void launch_mph_compact(const uint64_t *keys, int64_t n, int level, uint32_t n_blocks, const unsigned long long *collide,
+                        uint64_t *next, unsigned long long *next_count, cudaStream_t stream) {
+  if (n <= 0) return;
+  k_mph_compact<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keys, n, level, n_blocks, collide, next, next_count);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+void launch_mph_slots(const uint64_t *keys, int64_t n, PerfectHash mph, const void *table, uint32_t n_buckets,
+                      int slots_per_bucket, uint32_t *slot_of, unsigned long long *status, cudaStream_t stream) {
+  if (n <= 0) return;
+  k_mph_slots<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keys, n, mph, reinterpret_cast<const unsigned char *>(table),
+                                                              n_buckets, slots_per_bucket, slot_of, status);
   DMV_CUDA_CHECK(cudaGetLastError());
   g_launches++;
 }
