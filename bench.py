@@ -36,9 +36,12 @@ import sys
 import threading
 import time
 
-# pin the OpenMP threads of the CPU arm before libgomp is loaded (two boxes of the pool disagreed 6x without it)
-os.environ.setdefault("OMP_PROC_BIND", "spread")
-os.environ.setdefault("OMP_PLACES", "cores")
+# pin the OpenMP threads of the CPU arm before libgomp is loaded (two boxes of the pool disagreed 6x without it) -- only
+# when this process is alone: under torchrun every rank would bind its main thread to the SAME first place and the
+# ranks would time-share one core (8 GPUs: ms-scale launch jitter, measured)
+if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "cores")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -349,6 +352,8 @@ class Workload:
         if self.op.info("replicated"):
             return "replicated x: peer-direct all-gather of x over NVLink + row traversal" if self.op.info("peer_gather") > 0 \
                 else "replicated x: NCCL all-gather of x + row traversal"
+        if self.op.info("rounds") > 1:
+            return f"records: peer-direct NVLink stores from k_generate in {self.op.info('rounds')} overlapped rounds"
         if self.op.info("peer_direct"):
             return "records: peer-direct NVLink stores from k_generate"
         return "records: NCCL send/recv buckets"

@@ -108,7 +108,9 @@ def main():
             e1 = np.abs(y_host[pick] - y_ref).max() / scale
             e2 = np.abs(yd.cpu().numpy()[pick] - y_ref).max() / scale
             exch = ("replicated-x/" + ("peer-direct gather" if dop.op.info("peer_gather") == 1 else "nccl all-gather")
-                    if dop.op.info("replicated") else ("records/peer-direct" if dop.op.info("peer_direct") else "records/nccl"))
+                    if dop.op.info("replicated") else
+                    (f"records/peer-direct in {dop.op.info('rounds')} rounds" if dop.op.info("rounds") > 1 else
+                     ("records/peer-direct" if dop.op.info("peer_direct") else "records/nccl")))
             verdict(good, f"{name:26s} P={world} {'c128' if cplx else 'f64 '} N={n} rows_checked={pick.shape[0]}/rank "
                           f"basis_ok={ok_basis} err_host={e1:.1e} err_dev={e2:.1e} exchange={exch}")
         # Lanczos across the ranks (dot products reduced with NCCL): every rank must report the same energy
