@@ -332,7 +332,8 @@ struct dmv_context {
   DevBuf<unsigned char> d_mph_blocks, d_dense;   // dense index: perfect-hash blocks, dense table of (key, value) slots
   PerfectHash mph{};
   bool dense_index = false;
-  int opt_rows_index = -1;   // -1 auto (dense index through the perfect hash), 0 open-addressing table only
+  int opt_rows_index = -1;   // -1 auto / 0 open-addressing table; 1 dense index through a perfect hash (measured slower:
+                             // profiles/r02_rows_pipelines.md)
   DevBuf<uint32_t> d_slot_of;
   uint32_t table_slots = 0;
   int table_elt = 0;        // element type the slots are laid out for (0: not built)
@@ -916,7 +917,7 @@ void ensure_table(dmv_context *ctx, int elt) {
   const uint64_t *left_keys = ctx->d_reps.ptr;
   int64_t n_left = n;
   DevBuf<uint64_t> d_left[2];
-  ctx->dense_index = ctx->opt_rows_index != 0 && n >= 1;
+  ctx->dense_index = ctx->opt_rows_index == 1 && n >= 1;
   ctx->mph = PerfectHash{};
   if (ctx->dense_index) {
     if (n >= 2147483647ll) throw std::runtime_error("k_rows: more than 2^31 states");
@@ -1938,7 +1939,7 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
   } else if (key == "rows_index") {
-    if (value < -1 || value > 1) throw std::runtime_error("rows_index: -1 auto / 1 dense index (perfect hash), 0 open-addressing table");
+    if (value < -1 || value > 1) throw std::runtime_error("rows_index: -1 auto / 0 open-addressing table, 1 dense index (perfect hash)");
     ctx->opt_rows_index = (int)value;
     ctx->table_elt = 0;
     if (ctx->global) { ctx->global->opt_rows_index = (int)value; ctx->global->table_elt = 0; }

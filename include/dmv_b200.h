@@ -79,6 +79,8 @@ int dmv_synchronize(dmv_context *ctx);
  *                        k_pull); one rank only
  *          "gather"   = -1 auto | 0 use the queued k_pull instead of k_gather when "mode" selects rows
  *          "rows"     = -1 auto | 0 use the queued k_pull instead of k_rows
+ *          "rows_index" = -1 auto, 0 open-addressing table with the vector element in the slot | 1 dense table behind a
+ *                        two-level perfect hash (5 bits per state; measured slower, kept for reference)
  *          "gather_walk" = 0 every lane walks its emitting groups from the top bit | 1 group-major warp-uniform walk
  *                        (measured slower) | 2 from the bottom bit (round 1)
  *          "index"    = -1 auto (identity / Lin tables / directory) | 0 directory + binary search | 2 combinadic rank

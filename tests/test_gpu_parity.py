@@ -159,13 +159,13 @@ def test_local_matvec_matches_oracle(need_cuda, name, cplx, mode):
         yd = op.matvec(xd)
         torch.cuda.synchronize()
         assert _close(yd.cpu().numpy(), y_ref)
-    if mode == "pull" and op.info("rows"):        # k_rows without the dense index: the open-addressing table alone
-        op.set_option("rows_index", 0)
-        assert _close(op.matvec(x), y_ref)
+    if mode == "pull" and op.info("rows"):        # k_rows with the dense index (two-level perfect hash) instead of the table
         assert op.info("rows_dense") == 0
-        op.set_option("rows_index", -1)
+        op.set_option("rows_index", 1)
         assert _close(op.matvec(x), y_ref)
         assert 0.8 * reps.shape[0] <= op.info("rows_dense") <= reps.shape[0]
+        op.set_option("rows_index", -1)
+        assert _close(op.matvec(x), y_ref)
     gather_applies = not basis.has_permutation_symmetries()    # two-body operators: bit-parallel emit test
     # k_rows: permutation symmetries with trivial characters, real two-body operator
     rows_applies = basis.has_permutation_symmetries() and basis.group.all_characters_trivial
@@ -574,8 +574,8 @@ def test_symmetric_products_at_size_sampled_rows(need_cuda, name, states):
     rows = np.sort(np.random.default_rng(5).choice(states, size=4096, replace=False))
     expect = po.expected_rows(matrix, reps, x, rows)
     xd = torch.from_numpy(x).cuda()
-    # k_rows with the dense index (perfect hash), k_rows on the open-addressing table alone, scatter, queued rows
-    for mode, rows_opt, rows_index in ((-1, -1, -1), (-1, -1, 0), (0, -1, -1), (1, 0, -1)):
+    # k_rows (open-addressing table), k_rows with the dense index (perfect hash), scatter, queued rows
+    for mode, rows_opt, rows_index in ((-1, -1, -1), (-1, -1, 1), (0, -1, -1), (1, 0, -1)):
         if name == "heisenberg_chain_36_symm" and mode == 1:
             continue                                  # the queued kernel adds nothing new at this size
         op.set_option("mode", mode)
