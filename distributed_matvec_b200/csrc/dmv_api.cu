@@ -326,6 +326,7 @@ struct dmv_context {
   // hash table over this context's representatives (see table_slot in dmv_device.cuh)
   bool rows_ok = false;
   int opt_rows = -1;        // -1 auto (k_rows when it applies), 0 the queued k_pull
+  int opt_rows_ctas = 2;    // k_rows: 2 CTAs per SM (122 registers, default) | 3 (80 registers, spills)
   int opt_gather_walk = 0;  // k_gather: 0 per-lane walk from the top bit (default), 1 group-major warp-uniform walk
                             // (measured slower), 2 per-lane walk from the bottom bit (round 1)
   DevBuf<unsigned char> d_table;
@@ -523,6 +524,7 @@ KernelParams base_params(dmv_context *ctx) {
   p.row_begin = 0;
   p.row_end = ctx->n_states;
   p.gather_walk = ctx->opt_gather_walk;
+  p.rows_ctas = ctx->opt_rows_ctas;
   return p;
 }
 
@@ -1269,6 +1271,7 @@ void setup_replicated(dmv_context *ctx) {
     g->opt_rows = ctx->opt_rows;
     g->opt_gather_walk = ctx->opt_gather_walk;
     g->opt_rows_index = ctx->opt_rows_index;
+    g->opt_rows_ctas = ctx->opt_rows_ctas;
     if (ctx->opt_canon != g->opt_canon && g->proj == PROJ_GROUP) { g->opt_canon = ctx->opt_canon; upload_orbit(g); }
     if (dmv_basis_build(g) != 0) throw std::runtime_error(g_last_error);
   }
@@ -1938,6 +1941,9 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
   } else if (key == "gather") {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
+  } else if (key == "rows_ctas") {
+    ctx->opt_rows_ctas = value == 3 ? 3 : 2;
+    if (ctx->global) ctx->global->opt_rows_ctas = ctx->opt_rows_ctas;
   } else if (key == "rows_index") {
     if (value < -1 || value > 1) throw std::runtime_error("rows_index: -1 auto / 0 open-addressing table, 1 dense index (perfect hash)");
     ctx->opt_rows_index = (int)value;

@@ -112,6 +112,7 @@ struct KernelParams {
   // `table` then only holds the few per cent of the states the two levels could not place
   PerfectHash mph;
   const void *dense;
+  int32_t rows_ctas;           // k_rows: resident CTAs per SM the kernel is compiled for (2 default, 3: 80 registers)
 };
 
 // launchers (dmv_kernels.cu)

@@ -888,8 +888,8 @@ __device__ __forceinline__ void axpy(double2 &acc, double c, double2 v) { acc.x 
 
 // two CTAs per SM: the pipeline state must stay in registers (a spilled request waits for its load at once), and the
 // latency is hidden inside the lane, not by occupancy
-template <bool CE, int TK, bool MPH>
-__global__ void __launch_bounds__(kThreads, 2) k_rows(const KernelParams p) {
+template <bool CE, int TK, bool MPH, int CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS) k_rows(const KernelParams p) {
   using E = typename ValT<CE>::type;
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(p, PROJ_GROUP, sizeof(double), false);
@@ -1476,11 +1476,11 @@ void launch_accumulate_p(const KernelParams &p, bool cv, bool ce, int64_t count,
 }  // namespace
 
 namespace {
-template <bool CE, int TK, bool MPH>
+template <bool CE, int TK, bool MPH, int CTAS = 2>
 void launch_rows_t(const KernelParams &p, cudaStream_t stream) {
   const SmemLayout L = smem_layout(p, PROJ_GROUP, sizeof(double), false);
   const size_t smem_bytes = L.total;
-  auto kernel = k_rows<CE, TK, MPH>;
+  auto kernel = k_rows<CE, TK, MPH, CTAS>;
   if (smem_bytes > 48 * 1024)
     DMV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   int per_sm = 0;
@@ -1500,6 +1500,11 @@ void launch_rows_e(const KernelParams &p, cudaStream_t stream) {
     if (k == 6) launch_rows_t<CE, 6, true>(p, stream);
     else if (k == 4) launch_rows_t<CE, 4, true>(p, stream);
     else launch_rows_t<CE, 0, true>(p, stream);
+    return;
+  }
+  if (p.rows_ctas == 3) {   // three CTAs per SM (80 registers: the compiler spills part of the pipeline state)
+    if (k == 6) launch_rows_t<CE, 6, false, 3>(p, stream);
+    else launch_rows_t<CE, 0, false, 3>(p, stream);
     return;
   }
   if (k == 6) launch_rows_t<CE, 6, false>(p, stream);

@@ -24,6 +24,8 @@ def main():
         t0.record(); op.basis.build(); t1.record(); torch.cuda.synchronize()
         n = op.basis.numberStates()
         op.use_torch_stream()
+        if os.environ.get("DMV_ROWS_CTAS"):
+            op.set_option("rows_ctas", int(os.environ["DMV_ROWS_CTAS"]))
         if os.environ.get("DMV_ROWS_INDEX"):
             op.set_option("rows_index", int(os.environ["DMV_ROWS_INDEX"]))
         if os.environ.get("DMV_GATHER_WALK"):
