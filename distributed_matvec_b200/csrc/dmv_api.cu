@@ -114,9 +114,12 @@ NcclApi &nccl() {
       throw std::runtime_error(std::string(#expr) + ": " + nccl().GetErrorString(_r));        \
   } while (0)
 
-enum Timing { T_H2D = 0, T_GENERATE, T_EXCHANGE, T_ACCUMULATE, T_D2H, T_TOTAL, T_COUNT };
+// stages of one product (the coarse part of the reference's timing tree, DMV:1028-1052; the split of the fused kernels
+// into the reference's inner timers -- applyOffDiag / stateInfo / indexing / accessing -- comes from tools/ncu_tree.py)
+enum Timing { T_H2D = 0, T_GENERATE, T_EXCHANGE, T_ACCUMULATE, T_D2H, T_TOTAL, T_TABLE_FILL, T_COUNT };
 const char *kTimingNames[T_COUNT] = {"h2d", "generate(diag+offdiag+local accumulate)", "exchange(all-to-all)",
-                                     "accumulate(remote records)", "d2h", "total"};
+                                     "accumulate(remote records)", "d2h", "total",
+                                     "table refill (k_rows; part of generate)"};
 
 }  // namespace
 
@@ -384,6 +387,8 @@ struct dmv_context {
   static constexpr int kCopyChunks = 8;
   cudaEvent_t ev_chunk[kCopyChunks] = {};
   cudaEvent_t ev[T_COUNT + 2] = {};
+  cudaEvent_t ev_fill[2] = {};
+  bool fill_timed = false;
   double timings[T_COUNT] = {};
   // communicator
   ncclComm_t comm = nullptr;
@@ -456,6 +461,7 @@ struct dmv_context {
     for (void *q : peer_flagmem) if (q) cudaIpcCloseMemHandle(q);
     if (comm) nccl().CommDestroy(comm);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ev_fill) if (e) cudaEventDestroy(e);
     for (auto &e : ev_chunk) if (e) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (own_stream) cudaStreamDestroy(own_stream);
@@ -1000,14 +1006,19 @@ void ensure_table(dmv_context *ctx, int elt) {
 // y[rows] <- rows of H through k_rows.  `basis` owns the table (this rank's context, or the twin holding the whole
 // basis in the replicated-x product), x_all is indexed like basis' states (through pos when given), p names the rows.
 void rows_product(dmv_context *basis, KernelParams &p, int elt, const void *x_all, const uint32_t *pos,
-                  cudaStream_t stream, bool fill = true) {
+                  cudaStream_t stream, bool fill = true, dmv_context *timer = nullptr) {
+  if (!timer) timer = basis;   // whose event timeline the refill belongs to (the rank's context in the replicated form)
   cudaStream_t keep = basis->stream;
   basis->stream = stream;
   ensure_table(basis, elt);
   basis->stream = keep;
-  if (fill)   // (a product cut into row chunks refreshes the values once, with its first chunk)
+  if (fill) {   // (a product cut into row chunks refreshes the values once, with its first chunk)
+    CUDA_CHECK(cudaEventRecord(timer->ev_fill[0], stream));
     launch_table_fill(basis->n_states, elt == DMV_C128, x_all, basis->d_norms.ptr, pos, basis->d_slot_of.ptr,
                       basis->d_reps.ptr, basis->d_table.ptr, basis->dense_index ? basis->d_dense.ptr : nullptr, stream);
+    CUDA_CHECK(cudaEventRecord(timer->ev_fill[1], stream));
+    timer->fill_timed = true;
+  }
   select_tables(basis, p, true, false);
   p.uni_re = basis->gather_uni[0]; p.uni_im = basis->gather_uni[1];
   p.table = basis->d_table.ptr;
@@ -1121,6 +1132,12 @@ void collect_timings(dmv_context *ctx) {
   }
   ctx->timings[T_D2H] = ms(4, 5);
   ctx->timings[T_TOTAL] = ms(0, 5);
+  ctx->timings[T_TABLE_FILL] = 0.0;
+  if (ctx->fill_timed) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, ctx->ev_fill[0], ctx->ev_fill[1]) == cudaSuccess) ctx->timings[T_TABLE_FILL] = t;
+    ctx->fill_timed = false;
+  }
 }
 
 std::mutex g_bind_mutex;
@@ -1327,7 +1344,7 @@ void replicated_rows(dmv_context *ctx, int elt, const void *x_cat, void *y_dev) 
   }
   p.row_norms = ctx->d_norms.ptr;
   if (use_rows(g)) {   // bases with permutation symmetries: hash table over the whole basis, filled from the gathered x
-    rows_product(g, p, elt, x_cat, ctx->d_pos.ptr, ctx->stream);
+    rows_product(g, p, elt, x_cat, ctx->d_pos.ptr, ctx->stream, true, ctx);
     return;
   }
   // operators outside the bit-parallel test / non-trivial characters: the queued row traversal
@@ -1801,6 +1818,7 @@ int dmv_context_create(const dmv_basis_desc *basis, const dmv_operator_desc *op,
   ctx->stream = ctx->own_stream;
   CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (auto &e : ctx->ev) CUDA_CHECK(cudaEventCreate(&e));
+  for (auto &e : ctx->ev_fill) CUDA_CHECK(cudaEventCreate(&e));
   for (auto &e : ctx->ev_chunk) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   ctx->n_sites = basis->number_sites;
   ctx->hamming_weight = basis->hamming_weight;
