@@ -8,8 +8,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdmv_b200.so")
-SOURCES = ["dmv_kernels.cu", "dmv_gather.cu", "dmv_solver.cu", "dmv_group.cu", "dmv_api.cu"]
-HEADERS = ["dmv_device.cuh", "dmv_host.h", os.path.join("..", "..", "include", "dmv_b200.h")]
+SOURCES = ["dmv_kernels.cu", "dmv_gather.cu", "dmv_solver.cu", "dmv_group.cu", "dmv_api.cu", "dmv_exchange.cu",
+           "dmv_lanczos.cu", "dmv_plugin.cu"]
+HEADERS = ["dmv_device.cuh", "dmv_host.h", "dmv_context.h", os.path.join("..", "..", "include", "dmv_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
 

@@ -1,148 +1,13 @@
-// dmv_api.cu -- the C ABI of libdmv_b200.so (see include/dmv_b200.h) and the per-GPU context.
-#include <cuda_runtime.h>
-#include <dlfcn.h>
-#include <nccl.h>  // types only; the library itself is resolved with dlopen at dmv_comm_init
+// dmv_api.cu -- the C ABI of libdmv_b200.so (see include/dmv_b200.h): context, basis, the single-rank product and the
+// stepwise pieces of the distributed one.  Exchanges: dmv_exchange.cu; eigensolver: dmv_lanczos.cu; plugin table: dmv_plugin.cu.
+#include "dmv_context.h"
 
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <memory>
-#include <mutex>
-#include <stdexcept>
-#include <string>
-#include <vector>
-
-#include "../../include/dmv_b200.h"
-#include "dmv_host.h"
-
-using namespace dmv;
-
-namespace {
-
+namespace dmv { namespace host {
 thread_local std::string g_last_error;
+} }
 
-#define CUDA_CHECK(expr)                                                                        \
-  do {                                                                                          \
-    cudaError_t _e = (expr);                                                                    \
-    if (_e != cudaSuccess)                                                                      \
-      throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e));            \
-  } while (0)
+namespace dmv { namespace host {
 
-#define API_BEGIN try {
-#define API_END                                         \
-  return 0;                                             \
-  }                                                     \
-  catch (const std::exception &e) {                     \
-    g_last_error = e.what();                            \
-    return 1;                                           \
-  }                                                     \
-  catch (...) {                                         \
-    g_last_error = "unknown error";                     \
-    return 1;                                           \
-  }
-
-template <typename T>
-struct DevBuf {
-  T *ptr = nullptr;
-  size_t count = 0;
-  void alloc(size_t n) {
-    if (n <= count && ptr) return;
-    release();
-    if (n == 0) n = 1;
-    CUDA_CHECK(cudaMalloc(&ptr, n * sizeof(T)));
-    count = n;
-  }
-  void release() {
-    if (ptr) cudaFree(ptr);
-    ptr = nullptr;
-    count = 0;
-  }
-  void upload(const std::vector<T> &h, cudaStream_t s) {
-    alloc(h.size());
-    if (!h.empty()) CUDA_CHECK(cudaMemcpyAsync(ptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
-  }
-  ~DevBuf() { release(); }
-};
-
-bool is_device_pointer(const void *p) {
-  if (!p) return false;
-  cudaPointerAttributes attr;
-  cudaError_t e = cudaPointerGetAttributes(&attr, p);
-  if (e != cudaSuccess) { cudaGetLastError(); return false; }
-  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
-}
-
-// ---- NCCL through dlopen ------------------------------------------------------------------------
-struct NcclApi {
-  void *handle = nullptr;
-  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
-  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
-  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-  ncclResult_t (*GroupStart)() = nullptr;
-  ncclResult_t (*GroupEnd)() = nullptr;
-  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-  const char *(*GetErrorString)(ncclResult_t) = nullptr;
-};
-NcclApi &nccl() {
-  static NcclApi api;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    const char *names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char *n : names) {
-      api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-      if (api.handle) break;
-    }
-    if (!api.handle) return;
-#define LOAD(sym) api.sym = reinterpret_cast<decltype(api.sym)>(dlsym(api.handle, "nccl" #sym))
-    LOAD(GetUniqueId); LOAD(CommInitRank); LOAD(CommDestroy); LOAD(GroupStart); LOAD(GroupEnd);
-    LOAD(Send); LOAD(Recv); LOAD(AllGather); LOAD(AllReduce); LOAD(GetErrorString);
-#undef LOAD
-  });
-  if (!api.handle || !api.Send) throw std::runtime_error("NCCL (libnccl.so.2) is not available");
-  return api;
-}
-#define NCCL_CHECK(expr)                                                                       \
-  do {                                                                                         \
-    ncclResult_t _r = (expr);                                                                  \
-    if (_r != ncclSuccess)                                                                     \
-      throw std::runtime_error(std::string(#expr) + ": " + nccl().GetErrorString(_r));        \
-  } while (0)
-
-// stages of one product (the coarse part of the reference's timing tree, DMV:1028-1052; the split of the fused kernels
-// into the reference's inner timers -- applyOffDiag / stateInfo / indexing / accessing -- comes from tools/ncu_tree.py)
-enum Timing { T_H2D = 0, T_GENERATE, T_EXCHANGE, T_ACCUMULATE, T_D2H, T_TOTAL, T_TABLE_FILL, T_COUNT };
-const char *kTimingNames[T_COUNT] = {"h2d", "generate(diag+offdiag+local accumulate)", "exchange(all-to-all)",
-                                     "accumulate(remote records)", "d2h", "total",
-                                     "table refill (k_rows; part of generate)"};
-
-}  // namespace
-
-namespace {
-
-// Flip-mask groups of an operator in look-up-table form (see LutGroup in dmv_device.cuh).
-struct HostTables {
-  std::vector<LutGroup> groups;
-  std::vector<double> lut_re, lut_c;   // real parts only / interleaved complex
-  std::vector<OffTerm> terms;
-  std::vector<BpWord> bp;               // non-empty: bit-parallel emit test (see BpWord)
-  bool any_generic = false, any_s_out = false;
-};
-struct DevTables {
-  DevBuf<LutGroup> groups;
-  DevBuf<double> lut_re, lut_c;
-  DevBuf<OffTerm> terms;
-  DevBuf<BpWord> bp;
-  void upload(const HostTables &h, cudaStream_t s) {
-    groups.upload(h.groups, s); lut_re.upload(h.lut_re, s); lut_c.upload(h.lut_c, s); terms.upload(h.terms, s);
-    bp.upload(h.bp, s);
-  }
-};
 
 // support of a group: union of the masks of its terms
 uint64_t support_of(const std::vector<OffTerm> &terms) {
@@ -283,193 +148,6 @@ HostTables build_tables(const std::map<uint64_t, std::vector<OffTerm>> &by_x) {
   return H;
 }
 
-}  // namespace
-
-struct dmv_context {
-  int device = 0, rank = 0, num_ranks = 1;
-  // basis
-  int n_sites = 0, hamming_weight = -1, spin_inversion = 0;
-  bool has_permutations = false;
-  Projection proj = PROJ_NONE;
-  bool identity_index = false;
-  uint64_t site_mask = 0;
-  bool complex_coefficients = false;  // operator or characters are complex
-  HostOrbitProgram host_orbit;
-  DevBuf<uint64_t> d_orbit64;
-  DevBuf<int32_t> d_orbit32;
-  DevBuf<double> d_chars;
-  DevBuf<uint16_t> d_canon_lut;
-  DevBuf<uint64_t> d_canon_masks, d_cc_mask;
-  DevBuf<uint32_t> d_canon_lut2;
-  DevBuf<int32_t> d_cc_begin, d_cc_delta;
-  DevBuf<uint16_t> d_tor_lutm;
-  DevBuf<uint8_t> d_tor_frow;
-  DevBuf<uint32_t> d_tor_luts;
-  DevBuf<uint64_t> d_tor_net_mask;
-  DevBuf<int32_t> d_tor_net_delta;
-  int opt_canon = -1;    // -1 auto (block-rotation canonical form when the chain subgroup allows it), 0 walk the chain
-  OrbitProgram orbit{};  // device view
-  // operator
-  std::vector<DiagTerm> h_diag;
-  HostTables h_push, h_pull;          // column-traversal (scatter) / row-traversal (gather) tables
-  DevTables d_push, d_pull;
-  DevBuf<DiagTerm> d_diag;
-  std::vector<DiagClass> h_diag_classes;  // bit-parallel part of the diagonal; h_diag is reordered: rest first
-  DevBuf<DiagClass> d_diag_classes;
-  int n_diag_rest = 0;
-  size_t h_diag_kept = 0;   // number of diagonal terms of the operator (h_diag itself only keeps the non-class rest)
-  // options
-  int opt_mode = -1;    // -1 auto (pull when one rank owns the basis), 0 push (scatter), 1 pull (gather)
-  int opt_index = -1;   // -1 auto, 0 directory search, 2 combinadic rank
-  int opt_bitparallel = 1;  // 0: walk the groups one by one even when the bit-parallel test applies
-  int opt_gather = -1;      // row traversal kernel: -1 auto (k_gather when it applies), 0 always the queued k_pull
-  // k_gather applicability (set at context creation from the row-traversal tables)
-  bool gather_ok = false, gather_narrow = false, gather_uniform = false;
-  // k_rows applicability (bases with permutation symmetries, trivial characters, real bit-parallel operator) and its
-  // hash table over this context's representatives (see table_slot in dmv_device.cuh)
-  bool rows_ok = false;
-  int opt_rows = -1;        // -1 auto (k_rows when it applies), 0 the queued k_pull
-  int opt_rows_ctas = 2;    // k_rows: 2 CTAs per SM (122 registers, default) | 3 (80 registers, spills)
-  int opt_gather_walk = 0;  // k_gather: 0 per-lane walk from the top bit (default), 1 group-major warp-uniform walk
-                            // (measured slower), 2 per-lane walk from the bottom bit (round 1)
-  DevBuf<unsigned char> d_table;
-  DevBuf<unsigned char> d_mph_blocks, d_dense;   // dense index: perfect-hash blocks, dense table of (key, value) slots
-  PerfectHash mph{};
-  bool dense_index = false;
-  int opt_rows_index = -1;   // -1 auto / 0 open-addressing table; 1 dense index through a perfect hash (measured slower:
-                             // profiles/r02_rows_pipelines.md)
-  DevBuf<uint32_t> d_slot_of;
-  uint32_t table_slots = 0;
-  int table_elt = 0;        // element type the slots are laid out for (0: not built)
-  double gather_uni[2] = {0.0, 0.0};
-  int index_mode = INDEX_DIRECTORY;
-  DevBuf<uint32_t> d_binom, d_lin_a, d_lin_b;
-  int lin_bits = 0;
-  int binom_stride = 0;
-  uint64_t rank_total = 0;
-  // representatives of this rank
-  int64_t n_states = -1;
-  DevBuf<uint64_t> d_reps;
-  DevBuf<double> d_norms;
-  DevBuf<uint32_t> d_dir;
-  uint64_t n_buckets = 0;
-  int dir_shift = 0;
-  // vectors staged for host callers
-  DevBuf<double> d_x, d_y;
-  // outgoing / incoming records
-  bool planned = false;
-  std::vector<int64_t> send_counts;        // [num_ranks]
-  std::vector<int64_t> recv_counts;        // [num_ranks] (filled by dmv_comm plan exchange)
-  std::vector<int64_t> h_out_offset;       // [num_ranks + 1]
-  DevBuf<int64_t> d_out_offset;
-  DevBuf<unsigned long long> d_out_count;
-  DevBuf<uint64_t> d_out_betas, d_in_betas;
-  DevBuf<double> d_out_coeffs, d_in_coeffs;
-  int record_width = 2;                    // doubles per coefficient of the current buckets
-  int plan_grid = 0;                       // CTAs of the planned launches (exact warp-private regions)
-  int row_split = 1;                       // lanes per source state (chosen at plan time from the block size)
-  bool peer_direct = false;                // records are stored straight into the peers' incoming buffers
-  int ptr_width = 0;                       // record width the destination pointer table was built for
-  int opt_exchange = -1;                   // -1 auto (peer-direct when possible), 0 NCCL send/recv, 1 peer-direct
-  std::vector<void *> peer_betas, peer_coeffs;   // IPC-mapped incoming buffers of the peers
-  std::vector<int64_t> my_offset_in_peer;         // first slot of MY region in every peer's incoming buffer
-  DevBuf<int> d_barrier;
-  DevBuf<unsigned long long> d_warp_counts;
-  DevBuf<int64_t> d_warp_offsets, d_out_capacity;
-  DevBuf<uint64_t *> d_out_betas_ptr;
-  DevBuf<double *> d_out_coeffs_ptr;
-  std::vector<uint64_t *> h_out_betas_ptr;   // where the records for every destination go (local bucket or peer)
-  std::vector<double *> h_out_coeffs_ptr;
-  int64_t number_terms = 0;
-  DevBuf<unsigned long long> d_status;
-  // streams
-  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-  static constexpr int kCopyChunks = 8;
-  cudaEvent_t ev_chunk[kCopyChunks] = {};
-  cudaEvent_t ev[T_COUNT + 2] = {};
-  cudaEvent_t ev_fill[2] = {};
-  bool fill_timed = false;
-  double timings[T_COUNT] = {};
-  // communicator
-  ncclComm_t comm = nullptr;
-  // replicated-x product (exchange = 2, see setup_replicated): a single-rank twin context holding the WHOLE basis,
-  // the slot of every global state in the all-gathered x, and the gathered x itself
-  std::vector<double> k_off_v, k_diag_v;                      // copies of the creation arguments
-  std::vector<uint64_t> k_off_m, k_off_r, k_off_x, k_off_s, k_diag_m, k_diag_r, k_diag_s;
-  std::vector<int32_t> k_perms;
-  std::vector<uint8_t> k_flips;
-  std::vector<double> k_chars;
-  int64_t k_group_order = 0;
-  dmv_context *global = nullptr;
-  DevBuf<uint32_t> d_pos;
-  int64_t repl_block = 0;        // slot size per rank in the gathered x (the largest block)
-  DevBuf<double> d_xcat;
-  bool replicated = false, exchange_decided = false, timeline_replicated = false;
-  // peer-direct all-gather of x (launch_push_block): the peers' gathered vectors (two buffers, alternating by epoch) and
-  // flag words mapped with CUDA IPC
-  bool peer_gather = false;
-  int opt_peer_gather = -1;                 // -1 auto, 0 NCCL all-gather
-  std::vector<void *> peer_xcat, peer_flagmem;
-  DevBuf<unsigned> d_flags, d_push_done;    // [num_ranks] epochs raised by the peers; CTA counter of k_push_block
-  DevBuf<void *> d_peer_slot[2];            // [num_ranks] slot `rank` of every rank's buffer b
-  DevBuf<unsigned *> d_peer_flags;          // [num_ranks]
-  int peer_slot_elt = 0;                    // element width the slot pointers were computed for
-  unsigned gather_epoch = 0;
-  // record exchange in overlapped ROUNDS (peer-direct records; reference DMV:638-661, 818-852, 957-1011): the rows are cut
-  // into R rounds; round r's records land in the owners' buffers while round r + 1 is being generated, and the owner
-  // accumulates round r on a second stream as soon as every sender has raised its flag for it
-  struct Rounds {
-    bool ready = false, tried = false;
-    int R = 0, grid = 0, row_split = 1;
-    std::vector<int64_t> row_begin;           // [R + 1]
-    DevBuf<int64_t> d_warp_offsets;           // [R][warps][P]: first slot of every warp inside MY region of (round, dest)
-    DevBuf<int64_t> d_capacity;               // [R][P]
-    std::vector<int64_t> in_slice;            // [R + 1]: rounds inside my incoming buffer (records)
-    std::vector<int64_t> my_off;              // [R][P]: my region of round r inside rank q's incoming buffer
-    int64_t in_total = 0;
-    std::vector<int64_t> peer_total;          // [P]: in_total of every rank (start of its second buffer)
-    DevBuf<uint64_t> d_in_betas;              // two buffers (alternating products) of in_total records
-    DevBuf<double> d_in_coeffs;               // two doubles per record
-    std::vector<void *> peer_betas, peer_coeffs, peer_flags;
-    DevBuf<unsigned> d_flags;                 // [P] raised by the senders: product * R + round + 1
-    DevBuf<unsigned *> d_peer_flags;
-    DevBuf<uint64_t *> d_bptr;                // [2][R][P]
-    DevBuf<double *> d_cptr;
-    int ptr_width = 0;
-    unsigned seq = 0;
-    cudaStream_t acc_stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
-    int64_t terms = 0;
-  } rounds;
-  int opt_rounds = -1;                        // -1 auto, 0 / 1 off (generate everything, fence, accumulate), R > 1
-
-  // Lanczos work space (dmv_lanczos)
-  DevBuf<double> lz_v[4];
-  DevBuf<double> lz_scal;
-
-  ~dmv_context() {
-    delete global;
-    for (void *q : peer_betas) if (q) cudaIpcCloseMemHandle(q);
-    for (void *q : peer_coeffs) if (q) cudaIpcCloseMemHandle(q);
-    for (void *q : peer_xcat) if (q) cudaIpcCloseMemHandle(q);
-    for (void *q : rounds.peer_betas) if (q) cudaIpcCloseMemHandle(q);
-    for (void *q : rounds.peer_coeffs) if (q) cudaIpcCloseMemHandle(q);
-    for (void *q : rounds.peer_flags) if (q) cudaIpcCloseMemHandle(q);
-    if (rounds.acc_stream) cudaStreamDestroy(rounds.acc_stream);
-    if (rounds.ev_begin) cudaEventDestroy(rounds.ev_begin);
-    if (rounds.ev_done) cudaEventDestroy(rounds.ev_done);
-    for (void *q : peer_flagmem) if (q) cudaIpcCloseMemHandle(q);
-    if (comm) nccl().CommDestroy(comm);
-    for (auto &e : ev) if (e) cudaEventDestroy(e);
-    for (auto &e : ev_fill) if (e) cudaEventDestroy(e);
-    for (auto &e : ev_chunk) if (e) cudaEventDestroy(e);
-    if (copy_stream) cudaStreamDestroy(copy_stream);
-    if (own_stream) cudaStreamDestroy(own_stream);
-  }
-};
-
-namespace {
-
 bool use_gather(const dmv_context *ctx) {   // the lean row-gather kernel applies and is not switched off
   return ctx->gather_ok && ctx->opt_gather != 0 && ctx->opt_bitparallel != 0 && ctx->proj != PROJ_GROUP;
 }
@@ -534,7 +212,7 @@ KernelParams base_params(dmv_context *ctx) {
   return p;
 }
 
-// Split the diagonal into bit-parallel classes (m == 0, two sign bits, equal coefficient) and the rest.
+// Split the diagonal into bit-parallel classes (m =, two sign bits, equal coefficient) and the rest.
 void build_diag_classes(dmv_context *ctx) {
   std::vector<DiagTerm> rest;
   std::map<std::pair<double, double>, std::vector<DiagTerm>> by_v;
@@ -623,22 +301,6 @@ void check_status(dmv_context *ctx) {
     throw std::runtime_error(buf);
   }
 }
-
-// binomial table for the combinadic ranking of fixed-Hamming-weight states
-struct Binomials {
-  uint64_t c[65][65];
-  Binomials() {
-    for (int n = 0; n <= 64; ++n)
-      for (int k = 0; k <= 64; ++k) {
-        if (k == 0 || k == n) c[n][k] = (k <= n) ? 1 : 0;
-        else if (k > n) c[n][k] = 0;
-        else {
-          const unsigned __int128 v = (unsigned __int128)c[n - 1][k - 1] + c[n - 1][k];
-          c[n][k] = v > (unsigned __int128)~0ull ? ~0ull : (uint64_t)v;
-        }
-      }
-  }
-};
 const Binomials &binom() { static Binomials b; return b; }
 
 // Which state -> index kernel applies (the reference's per-basis `state_index_kernel`, FFI:90-93).
@@ -813,11 +475,6 @@ void zero_y_if_diag(dmv_context *ctx, int elt, void *y) {
   if (ctx->h_diag_kept > 0)
     CUDA_CHECK(cudaMemsetAsync(y, 0, (size_t)ctx->n_states * 8 * elt, ctx->stream));
 }
-
-struct VecStage {  // x / y either used in place (device pointers) or staged through context buffers
-  const void *x_dev; void *y_dev; bool y_host; void *y_user; size_t bytes;
-  const void *x_host_pending;   // host x whose upload is pipelined with generation (push traversal)
-};
 VecStage stage_vectors(dmv_context *ctx, int elt, const void *x, void *y) {
   VecStage v{};
   v.bytes = (size_t)ctx->n_states * 8 * elt;
@@ -1006,7 +663,7 @@ void ensure_table(dmv_context *ctx, int elt) {
 // y[rows] <- rows of H through k_rows.  `basis` owns the table (this rank's context, or the twin holding the whole
 // basis in the replicated-x product), x_all is indexed like basis' states (through pos when given), p names the rows.
 void rows_product(dmv_context *basis, KernelParams &p, int elt, const void *x_all, const uint32_t *pos,
-                  cudaStream_t stream, bool fill = true, dmv_context *timer = nullptr) {
+                  cudaStream_t stream, bool fill, dmv_context *timer) {
   if (!timer) timer = basis;   // whose event timeline the refill belongs to (the rank's context in the replicated form)
   cudaStream_t keep = basis->stream;
   basis->stream = stream;
@@ -1030,7 +687,7 @@ void rows_product(dmv_context *basis, KernelParams &p, int elt, const void *x_al
 }
 
 void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev,
-                 const void *x_host_pending = nullptr, int64_t row_begin = 0, int64_t row_end = 0) {
+                 const void *x_host_pending, int64_t row_begin, int64_t row_end) {
   if (use_pull(ctx)) {   // one rank owns the basis: traverse by rows (gather), see k_gather / k_pull
     KernelParams p = base_params(ctx);
     p.x = x_dev;
@@ -1140,659 +797,11 @@ void collect_timings(dmv_context *ctx) {
   }
 }
 
-std::mutex g_bind_mutex;
-std::map<const void *, dmv_context *> g_bindings;
+} }  // namespace dmv::host
 
-}  // namespace
-
-// ---- small kernels exposed with host-or-device pointers ----------------------------------------
-namespace {
-template <typename T>
-struct InArg {  // device view of an input array
-  DevBuf<T> buf; const T *ptr;
-  InArg(const T *p, size_t n, cudaStream_t s) {
-    if (is_device_pointer(p)) ptr = p;
-    else { buf.alloc(n); if (n) CUDA_CHECK(cudaMemcpyAsync(buf.ptr, p, n * sizeof(T), cudaMemcpyHostToDevice, s)); ptr = buf.ptr; }
-  }
-};
-template <typename T>
-struct OutArg {  // device view of an output array, copied back by finish()
-  DevBuf<T> buf; T *ptr; T *user; size_t n; bool host;
-  OutArg(T *p, size_t n_) : user(p), n(n_) {
-    host = !is_device_pointer(p);
-    if (host) { buf.alloc(n); ptr = buf.ptr; } else ptr = p;
-  }
-  void finish(cudaStream_t s, size_t used = (size_t)-1) {
-    if (host && user) { const size_t m = used == (size_t)-1 ? n : used; if (m) CUDA_CHECK(cudaMemcpyAsync(user, ptr, m * sizeof(T), cudaMemcpyDeviceToHost, s)); }
-  }
-};
-}  // namespace
-
-
-
-// One-time exchange of the plan: every rank learns how many records each peer sends it; then, when
-// possible, the peers' incoming buffers are mapped (CUDA IPC over NVLink) so that k_generate can store
-// remote records directly where the owner will read them.
-void setup_exchange(dmv_context *ctx) {
-  NcclApi &N = nccl();
-  const int P = ctx->num_ranks;
-  for (auto &q : ctx->peer_betas) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
-  for (auto &q : ctx->peer_coeffs) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
-  DevBuf<int64_t> d_send, d_all;
-  d_send.upload(ctx->send_counts, ctx->stream);
-  d_all.alloc((size_t)P * P);
-  NCCL_CHECK(N.AllGather(d_send.ptr, d_all.ptr, (size_t)P, ncclInt64, ctx->comm, ctx->stream));
-  std::vector<int64_t> all((size_t)P * P);   // all[r * P + q]: records r emits for q (own ones included)
-  CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.ptr, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  int64_t total_in = 0;
-  for (int q = 0; q < P; ++q) {
-    ctx->recv_counts[q] = (q == ctx->rank) ? 0 : all[(size_t)q * P + ctx->rank];
-    total_in += ctx->recv_counts[q];
-  }
-  ctx->d_in_betas.alloc((size_t)total_in);
-  ctx->d_in_coeffs.alloc((size_t)total_in * 2);
-  ctx->d_barrier.alloc(1);
-  CUDA_CHECK(cudaMemsetAsync(ctx->d_barrier.ptr, 0, sizeof(int), ctx->stream));
-  ctx->peer_direct = false;
-  if (ctx->opt_exchange == 0 || P > 32) return;
-
-  // ---- try to map the peers' incoming buffers
-  struct Handles { cudaIpcMemHandle_t betas, coeffs; int ok; int pad[15]; };
-  static_assert(sizeof(Handles) % 8 == 0, "handle block");
-  Handles mine{};
-  mine.ok = (cudaIpcGetMemHandle(&mine.betas, ctx->d_in_betas.ptr) == cudaSuccess &&
-             cudaIpcGetMemHandle(&mine.coeffs, ctx->d_in_coeffs.ptr) == cudaSuccess) ? 1 : 0;
-  cudaGetLastError();
-  DevBuf<char> d_mine, d_handles;
-  d_mine.alloc(sizeof(Handles));
-  d_handles.alloc(sizeof(Handles) * P);
-  CUDA_CHECK(cudaMemcpyAsync(d_mine.ptr, &mine, sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream));
-  NCCL_CHECK(N.AllGather(d_mine.ptr, d_handles.ptr, sizeof(Handles), ncclChar, ctx->comm, ctx->stream));
-  std::vector<Handles> handles(P);
-  CUDA_CHECK(cudaMemcpyAsync(handles.data(), d_handles.ptr, sizeof(Handles) * P, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  int ok = 1;
-  for (int q = 0; q < P; ++q) ok &= handles[q].ok;
-  ctx->peer_betas.assign(P, nullptr);
-  ctx->peer_coeffs.assign(P, nullptr);
-  if (ok) {
-    for (int q = 0; q < P && ok; ++q) {
-      if (q == ctx->rank) continue;
-      if (cudaIpcOpenMemHandle(&ctx->peer_betas[q], handles[q].betas, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-          cudaIpcOpenMemHandle(&ctx->peer_coeffs[q], handles[q].coeffs, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-        ok = 0;
-        cudaGetLastError();
-      }
-    }
-  }
-  // everybody must agree
-  int agree = ok;
-  CUDA_CHECK(cudaMemcpyAsync(ctx->d_barrier.ptr, &agree, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  NCCL_CHECK(N.AllReduce(ctx->d_barrier.ptr, ctx->d_barrier.ptr, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
-  CUDA_CHECK(cudaMemcpyAsync(&agree, ctx->d_barrier.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  if (!agree) {
-    for (auto &q : ctx->peer_betas) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
-    for (auto &q : ctx->peer_coeffs) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
-    if (ctx->opt_exchange == 1) throw std::runtime_error("peer-direct exchange requested but CUDA IPC mapping failed");
-    return;
-  }
-  // my region inside peer q's incoming buffer: after the regions of the ranks before me (q itself sends nothing)
-  ctx->my_offset_in_peer.assign(P, 0);
-  for (int q = 0; q < P; ++q) {
-    int64_t off = 0;
-    for (int r = 0; r < ctx->rank; ++r)
-      if (r != q) off += all[(size_t)r * P + q];
-    ctx->my_offset_in_peer[q] = off;
-  }
-  ctx->peer_direct = true;
-  ctx->ptr_width = 0;
-}
-
-// -------------------------------------------------------------------------------------------------
-// Replicated-x product.  With 180 GB of HBM per GPU every basis of BASELINE.json fits on ONE device many times
-// over, so for operators k_gather applies to, the ranks can trade the reference's record exchange (24 bytes per
-// off-diagonal term over NVLink, DMV:313-436) for one all-gather of x (E bytes per STATE): every rank keeps the
-// whole sorted basis (a single-rank twin context), gathers x from all ranks into slots of equal size, and computes
-// ITS rows by the atomics-free row traversal.  The hash partition of x, y and the representatives -- the layout the
-// callers see (SE:129-156) -- is unchanged.  Local part of the set-up; no communication here.
-void setup_replicated(dmv_context *ctx) {
-  require_states(ctx);
-  const int P = ctx->num_ranks;
-  if (P > 32) throw std::runtime_error("replicated-x product supports at most 32 ranks");
-  if (!ctx->global) {
-    dmv_basis_desc b{};
-    b.number_sites = ctx->n_sites; b.hamming_weight = ctx->hamming_weight; b.spin_inversion = ctx->spin_inversion;
-    if (ctx->proj == PROJ_GROUP) {
-      b.has_permutations = 1; b.group_order = ctx->k_group_order;
-      b.perms = ctx->k_perms.data(); b.flips = ctx->k_flips.data(); b.characters = ctx->k_chars.data();
-    }
-    dmv_operator_desc o{};
-    o.n_off = (int64_t)ctx->k_off_m.size(); o.off_v = ctx->k_off_v.data();
-    o.off_m = ctx->k_off_m.data(); o.off_r = ctx->k_off_r.data(); o.off_x = ctx->k_off_x.data(); o.off_s = ctx->k_off_s.data();
-    o.n_diag = (int64_t)ctx->k_diag_m.size(); o.diag_v = ctx->k_diag_v.data();
-    o.diag_m = ctx->k_diag_m.data(); o.diag_r = ctx->k_diag_r.data(); o.diag_s = ctx->k_diag_s.data();
-    // rough size check before enumerating: reps + directory + positions + gathered x
-    double states = 1.0;
-    if (ctx->hamming_weight >= 0) states = (double)binom().c[ctx->n_sites][ctx->hamming_weight];
-    else states = std::ldexp(1.0, ctx->n_sites);
-    if (ctx->spin_inversion != 0 && ctx->proj != PROJ_GROUP) states *= 0.5;
-    if (ctx->proj == PROJ_GROUP) states = 1.5 * states / (double)std::max<int64_t>(1, ctx->k_group_order) + 1e4;
-    size_t free_b = 0, total_b = 0;
-    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    if (states * 48.0 > 0.5 * (double)free_b) throw std::runtime_error("replicated-x product: the whole basis does not fit");
-    dmv_context *g = nullptr;
-    if (dmv_context_create(&b, &o, ctx->device, 0, 1, &g) != 0) throw std::runtime_error(g_last_error);
-    ctx->global = g;
-    g->opt_rows = ctx->opt_rows;
-    g->opt_gather_walk = ctx->opt_gather_walk;
-    g->opt_rows_index = ctx->opt_rows_index;
-    g->opt_rows_ctas = ctx->opt_rows_ctas;
-    if (ctx->opt_canon != g->opt_canon && g->proj == PROJ_GROUP) { g->opt_canon = ctx->opt_canon; upload_orbit(g); }
-    if (dmv_basis_build(g) != 0) throw std::runtime_error(g_last_error);
-  }
-  dmv_context *g = ctx->global;
-  CUDA_CHECK(cudaStreamSynchronize(g->stream));
-  const int64_t n = g->n_states;
-  // ---- slot of every global state: owner r = hash % P (SE:129-136), index inside r's ascending block
-  const int64_t chunk = 256, n_chunks = (n + chunk - 1) / chunk;
-  DevBuf<unsigned long long> d_counts, d_base;
-  d_counts.alloc((size_t)n_chunks * P);
-  d_base.alloc((size_t)n_chunks * P);
-  ctx->d_pos.alloc((size_t)n);
-  launch_owner_positions(g->d_reps.ptr, nullptr, n, P, chunk, false, d_counts.ptr, nullptr, 0, nullptr, ctx->stream);
-  std::vector<unsigned long long> counts((size_t)n_chunks * P), base((size_t)n_chunks * P);
-  CUDA_CHECK(cudaMemcpyAsync(counts.data(), d_counts.ptr, counts.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  std::vector<unsigned long long> total(P, 0);
-  for (int64_t c = 0; c < n_chunks; ++c)
-    for (int r = 0; r < P; ++r) { base[(size_t)c * P + r] = total[r]; total[r] += counts[(size_t)c * P + r]; }
-  if ((int64_t)total[ctx->rank] != ctx->n_states)
-    throw std::runtime_error("replicated-x product: this rank's block is not the hash partition of the full basis");
-  int64_t block = 0;
-  for (int r = 0; r < P; ++r) block = std::max<int64_t>(block, (int64_t)total[r]);
-  block = (block + 1) / 2 * 2;
-  if ((double)block * P >= 4294967295.0) throw std::runtime_error("replicated-x product: more than 2^32 slots");
-  d_base.upload(base, ctx->stream);
-  launch_owner_positions(g->d_reps.ptr, nullptr, n, P, chunk, true, d_counts.ptr, d_base.ptr, block, ctx->d_pos.ptr, ctx->stream);
-  ctx->repl_block = block;
-  ctx->d_xcat.alloc((size_t)block * P * 2 * 2);   // two buffers of P slots (alternating products), 16 bytes per element
-  CUDA_CHECK(cudaMemsetAsync(ctx->d_xcat.ptr, 0, (size_t)block * P * 2 * 2 * sizeof(double), ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-}
-
-// y (this rank's block) <- rows of H applied to the gathered x (slot r * repl_block holds rank r's block)
-void replicated_rows(dmv_context *ctx, int elt, const void *x_cat, void *y_dev) {
-  dmv_context *g = ctx->global;
-  KernelParams p = base_params(g);
-  p.x = x_cat;
-  p.y = y_dev;
-  p.status = ctx->d_status.ptr;
-  p.row_states = ctx->d_reps.ptr;
-  p.row_begin = 0;
-  p.row_end = ctx->n_states;
-  p.pos = ctx->d_pos.ptr;
-  p.x_row_offset = (int64_t)ctx->rank * ctx->repl_block;
-  if (use_gather(g)) {
-    select_tables(g, p, true, g->complex_coefficients);
-    p.row_split = choose_row_split(ctx->n_states, (int)g->h_pull.groups.size());
-    p.uni_re = g->gather_uni[0]; p.uni_im = g->gather_uni[1];
-    launch_gather(p, g->proj == PROJ_INVERSION, g->complex_coefficients, elt == DMV_C128, g->gather_narrow,
-                  g->index_mode == INDEX_LIN, g->gather_uniform, ctx->stream);
-    return;
-  }
-  p.row_norms = ctx->d_norms.ptr;
-  if (use_rows(g)) {   // bases with permutation symmetries: hash table over the whole basis, filled from the gathered x
-    rows_product(g, p, elt, x_cat, ctx->d_pos.ptr, ctx->stream, true, ctx);
-    return;
-  }
-  // operators outside the bit-parallel test / non-trivial characters: the queued row traversal
-  if (p.index.mode == INDEX_RANK) p.index.mode = INDEX_DIRECTORY;   // the incremental rank needs row index == rank
-  p.row_split = 1;
-  select_tables(g, p, true, complex_values(g, elt));
-  launch_pull(p, g->proj, complex_values(g, elt), elt == DMV_C128, ctx->stream);
-}
-
-// Collective set-up of the overlapped record exchange: per-round counting passes, exchange of the counts, incoming
-// buffers laid out round-major, CUDA IPC mapping of buffers and flags.  Leaves rounds.ready false when it does not apply
-// (one round, IPC impossible): the caller then uses the one-shot exchange.
-void setup_rounds(dmv_context *ctx) {
-  dmv_context::Rounds &Q = ctx->rounds;
-  NcclApi &N = nccl();
-  const int P = ctx->num_ranks;
-  Q.tried = true;
-  Q.ready = false;
-  int R = ctx->opt_rounds;
-  if (R < 0) R = ctx->n_states >= (1 << 18) ? 4 : 1;
-  // every rank must use the same number of rounds
-  ctx->d_barrier.alloc(1);
-  CUDA_CHECK(cudaMemcpyAsync(ctx->d_barrier.ptr, &R, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  NCCL_CHECK(N.AllReduce(ctx->d_barrier.ptr, ctx->d_barrier.ptr, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
-  CUDA_CHECK(cudaMemcpyAsync(&R, ctx->d_barrier.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  if (R <= 1 || P > 32 || ctx->opt_exchange == 0) return;
-  Q.R = R;
-  Q.row_split = 1;
-  Q.row_begin.assign(R + 1, 0);
-  for (int r = 0; r <= R; ++r) Q.row_begin[r] = std::min<int64_t>(ctx->n_states, (ctx->n_states * r / R + 31) / 32 * 32);
-  Q.row_begin[R] = ctx->n_states;
-  Q.grid = planned_grid((ctx->n_states + R - 1) / R, 1);
-  const size_t n_warps = (size_t)Q.grid * kWarpsPerCta;
-  // ---- counting pass per round: exact share of every warp for every destination
-  std::vector<int64_t> offsets((size_t)R * n_warps * P, 0), counts((size_t)R * P, 0);
-  ctx->d_warp_counts.alloc(n_warps * P);
-  ctx->d_out_count.alloc(P);
-  std::vector<unsigned long long> wc(n_warps * P);
-  Q.terms = 0;
-  for (int r = 0; r < R; ++r) {
-    CUDA_CHECK(cudaMemsetAsync(ctx->d_warp_counts.ptr, 0, sizeof(unsigned long long) * n_warps * P, ctx->stream));
-    KernelParams p = base_params(ctx);
-    p.grid_blocks = Q.grid;
-    p.row_split = 1;
-    p.row_begin = Q.row_begin[r];
-    p.row_end = Q.row_begin[r + 1];
-    p.warp_counts = ctx->d_warp_counts.ptr;
-    select_tables(ctx, p, false, ctx->complex_coefficients);
-    launch_generate(p, ctx->proj, ctx->complex_coefficients, false, /*count_only=*/true, ctx->stream);
-    CUDA_CHECK(cudaMemcpyAsync(wc.data(), ctx->d_warp_counts.ptr, sizeof(unsigned long long) * wc.size(),
-                               cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    for (int d = 0; d < P; ++d)
-      for (size_t w = 0; w < n_warps; ++w) {
-        offsets[((size_t)r * n_warps + w) * P + d] = counts[(size_t)r * P + d];
-        counts[(size_t)r * P + d] += (int64_t)wc[w * P + d];
-      }
-    for (int d = 0; d < P; ++d) Q.terms += counts[(size_t)r * P + d];
-  }
-  Q.d_warp_offsets.upload(offsets, ctx->stream);
-  if (!ctx->planned) ctx->number_terms = Q.terms;
-  std::vector<int64_t> capacity((size_t)R * P);
-  for (int r = 0; r < R; ++r)
-    for (int d = 0; d < P; ++d) capacity[(size_t)r * P + d] = d == ctx->rank ? 0 : counts[(size_t)r * P + d];
-  Q.d_capacity.upload(capacity, ctx->stream);
-  // ---- everybody's counts: all[s][r][d]
-  DevBuf<int64_t> d_send, d_all;
-  d_send.upload(counts, ctx->stream);
-  d_all.alloc((size_t)P * R * P);
-  NCCL_CHECK(N.AllGather(d_send.ptr, d_all.ptr, (size_t)R * P, ncclInt64, ctx->comm, ctx->stream));
-  std::vector<int64_t> all((size_t)P * R * P);
-  CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.ptr, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  auto cnt = [&](int s, int r, int d) { return all[((size_t)s * R + r) * P + d]; };
-  // incoming buffer of rank q, round-major: [round 0: sources 0 .. P-1 (without q)] [round 1: ...] ...
-  auto region = [&](int q, int r, int src) {   // first record of (round r, source src) inside q's buffer
-    int64_t off = 0;
-    for (int rr = 0; rr < r; ++rr)
-      for (int s = 0; s < P; ++s) if (s != q) off += cnt(s, rr, q);
-    for (int s = 0; s < src; ++s) if (s != q) off += cnt(s, r, q);
-    return off;
-  };
-  Q.in_slice.assign(R + 1, 0);
-  for (int r = 0; r <= R; ++r) Q.in_slice[r] = region(ctx->rank, r, 0);
-  Q.in_total = Q.in_slice[R];
-  Q.peer_total.assign(P, 0);
-  for (int q = 0; q < P; ++q) Q.peer_total[q] = region(q, R, 0);
-  Q.my_off.assign((size_t)R * P, 0);
-  for (int r = 0; r < R; ++r)
-    for (int q = 0; q < P; ++q) if (q != ctx->rank) Q.my_off[(size_t)r * P + q] = region(q, r, ctx->rank);
-  Q.d_in_betas.alloc((size_t)std::max<int64_t>(1, 2 * Q.in_total));
-  Q.d_in_coeffs.alloc((size_t)std::max<int64_t>(1, 4 * Q.in_total));
-  Q.d_flags.alloc(P);
-  CUDA_CHECK(cudaMemsetAsync(Q.d_flags.ptr, 0, sizeof(unsigned) * P, ctx->stream));
-  Q.seq = 0;
-  // ---- map the peers' buffers and flags
-  for (auto *v : {&Q.peer_betas, &Q.peer_coeffs, &Q.peer_flags})
-    for (auto &q : *v) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
-  struct Handles { cudaIpcMemHandle_t betas, coeffs, flags; int ok; int pad[15]; };
-  static_assert(sizeof(Handles) % 8 == 0, "handle block");
-  Handles mine{};
-  mine.ok = (cudaIpcGetMemHandle(&mine.betas, Q.d_in_betas.ptr) == cudaSuccess &&
-             cudaIpcGetMemHandle(&mine.coeffs, Q.d_in_coeffs.ptr) == cudaSuccess &&
-             cudaIpcGetMemHandle(&mine.flags, Q.d_flags.ptr) == cudaSuccess) ? 1 : 0;
-  cudaGetLastError();
-  DevBuf<char> d_mine, d_handles;
-  d_mine.alloc(sizeof(Handles));
-  d_handles.alloc(sizeof(Handles) * P);
-  CUDA_CHECK(cudaMemcpyAsync(d_mine.ptr, &mine, sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream));
-  NCCL_CHECK(N.AllGather(d_mine.ptr, d_handles.ptr, sizeof(Handles), ncclChar, ctx->comm, ctx->stream));
-  std::vector<Handles> handles(P);
-  CUDA_CHECK(cudaMemcpyAsync(handles.data(), d_handles.ptr, sizeof(Handles) * P, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  int ok = 1;
-  for (int q = 0; q < P; ++q) ok &= handles[q].ok;
-  Q.peer_betas.assign(P, nullptr); Q.peer_coeffs.assign(P, nullptr); Q.peer_flags.assign(P, nullptr);
-  for (int q = 0; q < P && ok; ++q) {
-    if (q == ctx->rank) continue;
-    if (cudaIpcOpenMemHandle(&Q.peer_betas[q], handles[q].betas, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-        cudaIpcOpenMemHandle(&Q.peer_coeffs[q], handles[q].coeffs, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-        cudaIpcOpenMemHandle(&Q.peer_flags[q], handles[q].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-      ok = 0;
-      cudaGetLastError();
-    }
-  }
-  int agree = ok;
-  CUDA_CHECK(cudaMemcpyAsync(ctx->d_barrier.ptr, &agree, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  NCCL_CHECK(N.AllReduce(ctx->d_barrier.ptr, ctx->d_barrier.ptr, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
-  CUDA_CHECK(cudaMemcpyAsync(&agree, ctx->d_barrier.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  if (!agree) {
-    for (auto *v : {&Q.peer_betas, &Q.peer_coeffs, &Q.peer_flags})
-      for (auto &q : *v) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
-    return;
-  }
-  std::vector<unsigned *> flags(P);
-  for (int q = 0; q < P; ++q) flags[q] = q == ctx->rank ? Q.d_flags.ptr : reinterpret_cast<unsigned *>(Q.peer_flags[q]);
-  Q.d_peer_flags.upload(flags, ctx->stream);
-  if (!Q.acc_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&Q.acc_stream, cudaStreamNonBlocking));
-  if (!Q.ev_begin) CUDA_CHECK(cudaEventCreateWithFlags(&Q.ev_begin, cudaEventDisableTiming));
-  if (!Q.ev_done) CUDA_CHECK(cudaEventCreateWithFlags(&Q.ev_done, cudaEventDisableTiming));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  Q.ptr_width = 0;
-  Q.ready = true;
-}
-
-// where my records of (buffer, round, destination) go: [2][R][P] pointers into the peers' incoming buffers
-void upload_round_pointers(dmv_context *ctx, int width) {
-  dmv_context::Rounds &Q = ctx->rounds;
-  const int P = ctx->num_ranks, R = Q.R;
-  std::vector<uint64_t *> bp((size_t)2 * R * P, nullptr);
-  std::vector<double *> cp((size_t)2 * R * P, nullptr);
-  for (int b = 0; b < 2; ++b)
-    for (int r = 0; r < R; ++r)
-      for (int q = 0; q < P; ++q) {
-        if (q == ctx->rank) continue;
-        const int64_t first = (int64_t)b * Q.peer_total[q] + Q.my_off[(size_t)r * P + q];
-        bp[((size_t)b * R + r) * P + q] = reinterpret_cast<uint64_t *>(Q.peer_betas[q]) + first;
-        cp[((size_t)b * R + r) * P + q] = reinterpret_cast<double *>(Q.peer_coeffs[q]) + first * width;
-      }
-  Q.d_bptr.upload(bp, ctx->stream);
-  Q.d_cptr.upload(cp, ctx->stream);
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  Q.ptr_width = width;
-}
-
-// One product through the overlapped rounds (x, y device pointers).  Main stream: generate round 0, raise flags,
-// generate round 1, ...; second stream: wait for every sender's flag of round r, accumulate its slice.  Returns with the
-// main stream waiting for the last accumulate.
-void rounds_product(dmv_context *ctx, int elt, const void *x_dev, void *y_dev) {
-  dmv_context::Rounds &Q = ctx->rounds;
-  const int P = ctx->num_ranks, R = Q.R;
-  const bool cv = complex_values(ctx, elt);
-  const int width = cv ? 2 : 1;
-  if (Q.ptr_width != width) upload_round_pointers(ctx, width);
-  ctx->record_width = width;
-  zero_y_if_diag(ctx, elt, y_dev);
-  CUDA_CHECK(cudaEventRecord(Q.ev_begin, ctx->stream));
-  CUDA_CHECK(cudaStreamWaitEvent(Q.acc_stream, Q.ev_begin, 0));
-  const int b = (int)(Q.seq & 1u);
-  const size_t n_warps = (size_t)Q.grid * kWarpsPerCta;
-  for (int r = 0; r < R; ++r) {
-    KernelParams p = base_params(ctx);
-    p.x = x_dev;
-    p.y = y_dev;
-    p.grid_blocks = Q.grid;
-    p.row_split = 1;
-    p.row_begin = Q.row_begin[r];
-    p.row_end = Q.row_begin[r + 1];
-    p.warp_offsets = Q.d_warp_offsets.ptr + (size_t)r * n_warps * P;
-    p.out_capacity = Q.d_capacity.ptr + (size_t)r * P;
-    p.out_betas_ptr = Q.d_bptr.ptr + ((size_t)b * R + r) * P;
-    p.out_coeffs_ptr = Q.d_cptr.ptr + ((size_t)b * R + r) * P;
-    select_tables(ctx, p, false, cv);
-    launch_generate(p, ctx->proj, cv, elt == DMV_C128, false, ctx->stream);
-    const unsigned value = Q.seq * (unsigned)R + (unsigned)r + 1u;
-    launch_raise_flags(Q.d_peer_flags.ptr, P, ctx->rank, value, ctx->stream);
-    // owner side, second stream: every sender has delivered round r -> search + accumulate its slice
-    launch_wait_flags(Q.d_flags.ptr, P, value, ctx->d_status.ptr, Q.acc_stream);
-    const int64_t first = (int64_t)b * Q.in_total + Q.in_slice[r], count = Q.in_slice[r + 1] - Q.in_slice[r];
-    if (count > 0) {
-      KernelParams pa = base_params(ctx);
-      pa.y = y_dev;
-      launch_accumulate(pa, ctx->proj, cv, elt == DMV_C128, count, Q.d_in_betas.ptr + first,
-                        Q.d_in_coeffs.ptr + first * width, Q.acc_stream);
-    }
-  }
-  ++Q.seq;
-  CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));   // end of generation
-  CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
-  CUDA_CHECK(cudaEventRecord(Q.ev_done, Q.acc_stream));
-  CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, Q.ev_done, 0));   // what is left of the accumulate is the exposed part
-}
-
-// Collective: map every rank's gathered-x buffers and flag words into every other rank (CUDA IPC over NVLink) so that
-// the all-gather of x becomes one kernel of peer stores + flags (launch_push_block).  Falls back to the NCCL all-gather
-// when any rank cannot map.
-void setup_peer_gather(dmv_context *ctx) {
-  NcclApi &N = nccl();
-  const int P = ctx->num_ranks;
-  ctx->peer_gather = false;
-  ctx->d_flags.alloc(P);
-  ctx->d_push_done.alloc(1);
-  CUDA_CHECK(cudaMemsetAsync(ctx->d_flags.ptr, 0, sizeof(unsigned) * P, ctx->stream));
-  CUDA_CHECK(cudaMemsetAsync(ctx->d_push_done.ptr, 0, sizeof(unsigned), ctx->stream));
-  ctx->gather_epoch = 0;
-  struct Handles { cudaIpcMemHandle_t xcat, flags; int ok; int pad[15]; };
-  static_assert(sizeof(Handles) % 8 == 0, "handle block");
-  Handles mine{};
-  mine.ok = (ctx->opt_peer_gather != 0 && cudaIpcGetMemHandle(&mine.xcat, ctx->d_xcat.ptr) == cudaSuccess &&
-             cudaIpcGetMemHandle(&mine.flags, ctx->d_flags.ptr) == cudaSuccess) ? 1 : 0;
-  cudaGetLastError();
-  DevBuf<char> d_mine, d_handles;
-  d_mine.alloc(sizeof(Handles));
-  d_handles.alloc(sizeof(Handles) * P);
-  CUDA_CHECK(cudaMemcpyAsync(d_mine.ptr, &mine, sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream));
-  NCCL_CHECK(N.AllGather(d_mine.ptr, d_handles.ptr, sizeof(Handles), ncclChar, ctx->comm, ctx->stream));
-  std::vector<Handles> handles(P);
-  CUDA_CHECK(cudaMemcpyAsync(handles.data(), d_handles.ptr, sizeof(Handles) * P, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  int ok = 1;
-  for (int q = 0; q < P; ++q) ok &= handles[q].ok;
-  for (auto &q : ctx->peer_xcat) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
-  for (auto &q : ctx->peer_flagmem) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
-  ctx->peer_xcat.assign(P, nullptr);
-  ctx->peer_flagmem.assign(P, nullptr);
-  if (ok) {
-    for (int q = 0; q < P && ok; ++q) {
-      if (q == ctx->rank) continue;
-      if (cudaIpcOpenMemHandle(&ctx->peer_xcat[q], handles[q].xcat, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-          cudaIpcOpenMemHandle(&ctx->peer_flagmem[q], handles[q].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-        ok = 0;
-        cudaGetLastError();
-      }
-    }
-  }
-  int agree = ok;   // everybody must agree; the all-reduce is also the barrier after which flags may be raised
-  ctx->d_barrier.alloc(1);
-  CUDA_CHECK(cudaMemcpyAsync(ctx->d_barrier.ptr, &agree, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  NCCL_CHECK(N.AllReduce(ctx->d_barrier.ptr, ctx->d_barrier.ptr, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
-  CUDA_CHECK(cudaMemcpyAsync(&agree, ctx->d_barrier.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  if (!agree) {
-    for (auto &q : ctx->peer_xcat) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
-    for (auto &q : ctx->peer_flagmem) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
-    return;
-  }
-  std::vector<unsigned *> flags(P);
-  for (int q = 0; q < P; ++q)
-    flags[q] = q == ctx->rank ? ctx->d_flags.ptr : reinterpret_cast<unsigned *>(ctx->peer_flagmem[q]);
-  ctx->d_peer_flags.upload(flags, ctx->stream);
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  ctx->peer_slot_elt = 0;
-  ctx->peer_gather = true;
-}
-
-// slot `rank` of buffer b of every rank's gathered vector, for elements of `elt` doubles
-void upload_peer_slots(dmv_context *ctx, int elt) {
-  const int P = ctx->num_ranks;
-  const size_t buffer_doubles = (size_t)ctx->repl_block * P * 2;   // buffers are sized for 16-byte elements
-  for (int b = 0; b < 2; ++b) {
-    std::vector<void *> slots(P);
-    for (int q = 0; q < P; ++q) {
-      double *base = q == ctx->rank ? ctx->d_xcat.ptr : reinterpret_cast<double *>(ctx->peer_xcat[q]);
-      slots[q] = base + b * buffer_doubles + (size_t)ctx->rank * ctx->repl_block * elt;
-    }
-    ctx->d_peer_slot[b].upload(slots, ctx->stream);
-  }
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  ctx->peer_slot_elt = elt;
-}
-
-// Collective: which exchange the distributed product uses.  exchange = -1 (auto) prefers the replicated-x product
-// when k_gather applies and the whole basis fits, else the record exchange (peer-direct / NCCL, see setup_exchange).
-void decide_exchange(dmv_context *ctx) {
-  NcclApi &N = nccl();
-  int ok = 0;
-  std::string why;
-  const bool want = (ctx->opt_exchange == 2 || ctx->opt_exchange == -1) && ctx->opt_mode != 0;
-  if (want && ctx->num_ranks <= 32) {
-    try { setup_replicated(ctx); ok = 1; } catch (const std::exception &e) { why = e.what(); ok = 0; }
-  } else {
-    why = "switched off (exchange / mode options) or more than 32 ranks";
-  }
-  ctx->d_barrier.alloc(1);
-  CUDA_CHECK(cudaMemcpyAsync(ctx->d_barrier.ptr, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  NCCL_CHECK(N.AllReduce(ctx->d_barrier.ptr, ctx->d_barrier.ptr, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
-  int agree = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&agree, ctx->d_barrier.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  ctx->replicated = agree != 0;
-  ctx->exchange_decided = true;
-  if (ctx->replicated) setup_peer_gather(ctx);
-  if (!ctx->replicated) {
-    delete ctx->global; ctx->global = nullptr;
-    ctx->d_pos.release(); ctx->d_xcat.release();
-    if (ctx->opt_exchange == 2)
-      throw std::runtime_error("replicated-x exchange requested but not possible on every rank: " + why);
-  }
-}
-
-// -------------------------------------------------------------------------------------------------
-// Block <-> hashed redistribution of vectors (arrFromBlockToHashed, reference src/BlockToHashed.chpl:87-208;
-// arrFromHashedToBlock, src/HashedToBlock.chpl:67-153).  "Block" = the global array in sorted-state order cut into
-// contiguous chunks, one per rank; "hashed" = every rank holds the elements of the states it owns, ascending.
-// positions: slot of element i of a chunk in the ordering "grouped by owner, stable": offsets[mask[i]] + #{j < i :
-// mask[j] == mask[i]}; counts[r] = elements owned by r.  One counting pass, host prefix sums, one writing pass.
-void hashed_positions(dmv_context *ctx, int64_t count, const uint8_t *d_masks, int P, std::vector<int64_t> &counts,
-                      uint32_t *d_pos) {
-  if (P > 32) throw std::runtime_error("block <-> hashed redistribution supports at most 32 ranks");
-  counts.assign(P, 0);
-  if (count <= 0) return;
-  if (count >= (1ll << 32)) throw std::runtime_error("chunks of more than 2^32 elements are not supported");
-  const int64_t chunk = 256, n_chunks = (count + chunk - 1) / chunk;
-  DevBuf<unsigned long long> d_counts, d_base;
-  d_counts.alloc((size_t)n_chunks * P);
-  launch_owner_positions(nullptr, d_masks, count, P, chunk, false, d_counts.ptr, nullptr, 0, nullptr, ctx->stream);
-  std::vector<unsigned long long> c((size_t)n_chunks * P), base((size_t)n_chunks * P);
-  CUDA_CHECK(cudaMemcpyAsync(c.data(), d_counts.ptr, c.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  for (int64_t k = 0; k < n_chunks; ++k)
-    for (int r = 0; r < P; ++r) counts[r] += (int64_t)c[(size_t)k * P + r];
-  std::vector<unsigned long long> run(P, 0);
-  unsigned long long off = 0;
-  for (int r = 0; r < P; ++r) { run[r] = off; off += (unsigned long long)counts[r]; }
-  for (int64_t k = 0; k < n_chunks; ++k)
-    for (int r = 0; r < P; ++r) { base[(size_t)k * P + r] = run[r]; run[r] += c[(size_t)k * P + r]; }
-  d_base.upload(base, ctx->stream);
-  launch_owner_positions(nullptr, d_masks, count, P, chunk, true, d_counts.ptr, d_base.ptr, 0, d_pos, ctx->stream);
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // d_base is released on return
-}
-
-// all[r * P + q] = what rank r reported for q (collective)
-std::vector<int64_t> all_gather_counts(dmv_context *ctx, const std::vector<int64_t> &mine) {
-  NcclApi &N = nccl();
-  const int P = ctx->num_ranks;
-  DevBuf<int64_t> d_mine, d_all;
-  d_mine.upload(mine, ctx->stream);
-  d_all.alloc((size_t)P * P);
-  NCCL_CHECK(N.AllGather(d_mine.ptr, d_all.ptr, (size_t)P, ncclInt64, ctx->comm, ctx->stream));
-  std::vector<int64_t> all((size_t)P * P);
-  CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.ptr, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  return all;
-}
-
-// -------------------------------------------------------------------------------------------------
-// Lowest eigenpair of a symmetric tridiagonal matrix (diagonal a[0..k), off-diagonal b[0..k-1)): Sturm bisection for
-// the eigenvalue, inverse iteration for the vector.  Host side of dmv_lanczos; k is at most a few hundred.
-double tridiagonal_lowest(const std::vector<double> &a, const std::vector<double> &b, std::vector<double> &vec) {
-  const int k = (int)a.size();
-  double lo = a[0], hi = a[0];
-  for (int i = 0; i < k; ++i) {
-    const double r = (i > 0 ? std::fabs(b[i - 1]) : 0.0) + (i + 1 < k ? std::fabs(b[i]) : 0.0);
-    lo = std::min(lo, a[i] - r);
-    hi = std::max(hi, a[i] + r);
-  }
-  auto below = [&](double x) {   // number of eigenvalues < x
-    int count = 0;
-    double q = a[0] - x;
-    for (int i = 0;; ++i) {
-      if (q < 0.0) ++count;
-      if (i + 1 == k) break;
-      if (std::fabs(q) < 1e-300) q = q < 0 ? -1e-300 : 1e-300;
-      q = a[i + 1] - x - b[i] * b[i] / q;
-    }
-    return count;
-  };
-  for (int it = 0; it < 200 && hi - lo > 4e-16 * std::max(1.0, std::max(std::fabs(lo), std::fabs(hi))); ++it) {
-    const double mid = 0.5 * (lo + hi);
-    if (below(mid) >= 1) hi = mid; else lo = mid;
-  }
-  const double theta = 0.5 * (lo + hi);
-  // inverse iteration on (T - shift I): LU of a tridiagonal matrix with partial pivoting (the dgttrf / dgttrs scheme)
-  vec.assign(k, 1.0 / std::sqrt((double)k));
-  const double scale = std::max(1.0, std::max(std::fabs(lo), std::fabs(hi)));
-  const double shift = theta - 1e-13 * scale;
-  if (k > 1) {
-    std::vector<double> dl(k - 1), d(k), du(k - 1), du2(k > 2 ? k - 2 : 0, 0.0);
-    std::vector<int> piv(k - 1);
-    for (int i = 0; i < k; ++i) d[i] = a[i] - shift;
-    for (int i = 0; i + 1 < k; ++i) { dl[i] = b[i]; du[i] = b[i]; }
-    const double tiny = 1e-300;
-    for (int i = 0; i + 1 < k; ++i) {
-      if (std::fabs(d[i]) >= std::fabs(dl[i])) {
-        if (std::fabs(d[i]) < tiny) d[i] = tiny;
-        const double f = dl[i] / d[i];
-        dl[i] = f;
-        d[i + 1] -= f * du[i];
-        piv[i] = i;
-      } else {
-        const double f = d[i] / dl[i];
-        d[i] = dl[i];
-        dl[i] = f;
-        const double t = du[i];
-        du[i] = d[i + 1];
-        d[i + 1] = t - f * d[i + 1];
-        if (i + 2 < k) { du2[i] = du[i + 1]; du[i + 1] = -f * du[i + 1]; }
-        piv[i] = i + 1;
-      }
-    }
-    if (std::fabs(d[k - 1]) < tiny) d[k - 1] = tiny;
-    for (int rep = 0; rep < 4; ++rep) {
-      std::vector<double> x = vec;
-      for (int i = 0; i + 1 < k; ++i) {
-        if (piv[i] == i) x[i + 1] -= dl[i] * x[i];
-        else { const double t = x[i]; x[i] = x[i + 1]; x[i + 1] = t - dl[i] * x[i]; }
-      }
-      x[k - 1] /= d[k - 1];
-      if (k > 1) x[k - 2] = (x[k - 2] - du[k - 2] * x[k - 1]) / d[k - 2];
-      for (int i = k - 3; i >= 0; --i) x[i] = (x[i] - du[i] * x[i + 1] - du2[i] * x[i + 2]) / d[i];
-      double nrm = 0.0;
-      for (double v : x) nrm += v * v;
-      nrm = std::sqrt(nrm);
-      if (!(nrm > 0.0) || !std::isfinite(nrm)) break;
-      for (int i = 0; i < k; ++i) vec[i] = x[i] / nrm;
-    }
-  }
-  if (k == 1) vec[0] = 1.0;
-  return theta;
-}
-
-// =================================================================================================
 extern "C" {
 
-void ls_chpl_init(void) {}      // no runtime to start (reference src/library.c:19-32 boots the Chapel runtime)
-void ls_chpl_finalize(void) {}  // reference src/library.c:34
+
 const char *dmv_last_error(void) { return g_last_error.c_str(); }
 int dmv_version(void) { return 100; }
 int64_t dmv_launch_count(void) { return launch_counter(); }
@@ -2273,303 +1282,6 @@ int dmv_local_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
   API_END
 }
 
-int dmv_comm_unique_id(void *id128) {
-  API_BEGIN
-  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
-  ncclUniqueId id;
-  NCCL_CHECK(nccl().GetUniqueId(&id));
-  memcpy(id128, &id, sizeof(id));
-  API_END
-}
-
-int dmv_comm_init(dmv_context *ctx, const void *id128) {
-  API_BEGIN
-  use_device(ctx);
-  ncclUniqueId id;
-  memcpy(&id, id128, sizeof(id));
-  NCCL_CHECK(nccl().CommInitRank(&ctx->comm, ctx->num_ranks, id, ctx->rank));
-  API_END
-}
-
-int dmv_matvec(dmv_context *ctx, int elt, const void *x, void *y) {
-  API_BEGIN
-  use_device(ctx);
-  require_states(ctx);
-  if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
-  const int P = ctx->num_ranks;
-  if (P == 1) {
-    const int rc = dmv_local_matvec(ctx, elt, x, y);
-    if (rc) throw std::runtime_error(g_last_error);
-    return 0;
-  }
-  if (!ctx->comm) throw std::runtime_error("dmv_matvec on several ranks needs dmv_comm_init");
-  NcclApi &N = nccl();
-  if (!ctx->exchange_decided) decide_exchange(ctx);
-  if (ctx->replicated) {
-    // ---- replicated-x product: all-gather x into equal slots, then this rank's rows by the row traversal
-    if (x == y) throw std::runtime_error("x and y must not alias");
-    const size_t esz = (size_t)8 * elt, bytes = (size_t)ctx->n_states * esz;
-    CUDA_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    void *y_dev = y;
-    const bool y_host = !is_device_pointer(y);
-    if (y_host) {
-      ctx->d_y.alloc((size_t)ctx->n_states * elt);
-      y_dev = ctx->d_y.ptr;
-      if (ctx->h_diag_kept == 0) CUDA_CHECK(cudaMemcpyAsync(y_dev, y, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    const double *x_cat = ctx->d_xcat.ptr;
-    if (ctx->peer_gather) {
-      // ---- peer-direct: my block goes straight into slot `rank` of every rank's buffer (epoch parity picks the buffer:
-      // a rank raises its flag for epoch e + 1 only after it has consumed buffer e)
-      const void *x_dev = x;
-      if (!is_device_pointer(x)) {
-        ctx->d_x.alloc((size_t)ctx->n_states * elt);
-        CUDA_CHECK(cudaMemcpyAsync(ctx->d_x.ptr, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        x_dev = ctx->d_x.ptr;
-      }
-      CUDA_CHECK(cudaEventRecord(ctx->ev[1], ctx->stream));
-      if (ctx->peer_slot_elt != elt) upload_peer_slots(ctx, elt);
-      const unsigned epoch = ++ctx->gather_epoch;
-      const int b = (int)(epoch & 1u);
-      const int64_t n_doubles = ctx->n_states * elt;
-      const bool wide = (n_doubles % 2 == 0) && (reinterpret_cast<uintptr_t>(x_dev) % 16 == 0) &&
-                        ((size_t)ctx->repl_block * elt) % 2 == 0;
-      launch_push_block(x_dev, n_doubles, P, ctx->d_peer_slot[b].ptr, ctx->d_push_done.ptr, ctx->d_peer_flags.ptr,
-                        ctx->rank, epoch, wide, ctx->stream);
-      launch_wait_flags(ctx->d_flags.ptr, P, epoch, ctx->d_status.ptr, ctx->stream);
-      x_cat = ctx->d_xcat.ptr + (size_t)b * ctx->repl_block * P * 2;
-    } else {
-      char *slot = reinterpret_cast<char *>(ctx->d_xcat.ptr) + (size_t)ctx->rank * ctx->repl_block * esz;
-      CUDA_CHECK(cudaMemcpyAsync(slot, x, bytes, cudaMemcpyDefault, ctx->stream));   // host or device x
-      CUDA_CHECK(cudaEventRecord(ctx->ev[1], ctx->stream));
-      NCCL_CHECK(N.AllGather(slot, ctx->d_xcat.ptr, (size_t)ctx->repl_block * elt, ncclDouble, ctx->comm, ctx->stream));
-    }
-    CUDA_CHECK(cudaEventRecord(ctx->ev[6], ctx->stream));
-    replicated_rows(ctx, elt, x_cat, y_dev);
-    CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    CUDA_CHECK(cudaEventRecord(ctx->ev[4], ctx->stream));
-    if (y_host) CUDA_CHECK(cudaMemcpyAsync(y, y_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaEventRecord(ctx->ev[5], ctx->stream));
-    ctx->timeline_replicated = true;
-    if (y_host || !is_device_pointer(x)) {
-      check_status(ctx);
-      collect_timings(ctx);
-    }
-    return 0;
-  }
-  ctx->timeline_replicated = false;
-  if (!ctx->rounds.tried) setup_rounds(ctx);
-  if (ctx->rounds.ready) {
-    // ---- record exchange in overlapped rounds (peer-direct NVLink stores + per-round flags)
-    VecStage v = stage_vectors(ctx, elt, x, y);
-    if (v.x_host_pending) {   // (single-rank pipelining of the upload does not apply here)
-      CUDA_CHECK(cudaMemcpyAsync(ctx->d_x.ptr, v.x_host_pending, v.bytes, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    rounds_product(ctx, elt, v.x_dev, v.y_dev);
-    finish_vectors(ctx, v);
-    if (v.y_host || !is_device_pointer(x)) {
-      check_status(ctx);
-      collect_timings(ctx);
-    }
-    return 0;
-  }
-  if (!ctx->planned) do_plan(ctx);
-  if (ctx->recv_counts[0] < 0) setup_exchange(ctx);
-  auto barrier = [&]() {
-    NCCL_CHECK(N.AllReduce(ctx->d_barrier.ptr, ctx->d_barrier.ptr, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
-  };
-  // peer-direct: nobody may overwrite my incoming buffer before I have consumed the previous product
-  if (ctx->peer_direct) barrier();
-  VecStage v = stage_vectors(ctx, elt, x, y);
-  do_generate(ctx, elt, v.x_dev, v.y_dev, v.x_host_pending);
-  CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  const int width = ctx->record_width;
-  int64_t total_in = 0;
-  if (ctx->peer_direct) {
-    // the records are already in the peers' incoming buffers (NVLink stores issued by k_generate, overlapped
-    // with generation); the all-reduce is the "every sender has finished" fence
-    barrier();
-    for (int q = 0; q < P; ++q) total_in += ctx->recv_counts[q];
-  } else {
-  NCCL_CHECK(N.GroupStart());
-  {
-    int64_t in_off = 0;
-    for (int q = 0; q < P; ++q) {
-      if (q == ctx->rank) continue;
-      const int64_t off = ctx->h_out_offset[q], cnt = ctx->h_out_offset[q + 1] - off;
-      if (cnt > 0) {
-        NCCL_CHECK(N.Send(ctx->d_out_betas.ptr + off, (size_t)cnt, ncclUint64, q, ctx->comm, ctx->stream));
-        NCCL_CHECK(N.Send(ctx->d_out_coeffs.ptr + off * width, (size_t)cnt * width, ncclDouble, q, ctx->comm, ctx->stream));
-      }
-      const int64_t rc = ctx->recv_counts[q];
-      if (rc > 0) {
-        NCCL_CHECK(N.Recv(ctx->d_in_betas.ptr + in_off, (size_t)rc, ncclUint64, q, ctx->comm, ctx->stream));
-        NCCL_CHECK(N.Recv(ctx->d_in_coeffs.ptr + in_off * width, (size_t)rc * width, ncclDouble, q, ctx->comm, ctx->stream));
-      }
-      in_off += rc;
-    }
-    total_in = in_off;
-  }
-  NCCL_CHECK(N.GroupEnd());
-  }
-  CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
-  do_accumulate(ctx, elt, total_in, ctx->d_in_betas.ptr, ctx->d_in_coeffs.ptr, v.y_dev);
-  finish_vectors(ctx, v);
-  if (v.y_host || !is_device_pointer(x)) {
-    check_status(ctx);
-    collect_timings(ctx);
-  }
-  API_END
-}
-
-// ---- block <-> hashed redistribution ("next" row f2)
-int dmv_hashed_positions(dmv_context *ctx, int64_t count, const uint8_t *masks, int num_ranks, int64_t *counts,
-                         uint32_t *positions) {
-  API_BEGIN
-  use_device(ctx);
-  if (count < 0 || num_ranks < 1) throw std::runtime_error("bad arguments");
-  InArg<uint8_t> m(masks, (size_t)count, ctx->stream);
-  OutArg<uint32_t> out(positions, (size_t)count);
-  std::vector<int64_t> c;
-  hashed_positions(ctx, count, m.ptr, num_ranks, c, out.ptr);
-  if (counts) std::copy(c.begin(), c.end(), counts);
-  out.finish(ctx->stream);
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  API_END
-}
-
-int dmv_permute(dmv_context *ctx, int elt, int64_t count, const uint32_t *positions, const void *in, void *out,
-                int gather) {
-  API_BEGIN
-  use_device(ctx);
-  if (elt != 1 && elt != 2) throw std::runtime_error("elt must be 1 (8-byte) or 2 (16-byte elements)");
-  if (in == out) throw std::runtime_error("in and out must not alias");
-  InArg<uint32_t> p(positions, (size_t)count, ctx->stream);
-  InArg<double> i(reinterpret_cast<const double *>(in), (size_t)count * elt, ctx->stream);
-  OutArg<double> o(reinterpret_cast<double *>(out), (size_t)count * elt);
-  launch_permute(count, elt, p.ptr, i.ptr, o.ptr, gather != 0, ctx->stream);
-  o.finish(ctx->stream);
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  API_END
-}
-
-int dmv_block_to_hashed(dmv_context *ctx, int elt, int64_t chunk_count, const uint8_t *masks_chunk,
-                        const void *block_chunk, void *hashed, int64_t hashed_count) {
-  API_BEGIN
-  use_device(ctx);
-  if (elt != 1 && elt != 2) throw std::runtime_error("elt must be 1 (8-byte) or 2 (16-byte elements)");
-  const int P = ctx->num_ranks;
-  InArg<uint8_t> m(masks_chunk, (size_t)chunk_count, ctx->stream);
-  InArg<double> in(reinterpret_cast<const double *>(block_chunk), (size_t)chunk_count * elt, ctx->stream);
-  OutArg<double> out(reinterpret_cast<double *>(hashed), (size_t)hashed_count * elt);
-  DevBuf<uint32_t> d_pos;
-  DevBuf<double> d_grouped;
-  d_pos.alloc((size_t)chunk_count);
-  d_grouped.alloc((size_t)chunk_count * elt);
-  std::vector<int64_t> counts;
-  hashed_positions(ctx, chunk_count, m.ptr, P, counts, d_pos.ptr);
-  launch_permute(chunk_count, elt, d_pos.ptr, in.ptr, d_grouped.ptr, false, ctx->stream);
-  if (P == 1) {
-    if (hashed_count != chunk_count) throw std::runtime_error("hashed block size does not match the masks");
-    CUDA_CHECK(cudaMemcpyAsync(out.ptr, d_grouped.ptr, (size_t)chunk_count * elt * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  } else {
-    if (!ctx->comm) throw std::runtime_error("dmv_block_to_hashed on several ranks needs dmv_comm_init");
-    NcclApi &N = nccl();
-    const std::vector<int64_t> all = all_gather_counts(ctx, counts);   // all[r * P + q]: chunk r holds for owner q
-    int64_t incoming = 0;
-    for (int r = 0; r < P; ++r) incoming += all[(size_t)r * P + ctx->rank];
-    if (incoming != hashed_count) throw std::runtime_error("hashed block size does not match the masks");
-    NCCL_CHECK(N.GroupStart());
-    int64_t send_off = 0, recv_off = 0;
-    for (int q = 0; q < P; ++q) {
-      const int64_t sc = counts[q], rc = all[(size_t)q * P + ctx->rank];
-      if (q == ctx->rank) {
-        if (sc > 0) CUDA_CHECK(cudaMemcpyAsync(out.ptr + recv_off * elt, d_grouped.ptr + send_off * elt, (size_t)sc * elt * 8,
-                                               cudaMemcpyDeviceToDevice, ctx->stream));
-      } else {
-        if (sc > 0) NCCL_CHECK(N.Send(d_grouped.ptr + send_off * elt, (size_t)sc * elt, ncclDouble, q, ctx->comm, ctx->stream));
-        if (rc > 0) NCCL_CHECK(N.Recv(out.ptr + recv_off * elt, (size_t)rc * elt, ncclDouble, q, ctx->comm, ctx->stream));
-      }
-      send_off += sc;
-      recv_off += rc;
-    }
-    NCCL_CHECK(N.GroupEnd());
-  }
-  out.finish(ctx->stream);
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  API_END
-}
-
-int dmv_hashed_to_block(dmv_context *ctx, int elt, int64_t chunk_count, const uint8_t *masks_chunk,
-                        const void *hashed, int64_t hashed_count, void *block_chunk) {
-  API_BEGIN
-  use_device(ctx);
-  if (elt != 1 && elt != 2) throw std::runtime_error("elt must be 1 (8-byte) or 2 (16-byte elements)");
-  const int P = ctx->num_ranks;
-  InArg<uint8_t> m(masks_chunk, (size_t)chunk_count, ctx->stream);
-  InArg<double> in(reinterpret_cast<const double *>(hashed), (size_t)hashed_count * elt, ctx->stream);
-  OutArg<double> out(reinterpret_cast<double *>(block_chunk), (size_t)chunk_count * elt);
-  DevBuf<uint32_t> d_pos;
-  DevBuf<double> d_grouped;
-  d_pos.alloc((size_t)chunk_count);
-  d_grouped.alloc((size_t)chunk_count * elt);
-  std::vector<int64_t> counts;   // counts[q]: positions of MY chunk owned by q = what q sends me
-  hashed_positions(ctx, chunk_count, m.ptr, P, counts, d_pos.ptr);
-  if (P == 1) {
-    if (hashed_count != chunk_count) throw std::runtime_error("hashed block size does not match the masks");
-    CUDA_CHECK(cudaMemcpyAsync(d_grouped.ptr, in.ptr, (size_t)chunk_count * elt * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  } else {
-    if (!ctx->comm) throw std::runtime_error("dmv_hashed_to_block on several ranks needs dmv_comm_init");
-    NcclApi &N = nccl();
-    const std::vector<int64_t> all = all_gather_counts(ctx, counts);   // all[r * P + q]: chunk r needs from owner q
-    int64_t outgoing = 0;
-    for (int r = 0; r < P; ++r) outgoing += all[(size_t)r * P + ctx->rank];
-    if (outgoing != hashed_count) throw std::runtime_error("hashed block size does not match the masks");
-    NCCL_CHECK(N.GroupStart());
-    int64_t send_off = 0, recv_off = 0;
-    for (int q = 0; q < P; ++q) {
-      // my hashed block is ascending in global position: the part for chunk q follows the parts for chunks < q
-      const int64_t sc = all[(size_t)q * P + ctx->rank], rc = counts[q];
-      if (q == ctx->rank) {
-        if (sc > 0) CUDA_CHECK(cudaMemcpyAsync(d_grouped.ptr + recv_off * elt, in.ptr + send_off * elt, (size_t)sc * elt * 8,
-                                               cudaMemcpyDeviceToDevice, ctx->stream));
-      } else {
-        if (sc > 0) NCCL_CHECK(N.Send(in.ptr + send_off * elt, (size_t)sc * elt, ncclDouble, q, ctx->comm, ctx->stream));
-        if (rc > 0) NCCL_CHECK(N.Recv(d_grouped.ptr + recv_off * elt, (size_t)rc * elt, ncclDouble, q, ctx->comm, ctx->stream));
-      }
-      send_off += sc;
-      recv_off += rc;
-    }
-    NCCL_CHECK(N.GroupEnd());
-  }
-  launch_permute(chunk_count, elt, d_pos.ptr, d_grouped.ptr, out.ptr, true, ctx->stream);
-  out.finish(ctx->stream);
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  API_END
-}
-
-// Replicated-x product without a communicator (the host owns the all-gather): set-up, then rows of H applied to
-// a caller-assembled x_cat (rank r's block at r * dmv_get_info("replicated_block") elements).  Device pointers.
-int dmv_replicated_setup(dmv_context *ctx) {
-  API_BEGIN
-  use_device(ctx);
-  setup_replicated(ctx);
-  API_END
-}
-
-int dmv_replicated_product(dmv_context *ctx, int elt, const void *x_cat, void *y) {
-  API_BEGIN
-  use_device(ctx);
-  require_states(ctx);
-  if (!ctx->global || ctx->repl_block <= 0) throw std::runtime_error("dmv_replicated_setup has not run");
-  if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
-  if (!is_device_pointer(x_cat) || !is_device_pointer(y)) throw std::runtime_error("dmv_replicated_product needs device pointers");
-  replicated_rows(ctx, elt, x_cat, y);
-  check_status(ctx);
-  API_END
-}
-
 // ---- several vectors per call (the reference's numVectors > 1, "not yet implemented" there: DMV:1101-1102, and what
 // PRIMME's blockSize > 1 would use, src/Diagonalize.chpl:154-158).  x, y: num_vectors arrays of dmv_number_states
 // elements, one after the other (the [numVectors, N] layout of the reference's BlockVector).  On one rank with device
@@ -2605,107 +1317,6 @@ int dmv_matvec_batch(dmv_context *ctx, int elt, int num_vectors, const void *x, 
                                        : dmv_matvec(ctx, elt, xb + (size_t)k * vec_bytes, yb + (size_t)k * vec_bytes);
     if (rc) throw std::runtime_error(g_last_error);
   }
-  API_END
-}
-
-// ---- Lanczos ground-state solver on the device ("next" row f3): the consumer of the product.  The reference hands its
-// matvec to PRIMME (src/Diagonalize.chpl:134-225); here the three-term recurrence, its dot products (NCCL all-reduce
-// across ranks) and the Ritz-vector accumulation all stay in HBM, only alpha_j / beta_j (two doubles) visit the host.
-int dmv_lanczos(dmv_context *ctx, int elt, int max_iters, double tol, uint64_t seed, double *eigenvalue,
-                void *eigenvector, int *iterations, double *residual) {
-  API_BEGIN
-  use_device(ctx);
-  require_states(ctx);
-  if (elt != DMV_F64 && elt != DMV_C128) throw std::runtime_error("elt must be DMV_F64 or DMV_C128");
-  if (max_iters < 1) throw std::runtime_error("max_iters must be positive");
-  const int P = ctx->num_ranks;
-  if (P > 1 && !ctx->comm) throw std::runtime_error("dmv_lanczos on several ranks needs dmv_comm_init");
-  const int64_t n = ctx->n_states;
-  const size_t words = (size_t)n * elt;
-  const bool ce = elt == DMV_C128;
-  for (auto &b : ctx->lz_v) b.alloc(words);
-  ctx->lz_scal.alloc(8);
-  double *scal = ctx->lz_scal.ptr;
-  cudaStream_t st = ctx->stream;
-  auto reduce = [&](int count) {   // sum the first `count` scalars over the ranks, bring them to the host
-    if (P > 1) NCCL_CHECK(nccl().AllReduce(scal, scal, (size_t)count, ncclDouble, ncclSum, ctx->comm, st));
-    double h[4] = {0, 0, 0, 0};
-    CUDA_CHECK(cudaMemcpyAsync(h, scal, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    return std::vector<double>(h, h + count);
-  };
-  auto product = [&](const double *x, double *y) {
-    CUDA_CHECK(cudaMemsetAsync(y, 0, words * 8, st));   // operators without a diagonal accumulate into y (DMV:1062-1069)
-    const int rc = P == 1 ? dmv_local_matvec(ctx, elt, x, y) : dmv_matvec(ctx, elt, x, y);
-    if (rc) throw std::runtime_error(g_last_error);
-  };
-  auto start_vector = [&](double *v) {
-    launch_fill((int64_t)words, seed, (uint64_t)ctx->rank << 40, v, st);
-    CUDA_CHECK(cudaMemsetAsync(scal, 0, 8 * sizeof(double), st));
-    launch_dot(n, ce, v, v, scal, st);
-    const double nrm = std::sqrt(reduce(1)[0]);
-    if (!(nrm > 0.0)) throw std::runtime_error("empty basis");
-    launch_scale((int64_t)words, 1.0 / nrm, v, v, false, st);
-  };
-  std::vector<double> alphas, betas, ritz;
-  double theta = 0.0, res = 0.0;
-  // every rank must take the same stopping decision: the Krylov space is exhausted at the GLOBAL dimension
-  int64_t n_global = n;
-  if (P > 1) {
-    const double mine = (double)n;
-    CUDA_CHECK(cudaMemcpyAsync(scal, &mine, sizeof(double), cudaMemcpyHostToDevice, st));
-    n_global = (int64_t)std::llround(reduce(1)[0]);
-  }
-  {
-    double *v = ctx->lz_v[0].ptr, *u = ctx->lz_v[1].ptr, *w = ctx->lz_v[2].ptr;
-    start_vector(v);
-    double beta_prev = 0.0;
-    for (int j = 0; j < max_iters; ++j) {
-      product(v, w);
-      CUDA_CHECK(cudaMemsetAsync(scal, 0, 8 * sizeof(double), st));
-      launch_dot(n, ce, v, w, scal, st);
-      const double alpha = reduce(1)[0];
-      const double coef[2] = {alpha, beta_prev};
-      CUDA_CHECK(cudaMemcpyAsync(scal + 4, coef, sizeof(coef), cudaMemcpyHostToDevice, st));
-      CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double), st));
-      launch_lanczos_update(n, ce, w, v, j > 0 ? u : nullptr, scal + 4, scal, st);
-      const double beta = std::sqrt(std::max(0.0, reduce(1)[0]));
-      alphas.push_back(alpha);
-      theta = tridiagonal_lowest(alphas, betas, ritz);
-      res = std::fabs(beta * ritz.back());
-      const bool done = res <= tol * std::max(1.0, std::fabs(theta)) || beta <= 1e-14 * std::max(1.0, std::fabs(alpha)) ||
-                        (int64_t)alphas.size() >= n_global;
-      if (done || j + 1 == max_iters) break;
-      betas.push_back(beta);
-      launch_scale((int64_t)words, 1.0 / beta, w, w, false, st);
-      double *t = u; u = v; v = w; w = t;   // v_prev <- v, v <- w / beta, old v_prev becomes scratch
-      beta_prev = beta;
-    }
-  }
-  if (eigenvalue) *eigenvalue = theta;
-  if (iterations) *iterations = (int)alphas.size();
-  if (residual) *residual = res;
-  if (eigenvector) {
-    // second pass with the stored alpha / beta (no dot products): Ritz vector = sum_j s_j v_j
-    double *v = ctx->lz_v[0].ptr, *u = ctx->lz_v[1].ptr, *w = ctx->lz_v[2].ptr, *acc = ctx->lz_v[3].ptr;
-    start_vector(v);
-    CUDA_CHECK(cudaMemsetAsync(acc, 0, words * 8, st));
-    const int k = (int)alphas.size();
-    for (int j = 0; j < k; ++j) {
-      launch_scale((int64_t)words, ritz[j], v, acc, true, st);
-      if (j + 1 == k) break;
-      product(v, w);
-      const double coef[2] = {alphas[j], j > 0 ? betas[j - 1] : 0.0};
-      CUDA_CHECK(cudaMemcpyAsync(scal + 4, coef, sizeof(coef), cudaMemcpyHostToDevice, st));
-      launch_lanczos_update(n, ce, w, v, j > 0 ? u : nullptr, scal + 4, scal, st);
-      CUDA_CHECK(cudaStreamSynchronize(st));   // coef lives on the host stack
-      launch_scale((int64_t)words, 1.0 / betas[j], w, w, false, st);
-      double *t = u; u = v; v = w; w = t;
-    }
-    CUDA_CHECK(cudaMemcpyAsync(eigenvector, acc, words * 8, cudaMemcpyDefault, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-  }
-  check_status(ctx);
   API_END
 }
 
@@ -2811,75 +1422,6 @@ int dmv_apply_off_diag(dmv_context *ctx, int64_t count, const uint64_t *alphas, 
   API_END
 }
 
-extern "C++" {
-namespace {
-dmv_context *bound_context(const void *key, const char *who) {
-  dmv_context *ctx = nullptr;
-  {
-    std::lock_guard<std::mutex> lock(g_bind_mutex);
-    auto it = g_bindings.find(key);
-    if (it != g_bindings.end()) ctx = it->second;
-  }
-  if (!ctx) { fprintf(stderr, "%s: handle is not bound to a dmv context (dmv_bind_operator)\n", who); abort(); }
-  return ctx;
-}
-template <typename T>
-dmv_external_array external_array(size_t n) {   // convertToExternalArray (BO:232): callee allocates, caller frees
-  dmv_external_array a;
-  a.elts = n ? malloc(n * sizeof(T)) : nullptr;
-  a.num_elts = n;
-  a.freer = n ? &free : nullptr;
-  if (n && !a.elts) { fprintf(stderr, "out of memory\n"); abort(); }
-  return a;
-}
-}  // namespace
-}  // extern "C++"
-
-void ls_chpl_operator_apply_diag(const void *ls_hs_operator_ptr, int64_t count, const uint64_t *alphas,
-                                 dmv_external_array *coeffs, int64_t /*num_tasks*/) {
-  dmv_context *ctx = bound_context(ls_hs_operator_ptr, "ls_chpl_operator_apply_diag");
-  *coeffs = external_array<double>((size_t)count);
-  if (dmv_apply_diag(ctx, count, alphas, (double *)coeffs->elts) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
-}
-
-void ls_chpl_operator_apply_off_diag(const void *ls_hs_operator_ptr, int64_t count, const uint64_t *alphas,
-                                     dmv_external_array *betas, dmv_external_array *coeffs,
-                                     dmv_external_array *offsets, int64_t /*num_tasks*/) {
-  dmv_context *ctx = bound_context(ls_hs_operator_ptr, "ls_chpl_operator_apply_off_diag");
-  const size_t T = (size_t)dmv_max_number_off_diag(ctx);
-  *offsets = external_array<int64_t>((size_t)count + 1);
-  if (T == 0) {   // BO:269-273
-    betas->elts = nullptr; betas->num_elts = 0; betas->freer = nullptr;
-    coeffs->elts = nullptr; coeffs->num_elts = 0; coeffs->freer = nullptr;
-    memset(offsets->elts, 0, ((size_t)count + 1) * sizeof(int64_t));
-    return;
-  }
-  *betas = external_array<uint64_t>((size_t)count * T);
-  *coeffs = external_array<double>((size_t)count * T * 2);
-  if (dmv_apply_off_diag(ctx, count, alphas, (uint64_t *)betas->elts, (double *)coeffs->elts,
-                         (int64_t *)offsets->elts) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
-}
-
-// reference src/StatesEnumeration.chpl:588-603: the bounds are accepted and ignored there too (the whole range of the
-// basis is enumerated); returns this locale's block
-void ls_chpl_enumerate_representatives(const void *ls_hs_basis_ptr, uint64_t /*lower*/, uint64_t /*upper*/,
-                                       dmv_external_array *dest) {
-  dmv_context *ctx = bound_context(ls_hs_basis_ptr, "ls_chpl_enumerate_representatives");
-  if (dmv_number_states(ctx) < 0 && dmv_basis_build(ctx) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
-  *dest = external_array<uint64_t>((size_t)dmv_number_states(ctx));
-  if (dmv_get_representatives(ctx, (uint64_t *)dest->elts, nullptr) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
-}
-
-// host-only self-check entry for the tridiagonal solver behind dmv_lanczos (no device needed)
-int dmv_debug_tridiagonal_lowest(int k, const double *diag, const double *offdiag, double *eigenvalue, double *vector) {
-  API_BEGIN
-  if (k < 1) throw std::runtime_error("empty matrix");
-  std::vector<double> a(diag, diag + k), b(offdiag, offdiag + (k - 1)), v;
-  *eigenvalue = tridiagonal_lowest(a, b, v);
-  if (vector) std::copy(v.begin(), v.end(), vector);
-  API_END
-}
-
 int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t count,
                             const uint64_t *states, uint64_t *reps, int32_t *stab) {
   API_BEGIN
@@ -2918,60 +1460,6 @@ int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t 
     if (stab) stab[k] = r.stab;
   }
   API_END
-}
-
-int dmv_bind_operator(const void *ls_hs_operator_ptr, dmv_context *ctx) {
-  API_BEGIN
-  std::lock_guard<std::mutex> lock(g_bind_mutex);
-  if (ctx) g_bindings[ls_hs_operator_ptr] = ctx;
-  else g_bindings.erase(ls_hs_operator_ptr);
-  API_END
-}
-
-// reference: src/DistributedMatrixVector.chpl:1095-1110.  Halts (abort) on error like the reference.
-void ls_chpl_matrix_vector_product(const void *ls_hs_operator_ptr, int num_vectors, double *x, double *y) {
-  dmv_context *ctx = nullptr;
-  {
-    std::lock_guard<std::mutex> lock(g_bind_mutex);
-    auto it = g_bindings.find(ls_hs_operator_ptr);
-    if (it != g_bindings.end()) ctx = it->second;
-  }
-  if (!ctx) { fprintf(stderr, "ls_chpl_matrix_vector_product: operator is not bound to a dmv context\n"); abort(); }
-  if (num_vectors != 1) {  // DMV:1101-1102
-    fprintf(stderr, "applying the Operator to more than 1 vector is not yet implemented\n");
-    abort();
-  }
-  if (dmv_local_matvec(ctx, DMV_F64, x, y) != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }
-}
-
-// reference: src/Diagonalize.chpl:134-162 -- the matrix-vector callback PRIMME drives (`primme.matrixMatvec`):
-// blockSize columns of real(64), leading dimensions ldx / ldy >= nLocal, column k through localMatrixVector.  The
-// reference reads the operator from primme->matrix; here the primme_params pointer itself is the handle, bound to a
-// context with dmv_bind_operator (no dependence on PRIMME's struct layout).  Contiguous columns go through
-// dmv_matvec_batch (four columns share one term walk in k_gather); collective when the context has several ranks.
-void ls_chpl_primme_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *block_size, void *primme, int *ierr) {
-  dmv_context *ctx = nullptr;
-  {
-    std::lock_guard<std::mutex> lock(g_bind_mutex);
-    auto it = g_bindings.find(primme);
-    if (it != g_bindings.end()) ctx = it->second;
-  }
-  if (!ctx) { fprintf(stderr, "ls_chpl_primme_matvec: primme_params is not bound to a dmv context\n"); abort(); }
-  const int64_t n = ctx->n_states;
-  if (*ldx < n || *ldy < n) { fprintf(stderr, "ls_chpl_primme_matvec: leading dimension below nLocal\n"); abort(); }   // :143-144
-  int rc = 0;
-  if (*ldx == n && *ldy == n) {
-    rc = dmv_matvec_batch(ctx, DMV_F64, *block_size, x, y);
-  } else {
-    for (int k = 0; k < *block_size && rc == 0; ++k) {
-      const double *xk = reinterpret_cast<const double *>(x) + *ldx * k;
-      double *yk = reinterpret_cast<double *>(y) + *ldy * k;
-      rc = ctx->num_ranks == 1 ? dmv_local_matvec(ctx, DMV_F64, xk, yk) : dmv_matvec(ctx, DMV_F64, xk, yk);
-    }
-  }
-  if (rc == 0 && is_device_pointer(y)) rc = dmv_synchronize(ctx);
-  if (rc != 0) { fprintf(stderr, "%s\n", dmv_last_error()); abort(); }   // the reference halts
-  *ierr = 0;                                                              // :160
 }
 
 }  // extern "C"

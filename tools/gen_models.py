@@ -6,7 +6,7 @@ inversion, symmetry generators) and the Hamiltonian term list (expression + site
 /root/reference/data/*.yaml.  This script extracts that semantic content and re-emits it in a
 normalised layout (no anchors, no comments, no solver-only keys such as `observables`,
 `number_vectors`, `output`, `max_primme_*`), so that tests, bench.py and smoke() can run on the GPU
-box where /root/reference does not exist.  tests/test_models.py re-checks semantic equality against
+box where /root/reference does not exist.  tests/test_host.py (test_model_inputs_equal_the_reference_inputs) re-checks semantic equality against
 /root/reference whenever it is present.
 
 Usage:  python tools/gen_models.py [/root/reference/data] [data]
