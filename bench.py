@@ -561,8 +561,20 @@ def main():
     w.close()
     del w
 
-    # ---- the other BASELINE configs, briefly: value, kernel time and their own parity figure
+    # ---- the other BASELINE configs, briefly: value, kernel time and their own parity figure.  A watchdog keeps them
+    # from costing the main line: if they are not through in time (a hung collective), every rank prints / exits.
     secondary = []
+    line["secondary"] = secondary
+
+    def give_up(signum, frame):
+        secondary.append({"error": "secondary workloads timed out; entries above are complete"})
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+
+    import signal
+    signal.signal(signal.SIGALRM, give_up)
+    signal.alarm(int(os.environ.get("DMV_SECONDARY_TIMEOUT", "420")))
     names = [] if args.secondary.strip().lower() in ("", "none") else [s for s in args.secondary.split(",") if s]
     for name in names:
         if name == main_name:
@@ -585,7 +597,7 @@ def main():
             del s
         except Exception as e:   # a secondary entry must not cost the main line
             secondary.append({"workload": name, "error": f"{type(e).__name__}: {e}"[:300]})
-    line["secondary"] = secondary
+    signal.alarm(0)
 
     if rank == 0:
         print(json.dumps(line), flush=True)
