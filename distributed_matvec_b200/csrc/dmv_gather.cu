@@ -474,9 +474,11 @@ __global__ void __launch_bounds__(256) k_push_block(const T *__restrict__ x, int
     const T v = x[i];
     for (int q = 0; q < num_ranks; ++q) peer_slot[q][i] = v;
   }
-  __threadfence_system();            // my stores are visible system-wide before this CTA is counted
+  // one system-scope fence per CTA, after the CTA barrier (cumulative: it covers the stores of the whole CTA); a fence in
+  // every warp costs ~0.7 ms per product on eight GPUs (measured: profiles/r02_scaling.md)
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned prev = atomicAdd(done, 1u);
     if (prev == gridDim.x - 1) {     // last CTA: every block of the grid has fenced its stores
       __threadfence();
@@ -524,8 +526,8 @@ void launch_push_block(const void *x, int64_t n_doubles, int num_ranks, void *co
                        unsigned *const *peer_flags, int rank, unsigned epoch, bool wide, cudaStream_t stream) {
   // wide: 16-byte words (x and every slot 16-byte aligned, even number of doubles)
   const int64_t words = wide ? n_doubles / 2 : n_doubles;
-  int64_t blocks = (words + 255) / 256;
-  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  int64_t blocks = (words + 4 * 256 - 1) / (4 * 256);   // a few words per thread: fewer CTAs to fence and count
+  if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
   if (blocks < 1) blocks = 1;
   if (wide)
     k_push_block<double2><<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const double2 *>(x), words, num_ranks,
