@@ -219,7 +219,7 @@ def count_terms_cpu(arm: CpuArm) -> int:
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (NVML, every 2 ms)."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every DMV_CLOCK_PERIOD_MS = 5 ms)."""
 
     def __init__(self, index: int):
         self.index = index
@@ -250,7 +250,7 @@ class ClockSampler:
                 for name, bit in bits.items():
                     if r & bit:
                         self.reasons.add(name)
-                self._stop.wait(0.002)
+                self._stop.wait(1e-3 * float(os.environ.get("DMV_CLOCK_PERIOD_MS", "5")))
         except Exception as e:  # NVML missing: fall back to one nvidia-smi query
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
@@ -421,9 +421,10 @@ def time_products(w: Workload, steps: int, warmup: int, flush, barrier, dist, lo
         sampler.__exit__()
     launches = nat.lib().dmv_launch_count() - launches0
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    t = torch.tensor([float(np.mean(step_ms)), float(np.min(step_ms))], dtype=torch.float64, device="cuda")
+    t = torch.tensor([float(np.mean(step_ms)), float(np.min(step_ms))] + step_ms, dtype=torch.float64, device="cuda")
     if w.world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    w.steps_ms = [round(float(v), 3) for v in t[2:]]          # every timed step, max over ranks
     w.op.synchronize()
     # dominant kernel: the generate stage of the library's own CUDA-event timeline
     kern = []
@@ -538,6 +539,7 @@ def main():
                    "l2": L2_NOTE},
         "run": {"terms_per_s": nnz_total / (ms_per_step * 1e-3), "partition": f"hash64_01 % {world}",
                 "exchange": w.exchange_name(), "kernel": w.kernel_name(), "ms_best_step": ms_best,
+                "steps_ms": w.steps_ms,
                 "basis_build_s": w.build_s, "torus_mode": w.op.info("torus_mode"), "canon_mode": w.op.info("canon_mode")},
         "max_rel_err": parity["max_rel_err"], "parity": parity,
         "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "states/s", "ms_per_step": e2e_ms,
