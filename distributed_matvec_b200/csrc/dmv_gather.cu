@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(256) k_push_block(const T *__restrict__ x, int
     __threadfence_system();
     const unsigned prev = atomicAdd(done, 1u);
     if (prev == gridDim.x - 1) {     // last CTA: every block of the grid has fenced its stores
-      __threadfence();
+      __threadfence_system();
       *done = 0;
       for (int q = 0; q < num_ranks; ++q) {
         unsigned *f = peer_flags[q] + rank;
