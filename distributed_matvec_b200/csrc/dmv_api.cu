@@ -374,6 +374,7 @@ void install_directory(dmv_context *ctx) {
   launch_build_directory(ctx->d_reps.ptr, n, ctx->d_dir.ptr, ctx->n_buckets, shift, ctx->stream);
   ctx->planned = false;
   ctx->table_elt = 0;
+  ctx->table_batch_slots = 0;
   // a new block also invalidates the exchange set-up: the replicated-x twin / slot table and the record plan
   ctx->exchange_decided = false;
   ctx->replicated = false;
@@ -686,6 +687,35 @@ void rows_product(dmv_context *basis, KernelParams &p, int elt, const void *x_al
   launch_rows(p, elt == DMV_C128, stream);
 }
 
+// the same for `nv` vectors at once (single rank; x / y: nv device vectors `stride` elements apart): k_rows_batch
+void rows_product_batch(dmv_context *ctx, int elt, int nv, const void *x, void *y, int64_t stride) {
+  const int64_t n = ctx->n_states;
+  cudaStream_t st = ctx->stream;
+  if (ctx->table_batch_slots == 0) {
+    if (2 * n + 16 >= 2147483647ll) throw std::runtime_error("k_rows_batch: table of more than 2^31 buckets");
+    const uint32_t buckets = (uint32_t)std::max<int64_t>(16, 2 * n);
+    ctx->d_table_batch.alloc((size_t)buckets * 64);
+    ctx->d_slot_of_batch.alloc((size_t)std::max<int64_t>(1, n));
+    CUDA_CHECK(cudaMemsetAsync(ctx->d_table_batch.ptr, 0xff, (size_t)buckets * 64, st));
+    launch_table_insert(ctx->d_reps.ptr, n, ctx->d_table_batch.ptr, buckets, 1, ctx->d_slot_of_batch.ptr, st, 64);
+    ctx->table_batch_slots = buckets;
+  }
+  launch_table_fill_batch(n, nv, elt, x, stride, ctx->d_norms.ptr, ctx->d_slot_of_batch.ptr, ctx->d_reps.ptr,
+                          ctx->d_table_batch.ptr, st);
+  KernelParams p = base_params(ctx);
+  p.x = x;
+  p.y = y;
+  select_tables(ctx, p, true, false);
+  p.uni_re = ctx->gather_uni[0]; p.uni_im = ctx->gather_uni[1];
+  p.table = ctx->d_table_batch.ptr;
+  p.table_slots = ctx->table_batch_slots;
+  p.batch = nv;
+  p.batch_elt = elt;
+  p.batch_stride = stride;
+  p.row_split = 1;
+  launch_rows_batch(p, st);
+}
+
 void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev,
                  const void *x_host_pending, int64_t row_begin, int64_t row_end) {
   if (use_pull(ctx)) {   // one rank owns the basis: traverse by rows (gather), see k_gather / k_pull
@@ -968,6 +998,9 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
   } else if (key == "gather") {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
+  } else if (key == "rows_batch") {
+    if (value < -1 || value > 1) throw std::runtime_error("rows_batch: -1 auto / 1 k_rows_batch for batched products, 0 vector by vector");
+    ctx->opt_rows_batch = (int)value;
   } else if (key == "rows_ctas") {
     ctx->opt_rows_ctas = value == 3 ? 3 : 2;
     if (ctx->global) ctx->global->opt_rows_ctas = ctx->opt_rows_ctas;
@@ -1310,6 +1343,16 @@ int dmv_matvec_batch(dmv_context *ctx, int elt, int num_vectors, const void *x, 
       p.uni_re = ctx->gather_uni[0]; p.uni_im = ctx->gather_uni[1];
       launch_gather(p, ctx->proj == PROJ_INVERSION, ctx->complex_coefficients, elt == DMV_C128, ctx->gather_narrow,
                     ctx->index_mode == INDEX_LIN, ctx->gather_uniform, ctx->stream);
+    }
+  }
+  if (ctx->num_ranks == 1 && use_pull(ctx) && !use_gather(ctx) && use_rows(ctx) && ctx->opt_rows_batch != 0 &&
+      is_device_pointer(x) && is_device_pointer(y)) {
+    // bases with permutation symmetries: up to six doubles per state share one orbit minimum and one look-up per term
+    const int per = 6 / elt;
+    while (num_vectors - k >= 2) {
+      const int nv = std::min(per, num_vectors - k);
+      rows_product_batch(ctx, elt, nv, xb + (size_t)k * vec_bytes, yb + (size_t)k * vec_bytes, ctx->n_states);
+      k += nv;
     }
   }
   for (; k < num_vectors; ++k) {

@@ -203,6 +203,11 @@ struct dmv_context {
   DevBuf<uint32_t> d_slot_of;
   uint32_t table_slots = 0;
   int table_elt = 0;        // element type the slots are laid out for (0: not built)
+  // k_rows_batch: 64-byte buckets { key, six doubles, spare }, two per state; built on the first batched product
+  DevBuf<unsigned char> d_table_batch;
+  DevBuf<uint32_t> d_slot_of_batch;
+  uint32_t table_batch_slots = 0;
+  int opt_rows_batch = -1;  // -1 / 1: batched products of symmetric bases go through k_rows_batch | 0: vector by vector
   double gather_uni[2] = {0.0, 0.0};
   int index_mode = INDEX_DIRECTORY;
   DevBuf<uint32_t> d_binom, d_lin_a, d_lin_b;
@@ -376,6 +381,7 @@ void finish_vectors(dmv_context *ctx, const VecStage &v);
 void upload_out_pointers(dmv_context *ctx);
 void do_plan(dmv_context *ctx);
 void ensure_table(dmv_context *ctx, int elt);
+void rows_product_batch(dmv_context *ctx, int elt, int nv, const void *x, void *y, int64_t stride);
 void rows_product(dmv_context *basis, KernelParams &p, int elt, const void *x_all, const uint32_t *pos, cudaStream_t stream, bool fill = true, dmv_context *timer = nullptr);
 void do_generate(dmv_context *ctx, int elt, const void *x_dev, void *y_dev, const void *x_host_pending = nullptr, int64_t row_begin = 0, int64_t row_end = 0);
 void do_accumulate(dmv_context *ctx, int elt, int64_t count, const uint64_t *betas, const double *coeffs, void *y_dev);

@@ -102,7 +102,8 @@ struct KernelParams {
   int64_t x_row_offset;
   // k_gather on several vectors at once: vector k of x / y starts batch_stride elements after vector k - 1
   int32_t gather_walk;         // k_gather: 0 per-lane walk from the top bit (default), 1 group-major, 2 per-lane from the bottom
-  int32_t batch;               // 0 / 1: one vector; 4: four vectors per launch
+  int32_t batch;               // 0 / 1: one vector; 4: four vectors per launch (k_gather); 2 .. 6: k_rows_batch
+  int32_t batch_elt;           // k_rows_batch: doubles per vector element (1 | 2); batch * batch_elt <= 6
   int64_t batch_stride;
   // k_rows (row traversal of bases with permutation symmetries): hash table over the representatives with the scaled
   // vector element in the slot (see table_slot in dmv_device.cuh)
@@ -129,7 +130,11 @@ void launch_rows(const KernelParams &p, bool complex_elements, cudaStream_t stre
 // hash table of k_rows: insert every state (slot_of[i] = its slot), then per product table[slot_of[i]] = x[src(i)] * norm[i]
 // with src(i) = pos ? pos[i] : i
 void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t n_buckets, int slots_per_bucket,
-                         uint32_t *slot_of, cudaStream_t stream);
+                         uint32_t *slot_of, cudaStream_t stream, int bucket_bytes = 32);
+// k_rows on several vectors at once: 64-byte buckets { key, six doubles, spare } shared by the vectors of the batch
+void launch_rows_batch(const KernelParams &p, cudaStream_t stream);
+void launch_table_fill_batch(int64_t n, int num_vectors, int elt, const void *x, int64_t stride, const double *norms,
+                             const uint32_t *slot_of, const uint64_t *reps, void *table, cudaStream_t stream);
 void launch_table_fill(int64_t n, bool complex_elements, const void *x, const double *norms, const uint32_t *pos,
                        const uint32_t *slot_of, const uint64_t *reps, void *table, void *dense, cudaStream_t stream);
 // perfect-hash set-up (k_rows dense index): mark the positions of `n` states at a level in seen / collide bit arrays

@@ -1065,16 +1065,128 @@ __global__ void __launch_bounds__(kThreads, CTAS) k_rows(const KernelParams p) {
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// k_rows_batch: k_rows on up to six real (three complex) vectors at once -- the product the block eigensolver asks for
+// (reference src/Diagonalize.chpl:134-162: PRIMME hands `blockSize` vectors to one matvec call).  The orbit minimum and the
+// look-up of a term are shared by the vectors: one bucket = 64 bytes = { key, d[0..5], spare }, d = the scaled elements of
+// the vectors at that state (three (re, im) pairs or six reals: the operator is real, so every double is treated alike),
+// fetched with two independent 256-bit loads.  One request per lane in flight, consumed after the orbit minimum of the
+// NEXT term; a bucket taken by another state continues with the next bucket through the same slot.
+// Cost model: one 64-byte request per term (17.8 G/s for tables >> L2, profiles/r02_random_access.md) against one 32-byte
+// request per term AND vector in k_rows.
+// -------------------------------------------------------------------------------------------------
+template <int TK>
+__global__ void __launch_bounds__(kThreads, 2) k_rows_batch(const KernelParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(p, PROJ_GROUP, sizeof(double), false);
+  const Tables<false> T = stage_tables<PROJ_GROUP, false>(p, smem, L);
+  __syncthreads();
+  const OrbitProgram &orbit = T.orbit;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const bool any_s_out = p.any_s_out != 0;
+  const unsigned char *__restrict__ table = reinterpret_cast<const unsigned char *>(p.table);
+  const uint32_t n_buckets = p.table_slots;
+  const int elt = p.batch_elt;            // doubles per vector element (1 | 2)
+  const int nd = p.batch * elt;           // doubles per state in use (<= 6)
+  const int64_t stride = p.batch_stride;  // elements between consecutive vectors
+  const double *__restrict__ xd = reinterpret_cast<const double *>(p.x);
+  double *__restrict__ yd = reinterpret_cast<double *>(p.y);
+  unsigned long long bad = 0, bad_state = 0;
+
+  const int64_t n_rows = p.row_end - p.row_begin;
+  const int64_t n_tiles = (n_rows + 31) / 32;
+  const int64_t warps_total = (int64_t)gridDim.x * kWarps;
+  for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += warps_total) {
+    const int64_t i = p.row_begin + tile * 32 + lane;
+    const bool valid = i < p.row_end;
+    const uint64_t b = valid ? __ldg(p.index.reps + i) : 0ull;
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int w = 0;
+    RowTerms rt = row_terms<false>(T, 0, 0, min(64, p.n_groups), b);
+    if (!valid) rt.mask = 0;
+    bool live = false, held = false;       // a request in flight; a term popped but not yet requested
+    uint64_t want = 0, want_n = 0;
+    double c = 0.0, c_n = 0.0;
+    uint32_t bk = 0;
+    uint64_t q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0, q5 = 0, q6 = 0, q7 = 0;
+    for (;;) {
+      while (valid && rt.mask == 0 && 64 * (w + 1) < p.n_groups) {
+        ++w;
+        rt = row_terms<false>(T, w, 64 * w, min(64 * w + 64, p.n_groups), b);
+      }
+      const bool has = rt.mask != 0;
+      if (!has && !live && !held) break;
+      // ---- the next term of the row (its orbit minimum covers the latency of the request in flight)
+      if (has && !held) {
+        uint64_t flip;
+        c_n = pop_term<false>(T, rt, 64 * w, b, any_s_out, flip);
+        const uint64_t raw = b ^ flip;
+        if constexpr (TK > 0) want_n = orbit_min_torus_sq<TK>(orbit, raw);
+        else want_n = orbit_representative(orbit, raw);
+        held = true;
+      }
+      // ---- consume the request in flight
+      bool retry = false;
+      if (live) {
+        if (q0 == want) {
+          acc[0] = fma(c, __longlong_as_double((long long)q1), acc[0]);
+          acc[1] = fma(c, __longlong_as_double((long long)q2), acc[1]);
+          acc[2] = fma(c, __longlong_as_double((long long)q3), acc[2]);
+          acc[3] = fma(c, __longlong_as_double((long long)q4), acc[3]);
+          acc[4] = fma(c, __longlong_as_double((long long)q5), acc[4]);
+          acc[5] = fma(c, __longlong_as_double((long long)q6), acc[5]);
+        } else if (q0 == kEmptyKey) {
+          if (c != 0.0) { ++bad; bad_state = want; }       // not a basis state (DMV:115-118)
+        } else {
+          retry = true;
+        }
+      }
+      // ---- issue: the continuation of a missed request, else the held term
+      if (retry) {
+        bk = bk + 1 == n_buckets ? 0 : bk + 1;
+      } else if (held) {
+        want = want_n; c = c_n; held = false;
+        bk = table_slot(want, n_buckets);
+        live = true;
+      } else {
+        live = false;
+      }
+      if (live) {
+        const unsigned char *q = table + (size_t)bk * 64;
+        load256(q, q0, q1, q2, q3);
+        load256(q + 32, q4, q5, q6, q7);
+      }
+    }
+    if (valid) {
+      const double inv_nb = 1.0 / __ldg(p.norms + i);
+      double dre = 0.0, dim = 0.0;
+      if (p.n_diag > 0) diagonal<false>(T, p.n_diag, b, dre, dim);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        if (j < nd) {
+          const int64_t at = ((int64_t)(j / elt) * stride + i) * elt + (j % elt);
+          const double base = p.n_diag > 0 ? dre * __ldg(xd + at) : yd[at];
+          yd[at] = fma(inv_nb, acc[j], base);
+        }
+      }
+    }
+  }
+  if (bad) {
+    if (atomicAdd(p.status, bad) == 0) p.status[1] = bad_state;
+  }
+}
+
 // hash table set-up: claim a slot per state (keys pre-set to kEmptyKey; slot 0 of a bucket, then slot 1 when the bucket
 // has two, then the next bucket), remember it in slot_of (= 2 bucket + slot)
 __global__ void k_table_insert(const uint64_t *__restrict__ reps, int64_t n, unsigned char *table, uint32_t n_buckets,
-                               int slots_per_bucket, uint32_t *slot_of) {
+                               int slots_per_bucket, uint32_t *slot_of, int bucket_bytes) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t key = reps[i];
   uint32_t b = table_slot(key, n_buckets);
   for (;;) {
-    unsigned long long *q = reinterpret_cast<unsigned long long *>(table + (size_t)b * 32);
+    unsigned long long *q = reinterpret_cast<unsigned long long *>(table + (size_t)b * bucket_bytes);
     if (atomicCAS(q, (unsigned long long)kEmptyKey, (unsigned long long)key) == (unsigned long long)kEmptyKey) {
       slot_of[i] = 2 * b;
       return;
@@ -1113,6 +1225,28 @@ __global__ void k_table_fill(int64_t n, const void *__restrict__ x, const double
       if (in_table) *reinterpret_cast<double *>(table + (size_t)(s >> 1) * 32 + 16 + 8 * (s & 1)) = v;
       else *reinterpret_cast<ulonglong2 *>(dense + (size_t)s * 16) = make_ulonglong2(key, (uint64_t)__double_as_longlong(v));
     }
+  }
+}
+
+// per batched product: bucket slot_of[i] / 2 of the 64-byte table <- { key, x_v[i] * norm[i] for the vectors v, 0 ... }
+// (two 256-bit stores = two full sectors)
+__global__ void k_table_fill_batch(int64_t n, int nd, int elt, const double *__restrict__ x, int64_t stride,
+                                   const double *__restrict__ norms, const uint32_t *__restrict__ slot_of,
+                                   const uint64_t *__restrict__ reps, unsigned char *table) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const double nrm = __ldg(norms + i);
+    uint64_t d[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      double v = 0.0;
+      if (j < nd) v = __ldg(x + ((int64_t)(j / elt) * stride + i) * elt + (j % elt)) * nrm;
+      d[j] = (uint64_t)__double_as_longlong(v);
+    }
+    unsigned char *q = table + (size_t)(__ldg(slot_of + i) >> 1) * 64;
+    const uint64_t key = __ldg(reps + i);
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(q), "l"(key), "l"(d[0]), "l"(d[1]), "l"(d[2]) : "memory");
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(q + 32), "l"(d[3]), "l"(d[4]), "l"(d[5]), "l"(0ull) : "memory");
   }
 }
 
@@ -1513,6 +1647,47 @@ void launch_rows_e(const KernelParams &p, cudaStream_t stream) {
 }
 }  // namespace
 
+namespace {
+template <int TK>
+void launch_rows_batch_t(const KernelParams &p, cudaStream_t stream) {
+  const SmemLayout L = smem_layout(p, PROJ_GROUP, sizeof(double), false);
+  const size_t smem_bytes = L.total;
+  auto kernel = k_rows_batch<TK>;
+  if (smem_bytes > 48 * 1024)
+    DMV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  int per_sm = 0;
+  DMV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem_bytes));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t tiles = (p.row_end - p.row_begin + 31) / 32;
+  const int blocks = grid_for(tiles, kWarps, sm_count() * per_sm);
+  kernel<<<blocks, kThreads, smem_bytes, stream>>>(p);
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+}  // namespace
+
+// p.batch vectors of p.batch_elt doubles per element (p.batch * p.batch_elt <= 6), p.table = the 64-byte-bucket table
+void launch_rows_batch(const KernelParams &p, cudaStream_t stream) {
+  if (p.row_end <= p.row_begin) return;
+  if (p.batch < 1 || (p.batch_elt != 1 && p.batch_elt != 2) || p.batch * p.batch_elt > 6)
+    throw std::runtime_error("k_rows_batch: at most six doubles per state");
+  const OrbitProgram &o = p.orbit;
+  const int k = (o.canon_mode != 0 && o.tor_mode == 2 && o.canon_k == o.canon_r) ? o.canon_k : 0;
+  if (k == 6) launch_rows_batch_t<6>(p, stream);
+  else if (k == 4) launch_rows_batch_t<4>(p, stream);
+  else launch_rows_batch_t<0>(p, stream);
+}
+
+void launch_table_fill_batch(int64_t n, int num_vectors, int elt, const void *x, int64_t stride, const double *norms,
+                             const uint32_t *slot_of, const uint64_t *reps, void *table, cudaStream_t stream) {
+  if (n <= 0) return;
+  const int blocks = grid_for(n, 256, sm_count() * 16);
+  k_table_fill_batch<<<blocks, 256, 0, stream>>>(n, num_vectors * elt, elt, reinterpret_cast<const double *>(x), stride, norms,
+                                                 slot_of, reps, reinterpret_cast<unsigned char *>(table));
+  DMV_CUDA_CHECK(cudaGetLastError());
+  g_launches++;
+}
+
 void launch_rows(const KernelParams &p, bool complex_elements, cudaStream_t stream) {
   if (p.row_end <= p.row_begin) return;
   if (complex_elements) launch_rows_e<true>(p, stream);
@@ -1520,10 +1695,10 @@ void launch_rows(const KernelParams &p, bool complex_elements, cudaStream_t stre
 }
 
 void launch_table_insert(const uint64_t *reps, int64_t n, void *table, uint32_t n_buckets, int slots_per_bucket,
-                         uint32_t *slot_of, cudaStream_t stream) {
+                         uint32_t *slot_of, cudaStream_t stream, int bucket_bytes) {
   if (n <= 0) return;
   k_table_insert<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reps, n, reinterpret_cast<unsigned char *>(table),
-                                                                 n_buckets, slots_per_bucket, slot_of);
+                                                                 n_buckets, slots_per_bucket, slot_of, bucket_bytes);
   DMV_CUDA_CHECK(cudaGetLastError());
   g_launches++;
 }

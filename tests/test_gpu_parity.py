@@ -436,12 +436,19 @@ def test_hermiticity_and_linearity_at_size(need_cuda):
 
 
 @pytest.mark.parametrize("name", ["heisenberg_chain_16", "heisenberg_chain_10", "heisenberg_kagome_16",
-                                  "anisotropic_bonds", "complex_hopping", "heisenberg_chain_24_symm", "no_diagonal"])
+                                  "anisotropic_bonds", "complex_hopping", "heisenberg_chain_24_symm", "no_diagonal",
+                                  "heisenberg_square_4x4", "heisenberg_kagome_12_symm", "no_diagonal_symm"])
 def test_matvec_batch(need_cuda, name):
     """numVectors > 1 (dmv_matvec_batch): every column equals the single-vector product -- bit for bit on the k_gather
     path (same order of operations per column), within rounding elsewhere -- for 1 .. 9 columns, real and complex,
-    device and host pointers; operators without a diagonal accumulate into Y (DMV:1062-1069)."""
-    if name == "no_diagonal":
+    device and host pointers; operators without a diagonal accumulate into Y (DMV:1062-1069).  Bases with permutation
+    symmetries take device batches through k_rows_batch (up to six doubles per state share one look-up per term)."""
+    if name == "no_diagonal_symm":     # translations + parity + spin inversion: the row kernels accumulate into Y
+        bonds = [[i, (i + 1) % 12] for i in range(12)]
+        basis, matrix = _custom(12, 6, [{"expression": "σ⁺₀ σ⁻₁", "sites": bonds}, {"expression": "σ⁻₀ σ⁺₁", "sites": bonds}],
+                                symmetries=[{"permutation": [(i + 1) % 12 for i in range(12)], "sector": 0},
+                                            {"permutation": [11 - i for i in range(12)], "sector": 0}], spin_inversion=1)
+    elif name == "no_diagonal":
         bonds = [[i, (i + 1) % 8] for i in range(8)]
         basis, matrix = _custom(8, 4, [{"expression": "σ⁺₀ σ⁻₁", "sites": bonds}, {"expression": "σ⁻₀ σ⁺₁", "sites": bonds}])
     else:
@@ -453,7 +460,7 @@ def test_matvec_batch(need_cuda, name):
     for cplx in (False, True):
         for k in (1, 3, 4, 9):
             X = np.stack([_x(n, cplx, 100 + j) for j in range(k)])
-            Y0 = np.stack([_x(n, cplx, 200 + j) for j in range(k)]) if name == "no_diagonal" else np.zeros_like(X)
+            Y0 = np.stack([_x(n, cplx, 200 + j) for j in range(k)]) if name.startswith("no_diagonal") else np.zeros_like(X)
             singles = np.stack([op.matvec(torch.from_numpy(X[j]).cuda(), torch.from_numpy(Y0[j].copy()).cuda()).cpu().numpy()
                                 for j in range(k)])
             Yd = op.matvec_batch(torch.from_numpy(X).cuda(), torch.from_numpy(Y0.copy()).cuda()).cpu().numpy()
@@ -463,7 +470,37 @@ def test_matvec_batch(need_cuda, name):
                 assert _close(Yd, singles), (name, cplx, k)
             Yh = op.matvec_batch(X, Y0.copy())
             assert _close(Yh, singles), (name, cplx, k)
+    if op.info("rows"):               # the same batches vector by vector (option rows_batch = 0)
+        op.set_option("rows_batch", 0)
+        X = np.stack([_x(n, True, 300 + j) for j in range(5)])
+        Y0 = np.stack([_x(n, True, 400 + j) for j in range(5)]) if name.startswith("no_diagonal") else np.zeros_like(X)
+        a = op.matvec_batch(torch.from_numpy(X).cuda(), torch.from_numpy(Y0.copy()).cuda()).cpu().numpy()
+        op.set_option("rows_batch", -1)
+        b = op.matvec_batch(torch.from_numpy(X).cuda(), torch.from_numpy(Y0.copy()).cuda()).cpu().numpy()
+        assert _close(a, b), name
     op.close()
+
+
+def test_rows_batch_at_size_sampled_rows(need_cuda):
+    """k_rows_batch at size (heisenberg_chain_32_symm, 4.7 M states; heisenberg_square_6x6, 15.8 M): three complex / six
+    real vectors in one call, sampled rows of EVERY vector against the oracle's column-by-column recomputation."""
+    for name, cplx, k in (("heisenberg_chain_32_symm", False, 6), ("heisenberg_square_6x6", True, 3)):
+        basis, matrix = _load(name)
+        po.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+        op = Operator(matrix)
+        op.basis.build()
+        reps = op.basis.representatives()
+        n = reps.shape[0]
+        rows = np.sort(np.random.default_rng(11).choice(n, size=1024, replace=False))
+        X = np.stack([_x(n, cplx, 500 + j) for j in range(k)])
+        Y = op.matvec_batch(torch.from_numpy(X).cuda())
+        torch.cuda.synchronize()
+        got = Y[:, torch.from_numpy(rows).cuda()].cpu().numpy()
+        for j in range(k):
+            expect = po.expected_rows(matrix, reps, X[j], rows)
+            assert _close(got[j], expect), (name, j, np.abs(got[j] - expect).max())
+        del Y
+        op.close()
 
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "matvec_golden.npz")
