@@ -819,8 +819,7 @@ void collect_timings(dmv_context *ctx) {
   }
   ctx->timings[T_D2H] = ms(4, 5);
   ctx->timings[T_TOTAL] = ms(0, 5);
-  ctx->timings[T_TABLE_FILL] = 0.0;
-  if (ctx->fill_timed) {
+  if (ctx->fill_timed) {   // (kept until the next refill: dmv_last_timings may collect twice)
     float t = 0;
     if (cudaEventElapsedTime(&t, ctx->ev_fill[0], ctx->ev_fill[1]) == cudaSuccess) ctx->timings[T_TABLE_FILL] = t;
     ctx->fill_timed = false;
@@ -1002,7 +1001,7 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
     if (value < -1 || value > 1) throw std::runtime_error("rows_batch: -1 auto / 1 k_rows_batch for batched products, 0 vector by vector");
     ctx->opt_rows_batch = (int)value;
   } else if (key == "rows_ctas") {
-    ctx->opt_rows_ctas = value == 3 ? 3 : 2;
+    ctx->opt_rows_ctas = (value == 2 || value == 4) ? (int)value : 3;
     if (ctx->global) ctx->global->opt_rows_ctas = ctx->opt_rows_ctas;
   } else if (key == "rows_index") {
     if (value < -1 || value > 1) throw std::runtime_error("rows_index: -1 auto / 0 open-addressing table, 1 dense index (perfect hash)");
@@ -1346,12 +1345,28 @@ int dmv_matvec_batch(dmv_context *ctx, int elt, int num_vectors, const void *x, 
     }
   }
   if (ctx->num_ranks == 1 && use_pull(ctx) && !use_gather(ctx) && use_rows(ctx) && ctx->opt_rows_batch != 0 &&
-      is_device_pointer(x) && is_device_pointer(y)) {
+      is_device_pointer(x) == is_device_pointer(y)) {
     // bases with permutation symmetries: up to six doubles per state share one orbit minimum and one look-up per term
+    // (host vectors -- what PRIMME hands over -- are staged a batch at a time)
     const int per = 6 / elt;
+    const bool on_host = !is_device_pointer(x);
     while (num_vectors - k >= 2) {
       const int nv = std::min(per, num_vectors - k);
-      rows_product_batch(ctx, elt, nv, xb + (size_t)k * vec_bytes, yb + (size_t)k * vec_bytes, ctx->n_states);
+      const void *xk = xb + (size_t)k * vec_bytes;
+      void *yk = yb + (size_t)k * vec_bytes;
+      if (on_host) {
+        ctx->d_x.alloc((size_t)ctx->n_states * elt * nv);
+        ctx->d_y.alloc((size_t)ctx->n_states * elt * nv);
+        CUDA_CHECK(cudaMemcpyAsync(ctx->d_x.ptr, xk, vec_bytes * nv, cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->h_diag_kept == 0)   // no diagonal: the product accumulates into y (DMV:1062-1069)
+          CUDA_CHECK(cudaMemcpyAsync(ctx->d_y.ptr, yk, vec_bytes * nv, cudaMemcpyHostToDevice, ctx->stream));
+        rows_product_batch(ctx, elt, nv, ctx->d_x.ptr, ctx->d_y.ptr, ctx->n_states);
+        CUDA_CHECK(cudaMemcpyAsync(yk, ctx->d_y.ptr, vec_bytes * nv, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        check_status(ctx);
+      } else {
+        rows_product_batch(ctx, elt, nv, xk, yk, ctx->n_states);
+      }
       k += nv;
     }
   }

@@ -191,7 +191,7 @@ struct dmv_context {
   // hash table over this context's representatives (see table_slot in dmv_device.cuh)
   bool rows_ok = false;
   int opt_rows = -1;        // -1 auto (k_rows when it applies), 0 the queued k_pull
-  int opt_rows_ctas = 2;    // k_rows: 2 CTAs per SM (122 registers, default) | 3 (80 registers, spills)
+  int opt_rows_ctas = 3;    // k_rows: resident CTAs per SM: 3 (80 registers, default) | 2 (122 registers) | 4 (64 registers)
   int opt_gather_walk = 0;  // k_gather: 0 per-lane walk from the top bit (default), 1 group-major warp-uniform walk
                             // (measured slower), 2 per-lane walk from the bottom bit (round 1)
   DevBuf<unsigned char> d_table;

@@ -1075,8 +1075,8 @@ __global__ void __launch_bounds__(kThreads, CTAS) k_rows(const KernelParams p) {
 // Cost model: one 64-byte request per term (17.8 G/s for tables >> L2, profiles/r02_random_access.md) against one 32-byte
 // request per term AND vector in k_rows.
 // -------------------------------------------------------------------------------------------------
-template <int TK>
-__global__ void __launch_bounds__(kThreads, 2) k_rows_batch(const KernelParams p) {
+template <int TK, int CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS) k_rows_batch(const KernelParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(p, PROJ_GROUP, sizeof(double), false);
   const Tables<false> T = stage_tables<PROJ_GROUP, false>(p, smem, L);
@@ -1636,23 +1636,31 @@ void launch_rows_e(const KernelParams &p, cudaStream_t stream) {
     else launch_rows_t<CE, 0, true>(p, stream);
     return;
   }
-  if (p.rows_ctas == 3) {   // three CTAs per SM (80 registers: the compiler spills part of the pipeline state)
-    if (k == 6) launch_rows_t<CE, 6, false, 3>(p, stream);
-    else launch_rows_t<CE, 0, false, 3>(p, stream);
+  if (p.rows_ctas == 2) {   // two CTAs per SM: 122 registers, nothing spills
+    if (k == 6) launch_rows_t<CE, 6, false>(p, stream);
+    else if (k == 4) launch_rows_t<CE, 4, false>(p, stream);
+    else launch_rows_t<CE, 0, false>(p, stream);
     return;
   }
-  if (k == 6) launch_rows_t<CE, 6, false>(p, stream);
-  else if (k == 4) launch_rows_t<CE, 4, false>(p, stream);
-  else launch_rows_t<CE, 0, false>(p, stream);
+  if (p.rows_ctas == 4) {   // four CTAs per SM: 64 registers
+    if (k == 6) launch_rows_t<CE, 6, false, 4>(p, stream);
+    else launch_rows_t<CE, 0, false, 4>(p, stream);
+    return;
+  }
+  // default: three CTAs per SM (80 registers; a few words of the pipeline state spill, 24 warps per SM more than pay for it:
+  // 6x6 24.9 -> 22.3 ms, chain_36_symm 53.5 -> 44.0 ms, profiles/r02_rows_pipelines.md)
+  if (k == 6) launch_rows_t<CE, 6, false, 3>(p, stream);
+  else if (k == 4) launch_rows_t<CE, 4, false, 3>(p, stream);
+  else launch_rows_t<CE, 0, false, 3>(p, stream);
 }
 }  // namespace
 
 namespace {
-template <int TK>
+template <int TK, int CTAS>
 void launch_rows_batch_t(const KernelParams &p, cudaStream_t stream) {
   const SmemLayout L = smem_layout(p, PROJ_GROUP, sizeof(double), false);
   const size_t smem_bytes = L.total;
-  auto kernel = k_rows_batch<TK>;
+  auto kernel = k_rows_batch<TK, CTAS>;
   if (smem_bytes > 48 * 1024)
     DMV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   int per_sm = 0;
@@ -1673,9 +1681,14 @@ void launch_rows_batch(const KernelParams &p, cudaStream_t stream) {
     throw std::runtime_error("k_rows_batch: at most six doubles per state");
   const OrbitProgram &o = p.orbit;
   const int k = (o.canon_mode != 0 && o.tor_mode == 2 && o.canon_k == o.canon_r) ? o.canon_k : 0;
-  if (k == 6) launch_rows_batch_t<6>(p, stream);
-  else if (k == 4) launch_rows_batch_t<4>(p, stream);
-  else launch_rows_batch_t<0>(p, stream);
+  if (p.rows_ctas == 2) {
+    if (k == 6) launch_rows_batch_t<6, 2>(p, stream);
+    else launch_rows_batch_t<0, 2>(p, stream);
+  } else {
+    if (k == 6) launch_rows_batch_t<6, 3>(p, stream);
+    else if (k == 4) launch_rows_batch_t<4, 3>(p, stream);
+    else launch_rows_batch_t<0, 3>(p, stream);
+  }
 }
 
 void launch_table_fill_batch(int64_t n, int num_vectors, int elt, const void *x, int64_t stride, const double *norms,
