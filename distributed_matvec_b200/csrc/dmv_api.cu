@@ -692,8 +692,15 @@ void rows_product_batch(dmv_context *ctx, int elt, int nv, const void *x, void *
   const int64_t n = ctx->n_states;
   cudaStream_t st = ctx->stream;
   if (ctx->table_batch_slots == 0) {
-    if (2 * n + 16 >= 2147483647ll) throw std::runtime_error("k_rows_batch: table of more than 2^31 buckets");
-    const uint32_t buckets = (uint32_t)std::max<int64_t>(16, 2 * n);
+    // one-slot buckets, 8 per state (1.07 probes per look-up; at 2 per state linear probing needs 1.5, and every extra
+    // probe is a trip of the lane without a new term: measured 46.7 ms instead of the single product's 22.4 on the 6x6
+    // square) while the table stays below a quarter of the free memory, else 4 or 2 per state
+    size_t free_b = 0, total_b = 0;
+    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    int64_t per_state = 8;
+    while (per_state > 2 && (double)per_state * n * 64.0 > 0.25 * (double)free_b) per_state /= 2;
+    if (per_state * n + 16 >= 2147483647ll) throw std::runtime_error("k_rows_batch: table of more than 2^31 buckets");
+    const uint32_t buckets = (uint32_t)std::max<int64_t>(16, per_state * n);
     ctx->d_table_batch.alloc((size_t)buckets * 64);
     ctx->d_slot_of_batch.alloc((size_t)std::max<int64_t>(1, n));
     CUDA_CHECK(cudaMemsetAsync(ctx->d_table_batch.ptr, 0xff, (size_t)buckets * 64, st));
@@ -997,6 +1004,9 @@ int dmv_set_option(dmv_context *ctx, const char *name, int64_t value) {
   } else if (key == "gather") {
     if (value < -1 || value > 0) throw std::runtime_error("gather: -1 auto, 0 off (queued k_pull for mode = 1)");
     ctx->opt_gather = (int)value;
+  } else if (key == "rows_batch_min") {
+    if (value < 2 || value > 6) throw std::runtime_error("rows_batch_min: 2 .. 6 doubles per state");
+    ctx->opt_rows_batch_min = (int)value;
   } else if (key == "rows_batch") {
     if (value < -1 || value > 1) throw std::runtime_error("rows_batch: -1 auto / 1 k_rows_batch for batched products, 0 vector by vector");
     ctx->opt_rows_batch = (int)value;
@@ -1350,7 +1360,9 @@ int dmv_matvec_batch(dmv_context *ctx, int elt, int num_vectors, const void *x, 
     // (host vectors -- what PRIMME hands over -- are staged a batch at a time)
     const int per = 6 / elt;
     const bool on_host = !is_device_pointer(x);
-    while (num_vectors - k >= 2) {
+    // (a batch costs 2.1 single products on the 6x6 square and chain_36_symm -- 64-byte buckets, one request per lane in
+    // flight: profiles/r02_rows_batch.md -- so it pays from three doubles per state on)
+    while ((num_vectors - k) * elt >= ctx->opt_rows_batch_min && num_vectors - k >= 2) {
       const int nv = std::min(per, num_vectors - k);
       const void *xk = xb + (size_t)k * vec_bytes;
       void *yk = yb + (size_t)k * vec_bytes;

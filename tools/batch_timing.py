@@ -35,6 +35,7 @@ def main():
         op.use_torch_stream()
         if os.environ.get("DMV_ROWS_CTAS"):
             op.set_option("rows_ctas", int(os.environ["DMV_ROWS_CTAS"]))
+        op.set_option("rows_batch_min", 2)
         n = op.basis.numberStates()
         print(f"== {name}: N={n} rows={op.info('rows')}", flush=True)
         rng = np.random.default_rng(42)
