@@ -207,7 +207,7 @@ struct dmv_context {
   DevBuf<unsigned char> d_table_batch;
   DevBuf<uint32_t> d_slot_of_batch;
   uint32_t table_batch_slots = 0;
-  int opt_rows_batch_min = 3;   // doubles per state (vectors x element width) from which a batch goes through k_rows_batch
+  int opt_rows_batch_min = 2;   // doubles per state (vectors x element width) from which a batch goes through k_rows_batch
   int opt_rows_batch = -1;  // -1 / 1: batched products of symmetric bases go through k_rows_batch | 0: vector by vector
   double gather_uni[2] = {0.0, 0.0};
   int index_mode = INDEX_DIRECTORY;

@@ -1681,14 +1681,11 @@ void launch_rows_batch(const KernelParams &p, cudaStream_t stream) {
     throw std::runtime_error("k_rows_batch: at most six doubles per state");
   const OrbitProgram &o = p.orbit;
   const int k = (o.canon_mode != 0 && o.tor_mode == 2 && o.canon_k == o.canon_r) ? o.canon_k : 0;
-  if (p.rows_ctas == 2) {
-    if (k == 6) launch_rows_batch_t<6, 2>(p, stream);
-    else launch_rows_batch_t<0, 2>(p, stream);
-  } else {
-    if (k == 6) launch_rows_batch_t<6, 3>(p, stream);
-    else if (k == 4) launch_rows_batch_t<4, 3>(p, stream);
-    else launch_rows_batch_t<0, 3>(p, stream);
-  }
+  // two CTAs per SM (120-128 registers: the eight words of the request stay in registers; at 80 registers part of them
+  // spills and the batch is 4 % slower: profiles/r02_rows_batch.md)
+  if (k == 6) launch_rows_batch_t<6, 2>(p, stream);
+  else if (k == 4) launch_rows_batch_t<4, 2>(p, stream);
+  else launch_rows_batch_t<0, 2>(p, stream);
 }
 
 void launch_table_fill_batch(int64_t n, int num_vectors, int elt, const void *x, int64_t stride, const double *norms,

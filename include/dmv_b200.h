@@ -81,11 +81,11 @@ int dmv_synchronize(dmv_context *ctx);
  *          "rows"     = -1 auto | 0 use the queued k_pull instead of k_rows
  *          "rows_index" = -1 auto, 0 open-addressing table with the vector element in the slot | 1 dense table behind a
  *                        two-level perfect hash (5 bits per state; measured slower, kept for reference)
- *          "rows_ctas" = 3 (default) | 2 | 4 resident CTAs per SM of k_rows / k_rows_batch (registers per thread 80 | 122 |
+ *          "rows_ctas" = 3 (default) | 2 | 4 resident CTAs per SM of k_rows (k_rows_batch: always 2) (registers per thread 80 | 122 |
  *                        64; at 80 a few words of the pipeline state spill and the extra warps more than pay for it)
  *          "rows_batch" = -1 auto, 1: dmv_matvec_batch on bases with permutation symmetries takes up to six doubles per
  *                        state (six real / three complex vectors) through k_rows_batch | 0 vector by vector;
- *                        "rows_batch_min" = doubles per state (vectors x element width, default 3) from which it is used
+ *                        "rows_batch_min" = doubles per state (vectors x element width, default 2) from which it is used
  *          "gather_walk" = 0 every lane walks its emitting groups from the top bit | 1 group-major warp-uniform walk
  *                        (measured slower) | 2 from the bottom bit (round 1)
  *          "index"    = -1 auto (identity / Lin tables / directory) | 0 directory + binary search | 2 combinadic rank
