@@ -1361,7 +1361,7 @@ int dmv_matvec_batch(dmv_context *ctx, int elt, int num_vectors, const void *x, 
     const int per = 6 / elt;
     const bool on_host = !is_device_pointer(x);
     // (a batch costs 1.5 - 1.6 single products on the 6x6 square -- 64-byte buckets, one request per lane in flight:
-    // profiles/r02_rows_batch.md -- so it pays from two vectors on)
+    // profiles/r02_rows_batch_6x6.md -- so it pays from two vectors on)
     while ((num_vectors - k) * elt >= ctx->opt_rows_batch_min && num_vectors - k >= 2) {
       const int nv = std::min(per, num_vectors - k);
       const void *xk = xb + (size_t)k * vec_bytes;

@@ -203,7 +203,8 @@ struct dmv_context {
   DevBuf<uint32_t> d_slot_of;
   uint32_t table_slots = 0;
   int table_elt = 0;        // element type the slots are laid out for (0: not built)
-  // k_rows_batch: 64-byte buckets { key, six doubles, spare }, two per state; built on the first batched product
+  // k_rows_batch: 64-byte buckets { key, six doubles, spare }, eight per state (fewer when memory is short); built on the first
+  // batched product
   DevBuf<unsigned char> d_table_batch;
   DevBuf<uint32_t> d_slot_of_batch;
   uint32_t table_batch_slots = 0;

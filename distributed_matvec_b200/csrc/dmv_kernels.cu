@@ -1682,7 +1682,7 @@ void launch_rows_batch(const KernelParams &p, cudaStream_t stream) {
   const OrbitProgram &o = p.orbit;
   const int k = (o.canon_mode != 0 && o.tor_mode == 2 && o.canon_k == o.canon_r) ? o.canon_k : 0;
   // two CTAs per SM (120-128 registers: the eight words of the request stay in registers; at 80 registers part of them
-  // spills and the batch is 4 % slower: profiles/r02_rows_batch.md)
+  // spills and the batch is 4 % slower: profiles/r02_rows_batch_6x6.md)
   if (k == 6) launch_rows_batch_t<6, 2>(p, stream);
   else if (k == 4) launch_rows_batch_t<4, 2>(p, stream);
   else launch_rows_batch_t<0, 2>(p, stream);
