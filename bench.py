@@ -427,14 +427,22 @@ def time_products(w: Workload, steps: int, warmup: int, flush, barrier, dist, lo
     w.steps_ms = [round(float(v), 3) for v in t[2:]]          # every timed step, max over ranks
     w.op.synchronize()
     # dominant kernel: the generate stage of the library's own CUDA-event timeline
-    kern = []
+    kern, refill = [], []
     for k in range(min(steps, 5)):
         flush.fill_(k)
         torch.cuda.synchronize()
         w.product()
         torch.cuda.synchronize()
-        kern.append(w.op.timings()["generate(diag+offdiag+local accumulate)"])
-    return float(t[0]), float(t[1]), float(np.mean(kern)), int(launches), (sampler.summary() if sampler else None)
+        tm = w.op.timings()
+        kern.append(tm["generate(diag+offdiag+local accumulate)"])
+        refill.append(tm.get("table refill (k_rows; part of generate)", 0.0))
+    # k_rows: the generate stage is k_table_fill (values of the hash table, once per product) + k_rows; the roofline is
+    # quoted on k_rows alone and the refill is reported beside it
+    w.table_refill_ms = float(np.mean(refill)) if w.kernel_name() == "k_rows" else 0.0
+    kernel_ms = float(np.mean(kern))
+    if 0.0 < w.table_refill_ms < kernel_ms:
+        kernel_ms -= w.table_refill_ms
+    return float(t[0]), float(t[1]), kernel_ms, int(launches), (sampler.summary() if sampler else None)
 
 
 def roofline_of(w: Workload, kernel_ms: float, clocks: dict | None, dtype: str) -> dict:
@@ -445,7 +453,8 @@ def roofline_of(w: Workload, kernel_ms: float, clocks: dict | None, dtype: str) 
     const = ncu_constants(f"{kernel}:{w.name}:{dtype}") if w.world == 1 else None
     out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
            "traffic": const.get("dram_bytes") if const else None, "peak_kind": peak_kind, "kernel": kernel,
-           "kernel_ms": kernel_ms, "algorithmic_bytes": int(bytes_alg),
+           "kernel_ms": kernel_ms, "table_refill_ms": getattr(w, "table_refill_ms", 0.0),
+           "algorithmic_bytes": int(bytes_alg),
            "model": "SURVEY 8(d): N (8 + 2E) + nnz (8 + 2E) bytes per product"}
     limiter = {}
     if const:
