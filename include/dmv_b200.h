@@ -207,8 +207,10 @@ int dmv_comm_init(dmv_context *ctx, const void *id128);
 /* ---- several vectors per call: numVectors > 1 of ls_chpl_matrix_vector_product, which the reference itself does not
  * implement (DMV:1101-1102 halts; its eigensolver loops over columns, src/Diagonalize.chpl:154-158).  x, y hold
  * num_vectors vectors of dmv_number_states elements one after the other (the [numVectors, N] layout of BlockVector).
- * With device pointers on one rank, four vectors at a time share the term walk and the index look-ups (k_gather);
- * otherwise this is the loop over dmv_local_matvec / dmv_matvec.  Semantics per vector as for a single product.
+ * On one rank: with device pointers and an operator k_gather applies to, four vectors at a time share the term walk and the
+ * index look-ups; on bases with permutation symmetries (k_rows) up to six doubles per state -- six real or three complex
+ * vectors -- share the orbit minimum and ONE 64-byte look-up per term (k_rows_batch; host vectors are staged a batch at a
+ * time).  Everything else is the loop over dmv_local_matvec / dmv_matvec.  Semantics per vector as for a single product.
  * (The ls_chpl_* entry keeps the reference's behaviour and halts for numVectors != 1.) */
 int dmv_matvec_batch(dmv_context *ctx, int elt, int num_vectors, const void *x, void *y);
 
@@ -269,11 +271,12 @@ void ls_chpl_operator_apply_off_diag(const void *ls_hs_operator_ptr, int64_t cou
 void ls_chpl_enumerate_representatives(const void *ls_hs_basis_ptr, uint64_t lower, uint64_t upper,
                                        dmv_external_array *dest);
 
-/* ---- self-check of the host-side group compiler (no device needed; NOT on the product path).
- * Compiles the symmetry group of `basis` into the device orbit program, verifies it against bit-by-bit
- * permutation and evaluates the compiled program on the host for `count` states: reps[k] = min_g g(s_k),
- * stab[k] = |{g : g(s_k) = s_k}|.  info[0..5] = {n_q, n_stages, n_t, n_left, n_right, has_flip}. */
-/* lowest eigenpair of a symmetric tridiagonal matrix: the host half of dmv_lanczos, exposed for the CPU tests */
+/* ---- host-side pieces exposed for the CPU tests (no device needed; NOT on the product path).
+ * dmv_debug_tridiagonal_lowest: lowest eigenpair of a symmetric tridiagonal matrix, the host half of dmv_lanczos.
+ * dmv_debug_compile_group: compiles the symmetry group of `basis` into the device orbit program, verifies it against
+ *   bit-by-bit permutation and evaluates the compiled program (the device functions themselves, compiled for the host)
+ *   for `count` states: reps[k] = min_g g(s_k), stab[k] = |{g : g(s_k) = s_k}|.
+ *   info[0..5] = {n_q, n_stages, n_t, n_left, n_right, has_flip}. */
 int dmv_debug_tridiagonal_lowest(int k, const double *diag, const double *offdiag, double *eigenvalue, double *vector);
 int dmv_debug_compile_group(const dmv_basis_desc *basis, int64_t *info, int64_t count,
                             const uint64_t *states, uint64_t *reps, int32_t *stab);
