@@ -187,6 +187,29 @@ def test_ground_state_energies_from_the_literature(name, scale, e0, tol):
     assert abs(val / scale - e0) < tol, (name, val / scale, e0)
 
 
+@pytest.mark.parametrize("name,n", [("heisenberg_chain_4", 4), ("heisenberg_chain_6", 6), ("heisenberg_chain_8", 8),
+                                    ("heisenberg_chain_10", 10), ("heisenberg_chain_12", 12), ("heisenberg_chain_16", 16),
+                                    ("heisenberg_chain_20", 20), ("heisenberg_chain_24_symm", 24)])
+def test_ring_ground_state_equals_bethe_ansatz(name, n):
+    """The lowest eigenvalue of every chain model equals the Bethe-ansatz ground-state energy of the ring (tests/bethe.py:
+    an exact, independent algorithm) to 1e-10 relative -- through every branch of computeOffDiag: unprojected (chain_4 ...
+    20; chain_12 without a Hamming weight: identity index), inversion only (chain_10: the ground state of a ring with odd
+    n / 2 is odd under spin inversion, and the file's sector -1 holds it) and the full projection (chain_24_symm)."""
+    import bethe
+    from scipy.sparse.linalg import LinearOperator, eigsh
+    basis, matrix, _ = _load(name)
+    reps, _ = po.enumerate_states(basis)
+    N = reps.shape[0]
+    op = LinearOperator((N, N), matvec=lambda v: po.matvec_global(matrix, reps, np.ascontiguousarray(v.ravel()), 1),
+                        dtype=np.float64)
+    if N <= 600:
+        val = np.linalg.eigvalsh(np.array([op.matvec(e) for e in np.eye(N)]).T)[0]
+    else:
+        val = eigsh(op, k=1, which="SA", tol=1e-13)[0][0]
+    want = 4.0 * bethe.heisenberg_ring_e0(n)
+    assert abs(val - want) <= 1e-10 * abs(want), (name, val, want)
+
+
 def test_symmetric_sector_spectrum_is_contained_in_full_spectrum():
     """Lowest level of the fully symmetric sector of the 4x4 torus = lowest level of the unprojected model."""
     basis_s, matrix_s, specs = _load("heisenberg_square_4x4")

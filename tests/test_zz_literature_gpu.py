@@ -8,6 +8,10 @@ symmetries), k_rows with the dihedral canonical form (chain_24_symm), with the s
 minimum, norm ratio (BO:198-202), index or coefficient anywhere in the basis moves the lowest eigenvalue; the 6 x 6 value
 E0 / N = -0.678872 J (Schulz, Ziman & Poilblanc 1996) is quoted to six digits.
 
+The chains are pinned harder: by the Bethe-ansatz ground-state energy of the ring (tests/bethe.py, an exact independent
+algorithm checked against the oracle on 4 ... 24 sites in tests/test_oracle_pins.py), to 1e-8 relative, up to
+heisenberg_chain_36_symm (63 M representatives, BASELINE.json configs[4]).
+
 Energies in units of J with H = J sum S_i.S_j; the sigma-form model files carry H = sum sigma.sigma = 4 sum S.S.
 (The file sorts last on purpose: it is the longest-running one.)
 """
@@ -25,16 +29,15 @@ DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 
 # (model, scale to S.S units, literature E0 in J, tolerance in J, kernel expected on one rank)
 LITERATURE_E0 = [
-    ("heisenberg_chain_16", 4.0, -7.142296361, 2e-8, "gather"),
-    ("heisenberg_chain_24", 4.0, -10.6700145, 2e-7, "gather"),
-    ("heisenberg_chain_24_symm", 4.0, -10.6700145, 2e-7, "rows"),
     ("heisenberg_square_4x4", 4.0, -0.7017802 * 16, 2e-6, "rows"),
     ("heisenberg_square_6x6", 4.0, -0.678872 * 36, 1.5e-4, "rows"),    # +- 4e-6 J per site
 ]
+# (model, sites, kernel expected on one rank); the largest last
+BETHE = [("heisenberg_chain_16", 16, "gather"), ("heisenberg_chain_24", 24, "gather"), ("heisenberg_chain_24_symm", 24, "rows"),
+         ("heisenberg_chain_32_symm", 32, "rows"), ("heisenberg_chain_36_symm", 36, "rows")]
 
 
-@pytest.mark.parametrize("name,scale,e0,tol,kernel", LITERATURE_E0)
-def test_ground_state_energy_from_the_literature(name, scale, e0, tol, kernel):
+def _ground_state(name, kernel):
     if not torch.cuda.is_available():
         pytest.fail("these tests need a CUDA device (no CPU fallback exists)")
     basis, matrix = load_config_from_yaml(os.path.join(DATA, name + ".yaml"))
@@ -43,6 +46,20 @@ def test_ground_state_energy_from_the_literature(name, scale, e0, tol, kernel):
         op.basis.build()
         assert op.info(kernel) == 1, (name, kernel)
         value, _, iters, res = op.lanczos(max_iters=400, tol=1e-11, eigenvector=False)
-        assert abs(value / scale - e0) < tol, (name, value / scale, e0, iters, res)
     finally:
         op.close()
+    return value, iters, res
+
+
+@pytest.mark.parametrize("name,scale,e0,tol,kernel", LITERATURE_E0)
+def test_ground_state_energy_from_the_literature(name, scale, e0, tol, kernel):
+    value, iters, res = _ground_state(name, kernel)
+    assert abs(value / scale - e0) < tol, (name, value / scale, e0, iters, res)
+
+
+@pytest.mark.parametrize("name,n,kernel", BETHE)
+def test_ring_ground_state_equals_bethe_ansatz(name, n, kernel):
+    import bethe
+    want = 4.0 * bethe.heisenberg_ring_e0(n)
+    value, iters, res = _ground_state(name, kernel)
+    assert abs(value - want) <= 1e-8 * abs(want), (name, value, want, iters, res)
