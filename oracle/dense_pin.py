@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE ONLY.  Shares with the product nothing but the expression to
 (`parse_expression`) and the YAML reader: the Hamiltonian is assembled on the full 2^n space as
 sum over bonds of kron(I, ..., A_i, ..., B_j, ..., I), the symmetry-adapted basis vectors are built
 explicitly from the projector  P = 1/|G| sum_g conj(chi(g)) U_g, and the projected matrix is
-B^dagger H B.  Used for n <= 16 (substitute pin 1).
+B^dagger H B.  Used for n <= 16 densely and up to n = 20 as a sparse matrix (substitute pin 1).
 """
 from __future__ import annotations
 
@@ -119,9 +119,10 @@ def symmetry_adapted_basis(basis):
     return np.array(reps, dtype=np.uint64), np.array(norms), B
 
 
-def projected_hamiltonian(term_specs: list[dict], basis):
-    """(representatives, norms, H_proj dense [N, N]) with H_proj = B^dagger H B."""
+def projected_hamiltonian(term_specs: list[dict], basis, dense: bool = True):
+    """(representatives, norms, H_proj [N, N]) with H_proj = B^dagger H B; dense = False keeps it sparse (CSR), which
+    carries the construction to 16 - 20 sites (heisenberg_kagome_16 of BASELINE.json at full size)."""
     H = full_hamiltonian(term_specs, basis.number_sites)
     reps, norms, B = symmetry_adapted_basis(basis)
-    Hp = (B.conj().T @ (H @ B)).toarray()
-    return reps, norms, Hp
+    Hp = B.conj().T @ (H @ B)
+    return reps, norms, (Hp.toarray() if dense else Hp.tocsr())

@@ -86,6 +86,52 @@ def test_oracle_matches_dense_construction(name):
             assert np.abs(y - y_dense).max() <= 1e-12 * max(1.0, np.abs(y_dense).max())
 
 
+@pytest.mark.parametrize("name", ["heisenberg_kagome_16", "heisenberg_chain_16", "heisenberg_chain_20"])
+def test_oracle_matches_sparse_kronecker_construction_at_size(name):
+    """The same construction kept sparse: heisenberg_kagome_16 (BASELINE.json configs[2], all 12 870 states) and rings
+    of 16 and 20 sites (184 756 states), real and complex x, P = 1 and 4 locales."""
+    basis, matrix, specs = _load(name)
+    reps, _ = po.enumerate_states(basis)
+    d_reps, _, Hp = dp.projected_hamiltonian(specs, basis, dense=False)
+    assert np.array_equal(reps, d_reps)
+    assert abs(Hp - Hp.conj().T).max() < 1e-12
+    rng = np.random.default_rng(1)
+    x = rng.random(reps.shape[0]) - 0.5
+    for v in (x, x + 1j * (rng.random(reps.shape[0]) - 0.5)):
+        y_kron = Hp @ v
+        if not np.iscomplexobj(v):
+            assert np.abs(y_kron.imag).max() < 1e-12
+            y_kron = y_kron.real
+        for P in (1, 4):
+            y = po.matvec_global(matrix, reps, v, P)
+            assert np.abs(y - y_kron).max() <= 1e-12 * max(1.0, np.abs(y_kron).max())
+
+
+def test_chain_24_equals_the_heisenberg_definition_at_size():
+    """heisenberg_chain_24 (BASELINE.json configs[1], all 2 704 156 states) against the textbook definition written
+    directly in numpy -- sigma.sigma on a bond is +1 on parallel spins, and on antiparallel spins -1 plus 2 x the state
+    with the two spins exchanged -- with none of the operator machinery (no expression parser, no term tables)."""
+    basis, matrix, _ = _load("heisenberg_chain_24")
+    reps, _ = po.enumerate_states(basis)
+    n = 24
+    assert reps.shape[0] == 2704156
+    rs = np.random.RandomState(42)          # the reference generator's recipe (input_for_matvec.py:8,31)
+    x = rs.rand(reps.shape[0]) - 0.5
+    y = np.zeros_like(x)
+    for i in range(n):
+        j = (i + 1) % n
+        bi = (reps >> np.uint64(i)) & np.uint64(1)
+        bj = (reps >> np.uint64(j)) & np.uint64(1)
+        anti = bi != bj
+        y += np.where(anti, -1.0, 1.0) * x
+        flipped = reps[anti] ^ np.uint64((1 << i) | (1 << j))
+        idx = np.searchsorted(reps, flipped)
+        assert np.array_equal(reps[idx], flipped)
+        y[anti] += 2.0 * x[idx]             # <a|H|b> = 2 for the exchanged pair; H symmetric, so row = column
+    got = po.matvec_global(matrix, reps, x, 1)
+    assert np.all(np.abs(got - y) <= np.maximum(1e-14, 1e-12 * np.maximum(np.abs(got), np.abs(y))))   # reference criterion
+
+
 def test_old_matrix_form_equals_expression_form():
     """data/old/*.yaml give the same models as explicit 4x4 matrices (reference data/old/heisenberg_chain_10.yaml:9-12)."""
     basis, matrix, _ = _load("heisenberg_chain_10")
