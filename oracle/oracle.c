@@ -8,8 +8,12 @@
  * PARITY UNPINNED: the reference (twesterhout/distributed-matvec @ 050c3f2) cannot be built in
  * this image (Chapel, GHC, HDF5 and liblattice_symmetries_haskell are absent) and its golden HDF5
  * vectors are downloaded at test time (reference Makefile:128-146), so no reference artefact pins
- * this restatement.  It is pinned instead by an independent dense Kronecker-product construction
- * (oracle/dense_pin.py), exact basis dimensions and physics known answers (tests/test_oracle_*.py).
+ * this restatement.  It is pinned instead by independent constructions (tests/test_oracle_pins.py):
+ * Kronecker-product matrices (oracle/dense_pin.py; dense to 16 sites, sparse to 20: heisenberg_kagome_16
+ * at full size), the Heisenberg definition in numpy on all 2 704 156 states of heisenberg_chain_24,
+ * exact basis dimensions, the Bethe-ansatz ground-state energy of every ring (tests/bethe.py, 1e-10;
+ * heisenberg_chain_32_symm at full size: tools/oracle_ground_state.py) and ground-state energies from
+ * the exact-diagonalisation literature (4x4 torus, 12-site kagome cluster).
  *
  * The arithmetic of term generation / symmetry projection / state indexing lives in the
  * third-party library lattice-symmetries-haskell (release `continuous`, build 14e7319, reference
