@@ -27,17 +27,19 @@ from distributed_matvec_b200 import Operator, load_config_from_yaml  # noqa: E40
 
 DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data")
 
-# (model, scale to S.S units, literature E0 in J, tolerance in J, kernel expected on one rank)
+# (model, scale to S.S units, literature E0 in J, tolerance in J, kernel expected on one rank, complex vectors)
 LITERATURE_E0 = [
-    ("heisenberg_square_4x4", 4.0, -0.7017802 * 16, 2e-6, "rows"),
-    ("heisenberg_square_6x6", 4.0, -0.678872 * 36, 1.5e-4, "rows"),    # +- 4e-6 J per site
+    ("heisenberg_square_4x4", 4.0, -0.7017802 * 16, 2e-6, "rows", False),
+    ("heisenberg_square_6x6", 4.0, -0.678872 * 36, 1.5e-4, "rows", True),    # +- 4e-6 J per site; the bench's dtype
 ]
-# (model, sites, kernel expected on one rank); the largest last
-BETHE = [("heisenberg_chain_16", 16, "gather"), ("heisenberg_chain_24", 24, "gather"), ("heisenberg_chain_24_symm", 24, "rows"),
-         ("heisenberg_chain_32_symm", 32, "rows"), ("heisenberg_chain_36_symm", 36, "rows")]
+# (model, sites, kernel expected on one rank, complex vectors); real(64) is the reference's element type, the two largest
+# bases run in the bench's complex128; the largest last
+BETHE = [("heisenberg_chain_16", 16, "gather", False), ("heisenberg_chain_24", 24, "gather", False),
+         ("heisenberg_chain_24_symm", 24, "rows", False), ("heisenberg_chain_32_symm", 32, "rows", False),
+         ("heisenberg_chain_36_symm", 36, "rows", True)]
 
 
-def _ground_state(name, kernel):
+def _ground_state(name, kernel, cplx):
     if not torch.cuda.is_available():
         pytest.fail("these tests need a CUDA device (no CPU fallback exists)")
     basis, matrix = load_config_from_yaml(os.path.join(DATA, name + ".yaml"))
@@ -45,21 +47,21 @@ def _ground_state(name, kernel):
     try:
         op.basis.build()
         assert op.info(kernel) == 1, (name, kernel)
-        value, _, iters, res = op.lanczos(max_iters=400, tol=1e-11, eigenvector=False)
+        value, _, iters, res = op.lanczos(max_iters=400, tol=1e-11, complex_vectors=cplx, eigenvector=False)
     finally:
         op.close()
     return value, iters, res
 
 
-@pytest.mark.parametrize("name,scale,e0,tol,kernel", LITERATURE_E0)
-def test_ground_state_energy_from_the_literature(name, scale, e0, tol, kernel):
-    value, iters, res = _ground_state(name, kernel)
+@pytest.mark.parametrize("name,scale,e0,tol,kernel,cplx", LITERATURE_E0)
+def test_ground_state_energy_from_the_literature(name, scale, e0, tol, kernel, cplx):
+    value, iters, res = _ground_state(name, kernel, cplx)
     assert abs(value / scale - e0) < tol, (name, value / scale, e0, iters, res)
 
 
-@pytest.mark.parametrize("name,n,kernel", BETHE)
-def test_ring_ground_state_equals_bethe_ansatz(name, n, kernel):
+@pytest.mark.parametrize("name,n,kernel,cplx", BETHE)
+def test_ring_ground_state_equals_bethe_ansatz(name, n, kernel, cplx):
     import bethe
     want = 4.0 * bethe.heisenberg_ring_e0(n)
-    value, iters, res = _ground_state(name, kernel)
+    value, iters, res = _ground_state(name, kernel, cplx)
     assert abs(value - want) <= 1e-8 * abs(want), (name, value, want, iters, res)
