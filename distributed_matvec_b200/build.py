@@ -44,8 +44,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stdout.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
-    subprocess.run(link, check=True)
+    tmp = f"{LIB}.tmp{os.getpid()}"   # link into a private file, then rename: a reader never sees a half-written library
+    link = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *objs, "-lcudart", "-ldl"]
+    try:
+        subprocess.run(link, check=True)
+        os.replace(tmp, LIB)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return LIB
 
 

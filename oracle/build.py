@@ -17,9 +17,17 @@ LIB = os.path.join(HERE, "liboracle.so")
 def build(force: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
         return LIB
+    # into a private file, then an atomic rename: several ranks of one box may get here together (bench.py checks parity
+    # on every rank), and none of them may ever load a half-written library
+    tmp = f"{LIB}.tmp{os.getpid()}"
     cmd = ["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-shared", "-std=c11", "-Wall",
-           "-Wextra", "-o", LIB, SRC, "-lm"]
-    subprocess.run(cmd, check=True)
+           "-Wextra", "-o", tmp, SRC, "-lm"]
+    try:
+        subprocess.run(cmd, check=True)
+        os.replace(tmp, LIB)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return LIB
 
 
