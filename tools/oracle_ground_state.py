@@ -3,7 +3,10 @@
 the Bethe-ansatz ground-state energy of the ring (tests/bethe.py).  heisenberg_chain_32_symm: 4 707 969 representatives,
 |G| = 128, about 17 s per product on 8 host threads (oracle_matvec_rows with the group as Benes networks).
 
-Usage:  python tools/oracle_ground_state.py heisenberg_chain_32_symm 32  >  profiles/r02_oracle_chain32_bethe.log
+Usage:  python tools/oracle_ground_state.py heisenberg_chain_32_symm 32 [threads] [max seconds]  >  profiles/r02_oracle_chain32_bethe.log
+
+The Ritz value of Lanczos is variational (theta_k >= E0 at every step), so a run cut short by `max seconds` still says
+something: theta_k - E0(Bethe) stays positive and falls geometrically.
 """
 import os
 import sys
@@ -23,6 +26,8 @@ from oracle import pyoracle as po  # noqa: E402
 def main():
     name, n_sites = sys.argv[1], int(sys.argv[2])
     threads = int(sys.argv[3]) if len(sys.argv) > 3 else (os.cpu_count() or 1)
+    max_seconds = float(sys.argv[4]) if len(sys.argv) > 4 else float("inf")
+    t_start = time.time()
     basis, matrix = omodel.load_model(os.path.join(ROOT, "data", name + ".yaml"))
     po.set_num_threads(threads)
     t = time.time()
@@ -48,6 +53,9 @@ def main():
         beta = float(np.linalg.norm(w))
         print(f"{j:4d}  theta {theta:.12f}  theta - bethe {theta - want:+.3e}  beta {beta:.3e}  {dt:.1f} s", flush=True)
         if last is not None and abs(theta - last) < 2e-12 * abs(theta):
+            break
+        if time.time() - t_start + dt > max_seconds:
+            print(f"stopped after {j + 1} iterations ({max_seconds:.0f} s allowed): not converged", flush=True)
             break
         last = theta
         betas.append(beta)
