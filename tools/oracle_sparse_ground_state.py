@@ -8,7 +8,11 @@ heisenberg_square_6x6 (the bench workload: 15 804 956 representatives, |G| = 576
 exact-diagonalisation literature gives E0 / N = -0.678872 J (Schulz, Ziman & Poilblanc 1996); the file is in sigma-form
 (H = 4 J sum S.S), so the lowest eigenvalue must be 4 x 36 x -0.678872 = -97.757568.
 
+heisenberg_chain_36_symm (63 068 876 representatives, |G| = 144, 1.17e9 entries, about 30 GB of host memory): the
+Bethe-ansatz energy of the 36-site ring (tests/bethe.py), -63.904943288257 in sigma units.
+
 Usage:  python tools/oracle_sparse_ground_state.py heisenberg_square_6x6 -97.757568 [threads] > profiles/r02_oracle_6x6_literature.log
+        python tools/oracle_sparse_ground_state.py heisenberg_chain_36_symm -63.904943288257 > profiles/r02_oracle_chain36_bethe.log
 """
 import ctypes as C
 import os
@@ -21,7 +25,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 import scipy.sparse as sp  # noqa: E402
-from scipy.sparse.linalg import eigsh  # noqa: E402
+from scipy.sparse.linalg import LinearOperator, eigsh  # noqa: E402
 
 from oracle import model as omodel  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
@@ -74,18 +78,18 @@ def main():
     nnz = int(indptr[-1])
     print(f"computeOffDiag over the whole basis: {nnz} entries in {time.time() - t:.0f} s ({threads} threads)", flush=True)
     # rows of this CSR matrix are the COLUMNS of H (transposed storage); H real symmetric <=> A == A^T
-    A = sp.csr_matrix((data, indices, indptr), shape=(N, N))
+    offdiag = sp.csr_matrix((data, indices, indptr), shape=(N, N))
     diag = po.apply_diag(matrix, reps, np.ones(N))
-    A = A + sp.diags(diag)
+    A = LinearOperator((N, N), dtype=np.float64, matvec=lambda x: offdiag @ x.ravel() + diag * x.ravel())
     rng = np.random.default_rng(3)
     u, v = rng.random(N) - 0.5, rng.random(N) - 0.5
-    lhs, rhs = float(u @ (A @ v)), float(v @ (A @ u))
+    lhs, rhs = float(u @ A.matvec(v)), float(v @ A.matvec(u))
     print(f"Hermiticity at size: u.(A v) = {lhs:.12f}, v.(A u) = {rhs:.12f}, relative difference "
           f"{abs(lhs - rhs) / max(abs(lhs), 1e-300):.2e}", flush=True)
     t = time.time()
     vals, _ = eigsh(A, k=1, which="SA", tol=1e-10, ncv=24, maxiter=5000)
     e0 = float(vals[0])
-    print(f"lowest eigenvalue (eigsh, {time.time() - t:.0f} s) = {e0:.9f};  literature = {want:.6f};  difference {e0 - want:+.2e} "
+    print(f"lowest eigenvalue (eigsh, {time.time() - t:.0f} s) = {e0:.9f};  outside value = {want:.9f};  difference {e0 - want:+.2e} "
           f"({(e0 - want) / basis.number_sites / 4:+.2e} J per site)")
 
 
