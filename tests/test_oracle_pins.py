@@ -35,6 +35,11 @@ def test_hash64_01_known_answers():
         return x ^ (x >> 31)
 
     assert po.hash64_01(0) == 0
+    # outside known answers: the first outputs of Vigna's splitmix64 generator seeded with 0 are this finaliser applied
+    # to k * 0x9e3779b97f4a7c15 (the published test vector of splitmix64.c)
+    golden = 0x9e3779b97f4a7c15
+    for k, out in enumerate([0xe220a8397b1dcdaf, 0x6e789e6aa1b965f4, 0x06c45d188009454f, 0xf88bb8a8724c81ec], start=1):
+        assert po.hash64_01((k * golden) & M) == out
     for x in [1, 2, 3, 0xdeadbeef, 2**63, M, 0x0123456789abcdef, 126, 2704156]:
         assert po.hash64_01(x) == ref(x)
     states = np.arange(1000, dtype=np.uint64) * np.uint64(2654435761)
