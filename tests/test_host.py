@@ -139,6 +139,20 @@ def test_group_compiler_matches_oracle(name):
         assert ext[9] == 1 and ext[10] == 8 and ext[11] <= 7 * 5
 
 
+@pytest.mark.parametrize("name", ["heisenberg_square_4x4", "heisenberg_chain_24_symm", "heisenberg_kagome_12_symm"])
+def test_canonical_form_sweep_over_a_whole_product(name):
+    """tools/canonical_form_sweep.py on the models small enough for the CPU suite: every state one product canonicalises
+    (alpha ^ x_t for every emitting term, and alpha itself) through the device functions compiled for the host and through
+    the oracle; representatives and norms agree bit for bit.  The same sweep at full size (6 x 6 square: 601 067 490
+    states; chain_36_symm: 1 230 759 430): profiles/r02_canonical_form_sweep_*.log."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "canonical_form_sweep.py"), name, "2"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "representative mismatches 0, norm mismatches 0" in out.stdout, out.stdout
+
+
 def test_tridiagonal_lowest_eigenpair():
     """Host half of dmv_lanczos (Sturm bisection + pivoted inverse iteration) against numpy, including nearly
     decoupled blocks, tiny off-diagonals and clustered eigenvalues."""
