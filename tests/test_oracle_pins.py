@@ -61,6 +61,23 @@ def test_exact_dimensions(name, dim):
     assert np.all(norms > 0)
 
 
+@pytest.mark.parametrize("name,dim", [
+    ("heisenberg_kagome_12_symm", 472), ("heisenberg_square_4x4", 107), ("heisenberg_chain_24_symm", 28968),
+    ("heisenberg_chain_32_symm", 4707969), ("heisenberg_square_6x6", 15804956), ("heisenberg_chain_36_symm", 63068876),
+    ("heisenberg_chain_40_symm", 861725794),
+])
+def test_dimensions_by_burnside_lemma(name, dim):
+    """The dimensions the at-size tests and bench lines assert from Burnside's lemma
+    (tests/burnside.py: cycle counting, no enumeration); for the models the CPU can enumerate, the oracle's enumeration
+    gives the same number."""
+    import burnside
+    basis, _, _ = _load(name)
+    g = basis.group
+    assert burnside.dimension(g.perms, g.flips, basis.hamming_weight) == dim
+    if dim < 100000:
+        assert po.enumerate_states(basis)[0].shape[0] == dim
+
+
 @pytest.mark.slow
 def test_exact_dimension_chain_24_symm():
     basis, _, _ = _load("heisenberg_chain_24_symm")
